@@ -1,0 +1,254 @@
+// HBM-bound helper kernels of the forward pass (vectorised, NHWC fp16, 16-byte accesses):
+//   K3  space-to-depth of the NCHW input image (Focus / FocusCustom)  network_blocks.py:330-361
+//   K3b SPP max-pools 5/9/13 written straight into the concat buffer   network_blocks.py:239-246
+//   nearest x2 upsample into a concat slice                            yolo_pafpn_p6.py:153-164
+//   K2  depthwise kxk conv + bias + act                                network_blocks.py:107-120
+#include <cuda_fp16.h>
+
+#include <algorithm>
+
+#include "yx_internal.h"
+
+namespace yx {
+
+__device__ __forceinline__ float act_f(float x, int act) {
+  switch (act) {
+    case YX_ACT_SILU: return x / (1.0f + __expf(-x));
+    case YX_ACT_HSWISH: return x * fminf(fmaxf(x + 3.0f, 0.0f), 6.0f) * (1.0f / 6.0f);
+    case YX_ACT_RELU: return fmaxf(x, 0.0f);
+    case YX_ACT_LRELU: return x > 0.0f ? x : 0.1f * x;
+    default: return x;
+  }
+}
+
+// ------------------------------------------------------------------------------------ S2D
+// One thread per output pixel: reads a 2x2 patch of each of the 3 planes (coalesced along x),
+// optionally applies the predict loop's input affine (main.py:164, img.mul_(s).add_(b) in the image
+// dtype), writes 16 fp16 channels (12 real + 4 zero so the stem conv's K is a multiple of 16).
+template <typename T>
+__device__ __forceinline__ float affine_in(T v, float scale, float shift, bool on);
+template <>
+__device__ __forceinline__ float affine_in<__half>(__half v, float scale, float shift, bool on) {
+  float x = __half2float(v);
+  if (on) {
+    x = __half2float(__float2half_rn(x * scale));   // half.mul_(s): fp32 opmath, rounded to half
+    x = __half2float(__float2half_rn(x + shift));   // half.add_(b)
+  }
+  return x;
+}
+template <>
+__device__ __forceinline__ float affine_in<float>(float v, float scale, float shift, bool on) {
+  return on ? (v * scale) + shift : v;
+}
+
+template <typename T>
+__global__ void s2d_kernel(const T* __restrict__ img, __half* __restrict__ out, int B, int H, int W, int pitch,
+                           int64_t dn, int order, float scale, float shift, int affine) {
+  const int Ho = H >> 1, Wo = W >> 1;
+  const int64_t total = (int64_t)B * Ho * Wo;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = i % Wo, y = (i / Wo) % Ho, b = i / ((int64_t)Wo * Ho);
+    __align__(16) __half v[16];
+#pragma unroll
+    for (int k = 12; k < 16; ++k) v[k] = __float2half(0.f);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const T* p = img + (((int64_t)b * 3 + c) * H + 2 * y) * W + 2 * x;
+      const float tl = affine_in<T>(p[0], scale, shift, affine), tr = affine_in<T>(p[1], scale, shift, affine);
+      const float bl = affine_in<T>(p[W], scale, shift, affine), br = affine_in<T>(p[W + 1], scale, shift, affine);
+      if (order == 1) {  // pixel_unshuffle: oc = c*4 + dy*2 + dx
+        v[c * 4 + 0] = __float2half_rn(tl); v[c * 4 + 1] = __float2half_rn(tr);
+        v[c * 4 + 2] = __float2half_rn(bl); v[c * 4 + 3] = __float2half_rn(br);
+      } else {           // Focus: [TL, BL, TR, BR] patch-major
+        v[0 + c] = __float2half_rn(tl); v[3 + c] = __float2half_rn(bl);
+        v[6 + c] = __float2half_rn(tr); v[9 + c] = __float2half_rn(br);
+      }
+    }
+    uint4* o = reinterpret_cast<uint4*>(out + b * dn + ((int64_t)y * Wo + x) * pitch);
+    o[0] = *reinterpret_cast<const uint4*>(&v[0]);
+    o[1] = *reinterpret_cast<const uint4*>(&v[8]);
+  }
+}
+
+int s2d_launch(const void* image, int image_dtype, int order, int B, int H, int W, float scale, float shift,
+               void* base, const yx_view& dst, cudaStream_t stream) {
+  YX_REQUIRE(H % 2 == 0 && W % 2 == 0, "image H and W must be even");
+  YX_REQUIRE(dst.n == B && dst.h == H / 2 && dst.w == W / 2 && dst.c == 16 && dst.pitch % 8 == 0 && dst.offset % 16 == 0,
+             "s2d dst must be [B,H/2,W/2,16]");
+  __half* out = reinterpret_cast<__half*>(static_cast<uint8_t*>(base) + dst.offset);
+  const int64_t total = (int64_t)B * (H / 2) * (W / 2);
+  const int threads = 256;
+  const int blocks = (int)std::min<int64_t>((total + threads - 1) / threads, 148 * 16);
+  const int affine = (scale != 1.0f || shift != 0.0f) ? 1 : 0;
+  if (image_dtype == YX_F16)
+    s2d_kernel<__half><<<blocks, threads, 0, stream>>>(static_cast<const __half*>(image), out, B, H, W, dst.pitch,
+                                                       dst.nstride, order, scale, shift, affine);
+  else if (image_dtype == YX_F32)
+    s2d_kernel<float><<<blocks, threads, 0, stream>>>(static_cast<const float*>(image), out, B, H, W, dst.pitch,
+                                                      dst.nstride, order, scale, shift, affine);
+  else
+    YX_REQUIRE(false, "image dtype must be YX_F16 or YX_F32");
+  YX_CUDA(cudaGetLastError());
+  return YX_OK;
+}
+
+// ------------------------------------------------------------------------------------ SPP
+__device__ __forceinline__ uint4 hmax8(uint4 a, uint4 b) {
+  uint4 r;
+  __half2* ra = reinterpret_cast<__half2*>(&a);
+  __half2* rb = reinterpret_cast<__half2*>(&b);
+  __half2* rr = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) rr[i] = __hmax2(ra[i], rb[i]);
+  return r;
+}
+
+// src: [B,h,w,C] (slice 0 of the concat buffer); dst: [B,h,w,3C] = slices 1..3 (pool 5, 9, 13).
+// One thread per (pixel, 8 channels); out-of-image taps are skipped (= -inf padding of nn.MaxPool2d).
+__global__ void spp_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int B, int H, int W, int C,
+                           int spitch, int dpitch, int64_t sn, int64_t dn) {
+  const int cv = C >> 3;
+  const int64_t total = (int64_t)B * H * W * cv;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = i % cv;
+    const int64_t pix = i / cv;
+    const int x = pix % W, y = (pix / W) % H, b = pix / ((int64_t)W * H);
+    const uint4 ninf = make_uint4(0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u);
+    uint4 m5 = ninf, m9 = ninf, m13 = ninf;
+    for (int dy = -6; dy <= 6; ++dy) {
+      const int yy = y + dy;
+      if (yy < 0 || yy >= H) continue;
+      const int ady = dy < 0 ? -dy : dy;
+      for (int dx = -6; dx <= 6; ++dx) {
+        const int xx = x + dx;
+        if (xx < 0 || xx >= W) continue;
+        const int adx = dx < 0 ? -dx : dx;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + b * sn + ((int64_t)yy * W + xx) * spitch) + c8);
+        m13 = hmax8(m13, v);
+        if (ady <= 4 && adx <= 4) m9 = hmax8(m9, v);
+        if (ady <= 2 && adx <= 2) m5 = hmax8(m5, v);
+      }
+    }
+    uint4* o = reinterpret_cast<uint4*>(dst + b * dn + ((int64_t)y * W + x) * dpitch);
+    o[c8] = m5;
+    o[cv + c8] = m9;
+    o[2 * cv + c8] = m13;
+  }
+}
+
+int spp_launch(void* base, const yx_view& src, const yx_view& dst, cudaStream_t stream) {
+  YX_REQUIRE(src.c % 8 == 0 && dst.c == 3 * src.c && dst.n == src.n && dst.h == src.h && dst.w == src.w,
+             "spp dst must be [B,h,w,3C]");
+  YX_REQUIRE(src.offset % 16 == 0 && dst.offset % 16 == 0 && src.pitch % 8 == 0 && dst.pitch % 8 == 0, "spp alignment");
+  const int64_t total = (int64_t)src.n * src.h * src.w * (src.c / 8);
+  const int threads = 256;
+  const int blocks = (int)std::min<int64_t>((total + threads - 1) / threads, 148 * 16);
+  spp_kernel<<<blocks, threads, 0, stream>>>(reinterpret_cast<const __half*>(static_cast<uint8_t*>(base) + src.offset),
+                                             reinterpret_cast<__half*>(static_cast<uint8_t*>(base) + dst.offset), src.n,
+                                             src.h, src.w, src.c, src.pitch, dst.pitch, src.nstride, dst.nstride);
+  YX_CUDA(cudaGetLastError());
+  return YX_OK;
+}
+
+// ------------------------------------------------------------------------------------ upsample
+__global__ void upsample2_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int B, int H, int W, int C,
+                                 int spitch, int dpitch, int64_t sn, int64_t dn) {
+  // H, W are the OUTPUT dims
+  const int cv = C >> 3;
+  const int64_t total = (int64_t)B * H * W * cv;
+  const int Hs = H >> 1, Ws = W >> 1;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = i % cv;
+    const int64_t pix = i / cv;
+    const int x = pix % W, y = (pix / W) % H, b = pix / ((int64_t)W * H);
+    const uint4 v =
+        __ldg(reinterpret_cast<const uint4*>(src + b * sn + ((int64_t)(y >> 1) * Ws + (x >> 1)) * spitch) + c8);
+    reinterpret_cast<uint4*>(dst + b * dn + ((int64_t)y * W + x) * dpitch)[c8] = v;
+  }
+}
+
+int upsample_launch(void* base, const yx_view& src, const yx_view& dst, cudaStream_t stream) {
+  YX_REQUIRE(dst.h == 2 * src.h && dst.w == 2 * src.w && dst.c == src.c && dst.n == src.n && src.c % 8 == 0,
+             "upsample dst must be [B,2h,2w,C]");
+  YX_REQUIRE(src.offset % 16 == 0 && dst.offset % 16 == 0 && src.pitch % 8 == 0 && dst.pitch % 8 == 0, "upsample alignment");
+  const int64_t total = (int64_t)dst.n * dst.h * dst.w * (dst.c / 8);
+  const int threads = 256;
+  const int blocks = (int)std::min<int64_t>((total + threads - 1) / threads, 148 * 16);
+  upsample2_kernel<<<blocks, threads, 0, stream>>>(
+      reinterpret_cast<const __half*>(static_cast<uint8_t*>(base) + src.offset),
+      reinterpret_cast<__half*>(static_cast<uint8_t*>(base) + dst.offset), dst.n, dst.h, dst.w, dst.c, src.pitch,
+      dst.pitch, src.nstride, dst.nstride);
+  YX_CUDA(cudaGetLastError());
+  return YX_OK;
+}
+
+// ------------------------------------------------------------------------------------ depthwise
+// weights fp16 [k*k][C], bias fp32 [C]; fp32 accumulate; one thread per (output pixel, 8 channels).
+__global__ void dwconv_kernel(const __half* __restrict__ src, __half* __restrict__ dst, const __half* __restrict__ wgt,
+                              const float* __restrict__ bias, int B, int H, int W, int Ho, int Wo, int C, int k,
+                              int stride, int act, int spitch, int dpitch, int64_t sn, int64_t dn) {
+  const int cv = C >> 3;
+  const int pad = k >> 1;
+  const int64_t total = (int64_t)B * Ho * Wo * cv;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = i % cv;
+    const int64_t pix = i / cv;
+    const int x = pix % Wo, y = (pix / Wo) % Ho, b = pix / ((int64_t)Wo * Ho);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int dy = 0; dy < k; ++dy) {
+      const int yy = y * stride + dy - pad;
+      if (yy < 0 || yy >= H) continue;
+      for (int dx = 0; dx < k; ++dx) {
+        const int xx = x * stride + dx - pad;
+        if (xx < 0 || xx >= W) continue;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + b * sn + ((int64_t)yy * W + xx) * spitch) + c8);
+        const uint4 w = __ldg(reinterpret_cast<const uint4*>(wgt + (int64_t)(dy * k + dx) * C) + c8);
+        const __half2* vh = reinterpret_cast<const __half2*>(&v);
+        const __half2* wh = reinterpret_cast<const __half2*>(&w);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 a = __half22float2(vh[j]), ww = __half22float2(wh[j]);
+          acc[2 * j] = fmaf(a.x, ww.x, acc[2 * j]);
+          acc[2 * j + 1] = fmaf(a.y, ww.y, acc[2 * j + 1]);
+        }
+      }
+    }
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float f0 = acc[2 * j] + bias[c8 * 8 + 2 * j], f1 = acc[2 * j + 1] + bias[c8 * 8 + 2 * j + 1];
+      f0 = act_f(__half2float(__float2half_rn(f0)), act);
+      f1 = act_f(__half2float(__float2half_rn(f1)), act);
+      oh[j] = __floats2half2_rn(f0, f1);
+    }
+    reinterpret_cast<uint4*>(dst + b * dn + ((int64_t)y * Wo + x) * dpitch)[c8] = o;
+  }
+}
+
+int dwconv_launch(void* base, const yx_op& op, const void* weights, const void* biases, cudaStream_t stream) {
+  const yx_view& s = op.src;
+  const yx_view& d = op.dst;
+  YX_REQUIRE(op.ksize == 3 || op.ksize == 5, "depthwise ksize must be 3 or 5");
+  YX_REQUIRE(op.stride == 1 || op.stride == 2, "depthwise stride must be 1 or 2");
+  const int pad = op.ksize / 2;
+  const int Ho = (s.h + 2 * pad - op.ksize) / op.stride + 1, Wo = (s.w + 2 * pad - op.ksize) / op.stride + 1;
+  YX_REQUIRE(d.h == Ho && d.w == Wo && d.c == s.c && d.n == s.n && s.c % 8 == 0, "depthwise dst geometry");
+  YX_REQUIRE(s.offset % 16 == 0 && d.offset % 16 == 0 && s.pitch % 8 == 0 && d.pitch % 8 == 0 && op.w_offset % 16 == 0,
+             "depthwise alignment");
+  const int64_t total = (int64_t)d.n * Ho * Wo * (d.c / 8);
+  const int threads = 256;
+  const int blocks = (int)std::min<int64_t>((total + threads - 1) / threads, 148 * 16);
+  dwconv_kernel<<<blocks, threads, 0, stream>>>(
+      reinterpret_cast<const __half*>(static_cast<uint8_t*>(base) + s.offset),
+      reinterpret_cast<__half*>(static_cast<uint8_t*>(base) + d.offset),
+      reinterpret_cast<const __half*>(static_cast<const uint8_t*>(weights) + op.w_offset),
+      reinterpret_cast<const float*>(static_cast<const uint8_t*>(biases) + op.b_offset), s.n, s.h, s.w, Ho, Wo, s.c,
+      op.ksize, op.stride, op.act, s.pitch, d.pitch, s.nstride, d.nstride);
+  YX_CUDA(cudaGetLastError());
+  return YX_OK;
+}
+
+}  // namespace yx

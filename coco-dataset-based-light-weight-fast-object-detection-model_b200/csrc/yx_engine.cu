@@ -1,0 +1,206 @@
+// Engine: executes a planned op list (built by the Python graph builder) on one stream.
+// Everything is resolved at create time — tensor maps, tile shapes, launch geometry — so a run is
+// a fixed sequence of kernel launches that can be replayed as a CUDA graph (bs1 latency).
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "yx_internal.h"
+
+namespace yx {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  char buf[512];
+  snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+  g_last_error = buf;
+  return YX_ERR_CUDA;
+}
+
+struct Step {
+  yx_op op;
+  ConvPlan conv;  // valid when op.kind == YX_OP_CONV
+  double flops = 0, bytes = 0;
+};
+
+}  // namespace yx
+
+struct yx_engine {
+  std::vector<yx::Step> steps;
+  void* arena = nullptr;
+  size_t arena_bytes = 0;
+  const void* weights = nullptr;
+  const void* biases = nullptr;
+  int in_h = 0, in_w = 0, batch = 0;
+  int num_sms = 148;
+  cudaGraphExec_t graph_exec = nullptr;
+  cudaStream_t graph_stream = nullptr;  // stream the graph was captured on (informational)
+};
+
+using namespace yx;
+
+static bool view_ok(const yx_view& v, size_t arena_bytes) {
+  if (v.n < 1 || v.h < 1 || v.w < 1 || v.c < 1 || v.pitch < v.c || v.offset < 0) return false;
+  if (v.nstride < (int64_t)v.h * v.w * v.pitch - (v.pitch - v.c)) return false;
+  const size_t end = (size_t)v.offset + ((size_t)(v.n - 1) * v.nstride + ((size_t)v.h * v.w - 1) * v.pitch + v.c) * 2;
+  return end <= arena_bytes;
+}
+
+static int run_step(yx_engine* e, const Step& s, const void* image, int image_dtype, float in_scale, float in_shift,
+                    cudaStream_t st) {
+  switch (s.op.kind) {
+    case YX_OP_CONV: return conv_launch(s.conv, st);
+    case YX_OP_S2D:
+      return s2d_launch(image, image_dtype, s.op.aux, e->batch, e->in_h, e->in_w, in_scale, in_shift, e->arena, s.op.dst, st);
+    case YX_OP_SPP: return spp_launch(e->arena, s.op.src, s.op.dst, st);
+    case YX_OP_UPSAMPLE: return upsample_launch(e->arena, s.op.src, s.op.dst, st);
+    case YX_OP_DWCONV: return dwconv_launch(e->arena, s.op, e->weights, e->biases, st);
+    default: set_error("unknown op kind"); return YX_ERR_INVALID;
+  }
+}
+
+extern "C" const char* yx_last_error(void) { return g_last_error.c_str(); }
+extern "C" int yx_abi_version(void) { return YX_ABI_VERSION; }
+
+extern "C" int yx_engine_create(const yx_op* ops, int n_ops, void* arena, size_t arena_bytes, const void* weights,
+                                size_t weights_bytes, const void* biases, size_t bias_bytes, int in_h, int in_w,
+                                int batch, yx_engine** out) {
+  YX_REQUIRE(ops && n_ops > 0 && arena && weights && biases && out, "null argument");
+  YX_REQUIRE(((uintptr_t)arena % 1024) == 0 && ((uintptr_t)weights % 256) == 0 && ((uintptr_t)biases % 256) == 0,
+             "arena must be 1024-byte aligned, weights/biases 256-byte aligned");
+  YX_REQUIRE(ops[0].kind == YX_OP_S2D, "the first op must be the image space-to-depth");
+  int dev = 0, sms = 148;
+  YX_CUDA(cudaGetDevice(&dev));
+  YX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  int cc_major = 0;
+  YX_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (cc_major != 10) {
+    set_error("yolox_b200 requires an sm_100 (Blackwell B200) device; there is no fallback path");
+    return YX_ERR_UNSUPPORTED;
+  }
+  auto* e = new yx_engine();
+  e->arena = arena; e->arena_bytes = arena_bytes; e->weights = weights; e->biases = biases;
+  e->in_h = in_h; e->in_w = in_w; e->batch = batch; e->num_sms = sms;
+  e->steps.resize(n_ops);
+  for (int i = 0; i < n_ops; ++i) {
+    Step& s = e->steps[i];
+    s.op = ops[i];
+    const yx_op& op = s.op;
+    char where[64];
+    snprintf(where, sizeof where, "op %d: ", i);
+    bool ok = view_ok(op.dst, arena_bytes);
+    if (op.kind != YX_OP_S2D) ok = ok && view_ok(op.src, arena_bytes);
+    if (op.kind == YX_OP_CONV && op.res.c > 0) ok = ok && view_ok(op.res, arena_bytes);
+    int rc = YX_OK;
+    if (!ok) {
+      set_error(std::string(where) + "view outside the arena");
+      rc = YX_ERR_INVALID;
+    } else if (op.kind == YX_OP_CONV) {
+      const size_t wend = (size_t)op.w_offset + (size_t)op.cout_pad * op.ksize * op.ksize * op.cin_pad * 2;
+      const size_t bend = (size_t)op.b_offset + (size_t)op.cout_pad * 4;
+      if (wend > weights_bytes || bend > bias_bytes || op.b_offset % 16 != 0) {
+        set_error(std::string(where) + "weight/bias range outside the blobs");
+        rc = YX_ERR_INVALID;
+      } else {
+        rc = conv_plan(op, arena, weights, biases, sms, &s.conv);
+        s.flops = s.conv.flops; s.bytes = s.conv.bytes;
+        if (rc != YX_OK) set_error(std::string(where) + g_last_error);
+      }
+    } else {
+      const double dpx = (double)op.dst.n * op.dst.h * op.dst.w;
+      if (op.kind == YX_OP_S2D) s.bytes = dpx * (12.0 * 2 /*image read, fp16*/ + 16.0 * 2);
+      else if (op.kind == YX_OP_SPP) s.bytes = dpx * (op.src.c * 2.0 + op.dst.c * 2.0);
+      else if (op.kind == YX_OP_UPSAMPLE) s.bytes = dpx * op.dst.c * 2.0 * 1.25;
+      else if (op.kind == YX_OP_DWCONV) {
+        s.bytes = 2.0 * ((double)op.src.n * op.src.h * op.src.w * op.src.c + dpx * op.dst.c);
+        s.flops = 2.0 * dpx * op.dst.c * op.ksize * op.ksize;
+      }
+    }
+    if (rc != YX_OK) { delete e; return rc; }
+  }
+  *out = e;
+  return YX_OK;
+}
+
+extern "C" void yx_engine_destroy(yx_engine* e) {
+  if (!e) return;
+  if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+  delete e;
+}
+
+extern "C" int yx_engine_num_launches(const yx_engine* e) { return e ? (int)e->steps.size() : 0; }
+
+extern "C" int yx_engine_run(yx_engine* e, const void* image, int image_dtype, float in_scale, float in_shift,
+                             int use_graph, void* stream) {
+  YX_REQUIRE(e && image, "null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = run_step(e, e->steps[0], image, image_dtype, in_scale, in_shift, st);
+  if (rc) return rc;
+  if (!use_graph) {
+    for (size_t i = 1; i < e->steps.size(); ++i)
+      if ((rc = run_step(e, e->steps[i], image, image_dtype, in_scale, in_shift, st)) != YX_OK) return rc;
+    return YX_OK;
+  }
+  if (!e->graph_exec) {
+    // capture ops 1..n-1 (none of them touches caller memory, so the graph is replayable as is)
+    cudaGraph_t graph = nullptr;
+    YX_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    for (size_t i = 1; i < e->steps.size() && rc == YX_OK; ++i)
+      rc = run_step(e, e->steps[i], image, image_dtype, in_scale, in_shift, st);
+    cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (rc != YX_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    YX_CUDA(ce);
+    ce = cudaGraphInstantiate(&e->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    YX_CUDA(ce);
+    e->graph_stream = st;
+  }
+  YX_CUDA(cudaGraphLaunch(e->graph_exec, st));
+  return YX_OK;
+}
+
+extern "C" int yx_engine_profile(yx_engine* e, const void* image, int image_dtype, int iters, void* stream,
+                                 float* ms_host, double* flops_host, double* bytes_host, int n_ops) {
+  YX_REQUIRE(e && image && ms_host && n_ops == (int)e->steps.size() && iters >= 1, "bad profile arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaEvent_t ev0, ev1;
+  YX_CUDA(cudaEventCreate(&ev0));
+  YX_CUDA(cudaEventCreate(&ev1));
+  int rc = YX_OK;
+  for (int i = 0; i < n_ops && rc == YX_OK; ++i) {
+    const Step& s = e->steps[i];
+    // every op is idempotent on the arena (each reads buffers that later ops do not overwrite
+    // before it re-runs in this loop only if the plan has no aliasing between its src and dst)
+    rc = run_step(e, s, image, image_dtype, 1.0f, 0.0f, st);  // warm
+    if (rc) break;
+    cudaEventRecord(ev0, st);
+    for (int k = 0; k < iters && rc == YX_OK; ++k) rc = run_step(e, s, image, image_dtype, 1.0f, 0.0f, st);
+    cudaEventRecord(ev1, st);
+    if (cudaEventSynchronize(ev1) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "profile sync", __FILE__, __LINE__); break; }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    ms_host[i] = ms / iters;
+    if (flops_host) flops_host[i] = s.flops;
+    if (bytes_host) bytes_host[i] = s.bytes;
+  }
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+  return rc;
+}
+
+extern "C" int yx_conv2d(const yx_op* op, void* base, const void* weights, const void* biases, void* stream) {
+  YX_REQUIRE(op && base && weights && biases, "null argument");
+  YX_REQUIRE(op->kind == YX_OP_CONV, "yx_conv2d expects a YX_OP_CONV op");
+  int dev = 0, sms = 148;
+  YX_CUDA(cudaGetDevice(&dev));
+  YX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  ConvPlan plan;
+  int rc = conv_plan(*op, base, weights, biases, sms, &plan);
+  if (rc) return rc;
+  return conv_launch(plan, static_cast<cudaStream_t>(stream));
+}

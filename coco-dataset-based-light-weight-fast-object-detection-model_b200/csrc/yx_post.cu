@@ -1,0 +1,657 @@
+// K4/K5/K6 — head decode, score thresholding + candidate compaction, per-image sort and batched
+// class-aware greedy NMS for all images of the batch in one launch each.
+//
+//   decode (infer flavour)    choijhanyangackr/yolox_infer/postprocess_utils.py:27-52
+//   decode (yolox flavour)    yolox/models/yolo_head.py:167-168,186-190,210-225
+//   candidate selection       postprocess_utils.py:86-103 ; yolox/utils/boxes.py:38-59
+//   NMS                       torchvision.ops.nms / batched_nms semantics (CPU kernel arithmetic:
+//                             every fp32 operation rounded separately, strict '>' on IoU, stable
+//                             descending score order; ties -> lower anchor index first)
+//
+// Arithmetic that decides KEPT INDEX SETS (IoU, coordinate-trick offsets) is written with
+// __fadd_rn/__fmul_rn/__fdiv_rn so nvcc cannot contract it into FMAs: results are bit-identical to
+// the CPU restatement in oracle/post_ref.c.
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+#include <algorithm>
+
+#include "yx_internal.h"
+
+namespace yx {
+
+struct LevelsDev {
+  int n;
+  int h[8], w[8], stride[8], off[9];
+};
+
+static int make_levels(const yx_levels* lv, int A, LevelsDev* out) {
+  YX_REQUIRE(lv != nullptr && lv->n_levels >= 1 && lv->n_levels <= 8, "levels: 1..8");
+  out->n = lv->n_levels;
+  int off = 0;
+  for (int i = 0; i < lv->n_levels; ++i) {
+    out->h[i] = lv->h[i]; out->w[i] = lv->w[i]; out->stride[i] = lv->stride[i]; out->off[i] = off;
+    off += lv->h[i] * lv->w[i];
+  }
+  out->off[lv->n_levels] = off;
+  YX_REQUIRE(off == A, "sum of level h*w must equal A");
+  return YX_OK;
+}
+
+__device__ __forceinline__ void anchor_geom(const LevelsDev& lv, int a, float* gx, float* gy, float* s) {
+  int l = 0;
+  while (l + 1 < lv.n && a >= lv.off[l + 1]) ++l;
+  const int r = a - lv.off[l];
+  *gx = (float)(r % lv.w[l]);
+  *gy = (float)(r / lv.w[l]);
+  *s = (float)lv.stride[l];
+}
+
+template <typename T> __device__ __forceinline__ float ldf(const T* p);
+template <> __device__ __forceinline__ float ldf<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float ldf<__half>(const __half* p) { return __half2float(*p); }
+
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+
+// postprocess_utils.py:37-44: cx=(tx+gx)*s ; half=exp(tw)*(s/2) ; xyxy = c -/+ half   (fp32)
+__device__ __forceinline__ float4 decode_box_xyxy(float t0, float t1, float t2, float t3, float gx, float gy, float s) {
+  const float cx = __fmul_rn(__fadd_rn(t0, gx), s), cy = __fmul_rn(__fadd_rn(t1, gy), s);
+  const float hw = __fmul_rn(expf(t2), s * 0.5f), hh = __fmul_rn(expf(t3), s * 0.5f);
+  return make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
+}
+
+// map fp32 to a uint32 whose unsigned order equals the float order
+__device__ __forceinline__ uint32_t f2sortable(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ uint64_t make_key(float score, int anchor) {
+  return (static_cast<uint64_t>(f2sortable(score)) << 32) | static_cast<uint64_t>(0xFFFFFFFFu - (uint32_t)anchor);
+}
+
+// ------------------------------------------------------------------------------------------------
+// workspace
+// ------------------------------------------------------------------------------------------------
+struct Workspace {
+  float4* box;     // [B][A]
+  float* objc;     // [B][A]
+  float* col5;     // [B][A]  value written to det column 5
+  float* score;    // [B][A]  NMS score
+  int* label;      // [B][A]
+  uint64_t* keys;  // [B][Apad]
+  float4* sbox;    // [B][A]  sorted (and offset) boxes
+  int* slabel;     // [B][A]
+  float4* kbox;    // [B][A]  kept boxes (uncapped mode)
+  int* klabel;     // [B][A]
+  int* kidx;       // [B][A]  kept candidate rank
+  int* count;      // [B]
+  int Apad;
+};
+
+static int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+static size_t ws_layout(int B, int A, uint8_t* base, Workspace* ws) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    uint8_t* p = base ? base + off : nullptr;
+    off += (bytes + 255) & ~size_t(255);
+    return p;
+  };
+  const size_t n = (size_t)B * A;
+  const int Apad = next_pow2(std::max(A, 2));
+  Workspace w;
+  w.box = (float4*)take(n * 16); w.objc = (float*)take(n * 4); w.col5 = (float*)take(n * 4);
+  w.score = (float*)take(n * 4); w.label = (int*)take(n * 4);
+  w.keys = (uint64_t*)take((size_t)B * Apad * 8);
+  w.sbox = (float4*)take(n * 16); w.slabel = (int*)take(n * 4);
+  w.kbox = (float4*)take(n * 16); w.klabel = (int*)take(n * 4); w.kidx = (int*)take(n * 4);
+  w.count = (int*)take((size_t)B * 4);
+  w.Apad = Apad;
+  if (ws) *ws = w;
+  return off;
+}
+
+// ------------------------------------------------------------------------------------------------
+// decode kernels
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void decode_infer_kernel(const T* __restrict__ reg, int64_t reg_sb, int64_t reg_sa, const T* __restrict__ obj,
+                                    int64_t obj_sb, int64_t obj_sa, const T* __restrict__ cls, int64_t cls_sb,
+                                    int64_t cls_sa, int B, int A, int C, LevelsDev lv, float* __restrict__ boxes,
+                                    float* __restrict__ obj_conf, float* __restrict__ cls_conf) {
+  const int64_t total = (int64_t)B * A;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int a = i % A, b = i / A;
+    float gx, gy, s;
+    anchor_geom(lv, a, &gx, &gy, &s);
+    const T* r = reg + b * reg_sb + a * reg_sa;
+    const float4 bx = decode_box_xyxy(ldf(r), ldf(r + 1), ldf(r + 2), ldf(r + 3), gx, gy, s);
+    reinterpret_cast<float4*>(boxes)[i] = bx;
+    const float oc = sigmoid_f(ldf(obj + b * obj_sb + a * obj_sa));
+    obj_conf[i] = oc;
+    const T* c = cls + b * cls_sb + a * cls_sa;
+    float* o = cls_conf + i * C;
+    for (int k = 0; k < C; ++k) o[k] = __fmul_rn(sigmoid_f(ldf(c + k)), oc);
+  }
+}
+
+// Fused decode + class max + threshold + compaction from raw logits: never writes [B,A,C].
+template <typename T, bool VEC8>
+__global__ void select_infer_kernel(const T* __restrict__ reg, int64_t reg_sb, int64_t reg_sa, const T* __restrict__ obj,
+                                    int64_t obj_sb, int64_t obj_sa, const T* __restrict__ cls, int64_t cls_sb,
+                                    int64_t cls_sa, int B, int A, int C, LevelsDev lv, float thr, Workspace ws) {
+  const int64_t total = (int64_t)B * A;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int a = i % A, b = i / A;
+    const float oc = sigmoid_f(ldf(obj + b * obj_sb + a * obj_sa));
+    const T* c = cls + b * cls_sb + a * cls_sa;
+    float best = -1.0f;
+    int bi = 0;
+    if (VEC8) {  // T == __half, 16-byte aligned rows, C % 8 == 0
+      const uint4* cv = reinterpret_cast<const uint4*>(c);
+      for (int k8 = 0; k8 < (C >> 3); ++k8) {
+        const uint4 v = __ldg(cv + k8);
+        const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(h[j]);
+          const float s0 = __fmul_rn(sigmoid_f(f.x), oc), s1 = __fmul_rn(sigmoid_f(f.y), oc);
+          if (s0 > best) { best = s0; bi = k8 * 8 + 2 * j; }
+          if (s1 > best) { best = s1; bi = k8 * 8 + 2 * j + 1; }
+        }
+      }
+    } else {
+      for (int k = 0; k < C; ++k) {
+        const float s0 = __fmul_rn(sigmoid_f(ldf(c + k)), oc);
+        if (s0 > best) { best = s0; bi = k; }
+      }
+    }
+    if (best >= thr) {  // torch.greater_equal(cls_conf_i, conf_threshold), postprocess_utils.py:87
+      float gx, gy, s;
+      anchor_geom(lv, a, &gx, &gy, &s);
+      const T* r = reg + b * reg_sb + a * reg_sa;
+      ws.box[i] = decode_box_xyxy(ldf(r), ldf(r + 1), ldf(r + 2), ldf(r + 3), gx, gy, s);
+      ws.objc[i] = oc; ws.col5[i] = best; ws.score[i] = best; ws.label[i] = bi;
+      const int pos = atomicAdd(ws.count + b, 1);
+      ws.keys[(int64_t)b * ws.Apad + pos] = make_key(best, a);
+    }
+  }
+}
+
+// Same selection from already decoded fp32 tensors (the reference-style two-call API).
+__global__ void select_decoded_kernel(const float* __restrict__ boxes, const float* __restrict__ obj_conf,
+                                      const float* __restrict__ cls_conf, int B, int A, int C, float thr, Workspace ws) {
+  const int64_t total = (int64_t)B * A;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int a = i % A, b = i / A;
+    const float* c = cls_conf + i * C;
+    float best = c[0];
+    int bi = 0;
+    for (int k = 1; k < C; ++k) {
+      const float v = c[k];
+      if (v > best) { best = v; bi = k; }
+    }
+    if (best >= thr) {
+      ws.box[i] = reinterpret_cast<const float4*>(boxes)[i];
+      ws.objc[i] = obj_conf[i]; ws.col5[i] = best; ws.score[i] = best; ws.label[i] = bi;
+      const int pos = atomicAdd(ws.count + b, 1);
+      ws.keys[(int64_t)b * ws.Apad + pos] = make_key(best, a);
+    }
+  }
+}
+
+template <typename T> __device__ __forceinline__ T from_f(float f);
+template <> __device__ __forceinline__ float from_f<float>(float f) { return f; }
+template <> __device__ __forceinline__ __half from_f<__half>(float f) { return __float2half_rn(f); }
+// round-trip through T: models arithmetic carried out in the tensor's dtype
+template <typename T> __device__ __forceinline__ float rnd(float f);
+template <> __device__ __forceinline__ float rnd<float>(float f) { return f; }
+template <> __device__ __forceinline__ float rnd<__half>(float f) { return __half2float(__float2half_rn(f)); }
+
+// yolox.utils.postprocess selection (boxes.py:38-57): in-place cxcywh -> xyxy in the tensor dtype,
+// class max, score = obj*class_conf (tensor dtype), >= thr.
+template <typename T>
+__global__ void select_yolox_kernel(T* __restrict__ pred, int B, int A, int C, float thr, Workspace ws) {
+  const int64_t total = (int64_t)B * A;
+  const int D = 5 + C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int a = i % A, b = i / A;
+    T* p = pred + i * D;
+    const float cx = ldf(p), cy = ldf(p + 1), w = ldf(p + 2), h = ldf(p + 3);
+    const float hw = rnd<T>(w * 0.5f), hh = rnd<T>(h * 0.5f);  // x/2 is exact unless subnormal
+    const float x1 = rnd<T>(__fsub_rn(cx, hw)), y1 = rnd<T>(__fsub_rn(cy, hh));
+    const float x2 = rnd<T>(__fadd_rn(cx, hw)), y2 = rnd<T>(__fadd_rn(cy, hh));
+    p[0] = from_f<T>(x1); p[1] = from_f<T>(y1); p[2] = from_f<T>(x2); p[3] = from_f<T>(y2);
+    const float oc = ldf(p + 4);
+    float best = ldf(p + 5);
+    int bi = 0;
+    for (int k = 1; k < C; ++k) {
+      const float v = ldf(p + 5 + k);
+      if (v > best) { best = v; bi = k; }
+    }
+    const float sc = rnd<T>(__fmul_rn(oc, best));
+    if (sc >= rnd<T>(thr)) {
+      ws.box[i] = make_float4(x1, y1, x2, y2);
+      ws.objc[i] = oc; ws.col5[i] = best; ws.score[i] = sc; ws.label[i] = bi;
+      const int pos = atomicAdd(ws.count + b, 1);
+      ws.keys[(int64_t)b * ws.Apad + pos] = make_key(sc, a);
+    }
+  }
+}
+
+// yolox head output assembly (+ optional decode) in dtype To from raw logits of dtype Ti.
+template <typename Ti, typename To>
+__global__ void head_assemble_kernel(const Ti* __restrict__ reg, int64_t reg_sb, int64_t reg_sa, const Ti* __restrict__ obj,
+                                     int64_t obj_sb, int64_t obj_sa, const Ti* __restrict__ cls, int64_t cls_sb,
+                                     int64_t cls_sa, int B, int A, int C, LevelsDev lv, int decode, To* __restrict__ out) {
+  const int64_t total = (int64_t)B * A;
+  const int D = 5 + C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int a = i % A, b = i / A;
+    const Ti* r = reg + b * reg_sb + a * reg_sa;
+    float t0 = ldf(r), t1 = ldf(r + 1), t2 = ldf(r + 2), t3 = ldf(r + 3);
+    To* o = out + i * D;
+    if (decode) {  // yolo_head.py:223-224, arithmetic in the tensor dtype
+      float gx, gy, s;
+      anchor_geom(lv, a, &gx, &gy, &s);
+      t0 = rnd<To>(__fmul_rn(rnd<To>(__fadd_rn(t0, gx)), s));
+      t1 = rnd<To>(__fmul_rn(rnd<To>(__fadd_rn(t1, gy)), s));
+      t2 = rnd<To>(__fmul_rn(rnd<To>(expf(t2)), s));
+      t3 = rnd<To>(__fmul_rn(rnd<To>(expf(t3)), s));
+    }
+    o[0] = from_f<To>(t0); o[1] = from_f<To>(t1); o[2] = from_f<To>(t2); o[3] = from_f<To>(t3);
+    o[4] = from_f<To>(sigmoid_f(ldf(obj + b * obj_sb + a * obj_sa)));
+    const Ti* c = cls + b * cls_sb + a * cls_sa;
+    for (int k = 0; k < C; ++k) o[5 + k] = from_f<To>(sigmoid_f(ldf(c + k)));
+  }
+}
+
+template <typename T>
+__global__ void decode_outputs_kernel(T* __restrict__ out, int B, int A, int D, LevelsDev lv) {
+  const int64_t total = (int64_t)B * A;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int a = i % A;
+    float gx, gy, s;
+    anchor_geom(lv, a, &gx, &gy, &s);
+    T* o = out + i * D;
+    o[0] = from_f<T>(__fmul_rn(rnd<T>(__fadd_rn(ldf(o), gx)), s));
+    o[1] = from_f<T>(__fmul_rn(rnd<T>(__fadd_rn(ldf(o + 1), gy)), s));
+    o[2] = from_f<T>(__fmul_rn(rnd<T>(expf(ldf(o + 2))), s));
+    o[3] = from_f<T>(__fmul_rn(rnd<T>(expf(ldf(o + 3))), s));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-image bitonic sort of the candidate keys, descending (one CTA per image)
+// ------------------------------------------------------------------------------------------------
+constexpr int kSortThreads = 1024;
+constexpr int kSortChunk = 8192;  // keys resident in shared memory (64 KB)
+
+__device__ __forceinline__ void cmpx(uint64_t& a, uint64_t& b, bool desc) {
+  if ((a < b) == desc) { const uint64_t t = a; a = b; b = t; }
+}
+
+__global__ void __launch_bounds__(kSortThreads, 1) sort_keys_kernel(Workspace ws) {
+  extern __shared__ uint64_t sk[];
+  const int b = blockIdx.x;
+  const int n = ws.count[b];
+  if (n <= 1) return;
+  uint64_t* keys = ws.keys + (int64_t)b * ws.Apad;
+  int N = 2;
+  while (N < n) N <<= 1;
+  for (int i = n + threadIdx.x; i < N; i += kSortThreads) keys[i] = 0;  // pads sort last
+  __syncthreads();
+  const int chunk = min(N, kSortChunk);
+  // phase 1: fully sort every chunk in shared memory (k = 2 .. chunk)
+  for (int c0 = 0; c0 < N; c0 += chunk) {
+    for (int i = threadIdx.x; i < chunk; i += kSortThreads) sk[i] = keys[c0 + i];
+    __syncthreads();
+    for (int k = 2; k <= chunk; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int t = threadIdx.x; t < (chunk >> 1); t += kSortThreads) {
+          const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+          cmpx(sk[i], sk[i | j], (((c0 + i) & k) == 0));
+        }
+        __syncthreads();
+      }
+    for (int i = threadIdx.x; i < chunk; i += kSortThreads) keys[c0 + i] = sk[i];
+    __syncthreads();
+  }
+  // phase 2: merge across chunks; strides >= chunk go through global memory (L2 resident)
+  for (int k = chunk << 1; k <= N; k <<= 1) {
+    for (int j = k >> 1; j >= chunk; j >>= 1) {
+      for (int t = threadIdx.x; t < (N >> 1); t += kSortThreads) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        uint64_t a = keys[i], c = keys[i | j];
+        const uint64_t a0 = a;
+        cmpx(a, c, ((i & k) == 0));
+        if (a != a0) { keys[i] = a; keys[i | j] = c; }
+      }
+      __syncthreads();
+    }
+    for (int c0 = 0; c0 < N; c0 += chunk) {
+      for (int i = threadIdx.x; i < chunk; i += kSortThreads) sk[i] = keys[c0 + i];
+      __syncthreads();
+      for (int j = chunk >> 1; j > 0; j >>= 1) {
+        for (int t = threadIdx.x; t < (chunk >> 1); t += kSortThreads) {
+          const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+          cmpx(sk[i], sk[i | j], (((c0 + i) & k) == 0));
+        }
+        __syncthreads();
+      }
+      for (int i = threadIdx.x; i < chunk; i += kSortThreads) keys[c0 + i] = sk[i];
+      __syncthreads();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// batched greedy NMS: one CTA per image, candidates visited in score order in blocks of 64;
+// each block is tested against the kept list (16 threads per candidate), then resolved with a
+// 64x64 suppression bitmask held in shared memory.
+// ------------------------------------------------------------------------------------------------
+constexpr int kNmsThreads = 1024;
+constexpr int kKeptSmem = 1024;  // kept boxes held in shared memory when max_det <= this
+
+__device__ __forceinline__ bool iou_gt(const float4 a, const float4 b, float thr) {
+  const float left = fmaxf(a.x, b.x), top = fmaxf(a.y, b.y);
+  const float right = fminf(a.z, b.z), bottom = fminf(a.w, b.w);
+  const float w = fmaxf(0.0f, __fsub_rn(right, left)), h = fmaxf(0.0f, __fsub_rn(bottom, top));
+  const float inter = __fmul_rn(w, h);
+  const float sa = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+  const float sb = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+  const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(sa, sb), inter));
+  return ovr > thr;
+}
+
+__global__ void __launch_bounds__(kNmsThreads, 1)
+nms_kernel(Workspace ws, int A, float nms_thr, int max_nms, int max_det, int mode, int det_rows, float* __restrict__ det,
+           int* __restrict__ det_count, int* __restrict__ det_anchor) {
+  __shared__ float4 s_kbox[kKeptSmem];
+  __shared__ int s_klab[kKeptSmem];
+  __shared__ float4 s_cbox[64];
+  __shared__ int s_clab[64];
+  __shared__ unsigned long long s_mask[64];
+  __shared__ int s_pre[64];
+  __shared__ float s_red[32];
+  __shared__ int s_kept;
+
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  int n = ws.count[b];
+  if (max_nms > 0 && n > max_nms) n = max_nms;
+  if (mode == YX_NMS_AUTO) mode = (4 * (int64_t)n > 100000) ? YX_NMS_VANILLA : YX_NMS_TRICK;
+  const uint64_t* keys = ws.keys + (int64_t)b * ws.Apad;
+  const int64_t ib = (int64_t)b * A;
+  float4* sbox = ws.sbox + ib;
+  int* slab = ws.slabel + ib;
+  int* kidx = ws.kidx + ib;
+  const bool kept_in_smem = (max_det > 0 && max_det <= kKeptSmem);
+  float4* kbox = kept_in_smem ? s_kbox : (ws.kbox + ib);
+  int* klab = kept_in_smem ? s_klab : (ws.klabel + ib);
+  const int cap = max_det > 0 ? max_det : 0x7fffffff;
+
+  // ---- gather the selected candidates in score order; coordinate-trick offsets -----------------
+  float mx = -INFINITY;
+  for (int i = tid; i < n; i += kNmsThreads) {
+    const int a = (int)(0xFFFFFFFFu - (uint32_t)(keys[i] & 0xFFFFFFFFull));
+    const float4 bx = ws.box[ib + a];
+    sbox[i] = bx;
+    slab[i] = ws.label[ib + a];
+    mx = fmaxf(fmaxf(mx, fmaxf(bx.x, bx.y)), fmaxf(bx.z, bx.w));
+  }
+  if (mode == YX_NMS_TRICK) {
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) s_red[wid] = mx;
+    __syncthreads();
+    mx = s_red[0];
+    for (int i = 1; i < kNmsThreads / 32; ++i) mx = fmaxf(mx, s_red[i]);
+    const float m1 = __fadd_rn(mx, 1.0f);  // boxes.max() + 1
+    for (int i = tid; i < n; i += kNmsThreads) {  // each thread re-reads only what it wrote
+      const float off = __fmul_rn((float)slab[i], m1);
+      float4 bx = sbox[i];
+      bx.x = __fadd_rn(bx.x, off); bx.y = __fadd_rn(bx.y, off); bx.z = __fadd_rn(bx.z, off); bx.w = __fadd_rn(bx.w, off);
+      sbox[i] = bx;
+    }
+  }
+  if (tid == 0) s_kept = 0;
+  __syncthreads();
+
+  // ---- greedy pass -------------------------------------------------------------------------------
+  const bool same_class_only = (mode == YX_NMS_VANILLA);
+  const int ci = tid >> 4, sub = tid & 15;  // candidate slot and sub-lane within the 16-thread group
+  for (int base = 0; base < n; base += 64) {
+    const int kept = s_kept;
+    if (kept >= cap) break;
+    const int m = min(64, n - base);
+    if (tid < 64) {
+      if (tid < m) { s_cbox[tid] = sbox[base + tid]; s_clab[tid] = slab[base + tid]; }
+    }
+    __syncthreads();
+    bool sup = false;
+    unsigned long long bits = 0ull;
+    if (ci < m) {
+      const float4 cb = s_cbox[ci];
+      const int cl = s_clab[ci];
+      for (int k = sub; k < kept; k += 16) {
+        if (same_class_only && klab[k] != cl) continue;
+        if (iou_gt(kbox[k], cb, nms_thr)) { sup = true; break; }
+      }
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = sub * 4 + jj;
+        if (j < ci && (!same_class_only || s_clab[j] == cl) && iou_gt(s_cbox[j], cb, nms_thr)) bits |= (1ull << j);
+      }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, sup);
+    const bool any_sup = ((bal >> (lane & 16)) & 0xFFFFu) != 0;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) bits |= __shfl_xor_sync(0xffffffffu, bits, o);
+    if (sub == 0 && ci < m) { s_pre[ci] = any_sup ? 1 : 0; s_mask[ci] = bits; }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long keptmask = 0ull;
+      int kn = kept;
+      for (int i = 0; i < m && kn < cap; ++i) {
+        if (!s_pre[i] && !(s_mask[i] & keptmask)) {
+          keptmask |= (1ull << i);
+          kbox[kn] = s_cbox[i]; klab[kn] = s_clab[i]; kidx[kn] = base + i;
+          ++kn;
+        }
+      }
+      s_kept = kn;
+    }
+    __syncthreads();
+  }
+
+  // ---- write detections (score order) -----------------------------------------------------------
+  const int kept = s_kept;
+  if (tid == 0) det_count[b] = kept;
+  float* drow = det + (int64_t)b * det_rows * 7;
+  for (int k = tid; k < det_rows; k += kNmsThreads) {
+    float* d = drow + (int64_t)k * 7;
+    if (k < kept) {
+      const int r = kidx[k];
+      const int a = (int)(0xFFFFFFFFu - (uint32_t)(keys[r] & 0xFFFFFFFFull));
+      const float4 bx = ws.box[ib + a];
+      d[0] = bx.x; d[1] = bx.y; d[2] = bx.z; d[3] = bx.w;
+      d[4] = ws.objc[ib + a]; d[5] = ws.col5[ib + a]; d[6] = (float)ws.label[ib + a];
+      if (det_anchor) det_anchor[(int64_t)b * det_rows + k] = a;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 7; ++j) d[j] = 0.0f;
+      if (det_anchor) det_anchor[(int64_t)b * det_rows + k] = -1;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host entry points
+// ------------------------------------------------------------------------------------------------
+static int grid_for(int64_t total, int threads) {
+  return (int)std::min<int64_t>((total + threads - 1) / threads, 148 * 8);
+}
+
+static int sort_and_nms(const Workspace& ws, int B, int A, float nms_thr, int max_nms, int max_det, int mode,
+                        int det_rows, float* det, int32_t* det_count, int32_t* det_anchor, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    YX_CUDA(cudaFuncSetAttribute(sort_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortChunk * 8));
+    attr = true;
+  }
+  sort_keys_kernel<<<B, kSortThreads, kSortChunk * 8, st>>>(ws);
+  YX_CUDA(cudaGetLastError());
+  nms_kernel<<<B, kNmsThreads, 0, st>>>(ws, A, nms_thr, max_nms, max_det, mode, det_rows, det, det_count, det_anchor);
+  YX_CUDA(cudaGetLastError());
+  return YX_OK;
+}
+
+static int check_ws(int B, int A, void* workspace, size_t bytes, Workspace* ws) {
+  YX_REQUIRE(B >= 1 && A >= 1, "B, A must be positive");
+  YX_REQUIRE(workspace != nullptr && ((uintptr_t)workspace % 256) == 0, "workspace must be 256-byte aligned");
+  const size_t need = ws_layout(B, A, static_cast<uint8_t*>(workspace), ws);
+  YX_REQUIRE(bytes >= need, "workspace too small (see yx_detect_workspace_bytes)");
+  return YX_OK;
+}
+
+}  // namespace yx
+
+using namespace yx;
+
+extern "C" size_t yx_detect_workspace_bytes(int B, int A) {
+  if (B < 1 || A < 1) return 0;
+  return ws_layout(B, A, nullptr, nullptr);
+}
+
+extern "C" int yx_decode_infer(const void* reg, int64_t reg_sb, int64_t reg_sa, const void* obj, int64_t obj_sb,
+                               int64_t obj_sa, const void* cls, int64_t cls_sb, int64_t cls_sa, int logits_dtype, int B,
+                               int A, int C, const yx_levels* lv_host, float* boxes, float* obj_conf, float* cls_conf,
+                               void* stream) {
+  LevelsDev lv;
+  int rc = make_levels(lv_host, A, &lv);
+  if (rc) return rc;
+  YX_REQUIRE(B >= 1 && C >= 1, "B, C must be positive");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int g = grid_for((int64_t)B * A, 256);
+  if (logits_dtype == YX_F16)
+    decode_infer_kernel<__half><<<g, 256, 0, st>>>((const __half*)reg, reg_sb, reg_sa, (const __half*)obj, obj_sb, obj_sa,
+                                                   (const __half*)cls, cls_sb, cls_sa, B, A, C, lv, boxes, obj_conf, cls_conf);
+  else if (logits_dtype == YX_F32)
+    decode_infer_kernel<float><<<g, 256, 0, st>>>((const float*)reg, reg_sb, reg_sa, (const float*)obj, obj_sb, obj_sa,
+                                                  (const float*)cls, cls_sb, cls_sa, B, A, C, lv, boxes, obj_conf, cls_conf);
+  else
+    YX_REQUIRE(false, "logits dtype must be YX_F16 or YX_F32");
+  YX_CUDA(cudaGetLastError());
+  return YX_OK;
+}
+
+extern "C" int yx_nms_main(const float* boxes, const float* obj_conf, const float* cls_conf, int B, int A, int C,
+                           float conf_thr, float nms_thr, int max_nms, int max_det, int mode, void* workspace,
+                           size_t workspace_bytes, float* det, int32_t* det_count, int32_t* det_anchor, void* stream) {
+  Workspace ws;
+  int rc = check_ws(B, A, workspace, workspace_bytes, &ws);
+  if (rc) return rc;
+  YX_REQUIRE(mode >= 0 && mode <= 3 && C >= 1, "bad nms mode / C");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int det_rows = max_det > 0 ? max_det : A;
+  YX_CUDA(cudaMemsetAsync(ws.count, 0, (size_t)B * 4, st));
+  select_decoded_kernel<<<grid_for((int64_t)B * A, 256), 256, 0, st>>>(boxes, obj_conf, cls_conf, B, A, C, conf_thr, ws);
+  YX_CUDA(cudaGetLastError());
+  return sort_and_nms(ws, B, A, nms_thr, max_nms, max_det, mode, det_rows, det, det_count, det_anchor, st);
+}
+
+extern "C" int yx_detect_main(const void* reg, int64_t reg_sb, int64_t reg_sa, const void* obj, int64_t obj_sb,
+                              int64_t obj_sa, const void* cls, int64_t cls_sb, int64_t cls_sa, int logits_dtype, int B,
+                              int A, int C, const yx_levels* lv_host, float conf_thr, float nms_thr, int max_nms,
+                              int max_det, int mode, void* workspace, size_t workspace_bytes, float* det,
+                              int32_t* det_count, int32_t* det_anchor, void* stream) {
+  LevelsDev lv;
+  int rc = make_levels(lv_host, A, &lv);
+  if (rc) return rc;
+  Workspace ws;
+  rc = check_ws(B, A, workspace, workspace_bytes, &ws);
+  if (rc) return rc;
+  YX_REQUIRE(mode >= 0 && mode <= 3 && C >= 1, "bad nms mode / C");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int det_rows = max_det > 0 ? max_det : A;
+  YX_CUDA(cudaMemsetAsync(ws.count, 0, (size_t)B * 4, st));
+  const int g = grid_for((int64_t)B * A, 128);
+  if (logits_dtype == YX_F16) {
+    const bool vec = (C % 8 == 0) && (cls_sa % 8 == 0) && (cls_sb % 8 == 0) && (((uintptr_t)cls) % 16 == 0);
+    if (vec)
+      select_infer_kernel<__half, true><<<g, 128, 0, st>>>((const __half*)reg, reg_sb, reg_sa, (const __half*)obj, obj_sb,
+                                                           obj_sa, (const __half*)cls, cls_sb, cls_sa, B, A, C, lv, conf_thr, ws);
+    else
+      select_infer_kernel<__half, false><<<g, 128, 0, st>>>((const __half*)reg, reg_sb, reg_sa, (const __half*)obj, obj_sb,
+                                                            obj_sa, (const __half*)cls, cls_sb, cls_sa, B, A, C, lv, conf_thr, ws);
+  } else if (logits_dtype == YX_F32) {
+    select_infer_kernel<float, false><<<g, 128, 0, st>>>((const float*)reg, reg_sb, reg_sa, (const float*)obj, obj_sb, obj_sa,
+                                                         (const float*)cls, cls_sb, cls_sa, B, A, C, lv, conf_thr, ws);
+  } else {
+    YX_REQUIRE(false, "logits dtype must be YX_F16 or YX_F32");
+  }
+  YX_CUDA(cudaGetLastError());
+  return sort_and_nms(ws, B, A, nms_thr, max_nms, max_det, mode, det_rows, det, det_count, det_anchor, st);
+}
+
+extern "C" int yx_head_assemble(const void* reg, int64_t reg_sb, int64_t reg_sa, const void* obj, int64_t obj_sb,
+                                int64_t obj_sa, const void* cls, int64_t cls_sb, int64_t cls_sa, int B, int A, int C,
+                                const yx_levels* lv_host, int decode, void* out, int out_dtype, void* stream) {
+  LevelsDev lv;
+  int rc = make_levels(lv_host, A, &lv);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int g = grid_for((int64_t)B * A, 128);
+  // engine logits are fp16
+  if (out_dtype == YX_F16)
+    head_assemble_kernel<__half, __half><<<g, 128, 0, st>>>((const __half*)reg, reg_sb, reg_sa, (const __half*)obj, obj_sb,
+                                                            obj_sa, (const __half*)cls, cls_sb, cls_sa, B, A, C, lv, decode,
+                                                            (__half*)out);
+  else if (out_dtype == YX_F32)
+    head_assemble_kernel<__half, float><<<g, 128, 0, st>>>((const __half*)reg, reg_sb, reg_sa, (const __half*)obj, obj_sb,
+                                                           obj_sa, (const __half*)cls, cls_sb, cls_sa, B, A, C, lv, decode,
+                                                           (float*)out);
+  else
+    YX_REQUIRE(false, "out dtype must be YX_F16 or YX_F32");
+  YX_CUDA(cudaGetLastError());
+  return YX_OK;
+}
+
+extern "C" int yx_decode_outputs(void* outputs, int dtype, int B, int A, int C, const yx_levels* lv_host, void* stream) {
+  LevelsDev lv;
+  int rc = make_levels(lv_host, A, &lv);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int g = grid_for((int64_t)B * A, 256);
+  if (dtype == YX_F16)
+    decode_outputs_kernel<__half><<<g, 256, 0, st>>>((__half*)outputs, B, A, 5 + C, lv);
+  else if (dtype == YX_F32)
+    decode_outputs_kernel<float><<<g, 256, 0, st>>>((float*)outputs, B, A, 5 + C, lv);
+  else
+    YX_REQUIRE(false, "dtype must be YX_F16 or YX_F32");
+  YX_CUDA(cudaGetLastError());
+  return YX_OK;
+}
+
+extern "C" int yx_postprocess_yolox(void* prediction, int dtype, int B, int A, int C, float conf_thr, float nms_thr,
+                                    int mode, void* workspace, size_t workspace_bytes, float* det, int32_t* det_count,
+                                    int32_t* det_anchor, void* stream) {
+  Workspace ws;
+  int rc = check_ws(B, A, workspace, workspace_bytes, &ws);
+  if (rc) return rc;
+  YX_REQUIRE(mode >= 0 && mode <= 3 && C >= 1, "bad nms mode / C");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  YX_CUDA(cudaMemsetAsync(ws.count, 0, (size_t)B * 4, st));
+  const int g = grid_for((int64_t)B * A, 128);
+  if (dtype == YX_F16)
+    select_yolox_kernel<__half><<<g, 128, 0, st>>>((__half*)prediction, B, A, C, conf_thr, ws);
+  else if (dtype == YX_F32)
+    select_yolox_kernel<float><<<g, 128, 0, st>>>((float*)prediction, B, A, C, conf_thr, ws);
+  else
+    YX_REQUIRE(false, "dtype must be YX_F16 or YX_F32");
+  YX_CUDA(cudaGetLastError());
+  return sort_and_nms(ws, B, A, nms_thr, /*max_nms=*/0, /*max_det=*/0, mode, A, det, det_count, det_anchor, st);
+}

@@ -1,0 +1,307 @@
+"""Graph builder: turns the module tree into the flat op list the native engine executes.
+
+Host logic only (pure Python + torch CPU tensors for weight packing) — unit-tested without a GPU.
+The builder implements the fusions that need no kernel support:
+  * concat elimination: producers write straight into channel slices of the consumer's buffer
+    (torch.cat at network_blocks.py:318, yolo_pafpn_p6.py:154-176 never materialises);
+  * CSP conv1+conv2 merged into one GEMM over the shared input (network_blocks.py:314-316);
+  * head cls_convs[0] + reg_convs[0] merged (same input, yolo_head.py:140-147);
+  * reg_pred + obj_pred merged into one 1x1 conv writing a packed [B,A,8] tensor.
+Buffers get arena offsets from a liveness-based first-fit allocator.
+"""
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _capi
+
+ALIGN = 1024
+
+
+def _rup(a: int, b: int) -> int:
+    return (a + b - 1) // b * b
+
+
+@dataclass
+class Buf:
+    name: str
+    n: int
+    h: int
+    w: int
+    c: int  # channel pitch
+    offset: int = -1
+    first: int = 10 ** 9
+    last: int = -1
+    pinned: bool = False  # outputs: kept alive to the end
+    nbytes_override: int = 0
+
+    @property
+    def nbytes(self) -> int:
+        return self.nbytes_override or _rup(self.n * self.h * self.w * self.c * 2, ALIGN)
+
+    def view(self, c_off: int = 0, c: Optional[int] = None) -> "V":
+        return V(self, c_off, self.c - c_off if c is None else c)
+
+
+@dataclass
+class V:
+    """Channel slice [c_off, c_off+c) of a buffer; optionally a pyramid-level window of a [B,A,C] output."""
+    buf: Buf
+    c_off: int
+    c: int
+    # level window (head outputs): element offset of the level's first anchor and the level dims
+    lvl_off: int = 0
+    h: int = 0
+    w: int = 0
+    nstride: int = 0
+
+    @property
+    def H(self):
+        return self.h or self.buf.h
+
+    @property
+    def W(self):
+        return self.w or self.buf.w
+
+    def to_c(self) -> _capi.View:
+        b = self.buf
+        assert b.offset >= 0, f"buffer {b.name} not placed"
+        v = _capi.View()
+        v.offset = b.offset + (self.lvl_off * b.c + self.c_off) * 2
+        v.nstride = self.nstride or b.h * b.w * b.c
+        v.n, v.h, v.w, v.c, v.pitch = b.n, self.H, self.W, self.c, b.c
+        return v
+
+
+@dataclass
+class PlannedOp:
+    kind: int
+    name: str
+    src: Optional[V]
+    dst: V
+    res: Optional[V] = None
+    ksize: int = 1
+    stride: int = 1
+    act: int = 0
+    weight: Optional[torch.Tensor] = None  # fp32 [cout, cin/groups, k, k]
+    bias: Optional[torch.Tensor] = None    # fp32 [cout]
+    aux: int = 0
+    cin_pad: int = 0
+    cout_pad: int = 0
+    w_offset: int = 0
+    b_offset: int = 0
+
+
+class Graph:
+    def __init__(self, batch: int, in_h: int, in_w: int):
+        self.batch, self.in_h, self.in_w = batch, in_h, in_w
+        self.bufs: List[Buf] = []
+        self.ops: List[PlannedOp] = []
+        self.arena_bytes = 0
+        self.weight_blob: Optional[torch.Tensor] = None
+        self.bias_blob: Optional[torch.Tensor] = None
+
+    # ---- buffers -------------------------------------------------------------------------
+    def new_buf(self, name: str, h: int, w: int, c: int, pinned: bool = False) -> Buf:
+        assert c % 8 == 0, f"{name}: channel pitch {c} must be a multiple of 8"
+        b = Buf(name, self.batch, h, w, c, pinned=pinned)
+        self.bufs.append(b)
+        return b
+
+    def new_output(self, name: str, anchors: int, c: int) -> Buf:
+        """[B, A, c] head output (h=A, w=1 as far as the allocator cares)."""
+        return self.new_buf(name, anchors, 1, c, pinned=True)
+
+    def _touch(self, v: Optional[V], idx: int):
+        if v is not None:
+            v.buf.first = min(v.buf.first, idx)
+            v.buf.last = max(v.buf.last, idx)
+
+    def _add(self, op: PlannedOp) -> V:
+        idx = len(self.ops)
+        self._touch(op.src, idx); self._touch(op.dst, idx); self._touch(op.res, idx)
+        self.ops.append(op)
+        return op.dst
+
+    # ---- ops -----------------------------------------------------------------------------
+    def s2d(self, dst: V, order: str) -> V:
+        assert dst.c == 16 and dst.buf.c == 16
+        return self._add(PlannedOp(_capi.OP_S2D, "s2d", None, dst, aux=1 if order == "unshuffle" else 0))
+
+    def conv(self, name: str, src: V, dst: V, weight: torch.Tensor, bias: torch.Tensor, stride: int, act: str,
+             res: Optional[V] = None) -> V:
+        cout, cin, k, k2 = weight.shape
+        assert k == k2 and k in (1, 3), f"{name}: unsupported kernel size {k}"
+        assert cin <= src.c <= _rup(cin, 16), f"{name}: src has {src.c} channels, weight expects {cin}"
+        assert cout <= dst.c <= _rup(cout, 16), f"{name}: dst has {dst.c} channels, weight gives {cout}"
+        pad = k // 2
+        ho, wo = (src.H + 2 * pad - k) // stride + 1, (src.W + 2 * pad - k) // stride + 1
+        assert (dst.H, dst.W) == (ho, wo), f"{name}: dst is {dst.H}x{dst.W}, conv gives {ho}x{wo}"
+        if res is not None:
+            assert (res.H, res.W, res.c) == (dst.H, dst.W, dst.c), f"{name}: residual shape mismatch"
+        return self._add(PlannedOp(_capi.OP_CONV, name, src, dst, res, k, stride, _capi.act_code(act),
+                                   weight.detach().float().cpu(), bias.detach().float().cpu(),
+                                   cin_pad=_rup(cin, 16), cout_pad=_rup(cout, 16)))
+
+    def dwconv(self, name: str, src: V, dst: V, weight: torch.Tensor, bias: torch.Tensor, stride: int, act: str) -> V:
+        c, one, k, _ = weight.shape
+        assert one == 1 and c == src.c == dst.c and k in (3, 5)
+        return self._add(PlannedOp(_capi.OP_DWCONV, name, src, dst, None, k, stride, _capi.act_code(act),
+                                   weight.detach().float().cpu(), bias.detach().float().cpu(), cin_pad=c, cout_pad=c))
+
+    def spp(self, src: V, dst: V) -> V:
+        assert dst.c == 3 * src.c
+        return self._add(PlannedOp(_capi.OP_SPP, "spp", src, dst))
+
+    def upsample(self, src: V, dst: V) -> V:
+        assert (dst.H, dst.W, dst.c) == (2 * src.H, 2 * src.W, src.c)
+        return self._add(PlannedOp(_capi.OP_UPSAMPLE, "upsample", src, dst))
+
+    # ---- finalisation --------------------------------------------------------------------
+    def place_buffers(self):
+        """Greedy-by-size first-fit over [first,last] live ranges."""
+        n_ops = len(self.ops)
+        for b in self.bufs:
+            assert b.last >= 0, f"buffer {b.name} is never used"
+            if b.pinned:
+                b.last = n_ops
+        placed: List[Buf] = []
+        for b in sorted(self.bufs, key=lambda x: -x.nbytes):
+            busy = sorted((p.offset, p.offset + p.nbytes) for p in placed
+                          if not (p.last < b.first or b.last < p.first))
+            off = 0
+            for lo, hi in busy:
+                if off + b.nbytes <= lo:
+                    break
+                off = max(off, hi)
+            b.offset = off
+            placed.append(b)
+        self.arena_bytes = max(b.offset + b.nbytes for b in self.bufs)
+        return self.arena_bytes
+
+    def pack_weights(self):
+        """fp16 KRSC blob [cout_pad][k*k][cin_pad] per conv (depthwise: [k*k][c]); fp32 bias blob."""
+        w_parts, b_parts, w_off, b_off = [], [], 0, 0
+        for op in self.ops:
+            if op.kind == _capi.OP_CONV:
+                cout, cin, k, _ = op.weight.shape
+                w = torch.zeros(op.cout_pad, k * k, op.cin_pad, dtype=torch.float16)
+                w[:cout, :, :cin] = op.weight.permute(0, 2, 3, 1).reshape(cout, k * k, cin).to(torch.float16)
+            elif op.kind == _capi.OP_DWCONV:
+                c, _, k, _ = op.weight.shape
+                cout = c
+                w = op.weight.reshape(c, k * k).t().contiguous().to(torch.float16)
+            else:
+                continue
+            b = torch.zeros(op.cout_pad, dtype=torch.float32)
+            b[:cout] = op.bias
+            op.w_offset, op.b_offset = w_off, b_off
+            w_parts.append(w.reshape(-1)); b_parts.append(b)
+            nw = _rup(w.numel() * 2, 256) // 2
+            if nw > w.numel():
+                w_parts.append(torch.zeros(nw - w.numel(), dtype=torch.float16))
+            nb = _rup(b.numel() * 4, 256) // 4
+            if nb > b.numel():
+                b_parts.append(torch.zeros(nb - b.numel(), dtype=torch.float32))
+            w_off += nw * 2; b_off += nb * 4
+        self.weight_blob = torch.cat(w_parts)
+        self.bias_blob = torch.cat(b_parts)
+
+    def c_ops(self):
+        arr = (_capi.Op * len(self.ops))()
+        for i, op in enumerate(self.ops):
+            o = arr[i]
+            o.kind, o.ksize, o.stride, o.act, o.aux = op.kind, op.ksize, op.stride, op.act, op.aux
+            if op.src is not None:
+                o.src = op.src.to_c()
+            o.dst = op.dst.to_c()
+            if op.res is not None:
+                o.res = op.res.to_c()
+            o.w_offset, o.b_offset, o.cin_pad, o.cout_pad = op.w_offset, op.b_offset, op.cin_pad, op.cout_pad
+        return arr
+
+    def finalize(self):
+        self.place_buffers()
+        self.pack_weights()
+        return self
+
+    # algorithmic work: conv flops / fp16 activation+weight bytes
+    def conv_flops(self) -> float:
+        t = 0.0
+        for op in self.ops:
+            if op.kind == _capi.OP_CONV:
+                cout, cin, k, _ = op.weight.shape
+                t += 2.0 * self.batch * op.dst.H * op.dst.W * cout * cin * k * k
+            elif op.kind == _capi.OP_DWCONV:
+                c, _, k, _ = op.weight.shape
+                t += 2.0 * self.batch * op.dst.H * op.dst.W * c * k * k
+        return t
+
+
+class Engine:
+    """Owns the device arena / weight blobs and the native engine handle for one (B, H, W)."""
+
+    def __init__(self, graph: Graph, device):
+        import torch
+        self.lib = _capi.load()
+        self.graph = graph
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("yolox_b200: the engine runs on CUDA (sm_100a) only; there is no CPU path")
+        with torch.cuda.device(self.device):
+            self.arena = torch.empty(graph.arena_bytes + ALIGN, dtype=torch.uint8, device=self.device)
+            pad = (-self.arena.data_ptr()) % ALIGN
+            self.arena_base = self.arena.data_ptr() + pad
+            self._arena_pad = pad
+            self.weights = graph.weight_blob.to(self.device)
+            self.biases = graph.bias_blob.to(self.device)
+            ops = graph.c_ops()
+            handle = _capi.c_vp()
+            _capi.check(self.lib.yx_engine_create(ops, len(graph.ops), self.arena_base, graph.arena_bytes,
+                                                  self.weights.data_ptr(), self.weights.numel() * 2,
+                                                  self.biases.data_ptr(), self.biases.numel() * 4,
+                                                  graph.in_h, graph.in_w, graph.batch, handle), "yx_engine_create")
+            self.handle = handle
+        self.n_launches = self.lib.yx_engine_num_launches(self.handle)
+
+    def tensor_of(self, buf: Buf):
+        """fp16 torch view [n, h, w, c] of an arena buffer (no copy)."""
+        import torch
+        n = buf.n * buf.h * buf.w * buf.c
+        start = self._arena_pad + buf.offset
+        return self.arena[start:start + 2 * n].view(torch.float16).view(buf.n, buf.h, buf.w, buf.c)
+
+    def run(self, image, in_scale: float = 1.0, in_shift: float = 0.0, use_graph: bool = False):
+        import torch
+        g = self.graph
+        _capi.require_cuda(image, "image")
+        if tuple(image.shape) != (g.batch, 3, g.in_h, g.in_w):
+            raise RuntimeError(f"engine built for {(g.batch, 3, g.in_h, g.in_w)}, got {tuple(image.shape)}")
+        if image.dtype == torch.float16:
+            dt = _capi.YX_F16
+        elif image.dtype == torch.float32:
+            dt = _capi.YX_F32
+        else:
+            raise RuntimeError(f"unsupported image dtype {image.dtype}")
+        image = image.contiguous()
+        _capi.check(self.lib.yx_engine_run(self.handle, image.data_ptr(), dt, float(in_scale), float(in_shift),
+                                           int(use_graph), _capi.current_stream_ptr()), "yx_engine_run")
+
+    def profile(self, image, iters: int = 5):
+        import ctypes
+        import torch
+        n = len(self.graph.ops)
+        ms = (ctypes.c_float * n)(); fl = (ctypes.c_double * n)(); by = (ctypes.c_double * n)()
+        dt = _capi.YX_F16 if image.dtype == torch.float16 else _capi.YX_F32
+        _capi.check(self.lib.yx_engine_profile(self.handle, image.contiguous().data_ptr(), dt, iters,
+                                               _capi.current_stream_ptr(), ms, fl, by, n), "yx_engine_profile")
+        return [dict(name=op.name, kind=op.kind, ms=ms[i], flops=fl[i], bytes=by[i]) for i, op in enumerate(self.graph.ops)]
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.yx_engine_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass

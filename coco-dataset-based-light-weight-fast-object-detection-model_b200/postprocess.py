@@ -1,0 +1,230 @@
+"""Reference-signature post-processing functions on top of the native decode / select / NMS kernels.
+
+  yolox_generate_grid, yolox_postprocess_output_torch_batch, yolox_nms_torch_batch
+        == choijhanyangackr/yolox_infer/postprocess_utils.py:6-129 (main.py:174,180,188 call them)
+  postprocess == yolox/utils/boxes.py:32-82 (mutates prediction[:, :, :4] to xyxy like the reference)
+  decode_outputs == YOLOXHead.decode_outputs, yolox/models/yolo_head.py:210-225 (in place)
+  detect_main — the fused production path (decode + threshold + NMS from raw logits, no host sync)
+
+All tensors must live on a CUDA device; there is no CPU path (the oracle under oracle/ is the checker).
+"""
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _capi
+
+_NMS_MODES = {"trick": _capi.NMS_TRICK, "vanilla": _capi.NMS_VANILLA, "agnostic": _capi.NMS_AGNOSTIC, "auto": 3}
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float16:
+        return _capi.YX_F16
+    if t.dtype == torch.float32:
+        return _capi.YX_F32
+    raise RuntimeError(f"unsupported dtype {t.dtype} (fp16 / fp32 only)")
+
+
+def _rows(t: torch.Tensor) -> torch.Tensor:
+    """[B,A,K] with a contiguous last dim (arbitrary batch / anchor strides are passed through)."""
+    _capi.require_cuda(t)
+    if t.dim() != 3:
+        raise RuntimeError("expected a [B, A, K] tensor")
+    return t if t.stride(2) == 1 or t.shape[2] == 1 else t.contiguous()
+
+
+def _workspace(B: int, A: int, device) -> torch.Tensor:
+    n = _capi.load().yx_detect_workspace_bytes(B, A)
+    ws = torch.empty(n + 256, dtype=torch.uint8, device=device)
+    off = (-ws.data_ptr()) % 256
+    return ws[off:off + n]
+
+
+def level_hw_of(img_size, strides) -> List[Tuple[int, int]]:
+    if isinstance(img_size, int):
+        img_size = (img_size, img_size)
+    return [(img_size[0] // s, img_size[1] // s) for s in strides]
+
+
+def yolox_generate_grid(img_size, strides=(8, 16, 32), dtype=torch.float32):
+    """postprocess_utils.py:6-24 — same values/shapes: grids (1,A,2) xy, scales (1,A,1)."""
+    hw = level_hw_of(img_size, strides)
+    grids, scales = [], []
+    for (h, w), s in zip(hw, strides):
+        yv, xv = torch.meshgrid([torch.arange(h), torch.arange(w)], indexing="ij")
+        grids.append(torch.stack((xv, yv), 2).view(1, -1, 2))
+        scales.append(torch.full((1, h * w, 1), s))
+    grids = torch.cat(grids, dim=1).to(dtype)
+    scales = torch.cat(scales, dim=1).to(dtype)
+    return grids, scales
+
+
+_GEOM = {}
+
+
+def _geometry(grids: torch.Tensor, scales: torch.Tensor):
+    """Pyramid (level_hw, strides) recovered from a grids/scales pair (one small read-back, cached per
+    tensor: main.py:171-178 builds them once per image size and reuses them for every batch)."""
+    key = (grids.data_ptr(), scales.data_ptr(), grids.shape[1], str(grids.device))
+    if key not in _GEOM:
+        if len(_GEOM) > 64:
+            _GEOM.clear()
+        sc = scales.reshape(-1).float().cpu()
+        gr = grids.reshape(-1, 2).float().cpu()
+        vals, counts = torch.unique_consecutive(sc, return_counts=True)
+        hw, off = [], 0
+        for v, c in zip(vals.tolist(), counts.tolist()):
+            w = int(gr[off:off + c, 0].max().item()) + 1
+            hw.append((c // w, w)); off += c
+        _GEOM[key] = (hw, tuple(int(v) for v in vals.tolist()))
+    return _GEOM[key]
+
+
+def yolox_postprocess_output_torch_batch(reg_output, obj_output, cls_output, grids, scales):
+    """postprocess_utils.py:27-52: fp32 xyxy boxes [B,A,4], obj_conf [B,A,1], cls_conf [B,A,C]=sig(cls)*sig(obj)."""
+    lib = _capi.load()
+    reg, obj, cls = _rows(reg_output), _rows(obj_output), _rows(cls_output)
+    if not (reg.dtype == obj.dtype == cls.dtype):
+        raise RuntimeError("reg/obj/cls must share a dtype")
+    B, A, C = cls.shape
+    hw, strides = _geometry(grids, scales)
+    lv = _capi.make_levels(hw, strides)
+    boxes = torch.empty(B, A, 4, dtype=torch.float32, device=cls.device)
+    obj_conf = torch.empty(B, A, 1, dtype=torch.float32, device=cls.device)
+    cls_conf = torch.empty(B, A, C, dtype=torch.float32, device=cls.device)
+    with torch.cuda.device(cls.device):
+        _capi.check(lib.yx_decode_infer(reg.data_ptr(), reg.stride(0), reg.stride(1), obj.data_ptr(), obj.stride(0),
+                                        obj.stride(1), cls.data_ptr(), cls.stride(0), cls.stride(1), _dt(cls), B, A, C,
+                                        lv, boxes.data_ptr(), obj_conf.data_ptr(), cls_conf.data_ptr(),
+                                        _capi.current_stream_ptr()), "yx_decode_infer")
+    return boxes, obj_conf, cls_conf
+
+
+def _split(det: torch.Tensor, count: torch.Tensor, dtype=None) -> List[Optional[torch.Tensor]]:
+    counts = count.cpu().tolist()  # the one host sync, as in the reference's boolean indexing
+    out = []
+    for i, n in enumerate(counts):
+        if n == 0:
+            out.append(None)
+        else:
+            d = det[i, :n].clone()
+            out.append(d if dtype is None else d.to(dtype))
+    return out
+
+
+def nms_main_raw(reg_boxes, obj_conf, cls_conf, nms_threshold, conf_threshold, max_num_nms, max_num_det, mode="auto"):
+    """Device-side result of yolox_nms_torch_batch: det [B,R,7], count [B], anchor [B,R] (no sync)."""
+    lib = _capi.load()
+    for t in (reg_boxes, obj_conf, cls_conf):
+        _capi.require_cuda(t)
+    boxes = reg_boxes.float().contiguous()
+    objc = obj_conf.float().contiguous()
+    clsc = cls_conf.float().contiguous()
+    B, A, C = clsc.shape
+    rows = max_num_det if max_num_det > 0 else A
+    det = torch.empty(B, rows, 7, dtype=torch.float32, device=clsc.device)
+    cnt = torch.empty(B, dtype=torch.int32, device=clsc.device)
+    anc = torch.empty(B, rows, dtype=torch.int32, device=clsc.device)
+    ws = _workspace(B, A, clsc.device)
+    with torch.cuda.device(clsc.device):
+        _capi.check(lib.yx_nms_main(boxes.data_ptr(), objc.data_ptr(), clsc.data_ptr(), B, A, C, float(conf_threshold),
+                                    float(nms_threshold), int(max_num_nms), int(max_num_det), _NMS_MODES[mode],
+                                    ws.data_ptr(), ws.numel(), det.data_ptr(), cnt.data_ptr(), anc.data_ptr(),
+                                    _capi.current_stream_ptr()), "yx_nms_main")
+    return det, cnt, anc
+
+
+def yolox_nms_torch_batch(reg_boxes, obj_conf, cls_conf, nms_threshold: float = 0.65, conf_threshold: float = 0.001,
+                          soft: bool = False, max_num_nms: int = 5000, max_num_det: int = 300,
+                          multi_class: bool = False, rmmop=None, class_agnostic: bool = False):
+    """postprocess_utils.py:55-129 (default mode + class_agnostic).  Returns list[B] of [n,7] or None."""
+    if soft:
+        raise ValueError("Soft-NMS is not installed, but using soft_nms.")  # nms.py:21,36
+    if multi_class or rmmop is not None:
+        raise NotImplementedError("multi_class / rmmop candidate modes are not built yet (SURVEY §8f N4)")
+    big = 2 ** 31 - 1
+    det, cnt, _ = nms_main_raw(reg_boxes, obj_conf, cls_conf, nms_threshold, conf_threshold, max_num_nms,
+                               0 if max_num_det >= big or max_num_det >= cls_conf.shape[1] else max_num_det,
+                               "agnostic" if class_agnostic else "auto")
+    return _split(det, cnt)
+
+
+def detect_main(reg, obj, cls, level_hw, strides, conf_threshold=0.001, nms_threshold=0.65, max_num_nms=5000,
+                max_num_det=300, mode="auto"):
+    """Fused decode + threshold + top-k + NMS from raw logits [B,A,*] (fp16/fp32).  No host sync.
+    Returns det [B,max_num_det,7] fp32 (rows beyond count are zero), count [B] int32, anchor [B,max_num_det]."""
+    lib = _capi.load()
+    reg, obj, cls = _rows(reg), _rows(obj), _rows(cls)
+    B, A, C = cls.shape
+    lv = _capi.make_levels(level_hw, strides)
+    rows = max_num_det if max_num_det > 0 else A
+    det = torch.empty(B, rows, 7, dtype=torch.float32, device=cls.device)
+    cnt = torch.empty(B, dtype=torch.int32, device=cls.device)
+    anc = torch.empty(B, rows, dtype=torch.int32, device=cls.device)
+    ws = _workspace(B, A, cls.device)
+    with torch.cuda.device(cls.device):
+        _capi.check(lib.yx_detect_main(reg.data_ptr(), reg.stride(0), reg.stride(1), obj.data_ptr(), obj.stride(0),
+                                       obj.stride(1), cls.data_ptr(), cls.stride(0), cls.stride(1), _dt(cls), B, A, C, lv,
+                                       float(conf_threshold), float(nms_threshold), int(max_num_nms), int(max_num_det),
+                                       _NMS_MODES[mode], ws.data_ptr(), ws.numel(), det.data_ptr(), cnt.data_ptr(),
+                                       anc.data_ptr(), _capi.current_stream_ptr()), "yx_detect_main")
+    return det, cnt, anc
+
+
+def head_assemble(reg8, cls, num_classes, level_hw, strides, decode: bool, out_dtype):
+    """[B,A,5+C] = [reg, sigmoid(obj), sigmoid(cls)] (+ decode) from the engine's packed fp16 logits."""
+    lib = _capi.load()
+    B, A, _ = cls.shape
+    C = num_classes
+    out = torch.empty(B, A, 5 + C, dtype=out_dtype, device=cls.device)
+    lv = _capi.make_levels(level_hw, strides)
+    obj = reg8[..., 4:5]
+    with torch.cuda.device(cls.device):
+        _capi.check(lib.yx_head_assemble(reg8.data_ptr(), reg8.stride(0), reg8.stride(1), obj.data_ptr(), obj.stride(0),
+                                         obj.stride(1), cls.data_ptr(), cls.stride(0), cls.stride(1), B, A, C, lv,
+                                         int(bool(decode)), out.data_ptr(), _dt(out), _capi.current_stream_ptr()),
+                    "yx_head_assemble")
+    return out
+
+
+def decode_outputs(outputs, level_hw, strides):
+    """In-place decode of outputs[..., :4] (yolo_head.py:210-225); returns the same tensor."""
+    lib = _capi.load()
+    _capi.require_cuda(outputs)
+    if not outputs.is_contiguous():
+        raise RuntimeError("decode_outputs works in place and needs a contiguous [B,A,5+C] tensor")
+    B, A, D = outputs.shape
+    lv = _capi.make_levels(level_hw, strides)
+    with torch.cuda.device(outputs.device):
+        _capi.check(lib.yx_decode_outputs(outputs.data_ptr(), _dt(outputs), B, A, D - 5, lv,
+                                          _capi.current_stream_ptr()), "yx_decode_outputs")
+    return outputs
+
+
+def postprocess_raw(prediction, num_classes, conf_threshold, nms_threshold, class_agnostic=False, mode=None):
+    lib = _capi.load()
+    _capi.require_cuda(prediction)
+    if not prediction.is_contiguous():
+        raise RuntimeError("postprocess mutates prediction in place and needs a contiguous [B,A,5+C] tensor")
+    B, A, D = prediction.shape
+    if D != 5 + num_classes:
+        raise RuntimeError(f"prediction has {D} columns, expected 5 + num_classes = {5 + num_classes}")
+    det = torch.empty(B, A, 7, dtype=torch.float32, device=prediction.device)
+    cnt = torch.empty(B, dtype=torch.int32, device=prediction.device)
+    anc = torch.empty(B, A, dtype=torch.int32, device=prediction.device)
+    ws = _workspace(B, A, prediction.device)
+    m = _NMS_MODES[mode] if mode else (_capi.NMS_AGNOSTIC if class_agnostic else 3)
+    with torch.cuda.device(prediction.device):
+        _capi.check(lib.yx_postprocess_yolox(prediction.data_ptr(), _dt(prediction), B, A, num_classes,
+                                             float(conf_threshold), float(nms_threshold), m, ws.data_ptr(), ws.numel(),
+                                             det.data_ptr(), cnt.data_ptr(), anc.data_ptr(),
+                                             _capi.current_stream_ptr()), "yx_postprocess_yolox")
+    return det, cnt, anc
+
+
+def postprocess(prediction, num_classes: int, conf_threshold: float = 0.7, nms_threshold: float = 0.45,
+                class_agnostic: bool = False):
+    """yolox/utils/boxes.py:32-82.  prediction[:, :, :4] is converted to xyxy IN PLACE (as the reference
+    does); returns list[B] of [n,7] = [x1,y1,x2,y2,obj,class_conf,class_pred] in prediction's dtype, or None."""
+    det, cnt, _ = postprocess_raw(prediction, num_classes, conf_threshold, nms_threshold, class_agnostic)
+    return _split(det, cnt, prediction.dtype)

@@ -1,0 +1,180 @@
+/* yolox_b200 — C ABI of the B200-native YOLOX inference hot path.
+ *
+ * The reference (aiha-lab/COCO-dataset-based-light-weight-fast-object-detection-model) has no
+ * FFI/plugin interface: its hot-path boundary is the Python call surface of L2.
+ * Each entry point below is what a reference-side binding for that surface would call; the
+ * `replaces:` line cites the reference code (relative to the reference root) whose device work it
+ * performs.  Python shims in the package mirror the reference signatures on top of these
+ * (see INTEGRATION.md for the ctypes stubs).
+ *
+ * Conventions
+ *  - plain C types only; every pointer is a DEVICE pointer unless the name ends in `_host`.
+ *  - `stream` is a cudaStream_t passed as void*; all work is stream-ordered, no host sync inside
+ *    (except yx_engine_profile / yx_engine_create, which are setup/diagnostic calls).
+ *  - return 0 on success, a negative yx_status otherwise; yx_last_error() gives the message.
+ *  - caller owns all buffers; the library owns only the opaque engine object.
+ *  - activations: NHWC fp16 inside the engine; public tensors keep the reference layouts.
+ */
+#ifndef YOLOX_B200_H_
+#define YOLOX_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YX_ABI_VERSION 1
+
+typedef enum yx_status {
+  YX_OK = 0,
+  YX_ERR_INVALID = -1,   /* bad argument / unsupported shape            */
+  YX_ERR_CUDA = -2,      /* a CUDA runtime / driver call failed         */
+  YX_ERR_UNSUPPORTED = -3
+} yx_status;
+
+typedef enum yx_act {  /* replaces: get_activation, yolox/models/network_blocks.py:12-24 */
+  YX_ACT_NONE = 0,
+  YX_ACT_SILU = 1,
+  YX_ACT_HSWISH = 2,
+  YX_ACT_RELU = 3,
+  YX_ACT_LRELU = 4     /* LeakyReLU(0.1) */
+} yx_act;
+
+typedef enum yx_dtype { YX_F16 = 0, YX_F32 = 1 } yx_dtype;
+
+typedef enum yx_op_kind {
+  YX_OP_CONV = 0,      /* BaseConv.fused_forward: conv(k in {1,3}, stride in {1,2}, same pad)+bias+act(+residual)
+                          replaces: network_blocks.py:73-84,199-205 ; yolox_infer/models/blocks.py:21-49 */
+  YX_OP_S2D = 1,       /* Focus / FocusCustom space-to-depth of the NCHW input image into NHWC[.,.,.,16]
+                          replaces: network_blocks.py:330-361 ; blocks.py:286-304 */
+  YX_OP_SPP = 2,       /* SPPBottleneck max-pools 5/9/13 written into the concat buffer
+                          replaces: network_blocks.py:239-246 */
+  YX_OP_UPSAMPLE = 3,  /* nn.Upsample(2,"nearest") into a concat slice; replaces: yolo_pafpn_p6.py:153-164 */
+  YX_OP_DWCONV = 4     /* depthwise kxk conv + bias + act; replaces: network_blocks.py:107-120 (dconv) */
+} yx_op_kind;
+
+/* A view of an NHWC fp16 tensor inside the activation arena.  Channel slices of a wider buffer
+ * (concat elimination) are expressed with pitch > c. */
+typedef struct yx_view {
+  int64_t offset;   /* byte offset from the arena base to element (0,0,0,0) of the view */
+  int64_t nstride;  /* elements between consecutive images (>= h*w*pitch; e.g. A*C for a pyramid
+                       level of a [B,A,C] head output) */
+  int32_t n, h, w, c;
+  int32_t pitch;    /* elements between consecutive pixels of the parent buffer (>= c, multiple of 8) */
+  int32_t _pad;
+} yx_view;
+
+typedef struct yx_op {
+  int32_t kind;       /* yx_op_kind */
+  int32_t ksize;      /* CONV/DWCONV: 1,3 (DWCONV also 5) */
+  int32_t stride;     /* CONV: 1 or 2 */
+  int32_t act;        /* yx_act */
+  yx_view src;        /* S2D: ignored (reads the external image) */
+  yx_view dst;
+  yx_view res;        /* residual added after the activation; res.c == 0 -> none */
+  int64_t w_offset;   /* byte offset into the weight blob: fp16 [cout_pad][k*k][cin_pad] (DWCONV: [k*k][c]) */
+  int64_t b_offset;   /* byte offset into the bias blob: fp32 [cout_pad] */
+  int32_t cin_pad;    /* multiple of 16 */
+  int32_t cout_pad;   /* multiple of 16 */
+  int32_t aux;        /* S2D: 0 = Focus order [TL,BL,TR,BR], 1 = pixel_unshuffle order */
+  int32_t _pad;
+} yx_op;
+
+typedef struct yx_engine yx_engine;
+
+const char* yx_last_error(void);
+int yx_abi_version(void);
+
+/* Build an engine from a fully planned op list (the Python graph builder owns the topology).
+ * arena / weights / biases must stay alive and at the same address for the engine's lifetime.
+ * replaces: the nn.Module graph built by build_yolox, choijhanyangackr/main.py:31-59. */
+int yx_engine_create(const yx_op* ops_host, int n_ops, void* arena, size_t arena_bytes,
+                     const void* weights, size_t weights_bytes, const void* biases, size_t bias_bytes,
+                     int in_h, int in_w, int batch, yx_engine** out);
+void yx_engine_destroy(yx_engine* e);
+
+/* Run every op on `stream`.  image: NCHW [batch,3,in_h,in_w], fp16 or fp32 (yx_dtype).
+ * in_scale/in_shift: optional input affine applied while the image is read (the predict loop's
+ * img.mul_(0.9).add_(11.4), main.py:164, evaluated in the image dtype); pass 1, 0 to disable.
+ * use_graph != 0 replays a captured CUDA graph for everything after the first (image-reading) op.
+ * replaces: YOLOXP6.forward / YOLOX.forward, yolox_infer/models/yolox_p6.py:31-34. */
+int yx_engine_run(yx_engine* e, const void* image, int image_dtype, float in_scale, float in_shift, int use_graph,
+                  void* stream);
+
+/* Diagnostic: per-op device time (ms, mean over iters, CUDA events on `stream`), host-synchronising.
+ * Also reports algorithmic flops / bytes per op so callers can print roofline fractions. */
+int yx_engine_profile(yx_engine* e, const void* image, int image_dtype, int iters, void* stream,
+                      float* ms_host, double* flops_host, double* bytes_host, int n_ops);
+int yx_engine_num_launches(const yx_engine* e); /* kernels launched by one yx_engine_run */
+
+/* ---- stand-alone operators (used by tests and by the reference-style Python functions) ---------- */
+
+/* One conv op outside an engine (same kernel the engine launches). Views are relative to `base`. */
+int yx_conv2d(const yx_op* op_host, void* base, const void* weights, const void* biases, void* stream);
+
+/* ---- head decode / candidate selection / NMS --------------------------------------------------- */
+
+typedef struct yx_levels {
+  int32_t n_levels;
+  int32_t h[8], w[8], stride[8];
+} yx_levels;
+
+typedef enum yx_nms_mode {
+  YX_NMS_TRICK = 0,     /* torchvision batched_nms coordinate trick: boxes + label*(max+1) */
+  YX_NMS_VANILLA = 1,   /* per-class NMS on the raw boxes */
+  YX_NMS_AGNOSTIC = 2,  /* class-agnostic torchvision.ops.nms */
+  YX_NMS_AUTO = 3       /* per image, torchvision 0.26's CUDA dispatch: VANILLA when the candidate
+                           boxes passed to batched_nms have numel() > 100000 (n > 25000), else TRICK */
+} yx_nms_mode;
+
+/* decode, infer flavour.  reg/obj/cls are raw logits with element strides (so permuted views and
+ * the engine's packed [B,A,8] reg+obj buffer can be passed as they are); outputs fp32 contiguous
+ * boxes[B,A,4] (xyxy), obj_conf[B,A], cls_conf[B,A,C] (= sigmoid(cls)*sigmoid(obj)).
+ * replaces: yolox_postprocess_output_torch_batch, yolox_infer/postprocess_utils.py:27-52. */
+int yx_decode_infer(const void* reg, int64_t reg_sb, int64_t reg_sa, const void* obj, int64_t obj_sb, int64_t obj_sa,
+                    const void* cls, int64_t cls_sb, int64_t cls_sa, int logits_dtype, int B, int A, int C,
+                    const yx_levels* lv_host, float* boxes, float* obj_conf, float* cls_conf, void* stream);
+
+/* Workspace (bytes) for the detection entry points below. */
+size_t yx_detect_workspace_bytes(int B, int A);
+
+/* Candidate selection + top-k + batched NMS + top-max_det from DECODED fp32 tensors.
+ * det[B,max_det,7] = [x1,y1,x2,y2,obj,cls_conf,label], det_count[B]; det_anchor[B,max_det] (may be NULL).
+ * max_nms <= 0: no candidate cap.  Rows beyond det_count are zero.
+ * replaces: yolox_nms_torch_batch (default mode), yolox_infer/postprocess_utils.py:55-129 and the
+ * torchvision.ops.batched_nms / nms it calls (yolox_infer/nms.py:19,40). */
+int yx_nms_main(const float* boxes, const float* obj_conf, const float* cls_conf, int B, int A, int C,
+                float conf_thr, float nms_thr, int max_nms, int max_det, int mode, void* workspace,
+                size_t workspace_bytes, float* det, int32_t* det_count, int32_t* det_anchor, void* stream);
+
+/* Fused decode + threshold + compaction + NMS straight from the raw head logits (no [B,A,C]
+ * fp32 tensor is ever materialised).  Same results as yx_decode_infer followed by yx_nms_main.
+ * replaces: main.py:180-188 (decode + NMS of the predict loop). */
+int yx_detect_main(const void* reg, int64_t reg_sb, int64_t reg_sa, const void* obj, int64_t obj_sb, int64_t obj_sa,
+                   const void* cls, int64_t cls_sb, int64_t cls_sa, int logits_dtype, int B, int A, int C,
+                   const yx_levels* lv_host, float conf_thr, float nms_thr, int max_nms, int max_det, int mode,
+                   void* workspace, size_t workspace_bytes, float* det, int32_t* det_count, int32_t* det_anchor,
+                   void* stream);
+
+/* yolox-package head output: out[B,A,5+C] = [reg, sigmoid(obj), sigmoid(cls)] in `out_dtype`, then
+ * (decode != 0) decoded in place like decode_outputs.
+ * replaces: yolox/models/yolo_head.py:167-168,186-190,210-225. */
+int yx_head_assemble(const void* reg, int64_t reg_sb, int64_t reg_sa, const void* obj, int64_t obj_sb, int64_t obj_sa,
+                     const void* cls, int64_t cls_sb, int64_t cls_sa, int B, int A, int C, const yx_levels* lv_host,
+                     int decode, void* out, int out_dtype, void* stream);
+/* In-place decode of outputs[..., :4]; replaces: YOLOXHead.decode_outputs, yolo_head.py:210-225. */
+int yx_decode_outputs(void* outputs, int dtype, int B, int A, int C, const yx_levels* lv_host, void* stream);
+
+/* yolox.utils.postprocess: converts prediction[:,:,:4] to xyxy IN PLACE, then threshold
+ * (obj*class_conf >= conf_thr) and NMS without caps.  det[B,A,7] rows = [x1,y1,x2,y2,obj,class_conf,class_pred].
+ * replaces: postprocess, yolox/utils/boxes.py:32-82. */
+int yx_postprocess_yolox(void* prediction, int dtype, int B, int A, int C, float conf_thr, float nms_thr, int mode,
+                         void* workspace, size_t workspace_bytes, float* det, int32_t* det_count,
+                         int32_t* det_anchor, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YOLOX_B200_H_ */

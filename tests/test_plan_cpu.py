@@ -1,0 +1,107 @@
+"""CPU checks of the host logic: module tree / state_dict surface, graph builder (concat elimination,
+merged convs), memory planner, weight packer — by interpreting the planned op list with torch and
+comparing with the oracle (which is pinned against the reference)."""
+import numpy as np
+import pytest
+import torch
+
+import yolox_b200 as yb
+from oracle import model_ref as mr
+from tests.plan_interp import run_graph_cpu
+
+torch.set_grad_enabled(False)
+
+
+def _q16(sd):
+    return {k: (v.half().float() if k.endswith("weight") else v) for k, v in sd.items()}
+
+
+def _infer_model(name):
+    cfg = mr.CONFIGS[name]
+    cls = yb.infer.YOLOXP6 if cfg.kind == "p6" else yb.infer.YOLOX
+    return cfg, cls(cfg.depth, cfg.width, act=cfg.act, num_classes=cfg.num_classes)
+
+
+@pytest.mark.parametrize("name,H,W,B", [("tiny_p6", 128, 192, 2), ("tiny", 96, 160, 1)])
+def test_infer_graph_matches_oracle(name, H, W, B):
+    cfg, model = _infer_model(name)
+    fused = mr.fold_bn(mr.synth_train_state(cfg, 3, calib_hw=(H, W)))
+    model.load_state_dict(fused, strict=True)       # reference key names, strict
+    assert set(model.state_dict().keys()) == set(fused.keys())
+    g = model.build_graph(B, H, W)
+    x = mr.synth_images(11, B, H, W)
+    reg8, cls = run_graph_cpu(g, x)
+    reg, obj, clso = mr.forward_raw(_q16(fused), cfg, x)   # the engine stores weights in fp16
+    np.testing.assert_allclose(reg8[..., :4].numpy(), reg.numpy(), rtol=2e-4, atol=2e-4)
+    np.testing.assert_allclose(reg8[..., 4:5].numpy(), obj.numpy(), rtol=2e-4, atol=2e-4)
+    np.testing.assert_allclose(cls[..., :cfg.num_classes].numpy(), clso.numpy(), rtol=2e-4, atol=2e-4)
+    assert float(reg8[..., 5:].abs().max()) == 0.0
+
+
+def test_yolox_flavour_bn_fold_and_nano_depthwise():
+    cfg = mr.CONFIGS["nano"]
+    H = W = 64
+    train = mr.synth_train_state(cfg, 5, calib_hw=(H, W))
+    backbone = yb.models.YOLOPAFPN(cfg.depth, cfg.width, in_channels=[256, 512, 1024], act=cfg.act, depthwise=True)
+    head = yb.models.YOLOXHead(cfg.num_classes, cfg.width, in_channels=[256, 512, 1024], act=cfg.act)
+    model = yb.models.YOLOX(backbone, head).eval()
+    sd = dict(train)
+    for k, v in model.state_dict().items():
+        if k.endswith("num_batches_tracked"):
+            sd[k] = v
+    model.load_state_dict(sd, strict=True)
+    x = mr.synth_images(12, 1, H, W)
+    ref = mr.forward_raw(_q16(mr.fold_bn(train)), cfg, x)
+    reg8, cls = run_graph_cpu(model.build_graph(1, H, W), x)
+    np.testing.assert_allclose(reg8[..., :4].numpy(), ref[0].numpy(), rtol=2e-4, atol=2e-4)
+    np.testing.assert_allclose(cls.numpy(), ref[2].numpy(), rtol=2e-4, atol=2e-4)
+    # fuse_model: same keys as the reference's fused checkpoint, same graph result
+    yb.models.fuse_model(model)
+    fused = mr.fold_bn(train)
+    assert set(model.state_dict().keys()) == set(fused.keys())
+    for k, v in model.state_dict().items():
+        np.testing.assert_allclose(v.numpy(), fused[k].numpy(), rtol=1e-5, atol=1e-6)
+    reg8b, clsb = run_graph_cpu(model.build_graph(1, H, W), x)
+    np.testing.assert_allclose(clsb.numpy(), cls.numpy(), rtol=1e-4, atol=1e-4)
+
+
+def test_m_p6_surface_and_work():
+    cfg, model = _infer_model("yolox_m_p6")
+    assert len(model.state_dict()) == 278
+    assert model.head.strides == (8, 16, 32, 64)
+    g = model.build_graph(2, 1280, 1280)
+    assert abs(g.conv_flops() / 2 / 1e9 - 315.28) < 0.05       # 315.28 GFLOP / image
+    assert sum(h * w for h, w in g.outputs["level_hw"]) == 34000
+    # planner: live ranges of overlapping buffers never share bytes
+    for i, a in enumerate(g.bufs):
+        for b in g.bufs[i + 1:]:
+            if not (a.last < b.first or b.last < a.first):
+                assert a.offset + a.nbytes <= b.offset or b.offset + b.nbytes <= a.offset, (a.name, b.name)
+    assert g.arena_bytes < sum(b.nbytes for b in g.bufs)
+
+
+def test_sparse_checkpoint_ingest():
+    """main.py:52-55: state_dict()[key].copy_(param.to_dense()) for a {"model": sparse_coo} checkpoint."""
+    cfg, model = _infer_model("tiny_p6")
+    train = mr.synth_train_state(cfg, 6, calibrate=False)
+    fused = mr.apply_masks(mr.fold_bn(train), mr.magnitude_masks(train, 49.0))
+    ckpt = mr.to_sparse_ckpt(fused)["model"]
+    for key, param in ckpt.items():
+        model.state_dict()[key].copy_(param.to_dense().data)
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, fused[k])
+    g = model.build_graph(1, 64, 64)
+    nz = float((g.weight_blob != 0).float().mean())
+    assert 0.3 < nz < 0.8
+
+
+def test_errors():
+    with pytest.raises(AttributeError):
+        yb.infer.YOLOXP6(0.33, 0.25, act="gelu")
+    cfg, model = _infer_model("tiny_p6")
+    with pytest.raises(RuntimeError):
+        model.build_graph(1, 100, 128)                          # not a multiple of 64
+    with pytest.raises(RuntimeError):
+        model(torch.zeros(1, 3, 64, 64))                        # CPU tensor: no CPU path
+    with pytest.raises(ValueError):
+        yb.postprocess.yolox_nms_torch_batch(None, None, None, soft=True)
