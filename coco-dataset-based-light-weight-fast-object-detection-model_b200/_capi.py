@@ -49,7 +49,7 @@ def make_levels(level_hw, strides) -> Levels:
 
 
 SYMBOLS = ["yx_last_error", "yx_abi_version", "yx_engine_create", "yx_engine_destroy", "yx_engine_run",
-           "yx_engine_profile", "yx_engine_num_launches", "yx_conv2d", "yx_decode_infer", "yx_detect_workspace_bytes",
+           "yx_engine_profile", "yx_engine_run_ops", "yx_engine_num_launches", "yx_conv2d", "yx_decode_infer", "yx_detect_workspace_bytes",
            "yx_nms_main", "yx_detect_main", "yx_head_assemble", "yx_decode_outputs", "yx_postprocess_yolox"]
 
 _lib = None
@@ -80,6 +80,7 @@ def load():
     lib.yx_engine_destroy.argtypes = [c_vp]
     lib.yx_engine_destroy.restype = None
     lib.yx_engine_run.argtypes = [c_vp, c_vp, c_i32, c_f32, c_f32, c_i32, c_vp]
+    lib.yx_engine_run_ops.argtypes = [c_vp, c_vp, c_i32, c_f32, c_f32, c_i32, c_i32, c_vp]
     lib.yx_engine_profile.argtypes = [c_vp, c_vp, c_i32, c_i32, c_vp, ctypes.POINTER(c_f32),
                                       ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), c_i32]
     lib.yx_engine_num_launches.argtypes = [c_vp]

@@ -164,6 +164,17 @@ extern "C" int yx_engine_run(yx_engine* e, const void* image, int image_dtype, f
   return YX_OK;
 }
 
+extern "C" int yx_engine_run_ops(yx_engine* e, const void* image, int image_dtype, float in_scale, float in_shift,
+                                 int first, int count, void* stream) {
+  YX_REQUIRE(e && image && first >= 0 && count >= 0 && first + count <= (int)e->steps.size(), "bad op range");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int i = first; i < first + count; ++i) {
+    int rc = run_step(e, e->steps[i], image, image_dtype, in_scale, in_shift, st);
+    if (rc) return rc;
+  }
+  return YX_OK;
+}
+
 extern "C" int yx_engine_profile(yx_engine* e, const void* image, int image_dtype, int iters, void* stream,
                                  float* ms_host, double* flops_host, double* bytes_host, int n_ops) {
   YX_REQUIRE(e && image && ms_host && n_ops == (int)e->steps.size() && iters >= 1, "bad profile arguments");

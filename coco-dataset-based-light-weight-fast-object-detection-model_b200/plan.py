@@ -288,6 +288,21 @@ class Engine:
         _capi.check(self.lib.yx_engine_run(self.handle, image.data_ptr(), dt, float(in_scale), float(in_shift),
                                            int(use_graph), _capi.current_stream_ptr()), "yx_engine_run")
 
+    def run_ops(self, image, first: int, count: int, in_scale: float = 1.0, in_shift: float = 0.0):
+        """Diagnostic: run ops [first, first+count) only."""
+        import torch
+        dt = _capi.YX_F16 if image.dtype == torch.float16 else _capi.YX_F32
+        _capi.check(self.lib.yx_engine_run_ops(self.handle, image.contiguous().data_ptr(), dt, float(in_scale),
+                                               float(in_shift), first, count, _capi.current_stream_ptr()),
+                    "yx_engine_run_ops")
+
+    def view_tensor(self, cview):
+        """Strided fp16 torch view [n,h,w,c] of a C view (no copy)."""
+        import torch
+        a16 = self.arena[self._arena_pad:self._arena_pad + (self.graph.arena_bytes // 2) * 2].view(torch.float16)
+        return torch.as_strided(a16, (cview.n, cview.h, cview.w, cview.c),
+                                (cview.nstride, cview.w * cview.pitch, cview.pitch, 1), cview.offset // 2)
+
     def profile(self, image, iters: int = 5):
         import ctypes
         import torch

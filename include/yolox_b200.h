@@ -103,6 +103,11 @@ void yx_engine_destroy(yx_engine* e);
 int yx_engine_run(yx_engine* e, const void* image, int image_dtype, float in_scale, float in_shift, int use_graph,
                   void* stream);
 
+/* Diagnostic: run ops [first, first+count) only (used by the per-op parity tests, which check every
+ * op of a real network against a CPU evaluation of the SAME device inputs). */
+int yx_engine_run_ops(yx_engine* e, const void* image, int image_dtype, float in_scale, float in_shift, int first,
+                      int count, void* stream);
+
 /* Diagnostic: per-op device time (ms, mean over iters, CUDA events on `stream`), host-synchronising.
  * Also reports algorithmic flops / bytes per op so callers can print roofline fractions. */
 int yx_engine_profile(yx_engine* e, const void* image, int image_dtype, int iters, void* stream,

@@ -1,0 +1,114 @@
+"""GPU test helper: runs ONE conv op through the C ABI (yx_conv2d, the kernel the engine launches)
+on seeded data and compares with torch's fp32 conv on the same fp16-rounded inputs."""
+import ctypes
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+import yolox_b200 as yb
+from yolox_b200 import _capi
+from oracle.model_ref import activation
+
+ACT_NAMES = {"none": "none", "silu": "silu", "hard_swish": "hard_swish", "relu": "relu", "lrelu": "lrelu"}
+
+
+def _rup(a, b):
+    return (a + b - 1) // b * b
+
+
+def run_conv_case(cin, cout, k, stride, H, W, B=2, act="silu", res=False, src_pitch=None, src_off=0,
+                  dst_pitch=None, dst_off=0, seed=0, dst_c=None, device="cuda"):
+    """Returns dict(max_err, ref_scale, out, ref).  src/dst may be channel slices of wider buffers
+    (pitch/off in channels).  dst_c: channels of the dst view (>= cout, e.g. 8 for the 5-channel reg+obj pred)."""
+    lib = _capi.load()
+    g = torch.Generator().manual_seed(seed)
+    pad = k // 2
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    src_pitch = src_pitch or cin
+    dst_c = dst_c or cout
+    dst_pitch = dst_pitch or dst_c
+    x = (torch.randn(B, H, W, src_pitch, generator=g) * 1.0).half()
+    w = (torch.randn(cout, cin, k, k, generator=g) * (1.0 / np.sqrt(cin * k * k))).half()
+    b = torch.randn(cout, generator=g) * 0.5
+    r = (torch.randn(B, Ho, Wo, dst_pitch, generator=g) * 1.0).half() if res else None
+    # arena: [src | dst | res] each 1024-aligned
+    sb, db = _rup(x.numel() * 2, 1024), _rup(B * Ho * Wo * dst_pitch * 2, 1024)
+    arena = torch.zeros(sb + 2 * db + 1024, dtype=torch.uint8, device=device)
+    base_off = (-arena.data_ptr()) % 1024
+    base = arena.data_ptr() + base_off
+
+    def region(off, n):
+        return arena[base_off + off: base_off + off + 2 * n].view(torch.float16)
+    region(0, x.numel()).copy_(x.reshape(-1).to(device))
+    dst_init = torch.full((B * Ho * Wo * dst_pitch,), 7.0, dtype=torch.float16, device=device)  # sentinel
+    region(sb, dst_init.numel()).copy_(dst_init)
+    if res:
+        region(sb + db, r.numel()).copy_(r.reshape(-1).to(device))
+    cin_pad, cout_pad = _rup(cin, 16), _rup(cout, 16)
+    wp = torch.zeros(cout_pad, k * k, cin_pad, dtype=torch.float16)
+    wp[:cout, :, :cin] = w.permute(0, 2, 3, 1).reshape(cout, k * k, cin)
+    bp = torch.zeros(cout_pad, dtype=torch.float32)
+    bp[:cout] = b
+    wd, bd = wp.to(device), bp.to(device)
+
+    op = _capi.Op()
+    op.kind, op.ksize, op.stride, op.act = _capi.OP_CONV, k, stride, _capi.act_code(act)
+    op.src.offset, op.src.nstride = src_off * 2, H * W * src_pitch
+    op.src.n, op.src.h, op.src.w, op.src.c, op.src.pitch = B, H, W, cin, src_pitch
+    op.dst.offset, op.dst.nstride = sb + dst_off * 2, Ho * Wo * dst_pitch
+    op.dst.n, op.dst.h, op.dst.w, op.dst.c, op.dst.pitch = B, Ho, Wo, dst_c, dst_pitch
+    if res:
+        op.res.offset, op.res.nstride = sb + db + dst_off * 2, Ho * Wo * dst_pitch
+        op.res.n, op.res.h, op.res.w, op.res.c, op.res.pitch = B, Ho, Wo, dst_c, dst_pitch
+    op.w_offset, op.b_offset, op.cin_pad, op.cout_pad = 0, 0, cin_pad, cout_pad
+    _capi.check(lib.yx_conv2d(ctypes.byref(op), base, wd.data_ptr(), bd.data_ptr(),
+                              torch.cuda.current_stream().cuda_stream), "yx_conv2d")
+    torch.cuda.synchronize()
+    out_full = region(sb, B * Ho * Wo * dst_pitch).view(B, Ho, Wo, dst_pitch).float().cpu()
+    out = out_full[..., dst_off:dst_off + cout]
+
+    xs = x[..., src_off:src_off + cin].float().permute(0, 3, 1, 2)
+    ref = F.conv2d(xs.to(device), w.float().to(device), b.to(device), stride=stride, padding=pad).cpu()
+    ref = activation(ref.half().float(), ACT_NAMES[act]).permute(0, 2, 3, 1)
+    if res:
+        ref = ref.half().float() + r[..., dst_off:dst_off + cout].float()
+    ref = ref.half().float()
+    err = (out - ref).abs()
+    # untouched channels of the wider dst buffer must still hold the sentinel
+    mask = torch.ones(dst_pitch, dtype=torch.bool)
+    mask[dst_off:dst_off + dst_c] = False
+    clobbered = bool((out_full[..., mask] != 7.0).any()) if mask.any() else False
+    pad_bad = bool((out_full[..., dst_off + cout:dst_off + dst_c] != 0).any()) if dst_c > cout else False
+    return dict(max_err=float(err.max()), mean_err=float(err.mean()), ref_scale=float(ref.abs().mean()),
+                clobbered=clobbered, pad_nonzero=pad_bad, out=out, ref=ref)
+
+
+CASES = [
+    # cin, cout, k, stride, H, W, kwargs
+    dict(cin=64, cout=64, k=1, stride=1, H=16, W=16, act="none"),
+    dict(cin=64, cout=64, k=1, stride=1, H=16, W=16, act="silu"),
+    dict(cin=128, cout=128, k=1, stride=1, H=32, W=32, act="hard_swish"),
+    dict(cin=48, cout=96, k=1, stride=1, H=40, W=40, act="silu"),            # K tail (48), odd tile shape
+    dict(cin=64, cout=64, k=3, stride=1, H=16, W=16, act="none"),
+    dict(cin=96, cout=96, k=3, stride=1, H=40, W=24, act="hard_swish", res=True),
+    dict(cin=192, cout=192, k=3, stride=1, H=20, W=20, act="silu"),
+    dict(cin=64, cout=128, k=3, stride=2, H=32, W=32, act="silu"),
+    dict(cin=48, cout=96, k=3, stride=2, H=64, W=48, act="hard_swish"),
+    dict(cin=16, cout=48, k=3, stride=1, H=64, W=64, act="silu", B=1),       # stem: K = 16
+    dict(cin=192, cout=384, k=1, stride=1, H=16, W=16, act="silu"),          # 2 N tiles of 192
+    dict(cin=384, cout=288, k=1, stride=1, H=16, W=16, act="hard_swish"),    # N tiles 192 + 96
+    dict(cin=192, cout=80, k=1, stride=1, H=20, W=20, act="none"),           # cls pred
+    dict(cin=192, cout=5, k=1, stride=1, H=20, W=20, act="none", dst_c=8),   # merged reg+obj pred
+    dict(cin=96, cout=96, k=1, stride=1, H=16, W=16, act="silu", src_pitch=192, src_off=96,
+         dst_pitch=288, dst_off=96),                                          # concat slices
+    dict(cin=64, cout=64, k=3, stride=1, H=13, W=13, act="silu"),            # odd spatial size (Nano 416)
+    dict(cin=1152, cout=864, k=1, stride=1, H=40, W=40, act="hard_swish", B=1),  # deep K, 4 N tiles
+    dict(cin=576, cout=768, k=3, stride=2, H=40, W=40, act="hard_swish", B=1),
+    dict(cin=192, cout=192, k=3, stride=1, H=160, W=160, act="hard_swish", B=2),  # many tiles per CTA
+]
+
+
+def tolerance(case):
+    # fp16 output rounding (2^-11 relative) of O(1) values + fp32 accumulation-order noise
+    return 1.5e-2

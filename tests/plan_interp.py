@@ -1,6 +1,12 @@
-"""Test helper: a CPU interpreter for plan.Graph op lists (torch fp32).  It executes exactly what the
-native engine is told to execute — arena offsets, channel slices, packed KRSC weight blobs, merged
-convs — so the graph builder / memory planner / weight packer can be verified without a GPU."""
+"""Test helpers (torch fp32 evaluation of planned ops):
+
+  run_graph_cpu            interprets a plan.Graph op list on the CPU — arena offsets, channel slices,
+                           packed KRSC weight blobs, merged convs — so the graph builder / memory planner /
+                           weight packer are verified without a GPU.
+  teacher_forced_errors    on the GPU: runs every op of a real engine ONE AT A TIME and compares its output
+                           with a torch fp32 evaluation of the SAME device inputs (no error accumulation
+                           across layers), in units of fp16 ulps.
+"""
 import numpy as np
 import torch
 import torch.nn.functional as F
@@ -14,6 +20,48 @@ ACT = {0: "none", 1: "silu", 2: "hard_swish", 3: "relu", 4: "lrelu"}
 def _act(x, code):
     from oracle.model_ref import activation
     return activation(x, ACT[code])
+
+
+def eval_op(o, image, src, res, wblob, bblob, q):
+    """Evaluate one planned op in fp32.  o: _capi.Op; image NCHW fp32 (S2D only); src/res NHWC fp32;
+    wblob fp32 view of the fp16 weight blob, bblob fp32.  q: rounding applied where the engine rounds to
+    fp16 (identity for an exact evaluation).  Returns NHWC [n,h,w,dst.c]."""
+    if o.kind == _capi.OP_S2D:
+        x = image
+        tl, tr, bl, br = x[..., ::2, ::2], x[..., ::2, 1::2], x[..., 1::2, ::2], x[..., 1::2, 1::2]
+        if o.aux == 1:
+            y = torch.stack((tl, tr, bl, br), dim=2).reshape(x.shape[0], 12, x.shape[2] // 2, x.shape[3] // 2)
+        else:
+            y = torch.cat((tl, bl, tr, br), dim=1)
+        y = F.pad(y, (0, 0, 0, 0, 0, 4))
+        return q(y.permute(0, 2, 3, 1))
+    if o.kind == _capi.OP_CONV:
+        k = o.ksize
+        x = src.permute(0, 3, 1, 2)
+        x = F.pad(x, (0, 0, 0, 0, 0, o.cin_pad - x.shape[1]))
+        w = wblob[o.w_offset // 2: o.w_offset // 2 + o.cout_pad * k * k * o.cin_pad]
+        w = w.view(o.cout_pad, k, k, o.cin_pad).permute(0, 3, 1, 2)
+        b = bblob[o.b_offset // 4: o.b_offset // 4 + o.cout_pad]
+        y = F.conv2d(x, w, b, stride=o.stride, padding=k // 2)
+        y = _act(q(y), o.act)
+        y = y.permute(0, 2, 3, 1)[..., :o.dst.c]
+        if o.res.c > 0:
+            y = q(y) + res
+        return q(y)
+    if o.kind == _capi.OP_DWCONV:
+        k = o.ksize
+        x = src.permute(0, 3, 1, 2)
+        c = x.shape[1]
+        w = wblob[o.w_offset // 2: o.w_offset // 2 + k * k * c].view(k, k, c).permute(2, 0, 1).unsqueeze(1)
+        b = bblob[o.b_offset // 4: o.b_offset // 4 + c]
+        y = _act(q(F.conv2d(x, w, b, stride=o.stride, padding=k // 2, groups=c)), o.act)
+        return q(y.permute(0, 2, 3, 1))
+    if o.kind == _capi.OP_SPP:
+        x = src.permute(0, 3, 1, 2)
+        return torch.cat([F.max_pool2d(x, ks, 1, ks // 2) for ks in (5, 9, 13)], 1).permute(0, 2, 3, 1)
+    if o.kind == _capi.OP_UPSAMPLE:
+        return F.interpolate(src.permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1)
+    raise AssertionError(f"unknown op kind {o.kind}")
 
 
 class ArenaSim:
@@ -38,61 +86,50 @@ class ArenaSim:
 
 
 def run_graph_cpu(g, image, quantize=False):
-    """image: NCHW fp32.  quantize=True rounds every stored activation / weight to fp16 like the engine."""
+    """image: NCHW fp32.  quantize=True rounds every stored activation to fp16 like the engine."""
     q = (lambda t: t.half().float()) if quantize else (lambda t: t)
     arena = ArenaSim(g.arena_bytes)
-    wblob = g.weight_blob.float()
-    bblob = g.bias_blob
+    wblob, bblob = g.weight_blob.float(), g.bias_blob
     ops = g.c_ops()
     for i, pop in enumerate(g.ops):
         o = ops[i]
-        if o.kind == _capi.OP_S2D:
-            x = image
-            tl, tr, bl, br = x[..., ::2, ::2], x[..., ::2, 1::2], x[..., 1::2, ::2], x[..., 1::2, 1::2]
-            if o.aux == 1:
-                y = torch.stack((tl, tr, bl, br), dim=2).reshape(x.shape[0], 12, x.shape[2] // 2, x.shape[3] // 2)
-            else:
-                y = torch.cat((tl, bl, tr, br), dim=1)
-            y = F.pad(y, (0, 0, 0, 0, 0, 4))
-            arena.write(o.dst, q(y.permute(0, 2, 3, 1)))
-        elif o.kind == _capi.OP_CONV:
-            k = o.ksize
-            x = arena.read(o.src).permute(0, 3, 1, 2)
-            assert not torch.isnan(x).any(), f"op {i} {pop.name}: reads uninitialised arena memory"
-            x = F.pad(x, (0, 0, 0, 0, 0, o.cin_pad - x.shape[1]))
-            w = wblob[o.w_offset // 2: o.w_offset // 2 + o.cout_pad * k * k * o.cin_pad]
-            w = w.view(o.cout_pad, k, k, o.cin_pad).permute(0, 3, 1, 2)
-            b = bblob[o.b_offset // 4: o.b_offset // 4 + o.cout_pad]
-            y = F.conv2d(x, w, b, stride=o.stride, padding=k // 2)
-            y = _act(q(y), o.act)
-            y = y.permute(0, 2, 3, 1)[..., :o.dst.c]
-            if o.res.c > 0:
-                r = arena.read(o.res)
-                assert not torch.isnan(r).any(), f"op {i} {pop.name}: residual reads uninitialised memory"
-                y = q(y) + r
-            arena.write(o.dst, q(y))
-        elif o.kind == _capi.OP_DWCONV:
-            k = o.ksize
-            x = arena.read(o.src).permute(0, 3, 1, 2)
-            c = x.shape[1]
-            w = wblob[o.w_offset // 2: o.w_offset // 2 + k * k * c].view(k, k, c).permute(2, 0, 1).unsqueeze(1)
-            b = bblob[o.b_offset // 4: o.b_offset // 4 + c]
-            y = _act(q(F.conv2d(x, w, b, stride=o.stride, padding=k // 2, groups=c)), o.act)
-            arena.write(o.dst, q(y.permute(0, 2, 3, 1)))
-        elif o.kind == _capi.OP_SPP:
-            x = arena.read(o.src).permute(0, 3, 1, 2)
-            ys = [F.max_pool2d(x, ks, 1, ks // 2) for ks in (5, 9, 13)]
-            arena.write(o.dst, torch.cat(ys, 1).permute(0, 2, 3, 1))
-        elif o.kind == _capi.OP_UPSAMPLE:
-            x = arena.read(o.src).permute(0, 3, 1, 2)
-            arena.write(o.dst, F.interpolate(x, scale_factor=2, mode="nearest").permute(0, 2, 3, 1))
-        else:
-            raise AssertionError(f"unknown op kind {o.kind}")
+        src = arena.read(o.src) if o.kind != _capi.OP_S2D else None
+        res = arena.read(o.res) if (o.kind == _capi.OP_CONV and o.res.c > 0) else None
+        for t, what in ((src, "src"), (res, "residual")):
+            assert t is None or not torch.isnan(t).any(), f"op {i} {pop.name}: {what} reads uninitialised arena memory"
+        arena.write(o.dst, eval_op(o, image, src, res, wblob, bblob, q))
     outs = g.outputs
-    A = outs["reg"].h
-    B = g.batch
+    A, B = outs["reg"].h, g.batch
 
     def out_tensor(buf):
-        v = buf.view().to_c()
-        return arena.read(v).reshape(B, A, buf.c)
+        return arena.read(buf.view().to_c()).reshape(B, A, buf.c)
     return out_tensor(outs["reg"]), out_tensor(outs["cls"])
+
+
+def teacher_forced_errors(model, x):
+    """Returns [(op index, name, max error in fp16 ulps of the reference value, max abs err)]."""
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        eng = model.engine_for(x)
+        g = eng.graph
+        ops = g.c_ops()
+        wblob, bblob = eng.weights.float(), eng.biases
+        q = lambda t: t.half().float()
+        xf = x.float()
+        out = []
+        for i, pop in enumerate(g.ops):
+            o = ops[i]
+            src = eng.view_tensor(o.src).float() if o.kind != _capi.OP_S2D else None
+            res = eng.view_tensor(o.res).float().clone() if (o.kind == _capi.OP_CONV and o.res.c > 0) else None
+            ref = eval_op(o, xf, src, res, wblob, bblob, q)       # before the op runs (dst may alias res)
+            eng.run_ops(x, i, 1)
+            torch.cuda.synchronize()
+            got = eng.view_tensor(o.dst).float()
+            err = (got - ref).abs()
+            ulp = torch.clamp(ref.abs(), min=2.0 ** -6) * 2.0 ** -10   # fp16 spacing (normal range floor 2^-6)
+            out.append((i, pop.name, float((err / ulp).max()), float(err.max())))
+        return out
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old

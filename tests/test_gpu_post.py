@@ -1,0 +1,149 @@
+"""GPU parity of decode / candidate selection / batched NMS (through the C ABI) against the CPU oracle
+and the reference-generated golden detections.  Index/box outputs of NMS are compared BIT-EXACTLY on
+identical decoded inputs; decode is compared within fp32 transcendental tolerance (expf/sigmoid)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import yolox_b200 as yb
+from oracle import post_ref as pr
+
+pytestmark = pytest.mark.gpu
+FILES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "post_*.npz")))
+DEV = "cuda"
+
+
+def _np(d):
+    return d.cpu().numpy() if d is not None else np.zeros((0, 7), np.float32)
+
+
+@pytest.mark.parametrize("path", FILES, ids=[os.path.basename(p) for p in FILES])
+def test_golden_main_flavour(path):
+    g = np.load(path)
+    img, strides = int(g["img"]), [int(s) for s in g["strides"]]
+    hw = [(img // s, img // s) for s in strides]
+    conf, thr = float(g["conf"]), float(g["nms_thr"])
+    reg, obj, cls = (torch.from_numpy(g[k]).to(DEV) for k in ("reg", "obj", "cls"))
+    grids, scales = yb.postprocess.yolox_generate_grid(img, strides, torch.float16)
+    boxes, oc, cc = yb.postprocess.yolox_postprocess_output_torch_batch(reg, obj, cls, grids.to(DEV), scales.to(DEV))
+    np.testing.assert_allclose(boxes.cpu().numpy(), g["boxes"], rtol=3e-6, atol=2e-4)
+    np.testing.assert_allclose(oc.cpu().numpy(), g["obj_conf"], rtol=3e-6, atol=1e-7)
+    np.testing.assert_allclose(cc.cpu().numpy(), g["cls_conf"], rtol=6e-6, atol=1e-7)
+    # NMS on the reference's own decoded tensors: bit-exact rows, same order
+    rb, ro, rc = (torch.from_numpy(g[k]).to(DEV) for k in ("boxes", "obj_conf", "cls_conf"))
+    for key, kw in (("main", {}), ("mainu", dict(max_num_nms=0, max_num_det=10 ** 9)), ("maina", dict(class_agnostic=True))):
+        dets = yb.postprocess.yolox_nms_torch_batch(rb, ro, rc, nms_threshold=thr, conf_threshold=conf, **kw)
+        for i, d in enumerate(dets):
+            want = g[f"{key}_det_{i}"]
+            # the golden ran torchvision's CPU dispatch (vanilla above 1000 boxes); kept SETS agree between the
+            # coordinate trick and vanilla except at fp32 ties, and the oracle test pins both modes, so compare
+            # against the oracle in the mode the GPU picked
+            n_cand = int((g["cls_conf"][i].max(-1) >= conf).sum())
+            cap = 5000 if key != "mainu" else 0
+            n_in = min(n_cand, cap) if cap else n_cand
+            mode = "agnostic" if key == "maina" else pr.torchvision_mode(n_in, "cuda")
+            ref, _ = pr.nms_image_main(g["boxes"][i], g["obj_conf"][i], g["cls_conf"][i], conf, thr,
+                                       max_nms=cap, max_det=300 if key != "mainu" else 10 ** 9, mode=mode)
+            np.testing.assert_array_equal(_np(d), ref, err_msg=f"{key} img {i}")
+            assert {tuple(r) for r in _np(d)} == {tuple(r) for r in want}, f"{key} img {i}: kept set differs from the reference"
+    # fused path == decode + nms
+    det, cnt, anc = yb.postprocess.detect_main(reg, obj, cls, hw, strides, conf, thr)
+    det2, cnt2, anc2 = yb.postprocess.nms_main_raw(boxes, oc, cc, thr, conf, 5000, 300)
+    assert torch.equal(det, det2) and torch.equal(cnt, cnt2) and torch.equal(anc, anc2)
+
+
+@pytest.mark.parametrize("path", FILES, ids=[os.path.basename(p) for p in FILES])
+def test_golden_yolox_postprocess(path):
+    g = np.load(path)
+    conf, thr = float(g["conf"]), float(g["nms_thr"])
+    pred = torch.from_numpy(g["yolox_pred"]).to(DEV)
+    C = pred.shape[2] - 5
+    keep = pred.clone()
+    res = yb.postprocess.postprocess(pred, C, conf, thr)
+    # in-place xyxy conversion like the reference (boxes.py:38-43)
+    xy = keep.clone()
+    xy[..., 0], xy[..., 1] = keep[..., 0] - keep[..., 2] / 2, keep[..., 1] - keep[..., 3] / 2
+    xy[..., 2], xy[..., 3] = keep[..., 0] + keep[..., 2] / 2, keep[..., 1] + keep[..., 3] / 2
+    assert torch.equal(pred[..., :4], xy[..., :4]) and torch.equal(pred[..., 4:], keep[..., 4:])
+    for i, d in enumerate(res):
+        score = g["yolox_pred"][i][:, 4] * g["yolox_pred"][i][:, 5:].max(-1)
+        mode = pr.torchvision_mode(int((score >= conf).sum()), "cuda")
+        ref, _, _ = pr.postprocess_image(g["yolox_pred"][i], conf, thr, mode)
+        np.testing.assert_array_equal(_np(d), ref)
+        assert {tuple(r) for r in _np(d)} == {tuple(r) for r in g[f"yolox_det_{i}"]}
+    res = yb.postprocess.postprocess(keep.clone(), C, conf, thr, class_agnostic=True)
+    for i, d in enumerate(res):
+        np.testing.assert_array_equal(_np(d), g[f"yoloxa_det_{i}"])
+
+
+def _stress_logits(seed, B, hw, C, dist):
+    rs = np.random.RandomState(seed)
+    A = sum(h * w for h, w in hw)
+    reg = rs.standard_normal((B, A, 4)).astype(np.float16)
+    obj = (rs.standard_normal((B, A, 1)) * 2 - 2).astype(np.float16)
+    cls = (rs.standard_normal((B, A, C)) * 2 - 2).astype(np.float16)
+    if dist == "ties":  # quantised scores -> many exact ties, duplicated boxes
+        obj = np.round(obj.astype(np.float32)).astype(np.float16)
+        cls = np.round(cls.astype(np.float32)).astype(np.float16)
+        reg = np.round(reg.astype(np.float32) * 2).astype(np.float16) / 2
+    return reg, obj, cls
+
+
+@pytest.mark.parametrize("dist,B,img,conf,thr", [("maxcand", 3, 1280, 0.001, 0.65), ("ties", 2, 640, 0.001, 0.55),
+                                                 ("maxcand", 2, 640, 0.9999, 0.5)])
+def test_full_size_against_oracle(dist, B, img, conf, thr):
+    """BASELINE config 4 sizes (A = 34 000 at 1280): fused device path vs C oracle per image, bit-exact
+    given the device's own decoded tensors; also covers the empty-result case (conf 0.9999)."""
+    strides = (8, 16, 32, 64)
+    hw = [(img // s, img // s) for s in strides]
+    reg, obj, cls = (torch.from_numpy(a).to(DEV) for a in _stress_logits(5, B, hw, 80, dist))
+    grids, scales = yb.postprocess.yolox_generate_grid(img, strides, torch.float16)
+    boxes, oc, cc = yb.postprocess.yolox_postprocess_output_torch_batch(reg, obj, cls, grids.to(DEV), scales.to(DEV))
+    det, cnt, anc = yb.postprocess.detect_main(reg, obj, cls, hw, strides, conf, thr)
+    for i in range(B):
+        n_cand = int((cc[i].max(-1)[0] >= conf).sum())
+        ref, aref = pr.nms_image_main(boxes[i].cpu().numpy(), oc[i].cpu().numpy(), cc[i].cpu().numpy(), conf, thr,
+                                      mode=pr.torchvision_mode(min(n_cand, 5000), "cuda"))
+        n = int(cnt[i])
+        assert n == len(ref)
+        np.testing.assert_array_equal(det[i, :n].cpu().numpy(), ref)
+        np.testing.assert_array_equal(anc[i, :n].cpu().numpy(), aref)
+        assert float(det[i, n:].abs().sum()) == 0.0
+        # properties: scores sorted descending; idempotence (NMS of the kept set keeps everything)
+        s = det[i, :n, 5]
+        assert bool((s[:-1] >= s[1:]).all()) if n > 1 else True
+    lists = yb.postprocess.yolox_nms_torch_batch(boxes, oc, cc, thr, conf)
+    assert all((l is None) == (int(c) == 0) for l, c in zip(lists, cnt))
+
+
+def test_uncapped_vanilla_dispatch():
+    """> 25 000 candidates without a cap -> torchvision's CUDA dispatch switches to per-class NMS."""
+    strides, img = (8, 16, 32, 64), 1280
+    hw = [(img // s, img // s) for s in strides]
+    reg, obj, cls = (torch.from_numpy(a).to(DEV) for a in _stress_logits(9, 1, hw, 80, "maxcand"))
+    grids, scales = yb.postprocess.yolox_generate_grid(img, strides, torch.float16)
+    boxes, oc, cc = yb.postprocess.yolox_postprocess_output_torch_batch(reg, obj, cls, grids.to(DEV), scales.to(DEV))
+    out = yb.postprocess.yolox_nms_torch_batch(boxes, oc, cc, 0.65, 0.001, max_num_nms=0, max_num_det=10 ** 9)
+    n_cand = int((cc[0].max(-1)[0] >= 0.001).sum())
+    assert n_cand > 25000
+    ref, _ = pr.nms_image_main(boxes[0].cpu().numpy(), oc[0].cpu().numpy(), cc[0].cpu().numpy(), 0.001, 0.65,
+                               max_nms=0, max_det=10 ** 9, mode="vanilla")
+    np.testing.assert_array_equal(out[0].cpu().numpy(), ref)
+
+
+def test_decode_outputs_and_head_assemble():
+    strides, img = (8, 16, 32), 320
+    hw = [(img // s, img // s) for s in strides]
+    A = sum(h * w for h, w in hw)
+    rs = np.random.RandomState(3)
+    out = torch.from_numpy(rs.standard_normal((2, A, 85)).astype(np.float32)).to(DEV)
+    ref = pr.decode_yolox(out[0].cpu().numpy(), hw, strides)
+    got = yb.postprocess.decode_outputs(out.clone(), hw, strides)
+    np.testing.assert_allclose(got[0].cpu().numpy(), ref, rtol=3e-6, atol=1e-5)
+    h = out.half()
+    got16 = yb.postprocess.decode_outputs(h.clone(), hw, strides)
+    np.testing.assert_allclose(got16[0, :, :2].float().cpu().numpy(), ref[:, :2], rtol=2e-3, atol=0.2)
+    assert torch.equal(got16[..., 4:], h[..., 4:])
