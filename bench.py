@@ -55,12 +55,13 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t0, self.t1 = index, [], None, None, None
 
     def start(self):
+        """Start early (nvidia-smi needs ~1 s to produce its first row); mark_begin/mark_end bracket the timed region."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -68,14 +69,23 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.12)
         self.proc.terminate()
+        inside = [r for t, r in self.rows if self.t0 is not None and self.t0 <= t <= (self.t1 or 1e30) + 0.06]
+        rows = inside if inside else [r for _, r in self.rows]
         sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx = float(r[1])
             except Exception:
@@ -84,7 +94,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=mx, reasons=sorted(reasons),
-                    samples=len(sm))
+                    samples=len(sm), in_timed_region=bool(inside))
 
 
 # ------------------------------------------------------------------------------------------
@@ -167,6 +177,9 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
     torch.set_grad_enabled(False)
     B, S = args.batch, args.size
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     model = build_model(dev)
     gen = torch.Generator().manual_seed(1234 + rank)
     host_imgs = [torch.empty(B, 3, S, S, dtype=torch.float16).pin_memory() for _ in range(2)]
@@ -199,16 +212,15 @@ def run_ours(args, rank, world, local_rank):
     n_launch_step = model.engine_for(dev_img).n_launches + 3  # + select, sort, nms kernels
 
     # ---- device-resident timing -------------------------------------------------------------
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     ev0.record()
     for _ in range(args.steps):
         det, cnt = step(dev_img)
     ev1.record()
     barrier()
+    sampler.mark_end()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], device=dev)

@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 #include "yx_internal.h"
 #include "yx_ptx.cuh"
@@ -29,18 +30,41 @@ constexpr int kAStageBytes = 128 * 128;  // 128 rows x 64 fp16
 constexpr int kMaxStages = 8;
 constexpr int kSmemLimit = 227 * 1024;
 constexpr int kBarBytes = 256;
+constexpr int kSmemTwoCtas = 112 * 1024;  // per-CTA budget that lets two CTAs share an SM
 
-__device__ __forceinline__ float apply_act(float x, int act) {
-  switch (act) {
-    case YX_ACT_SILU: return x / (1.0f + __expf(-x));
-    case YX_ACT_HSWISH: return x * fminf(fmaxf(x + 3.0f, 0.0f), 6.0f) * (1.0f / 6.0f);
-    case YX_ACT_RELU: return fmaxf(x, 0.0f);
-    case YX_ACT_LRELU: return x > 0.0f ? x : 0.1f * x;
-    default: return x;
+// arithmetic intensity (FLOP / byte of fp16 activation traffic) below which a layer is launched in the
+// two-CTAs-per-SM "streaming" shape.  B200 ridge = 1414.9 TF/s / 6527 GB/s = 217 FLOP/B.
+// YX_MEM_AI overrides it for experiments (0 = never, 1e9 = always).
+static double mem_bound_ai() {
+  static double v = -1.0;
+  if (v < 0) {
+    const char* e = getenv("YX_MEM_AI");
+    v = e ? atof(e) : 300.0;
   }
+  return v;
 }
 
-__global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+// Activation on the fp16-rounded conv output, evaluated in fp32 like torch's half kernels (opmath = float).
+// Compile-time ACT keeps the epilogue straight-line: the epilogue has ONE warp per scheduler, so it lives on
+// instruction-level parallelism across the 16 columns of a TMEM chunk (a runtime switch per element
+// serialised it to ~150 cycles/element in the first version — see profiles/r01_conv_tile_trace.txt).
+template <int ACT>
+__device__ __forceinline__ float apply_act(float x) {
+  if (ACT == YX_ACT_SILU) return __fdividef(x, 1.0f + __expf(-x));
+  if (ACT == YX_ACT_HSWISH) return x * fminf(fmaxf(x + 3.0f, 0.0f), 6.0f) * (1.0f / 6.0f);
+  if (ACT == YX_ACT_RELU) return fmaxf(x, 0.0f);
+  if (ACT == YX_ACT_LRELU) return x > 0.0f ? x : 0.1f * x;
+  return x;
+}
+
+// optional per-tile timeline (diagnostics): trace[tile_local * 8 + event] = clock64(), CTA 0 only
+#define YX_TRACE(ev, tl)                                                                   \
+  do {                                                                                     \
+    if (p.trace != nullptr && blockIdx.x == 0 && (tl) < 32) p.trace[(tl) * 8 + (ev)] = clock64(); \
+  } while (0)
+
+template <int ACT, bool HAS_RES>
+__global__ void __launch_bounds__(kThreads, 2) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5;
@@ -72,7 +96,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     mbar_init(bar_res, 1);
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  if (warp == 2) tmem_alloc(tmem_slot, p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -116,6 +140,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
             tma_load_3d(sB + s * p.b_stage_bytes, &p.tmW, bar_full + 8 * s, kc * 64, tap, n0);
           }
         }
+        YX_TRACE(0, (tile - (int)blockIdx.x) / (int)gridDim.x);
       }
     }
   } else if (warp == 1) {
@@ -130,7 +155,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
         mbar_wait(bar_tempty + 8 * acc, acc_ph ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * 256;
+        YX_TRACE(1, t);
+        const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
         uint32_t accum = 0;
         for (int tap = 0; tap < taps; ++tap) {
           for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
@@ -149,6 +175,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
           }
         }
         umma_commit(bar_tfull + 8 * acc);  // accumulator complete -> epilogue
+        YX_TRACE(2, t);
       }
     }
   } else {
@@ -167,56 +194,62 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       const int groups_cur = (bn_cur + 63) >> 6;
       const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
 
-      if (p.has_res && leader) {
+      if (HAS_RES && leader) {
         mbar_expect_tx(bar_res, groups_cur * p.a_box_bytes);
         for (int g = 0; g < groups_cur; ++g)
           tma_load_4d(sStage + g * kAStageBytes, &p.tmRes, bar_res, n0 + g * 64, x0, y0, img);
       }
       mbar_wait(bar_tfull + 8 * acc, acc_ph);
       tc_fence_after();
-      if (p.has_res) {
+      if (leader) YX_TRACE(3, t);
+      if (HAS_RES) {
         mbar_wait(bar_res, res_cnt & 1);
         ++res_cnt;
       }
-      const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(q * 32) << 16);
+      const uint32_t taddr = tmem_base + acc * p.acc_stride + (static_cast<uint32_t>(q * 32) << 16);
       for (int c0 = 0; c0 < bn_cur; c0 += 16) {
         uint32_t v[16];
         tmem_ld_32x32b_x16(taddr + c0, v);
         tmem_ld_wait();
         if (row_valid) {
+          float bb[16];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int c = c0 + h * 8;
-            const uint32_t addr =
-                sStage + (c >> 6) * kAStageBytes + row * 128 + ((((c & 63) >> 3) ^ (row & 7)) << 4);
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + 4));
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-            uint32_t rr[4] = {0, 0, 0, 0};
-            if (p.has_res)
-              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                           : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3])
-                           : "r"(addr));
-            uint32_t out[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              float f0 = __uint_as_float(v[h * 8 + 2 * i]) + bb[2 * i];
-              float f1 = __uint_as_float(v[h * 8 + 2 * i + 1]) + bb[2 * i + 1];
-              // the reference rounds the conv output to fp16 before its (separate) activation kernel
-              f0 = apply_act(__half2float(__float2half_rn(f0)), p.act);
-              f1 = apply_act(__half2float(__float2half_rn(f1)), p.act);
-              if (p.has_res) {
-                const __half2 rh = *reinterpret_cast<const __half2*>(&rr[i]);
-                f0 = __half2float(__float2half_rn(f0)) + __low2float(rh);
-                f1 = __half2float(__float2half_rn(f1)) + __high2float(rh);
-              }
-              const __half2 o = __floats2half2_rn(f0, f1);
-              out[i] = *reinterpret_cast<const uint32_t*>(&o);
-            }
-            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(out[0]), "r"(out[1]),
-                         "r"(out[2]), "r"(out[3])
-                         : "memory");
+          for (int j = 0; j < 4; ++j) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0) + j);
+            bb[4 * j] = b4.x; bb[4 * j + 1] = b4.y; bb[4 * j + 2] = b4.z; bb[4 * j + 3] = b4.w;
           }
+          // two 16-byte chunks (8 channels each) of this row's 128-byte swizzled staging line
+          const uint32_t line = sStage + (c0 >> 6) * kAStageBytes + row * 128;
+          const uint32_t a0 = line + ((((c0 & 63) >> 3) ^ (row & 7)) << 4);
+          const uint32_t a1 = line + (((((c0 & 63) >> 3) + 1) ^ (row & 7)) << 4);
+          uint32_t rr[8];
+          if (HAS_RES) {
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]) : "r"(a0));
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(rr[4]), "=r"(rr[5]), "=r"(rr[6]), "=r"(rr[7]) : "r"(a1));
+          }
+          uint32_t out[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            // the reference rounds the conv output to fp16 before its (separate) activation kernel
+            const __half2 pre = __floats2half2_rn(__uint_as_float(v[2 * i]) + bb[2 * i],
+                                                  __uint_as_float(v[2 * i + 1]) + bb[2 * i + 1]);
+            const float2 pf = __half22float2(pre);
+            float f0 = apply_act<ACT>(pf.x), f1 = apply_act<ACT>(pf.y);
+            if (HAS_RES) {  // half + half as torch computes it: exact fp32 sum of the two halves, rounded once
+              const float2 af = __half22float2(__floats2half2_rn(f0, f1));
+              const float2 rf = __half22float2(*reinterpret_cast<const __half2*>(&rr[i]));
+              f0 = af.x + rf.x;
+              f1 = af.y + rf.y;
+            }
+            const __half2 o = __floats2half2_rn(f0, f1);
+            out[i] = *reinterpret_cast<const uint32_t*>(&o);
+          }
+          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "r"(out[0]), "r"(out[1]), "r"(out[2]),
+                       "r"(out[3]) : "memory");
+          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a1), "r"(out[4]), "r"(out[5]), "r"(out[6]),
+                       "r"(out[7]) : "memory");
         }
       }
       // accumulator drained -> MMA warp may overwrite it
@@ -225,12 +258,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
       // publish the staged tile to the async proxy and store it
       fence_proxy_async_smem();
+      if (leader) YX_TRACE(4, t);
       named_bar_sync(1, 128);
       if (leader) {
+        YX_TRACE(5, t);
         for (int g = 0; g < groups_cur; ++g)
           tma_store_4d(&p.tmOut, sStage + g * kAStageBytes, n0 + g * 64, x0, y0, img);
         tma_store_commit();
         tma_store_wait_read0();
+        YX_TRACE(6, t);
       }
       named_bar_sync(1, 128);  // staging buffer reusable
     }
@@ -239,7 +275,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, 512);
+  if (warp == 2) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -353,8 +389,25 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
   p.tiles_h = ceil_div(Hout, p.TH);
   p.tiles_w = ceil_div(Wout, p.TW);
   p.n_tiles_m = d.n * p.tiles_h * p.tiles_w;
-  // N tiling: single tile when Cout <= 256, else the fewest 64-multiple tiles
-  if (p.cout16 <= 256) {
+  // Algorithmic work decides the launch shape.  Layers below the ridge (HBM-bound: all 1x1 convs at
+  // these channel counts, the 48/96-channel 3x3 convs) run TWO CTAs per SM with narrow N tiles so one
+  // CTA's epilogue / TMA-store latency hides behind the other's loads; tensor-bound layers keep one CTA
+  // per SM with the widest N tile (fewest re-reads of A) and the deepest smem pipeline.
+  const double px_out_ = (double)d.n * Hout * Wout;
+  const double flops_ = 2.0 * px_out_ * d.c * s.c * op.ksize * op.ksize;
+  const double bytes_ = 2.0 * ((double)s.n * s.h * s.w * s.c + px_out_ * d.c * (has_res ? 2 : 1));
+  const bool mem_bound = flops_ / bytes_ < mem_bound_ai();
+  int ctas_per_sm = 1;
+  if (mem_bound) {
+    if (p.cout16 <= 128) {
+      p.BN = p.cout16;
+      p.n_tiles_n = 1;
+    } else {
+      p.BN = 128;
+      p.n_tiles_n = ceil_div(p.cout16, 128);
+    }
+    ctas_per_sm = 2;
+  } else if (p.cout16 <= 256) {
     p.BN = p.cout16;
     p.n_tiles_n = 1;
   } else {
@@ -362,14 +415,20 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
     p.BN = round_up(ceil_div(p.cout16, nt), 64);
     p.n_tiles_n = ceil_div(p.cout16, p.BN);
   }
+  p.tmem_cols = 32;
+  while (p.tmem_cols < 2 * p.BN) p.tmem_cols <<= 1;
+  p.acc_stride = p.tmem_cols / 2;
   p.b_stage_bytes = p.BN * 128;
   p.a_box_bytes = p.TH * p.TW * 128;
   const int groups = ceil_div(p.BN, 64);
   const int fixed = groups * kAStageBytes + kBarBytes + 1024;  // staging + barriers + alignment slack
-  p.stages = std::min(kMaxStages, (kSmemLimit - fixed) / (kAStageBytes + p.b_stage_bytes));
+  const int budget = ctas_per_sm == 2 ? kSmemTwoCtas : kSmemLimit;
+  p.stages = std::min(kMaxStages, (budget - fixed) / (kAStageBytes + p.b_stage_bytes));
   YX_REQUIRE(p.stages >= 2, "not enough shared memory for a 2-stage pipeline");
   pl.smem_bytes = fixed + p.stages * (kAStageBytes + p.b_stage_bytes);
-  pl.grid = std::min(p.n_tiles_m * p.n_tiles_n, num_sms);
+  // never let a third CTA (which would stall in tcgen05.alloc) fit on an SM
+  if (ctas_per_sm == 2) pl.smem_bytes = std::max(pl.smem_bytes, 80 * 1024);
+  pl.grid = std::min(p.n_tiles_m * p.n_tiles_n, ctas_per_sm * num_sms);
   p.bias = reinterpret_cast<const float*>(static_cast<const uint8_t*>(biases) + op.b_offset);
 
   int rc;
@@ -412,15 +471,32 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
   return YX_OK;
 }
 
-int conv_launch(const ConvPlan& plan, cudaStream_t stream) {
+template <int ACT, bool HAS_RES>
+static int launch_variant(const ConvPlan& plan, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    YX_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    YX_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<ACT, HAS_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     attr_set = true;
   }
-  conv_igemm_kernel<<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.p);
+  conv_igemm_kernel<ACT, HAS_RES><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.p);
   YX_CUDA(cudaGetLastError());
   return YX_OK;
+}
+
+template <int ACT>
+static int launch_act(const ConvPlan& plan, cudaStream_t stream) {
+  return plan.p.has_res ? launch_variant<ACT, true>(plan, stream) : launch_variant<ACT, false>(plan, stream);
+}
+
+int conv_launch(const ConvPlan& plan, cudaStream_t stream) {
+  switch (plan.p.act) {
+    case YX_ACT_NONE: return launch_act<YX_ACT_NONE>(plan, stream);
+    case YX_ACT_SILU: return launch_act<YX_ACT_SILU>(plan, stream);
+    case YX_ACT_HSWISH: return launch_act<YX_ACT_HSWISH>(plan, stream);
+    case YX_ACT_RELU: return launch_act<YX_ACT_RELU>(plan, stream);
+    case YX_ACT_LRELU: return launch_act<YX_ACT_LRELU>(plan, stream);
+    default: set_error("unknown activation code"); return YX_ERR_INVALID;
+  }
 }
 
 }  // namespace yx

@@ -3,6 +3,7 @@
 // a fixed sequence of kernel launches that can be replayed as a CUDA graph (bs1 latency).
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -39,7 +40,7 @@ struct yx_engine {
   int in_h = 0, in_w = 0, batch = 0;
   int num_sms = 148;
   cudaGraphExec_t graph_exec = nullptr;
-  cudaStream_t graph_stream = nullptr;  // stream the graph was captured on (informational)
+  cudaStream_t graph_stream = nullptr;  // private stream used only to capture the graph
 };
 
 using namespace yx;
@@ -130,6 +131,7 @@ extern "C" int yx_engine_create(const yx_op* ops, int n_ops, void* arena, size_t
 extern "C" void yx_engine_destroy(yx_engine* e) {
   if (!e) return;
   if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+  if (e->graph_stream) cudaStreamDestroy(e->graph_stream);
   delete e;
 }
 
@@ -148,17 +150,20 @@ extern "C" int yx_engine_run(yx_engine* e, const void* image, int image_dtype, f
   }
   if (!e->graph_exec) {
     // capture ops 1..n-1 (none of them touches caller memory, so the graph is replayable as is)
+    // Captured on a private stream: the caller's stream may be the legacy default stream, which
+    // cannot be captured.  Capture executes nothing; the instantiated graph is launched on `st`.
     cudaGraph_t graph = nullptr;
-    YX_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    if (!e->graph_stream) YX_CUDA(cudaStreamCreateWithFlags(&e->graph_stream, cudaStreamNonBlocking));
+    cudaStream_t cs = e->graph_stream;
+    YX_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
     for (size_t i = 1; i < e->steps.size() && rc == YX_OK; ++i)
-      rc = run_step(e, e->steps[i], image, image_dtype, in_scale, in_shift, st);
-    cudaError_t ce = cudaStreamEndCapture(st, &graph);
+      rc = run_step(e, e->steps[i], image, image_dtype, in_scale, in_shift, cs);
+    cudaError_t ce = cudaStreamEndCapture(cs, &graph);
     if (rc != YX_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
     YX_CUDA(ce);
     ce = cudaGraphInstantiate(&e->graph_exec, graph, 0);
     cudaGraphDestroy(graph);
     YX_CUDA(ce);
-    e->graph_stream = st;
   }
   YX_CUDA(cudaGraphLaunch(e->graph_exec, st));
   return YX_OK;
@@ -213,5 +218,24 @@ extern "C" int yx_conv2d(const yx_op* op, void* base, const void* weights, const
   ConvPlan plan;
   int rc = conv_plan(*op, base, weights, biases, sms, &plan);
   if (rc) return rc;
+  if (getenv("YX_CONV_TRACE")) {  // diagnostics: print the per-tile timeline of CTA 0 (cycles)
+    long long* d = nullptr;
+    long long h[32 * 8];
+    YX_CUDA(cudaMalloc(&d, sizeof h));
+    YX_CUDA(cudaMemset(d, 0, sizeof h));
+    plan.p.trace = d;
+    rc = conv_launch(plan, static_cast<cudaStream_t>(stream));
+    YX_CUDA(cudaDeviceSynchronize());
+    YX_CUDA(cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    fprintf(stderr, "trace: grid %d smem %d stages %d BN %d TH %d TW %d tiles %d x %d  (cycles rel. to first event)\n"
+                    " tile  prod_done  mma_start  mma_commit  epi_tfull  epi_staged  store_issue  store_read\n",
+            plan.grid, plan.smem_bytes, plan.p.stages, plan.p.BN, plan.p.TH, plan.p.TW, plan.p.n_tiles_m, plan.p.n_tiles_n);
+    long long t0 = h[1] ? h[1] : h[0];
+    for (int t = 0; t < 32 && (h[t * 8 + 3] || t == 0); ++t)
+      fprintf(stderr, " %4d %10lld %10lld %10lld %10lld %10lld %10lld %10lld\n", t, h[t * 8 + 0] - t0, h[t * 8 + 1] - t0,
+              h[t * 8 + 2] - t0, h[t * 8 + 3] - t0, h[t * 8 + 4] - t0, h[t * 8 + 5] - t0, h[t * 8 + 6] - t0);
+    return rc;
+  }
   return conv_launch(plan, static_cast<cudaStream_t>(stream));
 }

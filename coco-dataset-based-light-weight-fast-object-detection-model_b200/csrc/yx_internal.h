@@ -43,6 +43,8 @@ struct ConvParams {
   int cin, cout16;
   int k_chunks;
   int stages, b_stage_bytes, a_box_bytes;
+  int tmem_cols, acc_stride;
+  long long* trace;           // diagnostics: per-tile timeline of CTA 0 (nullptr = off)  // TMEM columns allocated (power of two) and offset of accumulator 1
 };
 
 struct ConvPlan {

@@ -22,7 +22,13 @@ def _act(x, code):
     return activation(x, ACT[code])
 
 
-def eval_op(o, image, src, res, wblob, bblob, q):
+def ulp16(t):
+    """Spacing of fp16 numbers at |t| (normal range; subnormals share 2^-24)."""
+    e = torch.floor(torch.log2(torch.clamp(t.abs(), min=2.0 ** -14)))
+    return torch.pow(2.0, e - 10)
+
+
+def eval_op(o, image, src, res, wblob, bblob, q, want_band=False):
     """Evaluate one planned op in fp32.  o: _capi.Op; image NCHW fp32 (S2D only); src/res NHWC fp32;
     wblob fp32 view of the fp16 weight blob, bblob fp32.  q: rounding applied where the engine rounds to
     fp16 (identity for an exact evaluation).  Returns NHWC [n,h,w,dst.c]."""
@@ -42,12 +48,17 @@ def eval_op(o, image, src, res, wblob, bblob, q):
         w = wblob[o.w_offset // 2: o.w_offset // 2 + o.cout_pad * k * k * o.cin_pad]
         w = w.view(o.cout_pad, k, k, o.cin_pad).permute(0, 3, 1, 2)
         b = bblob[o.b_offset // 4: o.b_offset // 4 + o.cout_pad]
-        y = F.conv2d(x, w, b, stride=o.stride, padding=k // 2)
-        y = _act(q(y), o.act)
+        y0 = q(F.conv2d(x, w, b, stride=o.stride, padding=k // 2))
+        y = _act(y0, o.act)
+        band = None
+        if want_band:  # output change when the fp32 sum rounds to a NEIGHBOURING fp16 value (order of accumulation)
+            u = ulp16(y0)
+            band = torch.maximum((_act(y0 + u, o.act) - y).abs(), (_act(y0 - u, o.act) - y).abs())
+            band = band.permute(0, 2, 3, 1)[..., :o.dst.c]
         y = y.permute(0, 2, 3, 1)[..., :o.dst.c]
         if o.res.c > 0:
             y = q(y) + res
-        return q(y)
+        return (q(y), band) if want_band else q(y)
     if o.kind == _capi.OP_DWCONV:
         k = o.ksize
         x = src.permute(0, 3, 1, 2)
@@ -107,7 +118,8 @@ def run_graph_cpu(g, image, quantize=False):
 
 
 def teacher_forced_errors(model, x):
-    """Returns [(op index, name, max error in fp16 ulps of the reference value, max abs err)]."""
+    """Returns [(op index, name, max error / allowed rounding slack, max abs err)]; a ratio <= 1 means the op
+    differs from the fp32 evaluation by no more than one fp16 rounding step of its pre-activation sum."""
     old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -123,13 +135,21 @@ def teacher_forced_errors(model, x):
             o = ops[i]
             src = eng.view_tensor(o.src).float() if o.kind != _capi.OP_S2D else None
             res = eng.view_tensor(o.res).float().clone() if (o.kind == _capi.OP_CONV and o.res.c > 0) else None
-            ref = eval_op(o, xf, src, res, wblob, bblob, q)       # before the op runs (dst may alias res)
+            band = None
+            if o.kind == _capi.OP_CONV:                            # before the op runs (dst may alias res)
+                ref, band = eval_op(o, xf, src, res, wblob, bblob, q, want_band=True)
+            else:
+                ref = eval_op(o, xf, src, res, wblob, bblob, q)
             eng.run_ops(x, i, 1)
             torch.cuda.synchronize()
             got = eng.view_tensor(o.dst).float()
             err = (got - ref).abs()
-            ulp = torch.clamp(ref.abs(), min=2.0 ** -6) * 2.0 ** -10   # fp16 spacing (normal range floor 2^-6)
-            out.append((i, pop.name, float((err / ulp).max()), float(err.max())))
+            # allowed: one fp16 step of the pre-activation sum (different fp32 accumulation order) propagated
+            # through the activation, plus one fp16 step of the stored result
+            # (floor 2^-4: near zero the absolute fp32 summation noise of ~1e4 O(0.1) terms, not the fp16
+            # grid, limits agreement)
+            tol = ulp16(torch.clamp(ref.abs(), min=2.0 ** -4)) + (band if band is not None else 0.0)
+            out.append((i, pop.name, float((err / tol).max()), float(err.max())))
         return out
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
