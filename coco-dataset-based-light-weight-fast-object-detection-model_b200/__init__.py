@@ -13,8 +13,8 @@ from . import _capi
 
 _capi.load()  # fail loudly if the native library cannot be built / loaded
 
-from . import blocks, models, plan, postprocess  # noqa: E402
-from . import infer  # noqa: E402
+from . import blocks, dist, models, plan, postprocess, weights  # noqa: E402
+from . import infer, predict  # noqa: E402
 from .models import YOLOX, YOLOXCustomP6, YOLOPAFPN, YOLOPAFPNCustomP6, YOLOXHead, YOLOXHeadCustom, fuse_model  # noqa: E402,F401
 from .postprocess import (decode_outputs, detect_main, postprocess as postprocess_fn, yolox_generate_grid,  # noqa: E402,F401
                           yolox_nms_torch_batch, yolox_postprocess_output_torch_batch)

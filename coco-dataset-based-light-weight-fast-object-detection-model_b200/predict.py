@@ -1,0 +1,65 @@
+"""Predict entry point: the device side of choijhanyangackr/main.py (build_yolox :31-59 and the body of
+the run loop :153-203).  Host I/O around it (image folder dataset, COCO json) is the caller's, as in the
+reference."""
+from typing import Iterable, List, Optional, Tuple
+
+import torch
+
+from . import dist as ydist
+from . import infer, postprocess, weights
+
+
+def build_yolox(cfg: dict, device="cuda"):
+    """main.py:31-59: model selected by substring of cfg["model"]["type"]; sparse checkpoints densified."""
+    d, w = cfg["model"]["depth"], cfg["model"]["width"]
+    model_type = cfg["model"]["type"].lower()
+    if "dw" in model_type or "p6-v2" in model_type:
+        raise NotImplementedError(f"model type {model_type!r}: depthwise-5x5 / P6-v2 variants are a later row "
+                                  "(SURVEY §8f N4)")
+    model = infer.YOLOXP6(d, w) if "p6" in model_type else infer.YOLOX(d, w)
+    model.eval()
+    if cfg.get("ckpt") is not None:
+        weights.load_checkpoint(model, cfg["ckpt"], sparse=bool(cfg.get("sparse")))
+    model = model.to(device)
+    if cfg.get("half", True):
+        model = model.half()
+    return model
+
+
+class Predictor:
+    """One GPU's share of the predict loop: H2D -> (x*0.9+11.4 fused into the image read) -> forward ->
+    fused decode + NMS.  No host synchronisation; returns device tensors."""
+
+    def __init__(self, model, conf_threshold=0.001, nms_threshold=0.65, max_num_nms=5000, max_num_det=300,
+                 in_scale=0.9, in_shift=11.4, use_graph=False):
+        self.model = model
+        self.kw = dict(conf_threshold=conf_threshold, nms_threshold=nms_threshold, max_num_nms=max_num_nms,
+                       max_num_det=max_num_det)
+        self.in_scale, self.in_shift, self.use_graph = in_scale, in_shift, use_graph
+
+    @torch.no_grad()
+    def __call__(self, img: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """img: [B,3,H,W] fp16/fp32, BGR 0-255 (host pinned or device).  -> det [B,max_det,7], count [B]."""
+        dev = next(self.model.parameters()).device
+        if img.device != dev:
+            img = img.to(dev, non_blocking=True)                      # main.py:161
+        eng, reg8, cls = self.model.run_engine(img, self.in_scale, self.in_shift, self.use_graph)  # :164-167
+        C = self.model.head.num_classes
+        det, cnt, _ = postprocess.detect_main(reg8[..., :4], reg8[..., 4:5], cls[..., :C], self.model.head.hw,
+                                              self.model.head.strides, **self.kw)       # :180-188
+        return det, cnt
+
+    def predict_sharded(self, img_global: torch.Tensor):
+        """Batch-sharded multi-GPU step: this rank runs its contiguous slice, then ONE all-gather."""
+        import torch.distributed as tdist
+        world = tdist.get_world_size() if tdist.is_initialized() else 1
+        rank = tdist.get_rank() if tdist.is_initialized() else 0
+        n = img_global.shape[0]
+        per = -(-n // world)
+        s, e = ydist.shard_range(n, rank, world)
+        mine = img_global[s:e]
+        if e - s < per:                                                # pad so every rank runs the same batch
+            mine = torch.cat([mine, mine[-1:].expand(per - (e - s), -1, -1, -1)], 0)
+        det, cnt = self(mine)
+        det_all, cnt_all = ydist.all_gather_detections(det, cnt)
+        return ydist.gathered_for_images(det_all, cnt_all, n, world, per) if world > 1 else (det, cnt)

@@ -57,6 +57,8 @@ def eval_op(o, image, src, res, wblob, bblob, q, want_band=False):
             band = band.permute(0, 2, 3, 1)[..., :o.dst.c]
         y = y.permute(0, 2, 3, 1)[..., :o.dst.c]
         if o.res.c > 0:
+            if want_band:  # the activation output is itself rounded to fp16 before the residual add
+                band = band + ulp16(y)
             y = q(y) + res
         return (q(y), band) if want_band else q(y)
     if o.kind == _capi.OP_DWCONV:

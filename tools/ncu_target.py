@@ -1,0 +1,22 @@
+"""Short target for ncu: the bench step (forward + fused decode/NMS) on the bench workload, 3 steps."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import bench
+
+torch.set_grad_enabled(False)
+B = int(os.environ.get("YX_B", "64"))
+S = int(os.environ.get("YX_S", "1280"))
+dev = torch.device("cuda", 0)
+model = bench.build_model(dev)
+from yolox_b200 import postprocess as pp
+x = (torch.rand(B, 3, S, S, device=dev) * 255).half()
+for _ in range(int(os.environ.get("YX_STEPS", "3"))):
+    eng, reg8, cls = model.run_engine(x, 0.9, 11.4)
+    det, cnt, _ = pp.detect_main(reg8[..., :4], reg8[..., 4:5], cls[..., :80], model.head.hw, bench.MODEL["strides"],
+                                 bench.CONF_THR, bench.NMS_THR, bench.MAX_NMS, bench.MAX_DET)
+torch.cuda.synchronize()
+print("ok", int(cnt.sum()))
