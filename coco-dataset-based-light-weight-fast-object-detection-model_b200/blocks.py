@@ -179,9 +179,18 @@ class Focus(nn.Module):
         self.conv = BaseConv(in_channels * 4, out_channels, ksize, stride, act=act, bn=bn)
 
     def emit(self, g, name, out=None):
+        c = self.conv
+        if c.ksize == 3 and c.stride == 1 and c.groups == 1:
+            # row-packed stem: padded s2d rows + overlapping-view conv (3 taps of K=48 instead of 9 of K=16)
+            s2d = g.new_buf(name + ".s2d", g.in_h // 2, g.in_w // 2 + 4, 16)
+            g.s2d(s2d.view(), self.order, padded=True)
+            w, b = c.folded()
+            if out is None:
+                out = g.new_buf(name + ".conv", g.in_h // 2, g.in_w // 2, w.shape[0]).view()
+            return g.conv_rowpack(name + ".conv", s2d.view(), out, w, b, c.act_type)
         s2d = g.new_buf(name + ".s2d", g.in_h // 2, g.in_w // 2, 16)
         g.s2d(s2d.view(), self.order)
-        return self.conv.emit(g, name + ".conv", s2d.view(), out)
+        return c.emit(g, name + ".conv", s2d.view(), out)
 
     def forward(self, x):
         _no_eager(self)

@@ -43,7 +43,7 @@ __device__ __forceinline__ float affine_in<float>(float v, float scale, float sh
 
 template <typename T>
 __global__ void s2d_kernel(const T* __restrict__ img, __half* __restrict__ out, int B, int H, int W, int pitch,
-                           int64_t dn, int order, float scale, float shift, int affine) {
+                           int64_t dn, int order, int padded, float scale, float shift, int affine) {
   const int Ho = H >> 1, Wo = W >> 1;
   const int64_t total = (int64_t)B * Ho * Wo;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -64,17 +64,29 @@ __global__ void s2d_kernel(const T* __restrict__ img, __half* __restrict__ out, 
         v[6 + c] = __float2half_rn(tr); v[9 + c] = __float2half_rn(br);
       }
     }
-    uint4* o = reinterpret_cast<uint4*>(out + b * dn + ((int64_t)y * Wo + x) * pitch);
+    // padded layout (row-packed stem conv): row = [0 | pixels 0..Wo-1 | 0 0 0]
+    const int Wrow = padded ? Wo + 4 : Wo;
+    uint4* o = reinterpret_cast<uint4*>(out + b * dn + ((int64_t)y * Wrow + x + (padded ? 1 : 0)) * pitch);
     o[0] = *reinterpret_cast<const uint4*>(&v[0]);
     o[1] = *reinterpret_cast<const uint4*>(&v[8]);
+    if (padded) {
+      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+      if (x == 0) { o[-2] = z; o[-1] = z; }
+      if (x == Wo - 1) {
+#pragma unroll
+        for (int j = 2; j < 8; ++j) o[j] = z;
+      }
+    }
   }
 }
 
-int s2d_launch(const void* image, int image_dtype, int order, int B, int H, int W, float scale, float shift,
+int s2d_launch(const void* image, int image_dtype, int aux, int B, int H, int W, float scale, float shift,
                void* base, const yx_view& dst, cudaStream_t stream) {
+  const int order = aux & 1, padded = (aux >> 1) & 1;
   YX_REQUIRE(H % 2 == 0 && W % 2 == 0, "image H and W must be even");
-  YX_REQUIRE(dst.n == B && dst.h == H / 2 && dst.w == W / 2 && dst.c == 16 && dst.pitch % 8 == 0 && dst.offset % 16 == 0,
-             "s2d dst must be [B,H/2,W/2,16]");
+  YX_REQUIRE(dst.n == B && dst.h == H / 2 && dst.w == W / 2 + 4 * padded && dst.c == 16 && dst.pitch == 16 &&
+                 dst.offset % 16 == 0,
+             "s2d dst must be [B,H/2,W/2(+4 when padded),16]");
   __half* out = reinterpret_cast<__half*>(static_cast<uint8_t*>(base) + dst.offset);
   const int64_t total = (int64_t)B * (H / 2) * (W / 2);
   const int threads = 256;
@@ -82,10 +94,10 @@ int s2d_launch(const void* image, int image_dtype, int order, int B, int H, int 
   const int affine = (scale != 1.0f || shift != 0.0f) ? 1 : 0;
   if (image_dtype == YX_F16)
     s2d_kernel<__half><<<blocks, threads, 0, stream>>>(static_cast<const __half*>(image), out, B, H, W, dst.pitch,
-                                                       dst.nstride, order, scale, shift, affine);
+                                                       dst.nstride, order, padded, scale, shift, affine);
   else if (image_dtype == YX_F32)
     s2d_kernel<float><<<blocks, threads, 0, stream>>>(static_cast<const float*>(image), out, B, H, W, dst.pitch,
-                                                      dst.nstride, order, scale, shift, affine);
+                                                      dst.nstride, order, padded, scale, shift, affine);
   else
     YX_REQUIRE(false, "image dtype must be YX_F16 or YX_F32");
   YX_CUDA(cudaGetLastError());

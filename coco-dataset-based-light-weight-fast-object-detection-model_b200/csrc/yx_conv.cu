@@ -105,8 +105,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_igemm_kernel(const __grid_co
 
   const int n_tiles = p.n_tiles_m * p.n_tiles_n;
   const int tiles_per_img = p.tiles_h * p.tiles_w;
-  const int taps = p.ksize * p.ksize;
-  const int pad = p.ksize >> 1;
+  const int taps = p.ky * p.kx;
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -118,12 +117,13 @@ __global__ void __launch_bounds__(kThreads, 2) conv_igemm_kernel(const __grid_co
         const int y0 = (r / p.tiles_w) * p.TH, x0 = (r % p.tiles_w) * p.TW;
         const int n0 = nt * p.BN;
         for (int tap = 0; tap < taps; ++tap) {
-          const int dy = tap / p.ksize, dx = tap % p.ksize;
+          const int dy = tap / p.kx, dx = tap % p.kx;
           int mi = 0, cx, cy;
           if (p.stride == 1) {
-            cx = x0 + dx - pad;
-            cy = y0 + dy - pad;
+            cx = x0 + dx - p.pad_x;
+            cy = y0 + dy - p.pad_y;
           } else {
+            const int pad = p.pad_y;
             // input row 2*y + dy - pad.  For k=3,pad=1: dy=0 -> odd row of cell y-1; dy=1 -> even row
             // of cell y; dy=2 -> odd row of cell y.  k=1 (pad 0): even row/col of cell y.
             const int oy = dy - pad, ox = dx - pad;
@@ -364,13 +364,23 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
   YX_REQUIRE(op.stride == 1 || op.stride == 2, "conv stride must be 1 or 2");
   YX_REQUIRE(op.cin_pad % 16 == 0 && op.cout_pad % 16 == 0, "cin_pad/cout_pad must be multiples of 16");
   YX_REQUIRE(s.c <= op.cin_pad && s.c % 8 == 0, "src channels must be a multiple of 8 and <= cin_pad");
+  YX_REQUIRE(op.aux == 0 || op.aux == 1, "conv aux must be 0 or 1 (row-packed)");
   YX_REQUIRE(d.c % 8 == 0 && d.c <= op.cout_pad, "dst channels must be a multiple of 8 and <= cout_pad");
   YX_REQUIRE(s.pitch % 8 == 0 && d.pitch % 8 == 0 && s.offset % 16 == 0 && d.offset % 16 == 0 && s.nstride % 8 == 0 &&
                  d.nstride % 8 == 0,
              "views must be 16-byte aligned");
+  // aux == 1: "row-packed" 3x3 conv over a 16-channel tensor stored with 1 zero column on the left and 3 on
+  // the right (the s2d output).  TMA reads it through an OVERLAPPING view (64 channels per pixel, pixel pitch 16),
+  // so the 128-byte smem row of pixel x holds pixels x-1..x+2 = the three horizontal taps (+1 ignored): the
+  // conv becomes 3 vertical taps with K = 48 instead of 9 taps with K = 16, and every TMA row is a full line.
+  const bool rowpack = op.aux == 1;
+  if (rowpack)
+    YX_REQUIRE(op.ksize == 3 && op.stride == 1 && s.c == 16 && s.pitch == 16 && op.cin_pad == 48 && s.w > 4 &&
+                   op.res.c == 0,
+               "row-packed conv needs k=3, s=1, a padded 16-channel source and cin_pad = 48");
   const int pad = op.ksize / 2;
-  const int Hout = (s.h + 2 * pad - op.ksize) / op.stride + 1;
-  const int Wout = (s.w + 2 * pad - op.ksize) / op.stride + 1;
+  const int Hout = rowpack ? s.h : (s.h + 2 * pad - op.ksize) / op.stride + 1;
+  const int Wout = rowpack ? s.w - 4 : (s.w + 2 * pad - op.ksize) / op.stride + 1;
   YX_REQUIRE(d.h == Hout && d.w == Wout && d.n == s.n, "dst spatial dims do not match the conv geometry");
   const bool has_res = op.res.c > 0;
   if (has_res)
@@ -382,6 +392,8 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
   memset(&pl, 0, sizeof pl);
   ConvParams& p = pl.p;
   p.ksize = op.ksize; p.stride = op.stride; p.act = op.act; p.has_res = has_res;
+  p.ky = op.ksize; p.kx = rowpack ? 1 : op.ksize;
+  p.pad_y = pad; p.pad_x = rowpack ? 0 : pad;
   p.cin = op.cin_pad;
   p.cout16 = op.cout_pad;
   p.k_chunks = ceil_div(p.cin, 64);
@@ -394,7 +406,8 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
   // CTA's epilogue / TMA-store latency hides behind the other's loads; tensor-bound layers keep one CTA
   // per SM with the widest N tile (fewest re-reads of A) and the deepest smem pipeline.
   const double px_out_ = (double)d.n * Hout * Wout;
-  const double flops_ = 2.0 * px_out_ * d.c * s.c * op.ksize * op.ksize;
+  const int cin_real = rowpack ? 12 : s.c;
+  const double flops_ = 2.0 * px_out_ * d.c * cin_real * op.ksize * op.ksize;
   const double bytes_ = 2.0 * ((double)s.n * s.h * s.w * s.c + px_out_ * d.c * (has_res ? 2 : 1));
   const bool mem_bound = flops_ / bytes_ < mem_bound_ai();
   int ctas_per_sm = 1;
@@ -432,7 +445,14 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
   p.bias = reinterpret_cast<const float*>(static_cast<const uint8_t*>(biases) + op.b_offset);
 
   int rc;
-  if (op.stride == 1) {
+  if (rowpack) {
+    uint64_t dims[4] = {64, (uint64_t)Wout, (uint64_t)s.h, (uint64_t)s.n};
+    uint64_t st[4] = {2, 32, (uint64_t)s.w * 32, (uint64_t)s.nstride * 2};
+    uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)p.TH, 1};
+    if ((rc = encode_map(&p.tmA[0], static_cast<uint8_t*>(base) + s.offset, 4, dims, st, box, true, "A-rowpack")) != YX_OK)
+      return rc;
+    for (int i = 1; i < 4; ++i) p.tmA[i] = p.tmA[0];
+  } else if (op.stride == 1) {
     yx_view sv = s;
     if ((rc = encode_view(&p.tmA[0], base, sv, p.TW, p.TH, "A")) != YX_OK) return rc;
     for (int i = 1; i < 4; ++i) p.tmA[i] = p.tmA[0];
@@ -449,7 +469,7 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
       }
   }
   {
-    const int taps = op.ksize * op.ksize;
+    const int taps = p.ky * p.kx;
     uint64_t dims[3] = {(uint64_t)op.cin_pad, (uint64_t)taps, (uint64_t)op.cout_pad};
     uint64_t st[3] = {2, (uint64_t)op.cin_pad * 2, (uint64_t)op.cin_pad * 2 * taps};
     uint32_t box[3] = {64, 1, (uint32_t)p.BN};
@@ -464,9 +484,9 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
     p.tmRes = p.tmOut;
   }
   const double px_out = (double)d.n * Hout * Wout;
-  pl.flops = 2.0 * px_out * d.c * s.c * op.ksize * op.ksize;
+  pl.flops = 2.0 * px_out * d.c * cin_real * op.ksize * op.ksize;
   pl.bytes = 2.0 * ((double)s.n * s.h * s.w * s.c + px_out * d.c * (has_res ? 2 : 1)) +
-             2.0 * (double)d.c * s.c * op.ksize * op.ksize;
+             2.0 * (double)d.c * cin_real * op.ksize * op.ksize;
   *out = pl;
   return YX_OK;
 }

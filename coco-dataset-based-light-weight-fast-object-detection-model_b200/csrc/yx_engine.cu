@@ -102,7 +102,7 @@ extern "C" int yx_engine_create(const yx_op* ops, int n_ops, void* arena, size_t
       set_error(std::string(where) + "view outside the arena");
       rc = YX_ERR_INVALID;
     } else if (op.kind == YX_OP_CONV) {
-      const size_t wend = (size_t)op.w_offset + (size_t)op.cout_pad * op.ksize * op.ksize * op.cin_pad * 2;
+      const size_t wend = (size_t)op.w_offset + (size_t)op.cout_pad * op.ksize * (op.aux == 1 ? 1 : op.ksize) * op.cin_pad * 2;
       const size_t bend = (size_t)op.b_offset + (size_t)op.cout_pad * 4;
       if (wend > weights_bytes || bend > bias_bytes || op.b_offset % 16 != 0) {
         set_error(std::string(where) + "weight/bias range outside the blobs");

@@ -38,6 +38,7 @@ struct ConvParams {
   CUtensorMap tmRes;   // residual, same geometry as tmOut
   const float* bias;
   int ksize, stride, act, has_res;
+  int ky, kx, pad_y, pad_x;     // tap grid actually iterated (3x1 for the row-packed stem conv)
   int TH, TW, tiles_h, tiles_w;  // spatial tiling of the output
   int n_tiles_m, n_tiles_n, BN;
   int cin, cout16;
@@ -59,7 +60,7 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
 int conv_launch(const ConvPlan& plan, cudaStream_t stream);
 
 // ------------------------------------------------------------------ aux ops (yx_aux.cu)
-int s2d_launch(const void* image, int image_dtype, int order, int B, int H, int W, float scale, float shift,
+int s2d_launch(const void* image, int image_dtype, int aux, int B, int H, int W, float scale, float shift,
                void* base, const yx_view& dst, cudaStream_t stream);
 int spp_launch(void* base, const yx_view& src, const yx_view& dst, cudaStream_t stream);
 int upsample_launch(void* base, const yx_view& src, const yx_view& dst, cudaStream_t stream);

@@ -152,16 +152,31 @@ __global__ void select_infer_kernel(const T* __restrict__ reg, int64_t reg_sb, i
     float best = -1.0f;
     int bi = 0;
     if (VEC8) {  // T == __half, 16-byte aligned rows, C % 8 == 0
+      // score(x) = sigmoid_f(x) * oc is NON-DECREASING in the logit x over all fp16 inputs (checked exhaustively
+      // by tests/test_gpu_post.py::test_score_monotonic_in_logit), so a class whose logit does not exceed the
+      // logit of the running best cannot have a strictly greater score: the exact first-max of the 80 products
+      // needs a sigmoid only when a new running-max logit appears (~5 of 80 on average).
       const uint4* cv = reinterpret_cast<const uint4*>(c);
+      float best_logit = -INFINITY;
+      {  // class 0 is always evaluated (also covers a -inf logit, whose score 0 still beats the -1 sentinel)
+        const float x0 = ldf(c);
+        const float s = __fmul_rn(sigmoid_f(x0), oc);
+        if (s > best) { best = s; bi = 0; best_logit = x0; }
+      }
       for (int k8 = 0; k8 < (C >> 3); ++k8) {
         const uint4 v = __ldg(cv + k8);
         const __half2* h = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float2 f = __half22float2(h[j]);
-          const float s0 = __fmul_rn(sigmoid_f(f.x), oc), s1 = __fmul_rn(sigmoid_f(f.y), oc);
-          if (s0 > best) { best = s0; bi = k8 * 8 + 2 * j; }
-          if (s1 > best) { best = s1; bi = k8 * 8 + 2 * j + 1; }
+          if (f.x > best_logit || f.x != f.x) {
+            const float s0 = __fmul_rn(sigmoid_f(f.x), oc);
+            if (s0 > best) { best = s0; bi = k8 * 8 + 2 * j; best_logit = f.x; }
+          }
+          if (f.y > best_logit || f.y != f.y) {
+            const float s1 = __fmul_rn(sigmoid_f(f.y), oc);
+            if (s1 > best) { best = s1; bi = k8 * 8 + 2 * j + 1; best_logit = f.y; }
+          }
         }
       }
     } else {

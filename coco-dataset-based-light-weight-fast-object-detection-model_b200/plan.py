@@ -125,9 +125,24 @@ class Graph:
         return op.dst
 
     # ---- ops -----------------------------------------------------------------------------
-    def s2d(self, dst: V, order: str) -> V:
+    def s2d(self, dst: V, order: str, padded: bool = False) -> V:
+        """padded: rows are [0 | W/2 pixels | 0 0 0] for the row-packed stem conv (aux bit 1)."""
         assert dst.c == 16 and dst.buf.c == 16
-        return self._add(PlannedOp(_capi.OP_S2D, "s2d", None, dst, aux=1 if order == "unshuffle" else 0))
+        return self._add(PlannedOp(_capi.OP_S2D, "s2d", None, dst,
+                                   aux=(1 if order == "unshuffle" else 0) | (2 if padded else 0)))
+
+    def conv_rowpack(self, name: str, src: V, dst: V, weight: torch.Tensor, bias: torch.Tensor, act: str) -> V:
+        """3x3/s1 conv over the padded 16-channel s2d tensor, executed as 3 vertical taps with K = 48:
+        the engine reads the source through an overlapping 64-channel view, so one 128-byte TMA row holds the
+        three horizontal neighbours of a pixel.  weight: the ordinary [cout, 12, 3, 3] tensor."""
+        cout, cin, k, k2 = weight.shape
+        assert (cin, k, k2) == (12, 3, 3) and src.c == 16 and src.buf.c == 16 and dst.c == cout
+        assert (dst.H, dst.W) == (src.H, src.W - 4)
+        w = torch.zeros(cout, 3, 16, 3, dtype=torch.float32)           # [cout, dx, c(16), dy]
+        w[:, :, :12, :] = weight.detach().float().cpu().permute(0, 3, 1, 2)
+        w48 = w.reshape(cout, 48, 3, 1)                                  # cin index = dx*16 + c ; kernel (3, 1)
+        return self._add(PlannedOp(_capi.OP_CONV, name, src, dst, None, 3, 1, _capi.act_code(act), w48,
+                                   bias.detach().float().cpu(), aux=1, cin_pad=48, cout_pad=_rup(cout, 16)))
 
     def conv(self, name: str, src: V, dst: V, weight: torch.Tensor, bias: torch.Tensor, stride: int, act: str,
              res: Optional[V] = None) -> V:
@@ -185,9 +200,9 @@ class Graph:
         w_parts, b_parts, w_off, b_off = [], [], 0, 0
         for op in self.ops:
             if op.kind == _capi.OP_CONV:
-                cout, cin, k, _ = op.weight.shape
-                w = torch.zeros(op.cout_pad, k * k, op.cin_pad, dtype=torch.float16)
-                w[:cout, :, :cin] = op.weight.permute(0, 2, 3, 1).reshape(cout, k * k, cin).to(torch.float16)
+                cout, cin, kh, kw = op.weight.shape
+                w = torch.zeros(op.cout_pad, kh * kw, op.cin_pad, dtype=torch.float16)
+                w[:cout, :, :cin] = op.weight.permute(0, 2, 3, 1).reshape(cout, kh * kw, cin).to(torch.float16)
             elif op.kind == _capi.OP_DWCONV:
                 c, _, k, _ = op.weight.shape
                 cout = c
@@ -230,7 +245,9 @@ class Graph:
     def conv_flops(self) -> float:
         t = 0.0
         for op in self.ops:
-            if op.kind == _capi.OP_CONV:
+            if op.kind == _capi.OP_CONV and op.aux == 1:
+                t += 2.0 * self.batch * op.dst.H * op.dst.W * op.weight.shape[0] * 12 * 9
+            elif op.kind == _capi.OP_CONV:
                 cout, cin, k, _ = op.weight.shape
                 t += 2.0 * self.batch * op.dst.H * op.dst.W * cout * cin * k * k
             elif op.kind == _capi.OP_DWCONV:

@@ -78,7 +78,9 @@ typedef struct yx_op {
   int64_t b_offset;   /* byte offset into the bias blob: fp32 [cout_pad] */
   int32_t cin_pad;    /* multiple of 16 */
   int32_t cout_pad;   /* multiple of 16 */
-  int32_t aux;        /* S2D: 0 = Focus order [TL,BL,TR,BR], 1 = pixel_unshuffle order */
+  int32_t aux;        /* S2D: bit0 = channel order (0 Focus [TL,BL,TR,BR], 1 pixel_unshuffle), bit1 = padded rows
+                         [0 | W/2 pixels | 0 0 0].  CONV: 1 = row-packed 3x3 over that padded 16-channel tensor
+                         (weights [cout_pad][3 (dy)][48 = dx*16 + c]; cin_pad = 48) */
   int32_t _pad;
 } yx_op;
 

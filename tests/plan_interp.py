@@ -35,12 +35,29 @@ def eval_op(o, image, src, res, wblob, bblob, q, want_band=False):
     if o.kind == _capi.OP_S2D:
         x = image
         tl, tr, bl, br = x[..., ::2, ::2], x[..., ::2, 1::2], x[..., 1::2, ::2], x[..., 1::2, 1::2]
-        if o.aux == 1:
+        if o.aux & 1:
             y = torch.stack((tl, tr, bl, br), dim=2).reshape(x.shape[0], 12, x.shape[2] // 2, x.shape[3] // 2)
         else:
             y = torch.cat((tl, bl, tr, br), dim=1)
         y = F.pad(y, (0, 0, 0, 0, 0, 4))
+        if o.aux & 2:                      # padded rows: [0 | pixels | 0 0 0]
+            y = F.pad(y, (1, 3))
         return q(y.permute(0, 2, 3, 1))
+    if o.kind == _capi.OP_CONV and o.aux == 1:
+        # row-packed stem conv: pixel x of the GEMM sees buffer columns x, x+1, x+2 (= image pixels x-1, x, x+1)
+        W = src.shape[2] - 4
+        x48 = torch.cat([src[:, :, 0:W], src[:, :, 1:W + 1], src[:, :, 2:W + 2]], dim=3).permute(0, 3, 1, 2)
+        w = wblob[o.w_offset // 2: o.w_offset // 2 + o.cout_pad * 3 * 48].view(o.cout_pad, 3, 1, 48).permute(0, 3, 1, 2)
+        b = bblob[o.b_offset // 4: o.b_offset // 4 + o.cout_pad]
+        y0 = q(F.conv2d(x48, w, b, stride=1, padding=(1, 0)))
+        y = _act(y0, o.act)
+        band = None
+        if want_band:
+            u = ulp16(y0)
+            band = torch.maximum((_act(y0 + u, o.act) - y).abs(), (_act(y0 - u, o.act) - y).abs())
+            band = band.permute(0, 2, 3, 1)[..., :o.dst.c]
+        y = q(y.permute(0, 2, 3, 1)[..., :o.dst.c])
+        return (y, band) if want_band else y
     if o.kind == _capi.OP_CONV:
         k = o.ksize
         x = src.permute(0, 3, 1, 2)

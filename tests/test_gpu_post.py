@@ -147,3 +147,20 @@ def test_decode_outputs_and_head_assemble():
     got16 = yb.postprocess.decode_outputs(h.clone(), hw, strides)
     np.testing.assert_allclose(got16[0, :, :2].float().cpu().numpy(), ref[:, :2], rtol=2e-3, atol=0.2)
     assert torch.equal(got16[..., 4:], h[..., 4:])
+
+
+def test_score_monotonic_in_logit():
+    """The fused select kernel skips classes whose logit does not exceed the running best's logit; that is exact
+    iff sigmoid(x)*obj computed by the device is non-decreasing in x.  Check it over EVERY finite fp16 logit."""
+    bits = np.arange(0, 0x7C00, dtype=np.uint16)                      # +0 .. largest finite
+    pos = bits.view(np.float16)
+    allv = np.concatenate([-pos[::-1], pos]).astype(np.float16)       # ascending, -65504 .. 65504
+    A = len(allv)
+    cls = torch.from_numpy(allv).to(DEV).view(1, A, 1)
+    reg = torch.zeros(1, A, 4, dtype=torch.float16, device=DEV)
+    grids, scales = yb.postprocess.yolox_generate_grid((8, 8 * A), (8,), torch.float32)  # x up to 63487: not fp16-exact
+    for o in (-12.0, -3.0, 0.0, 0.7, 5.0, 30.0):
+        obj = torch.full((1, A, 1), o, dtype=torch.float16, device=DEV)
+        _, oc, cc = yb.postprocess.yolox_postprocess_output_torch_batch(reg, obj, cls, grids.to(DEV), scales.to(DEV))
+        s = cc.view(-1)
+        assert bool((s[1:] >= s[:-1]).all()), f"score not monotone for obj logit {o}"
