@@ -310,12 +310,63 @@ __device__ __forceinline__ void cmpx(uint64_t& a, uint64_t& b, bool desc) {
   if ((a < b) == desc) { const uint64_t t = a; a = b; b = t; }
 }
 
-__global__ void __launch_bounds__(kSortThreads, 1) sort_keys_kernel(Workspace ws) {
+__global__ void __launch_bounds__(kSortThreads, 1) sort_keys_kernel(Workspace ws, int max_nms) {
   extern __shared__ uint64_t sk[];
+  __shared__ int s_hist[256];
+  __shared__ unsigned long long s_prefix;
+  __shared__ int s_need, s_cnt;
   const int b = blockIdx.x;
   const int n = ws.count[b];
   if (n <= 1) return;
   uint64_t* keys = ws.keys + (int64_t)b * ws.Apad;
+
+  if (max_nms > 0 && n > max_nms && max_nms <= kSortChunk) {
+    // ---- top-k first (postprocess_utils.py:100-103 keeps the max_nms best): MSB-first radix SELECT of the
+    // k-th largest 64-bit key (8 passes of 8 bits over L2-resident keys), then only those k keys are sorted,
+    // entirely in shared memory.  Keys are unique (anchor index in the low word), so ">= pivot" is exactly k.
+    if (threadIdx.x == 0) { s_prefix = 0ull; s_need = max_nms; }
+    for (int pass = 0; pass < 8; ++pass) {
+      const int shift = 56 - 8 * pass;
+      for (int i = threadIdx.x; i < 256; i += kSortThreads) s_hist[i] = 0;
+      __syncthreads();
+      const unsigned long long prefix = s_prefix;
+      for (int i = threadIdx.x; i < n; i += kSortThreads) {
+        const unsigned long long key = keys[i];
+        if (pass == 0 || (key >> (shift + 8)) == prefix) atomicAdd(&s_hist[(key >> shift) & 255ull], 1);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int need = s_need, bin = 255;
+        for (; bin > 0; --bin) {
+          if (s_hist[bin] >= need) break;
+          need -= s_hist[bin];
+        }
+        s_need = need;
+        s_prefix = (prefix << 8) | (unsigned long long)bin;
+      }
+      __syncthreads();
+    }
+    const unsigned long long pivot = s_prefix;
+    if (threadIdx.x == 0) s_cnt = 0;
+    for (int i = threadIdx.x; i < kSortChunk; i += kSortThreads) sk[i] = 0ull;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += kSortThreads) {
+      const unsigned long long key = keys[i];
+      if (key >= pivot) sk[atomicAdd(&s_cnt, 1)] = key;
+    }
+    __syncthreads();
+    for (int k = 2; k <= kSortChunk; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int t = threadIdx.x; t < (kSortChunk >> 1); t += kSortThreads) {
+          const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+          cmpx(sk[i], sk[i | j], ((i & k) == 0));
+        }
+        __syncthreads();
+      }
+    for (int i = threadIdx.x; i < max_nms; i += kSortThreads) keys[i] = sk[i];
+    return;
+  }
+
   int N = 2;
   while (N < n) N <<= 1;
   for (int i = n + threadIdx.x; i < N; i += kSortThreads) keys[i] = 0;  // pads sort last
@@ -517,7 +568,7 @@ static int sort_and_nms(const Workspace& ws, int B, int A, float nms_thr, int ma
     YX_CUDA(cudaFuncSetAttribute(sort_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortChunk * 8));
     attr = true;
   }
-  sort_keys_kernel<<<B, kSortThreads, kSortChunk * 8, st>>>(ws);
+  sort_keys_kernel<<<B, kSortThreads, kSortChunk * 8, st>>>(ws, max_nms);
   YX_CUDA(cudaGetLastError());
   nms_kernel<<<B, kNmsThreads, 0, st>>>(ws, A, nms_thr, max_nms, max_det, mode, det_rows, det, det_count, det_anchor);
   YX_CUDA(cudaGetLastError());
