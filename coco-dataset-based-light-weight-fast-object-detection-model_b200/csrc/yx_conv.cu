@@ -57,6 +57,59 @@ __device__ __forceinline__ float apply_act(float x) {
   return x;
 }
 
+// Drains one 128-lane accumulator: TMEM -> registers (16 columns at a time) -> +bias -> round to fp16 ->
+// activation (fp32) -> (+ residual already sitting in the staging line) -> fp16 -> 128-byte-swizzled smem
+// staging [group of 64 ch][row][128 B] that the TMA store reads.  `bias` points at this N tile's first channel.
+template <int ACT, bool HAS_RES>
+__device__ __forceinline__ void epilogue_convert(uint32_t taddr, int bn_cur, int row, bool row_valid, uint32_t sStage,
+                                                 const float* __restrict__ bias) {
+  for (int c0 = 0; c0 < bn_cur; c0 += 16) {
+    uint32_t v[16];
+    tmem_ld_32x32b_x16(taddr + c0, v);
+    tmem_ld_wait();
+    if (row_valid) {
+      float bb[16];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c0) + j);
+        bb[4 * j] = b4.x; bb[4 * j + 1] = b4.y; bb[4 * j + 2] = b4.z; bb[4 * j + 3] = b4.w;
+      }
+      // two 16-byte chunks (8 channels each) of this row's 128-byte swizzled staging line
+      const uint32_t line = sStage + (c0 >> 6) * kAStageBytes + row * 128;
+      const uint32_t a0 = line + ((((c0 & 63) >> 3) ^ (row & 7)) << 4);
+      const uint32_t a1 = line + (((((c0 & 63) >> 3) + 1) ^ (row & 7)) << 4);
+      uint32_t rr[8];
+      if (HAS_RES) {
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]) : "r"(a0));
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(rr[4]), "=r"(rr[5]), "=r"(rr[6]), "=r"(rr[7]) : "r"(a1));
+      }
+      uint32_t out[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        // the reference rounds the conv output to fp16 before its (separate) activation kernel
+        const __half2 pre = __floats2half2_rn(__uint_as_float(v[2 * i]) + bb[2 * i],
+                                              __uint_as_float(v[2 * i + 1]) + bb[2 * i + 1]);
+        const float2 pf = __half22float2(pre);
+        float f0 = apply_act<ACT>(pf.x), f1 = apply_act<ACT>(pf.y);
+        if (HAS_RES) {  // half + half as torch computes it: exact fp32 sum of the two halves, rounded once
+          const float2 af = __half22float2(__floats2half2_rn(f0, f1));
+          const float2 rf = __half22float2(*reinterpret_cast<const __half2*>(&rr[i]));
+          f0 = af.x + rf.x;
+          f1 = af.y + rf.y;
+        }
+        const __half2 o = __floats2half2_rn(f0, f1);
+        out[i] = *reinterpret_cast<const uint32_t*>(&o);
+      }
+      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "r"(out[0]), "r"(out[1]), "r"(out[2]),
+                   "r"(out[3]) : "memory");
+      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a1), "r"(out[4]), "r"(out[5]), "r"(out[6]),
+                   "r"(out[7]) : "memory");
+    }
+  }
+}
+
 // optional per-tile timeline (diagnostics): trace[tile_local * 8 + event] = clock64(), CTA 0 only
 #define YX_TRACE(ev, tl)                                                                   \
   do {                                                                                     \
@@ -110,35 +163,39 @@ __global__ void __launch_bounds__(kThreads, 2) conv_igemm_kernel(const __grid_co
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0) {
-      uint32_t it = 0;
+      uint32_t it = 0, s = 0, ph = 0;  // ring slot / phase kept incrementally (no div/mod on the issue path)
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int nt = tile % p.n_tiles_n, mt = tile / p.n_tiles_n;
         const int img = mt / tiles_per_img, r = mt % tiles_per_img;
         const int y0 = (r / p.tiles_w) * p.TH, x0 = (r % p.tiles_w) * p.TW;
         const int n0 = nt * p.BN;
+        int dy = 0, dx = 0;
         for (int tap = 0; tap < taps; ++tap) {
-          const int dy = tap / p.kx, dx = tap % p.kx;
           int mi = 0, cx, cy;
           if (p.stride == 1) {
             cx = x0 + dx - p.pad_x;
             cy = y0 + dy - p.pad_y;
           } else {
-            const int pad = p.pad_y;
             // input row 2*y + dy - pad.  For k=3,pad=1: dy=0 -> odd row of cell y-1; dy=1 -> even row
             // of cell y; dy=2 -> odd row of cell y.  k=1 (pad 0): even row/col of cell y.
-            const int oy = dy - pad, ox = dx - pad;
+            const int oy = dy - p.pad_y, ox = dx - p.pad_y;
             const int py = oy & 1, px = ox & 1;
             mi = py * 2 + px;
             cy = y0 + ((oy - py) >> 1);
             cx = x0 + ((ox - px) >> 1);
           }
           for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
-            const uint32_t s = it % p.stages, ph = (it / p.stages) & 1;
             mbar_wait(bar_empty + 8 * s, ph ^ 1);
-            mbar_expect_tx(bar_full + 8 * s, p.a_box_bytes + p.b_stage_bytes);
-            tma_load_4d(sA + s * kAStageBytes, &p.tmA[mi], bar_full + 8 * s, kc * 64, cx, cy, img);
-            tma_load_3d(sB + s * p.b_stage_bytes, &p.tmW, bar_full + 8 * s, kc * 64, tap, n0);
+            if (p.noload && it >= (uint32_t)p.stages) {  // diagnostics: MMA rate with operands already resident
+              mbar_arrive(bar_full + 8 * s);
+            } else {
+              mbar_expect_tx(bar_full + 8 * s, p.a_box_bytes + p.b_stage_bytes);
+              tma_load_4d(sA + s * kAStageBytes, &p.tmA[mi], bar_full + 8 * s, kc * 64, cx, cy, img);
+              tma_load_3d(sB + s * p.b_stage_bytes, &p.tmW, bar_full + 8 * s, kc * 64, tap, n0);
+            }
+            if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
           }
+          if (++dx == p.kx) { dx = 0; ++dy; }
         }
         YX_TRACE(0, (tile - (int)blockIdx.x) / (int)gridDim.x);
       }
@@ -146,7 +203,16 @@ __global__ void __launch_bounds__(kThreads, 2) conv_igemm_kernel(const __grid_co
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
     if (lane == 0) {
-      uint32_t it = 0, t = 0;
+      // The whole tensor pipe is fed by THIS thread: everything per k-iteration is incremental 32-bit math
+      // (a div/mod + 64-bit descriptor rebuild per iteration cost ~830 cycles per 4 MMAs, 2x their execution
+      // time — profiles/r01_conv_tile_trace.txt).
+      uint32_t t = 0, s = 0, ph = 0;
+      const uint32_t hi = sdesc_hi(1024);
+      const uint32_t a_lo0 = sdesc_lo(sA), b_lo0 = sdesc_lo(sB);
+      const uint32_t a_step = kAStageBytes >> 4, b_step = p.b_stage_bytes >> 4;
+      uint32_t a_lo = a_lo0, b_lo = b_lo0;
+      const int ks_last = (p.cin - (p.k_chunks - 1) * 64) >> 4;
+      const int k_iters = taps * p.k_chunks;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
         const int nt = tile % p.n_tiles_n;
         const int n0 = nt * p.BN;
@@ -158,21 +224,20 @@ __global__ void __launch_bounds__(kThreads, 2) conv_igemm_kernel(const __grid_co
         YX_TRACE(1, t);
         const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
         uint32_t accum = 0;
-        for (int tap = 0; tap < taps; ++tap) {
-          for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
-            const uint32_t s = it % p.stages, ph = (it / p.stages) & 1;
-            mbar_wait(bar_full + 8 * s, ph);
-            tc_fence_after();
-            const int ksteps = min(64, p.cin - kc * 64) >> 4;
-            const uint64_t adesc = make_sdesc_sw128(sA + s * kAStageBytes);
-            const uint64_t bdesc = make_sdesc_sw128(sB + s * p.b_stage_bytes);
-            for (int ks = 0; ks < ksteps; ++ks) {
-              // advance 16 fp16 = 32 bytes along K inside the 128-byte swizzle row: +2 in (addr >> 4)
-              umma_f16_ss(d_tmem, adesc + 2 * ks, bdesc + 2 * ks, idesc, accum);
-              accum = 1;
-            }
-            umma_commit(bar_empty + 8 * s);  // frees the smem stage when these MMAs retire
-          }
+        int kc = 0;
+        for (int i = 0; i < k_iters; ++i) {
+          mbar_wait(bar_full + 8 * s, ph);
+          tc_fence_after();
+          const int ksteps = (kc == p.k_chunks - 1) ? ks_last : 4;
+          umma_f16_ss_lohi(d_tmem, a_lo, hi, b_lo, hi, idesc, accum);
+          if (ksteps > 1) umma_f16_ss_lohi(d_tmem, a_lo + 2, hi, b_lo + 2, hi, idesc, 1u);
+          if (ksteps > 2) umma_f16_ss_lohi(d_tmem, a_lo + 4, hi, b_lo + 4, hi, idesc, 1u);
+          if (ksteps > 3) umma_f16_ss_lohi(d_tmem, a_lo + 6, hi, b_lo + 6, hi, idesc, 1u);
+          accum = 1;
+          umma_commit(bar_empty + 8 * s);  // frees the smem stage when these MMAs retire
+          a_lo += a_step; b_lo += b_step;
+          if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; a_lo = a_lo0; b_lo = b_lo0; }
+          if (++kc == p.k_chunks) kc = 0;
         }
         umma_commit(bar_tfull + 8 * acc);  // accumulator complete -> epilogue
         YX_TRACE(2, t);
@@ -207,51 +272,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_igemm_kernel(const __grid_co
         ++res_cnt;
       }
       const uint32_t taddr = tmem_base + acc * p.acc_stride + (static_cast<uint32_t>(q * 32) << 16);
-      for (int c0 = 0; c0 < bn_cur; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld_32x32b_x16(taddr + c0, v);
-        tmem_ld_wait();
-        if (row_valid) {
-          float bb[16];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0) + j);
-            bb[4 * j] = b4.x; bb[4 * j + 1] = b4.y; bb[4 * j + 2] = b4.z; bb[4 * j + 3] = b4.w;
-          }
-          // two 16-byte chunks (8 channels each) of this row's 128-byte swizzled staging line
-          const uint32_t line = sStage + (c0 >> 6) * kAStageBytes + row * 128;
-          const uint32_t a0 = line + ((((c0 & 63) >> 3) ^ (row & 7)) << 4);
-          const uint32_t a1 = line + (((((c0 & 63) >> 3) + 1) ^ (row & 7)) << 4);
-          uint32_t rr[8];
-          if (HAS_RES) {
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]) : "r"(a0));
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(rr[4]), "=r"(rr[5]), "=r"(rr[6]), "=r"(rr[7]) : "r"(a1));
-          }
-          uint32_t out[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            // the reference rounds the conv output to fp16 before its (separate) activation kernel
-            const __half2 pre = __floats2half2_rn(__uint_as_float(v[2 * i]) + bb[2 * i],
-                                                  __uint_as_float(v[2 * i + 1]) + bb[2 * i + 1]);
-            const float2 pf = __half22float2(pre);
-            float f0 = apply_act<ACT>(pf.x), f1 = apply_act<ACT>(pf.y);
-            if (HAS_RES) {  // half + half as torch computes it: exact fp32 sum of the two halves, rounded once
-              const float2 af = __half22float2(__floats2half2_rn(f0, f1));
-              const float2 rf = __half22float2(*reinterpret_cast<const __half2*>(&rr[i]));
-              f0 = af.x + rf.x;
-              f1 = af.y + rf.y;
-            }
-            const __half2 o = __floats2half2_rn(f0, f1);
-            out[i] = *reinterpret_cast<const uint32_t*>(&o);
-          }
-          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "r"(out[0]), "r"(out[1]), "r"(out[2]),
-                       "r"(out[3]) : "memory");
-          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a1), "r"(out[4]), "r"(out[5]), "r"(out[6]),
-                       "r"(out[7]) : "memory");
-        }
-      }
+      epilogue_convert<ACT, HAS_RES>(taddr, bn_cur, row, row_valid, sStage, p.bias + n0);
       // accumulator drained -> MMA warp may overwrite it
       tc_fence_before();
       __syncwarp();
@@ -269,6 +290,200 @@ __global__ void __launch_bounds__(kThreads, 2) conv_igemm_kernel(const __grid_co
         YX_TRACE(6, t);
       }
       named_bar_sync(1, 128);  // staging buffer reusable
+    }
+    if (leader) tma_store_wait_all0();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// --------------------------------------------------------------------------------------------
+// 3x3 / stride-1 variant with HALO REUSE.
+// The generic kernel re-fetches every activation byte 9x (one shifted box per tap) and each of those
+// fetches is also a 16 KB shared-memory write; ncu shows the tensor-bound layers limited by exactly that
+// (shared-memory fill + operand reads ~ 200 B/cycle/SM against 128).  Here ONE (TH+2)x(TW+2) halo box is
+// loaded per 64-channel chunk and the nine taps are nine DESCRIPTORS into it: with TW = 8 every tile row
+// is one 8-row swizzle atom, atoms are (TW+2)*128 = 1280 B apart (SBO), and a tap shift moves the start
+// address by (dy*10+dx)*128 B.  Such starts are not 1024-B aligned; measured on B200: the MMA unit applies the
+// 128-B swizzle XOR to ABSOLUTE shared-memory address bits (like TMA when it wrote the 1024-B aligned box), so
+// the descriptor's base_offset field must stay 0 — setting it to (addr >> 7) & 7 reads garbage
+// (profiles/r01_halo_descriptor_experiment.txt).
+// MH = 1 or 2 stacked 128-pixel halves per CTA share every weight tile (halves the weight stream).
+// Rings: A (halo, one slot per chunk) and B (one slot per (tap, chunk)) are pipelined independently.
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t make_sdesc_sw128_halo(uint32_t smem_addr, uint32_t sbo_bytes, bool with_base_offset) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  if (with_base_offset) d |= static_cast<uint64_t>((smem_addr >> 7) & 7u) << 49;  // swizzle phase of the start row
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+template <int ACT, bool HAS_RES>
+__global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_constant__ ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int MH = p.mh;
+  constexpr int HW = 10;  // halo row width in pixels (TW = 8)
+
+  const int groups = (p.BN + 63) >> 6;
+  const uint32_t sA = smem_base;
+  const uint32_t sB = sA + p.stages_a * p.a_stage_bytes;
+  const uint32_t sStage = sB + p.stages * p.b_stage_bytes;
+  const uint32_t sBar = sStage + groups * kAStageBytes;
+  // barriers: fullA[4] emptyA[4] fullB[8] emptyB[8] tfull[2] tempty[2] res, tmem slot
+  const uint32_t bar_fa = sBar, bar_ea = sBar + 32, bar_fb = sBar + 64, bar_eb = sBar + 128;
+  const uint32_t bar_tfull = sBar + 192, bar_tempty = sBar + 208, bar_res = sBar + 224, tmem_slot = sBar + 232;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA[0]);
+    tma_prefetch_desc(&p.tmW);
+    tma_prefetch_desc(&p.tmOut);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages_a; ++s) { mbar_init(bar_fa + 8 * s, 1); mbar_init(bar_ea + 8 * s, 1); }
+    for (int s = 0; s < p.stages; ++s) { mbar_init(bar_fb + 8 * s, 1); mbar_init(bar_eb + 8 * s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 4); }
+    mbar_init(bar_res, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int n_tiles = p.n_tiles_m * p.n_tiles_n;
+  const int tiles_per_img = p.tiles_h * p.tiles_w;
+  const int TH = 16 * MH;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---------------- TMA producer ----------------
+      uint32_t sa = 0, pha = 0, sb = 0, phb = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles_n, mt = tile / p.n_tiles_n;
+        const int img = mt / tiles_per_img, r = mt % tiles_per_img;
+        const int y0 = (r / p.tiles_w) * TH, x0 = (r % p.tiles_w) * 8;
+        const int n0 = nt * p.BN;
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          mbar_wait(bar_ea + 8 * sa, pha ^ 1);
+          mbar_expect_tx(bar_fa + 8 * sa, p.a_box_bytes);
+          tma_load_4d(sA + sa * p.a_stage_bytes, &p.tmA[0], bar_fa + 8 * sa, kc * 64, x0 - 1, y0 - 1, img);
+          if (++sa == (uint32_t)p.stages_a) { sa = 0; pha ^= 1; }
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(bar_eb + 8 * sb, phb ^ 1);
+            mbar_expect_tx(bar_fb + 8 * sb, p.b_stage_bytes);
+            tma_load_3d(sB + sb * p.b_stage_bytes, &p.tmW, bar_fb + 8 * sb, kc * 64, tap, n0);
+            if (++sb == (uint32_t)p.stages) { sb = 0; phb ^= 1; }
+          }
+        }
+        YX_TRACE(0, (tile - (int)blockIdx.x) / (int)gridDim.x);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ---------------- MMA issuer (all per-iteration state incremental, 32-bit) ----------------
+      uint32_t t = 0, sa = 0, pha = 0, sb = 0, phb = 0;
+      const uint32_t a_hi = sdesc_hi(HW * 128), b_hi = sdesc_hi(1024);
+      const uint32_t b_lo0 = sdesc_lo(sB), b_step = p.b_stage_bytes >> 4;
+      uint32_t b_lo = b_lo0;
+      const int ks_last = (p.cin - (p.k_chunks - 1) * 64) >> 4;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+        const int nt = tile % p.n_tiles_n;
+        const int n0 = nt * p.BN;
+        const int bn_cur = min(p.BN, p.cout16 - n0);
+        const uint32_t idesc = make_idesc_f16(bn_cur);
+        const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
+        mbar_wait(bar_tempty + 8 * acc, acc_ph ^ 1);
+        tc_fence_after();
+        YX_TRACE(1, t);
+        const uint32_t d0 = tmem_base + (acc * MH) * p.acc_stride, d1 = d0 + p.acc_stride;
+        uint32_t accum = 0;
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          mbar_wait(bar_fa + 8 * sa, pha);
+          const int ksteps = (kc == p.k_chunks - 1) ? ks_last : 4;
+          // tap (dy,dx) of half h starts (16h + dy) halo rows down and dx pixels right: rows are 128 B = 8 units
+          uint32_t a_tap = sdesc_lo(sA + sa * p.a_stage_bytes);
+          for (int dy = 0; dy < 3; ++dy, a_tap += (HW - 3) * 8) {
+            for (int dx = 0; dx < 3; ++dx, a_tap += 8) {
+              mbar_wait(bar_fb + 8 * sb, phb);
+              tc_fence_after();
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                if (ks < ksteps) {
+                  umma_f16_ss_lohi(d0, a_tap + 2 * ks, a_hi, b_lo + 2 * ks, b_hi, idesc, accum | (ks > 0));
+                  if (MH == 2)
+                    umma_f16_ss_lohi(d1, a_tap + 16 * HW * 8 + 2 * ks, a_hi, b_lo + 2 * ks, b_hi, idesc, accum | (ks > 0));
+                }
+              accum = 1;
+              umma_commit(bar_eb + 8 * sb);
+              b_lo += b_step;
+              if (++sb == (uint32_t)p.stages) { sb = 0; phb ^= 1; b_lo = b_lo0; }
+            }
+          }
+          umma_commit(bar_ea + 8 * sa);
+          if (++sa == (uint32_t)p.stages_a) { sa = 0; pha ^= 1; }
+        }
+        umma_commit(bar_tfull + 8 * acc);
+        YX_TRACE(2, t);
+      }
+    }
+  } else {
+    // ---------------- epilogue (warps 2..5) ----------------
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const bool leader = (warp == 2 && lane == 0);
+    uint32_t t = 0, res_cnt = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+      const int nt = tile % p.n_tiles_n, mt = tile / p.n_tiles_n;
+      const int img = mt / tiles_per_img, r = mt % tiles_per_img;
+      const int y0 = (r / p.tiles_w) * TH, x0 = (r % p.tiles_w) * 8;
+      const int n0 = nt * p.BN;
+      const int bn_cur = min(p.BN, p.cout16 - n0);
+      const int groups_cur = (bn_cur + 63) >> 6;
+      const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
+      for (int h = 0; h < MH; ++h) {
+        const int yh = y0 + 16 * h;
+        if (HAS_RES && leader) {
+          mbar_expect_tx(bar_res, groups_cur * kAStageBytes);
+          for (int g = 0; g < groups_cur; ++g)
+            tma_load_4d(sStage + g * kAStageBytes, &p.tmRes, bar_res, n0 + g * 64, x0, yh, img);
+        }
+        if (h == 0) {
+          mbar_wait(bar_tfull + 8 * acc, acc_ph);
+          tc_fence_after();
+          if (leader) YX_TRACE(3, t);
+        }
+        if (HAS_RES) {
+          mbar_wait(bar_res, res_cnt & 1);
+          ++res_cnt;
+        }
+        const uint32_t taddr = tmem_base + (acc * MH + h) * p.acc_stride + (static_cast<uint32_t>(q * 32) << 16);
+        epilogue_convert<ACT, HAS_RES>(taddr, bn_cur, row, true, sStage, p.bias + n0);
+        if (h == MH - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+        }
+        fence_proxy_async_smem();
+        if (leader && h == MH - 1) YX_TRACE(4, t);
+        named_bar_sync(1, 128);
+        if (leader) {
+          for (int g = 0; g < groups_cur; ++g)
+            tma_store_4d(&p.tmOut, sStage + g * kAStageBytes, n0 + g * 64, x0, yh, img);
+          tma_store_commit();
+          tma_store_wait_read0();
+          if (h == MH - 1) YX_TRACE(6, t);
+        }
+        named_bar_sync(1, 128);
+      }
     }
     if (leader) tma_store_wait_all0();
   }
@@ -444,8 +659,58 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
   pl.grid = std::min(p.n_tiles_m * p.n_tiles_n, ctas_per_sm * num_sms);
   p.bias = reinterpret_cast<const float*>(static_cast<const uint8_t*>(biases) + op.b_offset);
 
+  // ---- halo-reuse shape for 3x3 / stride 1 (see conv3x3_halo_kernel) ------------------------------
+  // YX_HALO=0 disables it (2 = diagnostic: set the descriptor base_offset); YX_HALO_MH / YX_HALO_BN force the stacked halves / N tile for experiments.
+  static const int halo_env = getenv("YX_HALO") ? atoi(getenv("YX_HALO")) : 1;
+  static const int halo_mh_env = getenv("YX_HALO_MH") ? atoi(getenv("YX_HALO_MH")) : 0;
+  static const int halo_bn_env = getenv("YX_HALO_BN") ? atoi(getenv("YX_HALO_BN")) : 0;
+  p.halo = 0;
+  if (halo_env && op.ksize == 3 && op.stride == 1 && !rowpack && Hout >= 16 && Wout >= 8) {
+    const double eff16 = (double)(ceil_div(Hout, 16) * 16) * (ceil_div(Wout, 8) * 8) / ((double)Hout * Wout);
+    if (eff16 <= 1.25) {
+      int bn, mh;
+      if (p.cout16 <= 128) { bn = p.cout16; mh = 2; }
+      else if (p.cout16 % 128 == 0) { bn = 128; mh = 2; }
+      else if (p.cout16 <= 256) { bn = p.cout16; mh = 1; }
+      else { bn = round_up(ceil_div(p.cout16, ceil_div(p.cout16, 256)), 64); mh = 1; }
+      if (halo_bn_env > 0 && halo_bn_env % 16 == 0 && halo_bn_env <= 256 && (halo_bn_env % 64 == 0 || halo_bn_env >= p.cout16))
+        bn = std::min(halo_bn_env, p.cout16);
+      if (halo_mh_env == 1 || halo_mh_env == 2) mh = halo_mh_env;
+      int stride_cols = 32;
+      while (stride_cols < bn) stride_cols <<= 1;
+      if (2 * mh * stride_cols > 512) mh = 1;
+      const double eff32 = (double)(ceil_div(Hout, 32) * 32) / (ceil_div(Hout, 16) * 16);
+      if (mh == 2 && eff32 > 1.2) mh = 1;
+      p.halo = halo_env == 2 ? 2 : 1; p.mh = mh; p.BN = bn;
+      p.n_tiles_n = ceil_div(p.cout16, bn);
+      p.TH = 16 * mh; p.TW = 8;
+      p.tiles_h = ceil_div(Hout, p.TH);
+      p.tiles_w = ceil_div(Wout, 8);
+      p.n_tiles_m = d.n * p.tiles_h * p.tiles_w;
+      p.acc_stride = stride_cols;
+      p.tmem_cols = 2 * mh * stride_cols;
+      p.b_stage_bytes = bn * 128;
+      p.a_box_bytes = (p.TH + 2) * 10 * 128;
+      p.a_stage_bytes = round_up(p.a_box_bytes, 1024);
+      p.stages_a = 2;
+      const int hfixed = ceil_div(bn, 64) * kAStageBytes + kBarBytes + 1024 + p.stages_a * p.a_stage_bytes;
+      p.stages = std::min(kMaxStages, (kSmemLimit - hfixed) / p.b_stage_bytes);
+      YX_REQUIRE(p.stages >= 3, "halo conv: not enough shared memory for the weight ring");
+      pl.smem_bytes = hfixed + p.stages * p.b_stage_bytes;
+      pl.smem_bytes = std::max(pl.smem_bytes, 120 * 1024);  // one CTA per SM (it may own all 512 TMEM columns)
+      pl.grid = std::min(p.n_tiles_m * p.n_tiles_n, num_sms);
+    }
+  }
+
   int rc;
-  if (rowpack) {
+  if (p.halo) {
+    uint64_t dims[4] = {(uint64_t)s.c, (uint64_t)s.w, (uint64_t)s.h, (uint64_t)s.n};
+    uint64_t st[4] = {2, (uint64_t)s.pitch * 2, (uint64_t)s.pitch * 2 * s.w, (uint64_t)s.nstride * 2};
+    uint32_t box[4] = {64, 10, (uint32_t)(p.TH + 2), 1};
+    if ((rc = encode_map(&p.tmA[0], static_cast<uint8_t*>(base) + s.offset, 4, dims, st, box, true, "A-halo")) != YX_OK)
+      return rc;
+    for (int i = 1; i < 4; ++i) p.tmA[i] = p.tmA[0];
+  } else if (rowpack) {
     uint64_t dims[4] = {64, (uint64_t)Wout, (uint64_t)s.h, (uint64_t)s.n};
     uint64_t st[4] = {2, 32, (uint64_t)s.w * 32, (uint64_t)s.nstride * 2};
     uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)p.TH, 1};
@@ -477,9 +742,10 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
     YX_REQUIRE(op.w_offset % 16 == 0, "weight offset must be 16-byte aligned");
     if ((rc = encode_map(&p.tmW, addr, 3, dims, st, box, true, "W")) != YX_OK) return rc;
   }
-  if ((rc = encode_view(&p.tmOut, base, d, p.TW, p.TH, "out")) != YX_OK) return rc;
+  const int store_th = p.halo ? 16 : p.TH;  // the halo kernel stores one 16x8 half at a time
+  if ((rc = encode_view(&p.tmOut, base, d, p.TW, store_th, "out")) != YX_OK) return rc;
   if (has_res) {
-    if ((rc = encode_view(&p.tmRes, base, op.res, p.TW, p.TH, "res")) != YX_OK) return rc;
+    if ((rc = encode_view(&p.tmRes, base, op.res, p.TW, store_th, "res")) != YX_OK) return rc;
   } else {
     p.tmRes = p.tmOut;
   }
@@ -498,7 +764,16 @@ static int launch_variant(const ConvPlan& plan, cudaStream_t stream) {
     YX_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<ACT, HAS_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     attr_set = true;
   }
-  conv_igemm_kernel<ACT, HAS_RES><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.p);
+  if (plan.p.halo) {
+    static bool halo_attr_set = false;
+    if (!halo_attr_set) {
+      YX_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<ACT, HAS_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+      halo_attr_set = true;
+    }
+    conv3x3_halo_kernel<ACT, HAS_RES><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.p);
+  } else {
+    conv_igemm_kernel<ACT, HAS_RES><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.p);
+  }
   YX_CUDA(cudaGetLastError());
   return YX_OK;
 }

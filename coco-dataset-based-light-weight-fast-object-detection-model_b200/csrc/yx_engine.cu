@@ -224,6 +224,7 @@ extern "C" int yx_conv2d(const yx_op* op, void* base, const void* weights, const
     YX_CUDA(cudaMalloc(&d, sizeof h));
     YX_CUDA(cudaMemset(d, 0, sizeof h));
     plan.p.trace = d;
+    plan.p.noload = getenv("YX_CONV_NOLOAD") ? 1 : 0;
     rc = conv_launch(plan, static_cast<cudaStream_t>(stream));
     YX_CUDA(cudaDeviceSynchronize());
     YX_CUDA(cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost));

@@ -44,7 +44,9 @@ struct ConvParams {
   int cin, cout16;
   int k_chunks;
   int stages, b_stage_bytes, a_box_bytes;
+  int halo, mh, stages_a, a_stage_bytes;  // conv3x3_halo_kernel: stacked 128-pixel halves, halo ring
   int tmem_cols, acc_stride;
+  int noload;                 // diagnostics: skip TMA loads after the ring is primed (results are garbage)
   long long* trace;           // diagnostics: per-tile timeline of CTA 0 (nullptr = off)  // TMEM columns allocated (power of two) and offset of accumulator 1
 };
 

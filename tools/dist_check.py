@@ -1,0 +1,25 @@
+"""2-GPU functional check of Predictor.predict_sharded: sharded + all-gathered detections == single-GPU run."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+
+import bench
+import yolox_b200 as yb
+
+torch.set_grad_enabled(False)
+rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+model = bench.build_model(torch.device("cuda", local))
+pred = yb.predict.Predictor(model)
+g = torch.Generator().manual_seed(7)
+img = (torch.rand(7, 3, 256, 320, generator=g) * 255).half().cuda()      # 7 images over 2 ranks: 4 + 3(+1 pad)
+det_all, cnt_all = pred.predict_sharded(img)
+det_one, cnt_one = pred(img)
+ok = torch.equal(det_all, det_one) and torch.equal(cnt_all, cnt_one)
+print(f"dist_check rank {rank}: sharded==single {ok} counts {cnt_all.tolist()}", flush=True)
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
