@@ -36,6 +36,13 @@ class Op(ctypes.Structure):
                 ("aux", c_i32), ("_pad", c_i32)]
 
 
+class ConvTune(ctypes.Structure):
+    """Mirror of yx_conv_tune (include/yolox_b200.h)."""
+    _fields_ = [("variant", c_i32), ("n_tile", c_i32), ("ctas_per_sm", c_i32), ("halves", c_i32),
+                ("epilogue_groups", c_i32), ("staging_buffers", c_i32), ("second_producer", c_i32),
+                ("no_resident_weights", c_i32)]
+
+
 class Levels(ctypes.Structure):
     _fields_ = [("n_levels", c_i32), ("h", c_i32 * 8), ("w", c_i32 * 8), ("stride", c_i32 * 8)]
 
@@ -49,7 +56,8 @@ def make_levels(level_hw, strides) -> Levels:
 
 
 SYMBOLS = ["yx_last_error", "yx_abi_version", "yx_engine_create", "yx_engine_destroy", "yx_engine_run",
-           "yx_engine_profile", "yx_engine_run_ops", "yx_engine_num_launches", "yx_conv2d", "yx_decode_infer", "yx_detect_workspace_bytes",
+           "yx_engine_profile", "yx_engine_run_ops", "yx_engine_num_launches", "yx_engine_tune", "yx_engine_op_desc",
+           "yx_conv2d", "yx_conv2d_ex", "yx_decode_infer", "yx_detect_workspace_bytes",
            "yx_nms_main", "yx_detect_main", "yx_head_assemble", "yx_decode_outputs", "yx_postprocess_yolox"]
 
 _lib = None
@@ -85,6 +93,9 @@ def load():
                                       ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), c_i32]
     lib.yx_engine_num_launches.argtypes = [c_vp]
     lib.yx_conv2d.argtypes = [ctypes.POINTER(Op), c_vp, c_vp, c_vp, c_vp]
+    lib.yx_conv2d_ex.argtypes = [ctypes.POINTER(Op), c_vp, c_vp, c_vp, ctypes.POINTER(ConvTune), c_vp]
+    lib.yx_engine_tune.argtypes = [c_vp, c_vp, c_i32, c_f32, c_f32, c_i32, c_vp]
+    lib.yx_engine_op_desc.argtypes = [c_vp, c_i32, ctypes.c_char_p, c_i32]
     logits = [c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64]
     lib.yx_decode_infer.argtypes = logits + [c_i32, c_i32, c_i32, c_i32, ctypes.POINTER(Levels), c_vp, c_vp, c_vp, c_vp]
     lib.yx_nms_main.argtypes = [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_f32, c_f32, c_i32, c_i32, c_i32, c_vp, c_sz,

@@ -4,37 +4,47 @@
 // (yolox/models/network_blocks.py:73-84,199-205; choijhanyangackr/yolox_infer/models/blocks.py:21-49).
 //
 // GEMM view:  D[M = pixels, N = Cout] = sum over (tap, cin) A[pixel shifted by tap, cin] * W[cout, tap, cin]
-//   * M tile  = TH x TW output pixels of one image (<= 128 rows -> one UMMA M=128 tile; TMEM lane = row)
+//   * M tile  = 128 output pixels of one image (TMEM lane = pixel); MH such tiles may be stacked per CTA
 //   * K chunk = 64 input channels of one filter tap = one 128-byte swizzled smem row per pixel
-//   * A operand: one 4-D TMA box (64 ch, TW, TH, 1) per (tap, chunk), shifted by the tap offset;
-//     TMA zero-fills outside the image (= conv zero padding) and beyond the channel extent.
-//     Stride 2 uses four parity views (even/odd rows x even/odd cols) of the input, so every tap
-//     is again a dense box.
-//   * B operand: 3-D TMA box (64 ch, 1 tap, BN couts) of the KRSC weight tensor.
-//   * accumulators: fp32 in TMEM, double buffered (2 x 256 columns) so the epilogue of tile i
-//     overlaps the MMAs of tile i+1.
-// Warp roles (192 threads, persistent CTA, 1 CTA/SM): warp 0 = TMA producer, warp 1 = MMA issuer,
-// warps 2..5 = epilogue (TMEM -> regs -> bias/act/residual -> swizzled smem -> TMA store).
+//   * accumulators: fp32 in TMEM, double buffered, so the epilogue of tile i overlaps the MMAs of tile i+1
+//
+// Two operand-A strategies share one kernel (template HALO):
+//   generic  one 4-D TMA box (64 ch, TW, TH, 1) per (tap, chunk), shifted by the tap offset; TMA zero-fills
+//            outside the image (= conv padding) and beyond the channel extent.  Stride 2 uses four parity views.
+//   halo     3x3 / stride 1: ONE (TH+2)x(8+2) halo box per chunk, the nine taps are nine smem DESCRIPTORS into
+//            it (start = base + (dy*10+dx)*128 B, SBO = 1280 B).  9x fewer activation bytes through L2->smem.
+//
+// What the round-1 probes showed (profiles/r01_tma_issue_probe.txt): ONE thread can issue only about one tiled TMA
+// load per 400-600 cycles (mbarrier wait + expect_tx + UTMALDG are each long-latency and serialise in a single
+// thread), independent of the box size; more producer WARPS scale linearly up to ~72 B/clk/SM.  Hence:
+//   * A and B (weights) have their own rings and their own producer warps (warp 0: A, warp 2: B, warp 3: a second
+//     producer for whichever operand has more loads);
+//   * B is kept RESIDENT in shared memory for the CTA's lifetime whenever the layer's whole weight tile fits
+//     (1x1 convs and small 3x3 convs), which removes half of the loads of the HBM-bound layers;
+//   * the output staging buffer is double buffered so the TMA store of tile i drains while tile i+1 is converted,
+//     and the conversion can be spread over two epilogue warpgroups.
+// Warp roles: 0 = A producer, 1 = MMA issuer, 2 = B producer (+TMEM alloc), 3 = second producer,
+//             4..7 = epilogue group 0, 8..11 = epilogue group 1 (optional).
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <vector>
 
 #include "yx_internal.h"
 #include "yx_ptx.cuh"
 
 namespace yx {
 
-constexpr int kThreads = 192;
-constexpr int kAStageBytes = 128 * 128;  // 128 rows x 64 fp16
-constexpr int kMaxStages = 8;
+constexpr int kTileBytes = 128 * 128;  // 128 rows x 64 fp16: one generic A stage / one staging group
 constexpr int kSmemLimit = 227 * 1024;
-constexpr int kBarBytes = 256;
-constexpr int kSmemTwoCtas = 112 * 1024;  // per-CTA budget that lets two CTAs share an SM
+constexpr int kBarBytes = 1024;
+constexpr int kSmemTwoCtas = 113 * 1024;  // per-CTA budget that lets two CTAs share an SM
+constexpr int kMaxARing = 8, kMaxBRing = 32;
+constexpr int kHaloW = 10;  // halo row width in pixels (TW = 8)
 
-// arithmetic intensity (FLOP / byte of fp16 activation traffic) below which a layer is launched in the
-// two-CTAs-per-SM "streaming" shape.  B200 ridge = 1414.9 TF/s / 6527 GB/s = 217 FLOP/B.
-// YX_MEM_AI overrides it for experiments (0 = never, 1e9 = always).
+// arithmetic intensity (FLOP / byte of fp16 activation traffic) below which the DEFAULT (untuned) launch shape is
+// the two-CTAs-per-SM streaming one.  B200 ridge = 1414.9 TF/s / 6527 GB/s = 217 FLOP/B.
 static double mem_bound_ai() {
   static double v = -1.0;
   if (v < 0) {
@@ -45,9 +55,7 @@ static double mem_bound_ai() {
 }
 
 // Activation on the fp16-rounded conv output, evaluated in fp32 like torch's half kernels (opmath = float).
-// Compile-time ACT keeps the epilogue straight-line: the epilogue has ONE warp per scheduler, so it lives on
-// instruction-level parallelism across the 16 columns of a TMEM chunk (a runtime switch per element
-// serialised it to ~150 cycles/element in the first version — see profiles/r01_conv_tile_trace.txt).
+// Compile-time ACT keeps the epilogue straight-line (profiles/r01_conv_tile_trace.txt).
 template <int ACT>
 __device__ __forceinline__ float apply_act(float x) {
   if (ACT == YX_ACT_SILU) return __fdividef(x, 1.0f + __expf(-x));
@@ -57,290 +65,102 @@ __device__ __forceinline__ float apply_act(float x) {
   return x;
 }
 
-// Drains one 128-lane accumulator: TMEM -> registers (16 columns at a time) -> +bias -> round to fp16 ->
-// activation (fp32) -> (+ residual already sitting in the staging line) -> fp16 -> 128-byte-swizzled smem
-// staging [group of 64 ch][row][128 B] that the TMA store reads.  `bias` points at this N tile's first channel.
+// 16 accumulator columns of one row: +bias -> round to fp16 -> activation (fp32) -> (+ residual already sitting
+// in the staging line) -> fp16 -> two 16-byte chunks of the row's 128-byte-swizzled staging line.
+template <int ACT, bool HAS_RES>
+__device__ __forceinline__ void convert16(const uint32_t (&v)[16], int c0, int row, uint32_t sStage, uint32_t sBiasTile) {
+  float bb[16];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(bb[4 * j]), "=f"(bb[4 * j + 1]), "=f"(bb[4 * j + 2]), "=f"(bb[4 * j + 3])
+                 : "r"(sBiasTile + (c0 + 4 * j) * 4));
+  const uint32_t line = sStage + (c0 >> 6) * kTileBytes + row * 128;
+  const uint32_t a0 = line + ((((c0 & 63) >> 3) ^ (row & 7)) << 4);
+  const uint32_t a1 = line + (((((c0 & 63) >> 3) + 1) ^ (row & 7)) << 4);
+  uint32_t rr[8];
+  if (HAS_RES) {
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]) : "r"(a0));
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(rr[4]), "=r"(rr[5]), "=r"(rr[6]), "=r"(rr[7]) : "r"(a1));
+  }
+  uint32_t out[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    // the reference rounds the conv output to fp16 before its (separate) activation kernel
+    const __half2 pre = __floats2half2_rn(__uint_as_float(v[2 * i]) + bb[2 * i], __uint_as_float(v[2 * i + 1]) + bb[2 * i + 1]);
+    const float2 pf = __half22float2(pre);
+    float f0 = apply_act<ACT>(pf.x), f1 = apply_act<ACT>(pf.y);
+    if (HAS_RES) {  // half + half as torch computes it: exact fp32 sum of the two halves, rounded once
+      const float2 af = __half22float2(__floats2half2_rn(f0, f1));
+      const float2 rf = __half22float2(*reinterpret_cast<const __half2*>(&rr[i]));
+      f0 = af.x + rf.x;
+      f1 = af.y + rf.y;
+    }
+    const __half2 o = __floats2half2_rn(f0, f1);
+    out[i] = *reinterpret_cast<const uint32_t*>(&o);
+  }
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "r"(out[0]), "r"(out[1]), "r"(out[2]), "r"(out[3]) : "memory");
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a1), "r"(out[4]), "r"(out[5]), "r"(out[6]), "r"(out[7]) : "memory");
+}
+
+// Drains this warp's share of one 128-lane accumulator.  The 16-column chunks of the tile are dealt round-robin to
+// the `groups` epilogue warpgroups; each warp keeps two TMEM loads in flight per wait.
 template <int ACT, bool HAS_RES>
 __device__ __forceinline__ void epilogue_convert(uint32_t taddr, int bn_cur, int row, bool row_valid, uint32_t sStage,
-                                                 const float* __restrict__ bias) {
-  for (int c0 = 0; c0 < bn_cur; c0 += 16) {
-    uint32_t v[16];
-    tmem_ld_32x32b_x16(taddr + c0, v);
+                                                 uint32_t sBiasTile, int group, int groups) {
+  const int nch = bn_cur >> 4;
+  for (int j = group; j < nch; j += 2 * groups) {
+    const int j2 = j + groups;
+    const bool two = j2 < nch;  // warp-uniform
+    uint32_t v0[16], v1[16];
+    tmem_ld_32x32b_x16(taddr + j * 16, v0);
+    if (two) tmem_ld_32x32b_x16(taddr + j2 * 16, v1);
     tmem_ld_wait();
     if (row_valid) {
-      float bb[16];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c0) + j);
-        bb[4 * j] = b4.x; bb[4 * j + 1] = b4.y; bb[4 * j + 2] = b4.z; bb[4 * j + 3] = b4.w;
-      }
-      // two 16-byte chunks (8 channels each) of this row's 128-byte swizzled staging line
-      const uint32_t line = sStage + (c0 >> 6) * kAStageBytes + row * 128;
-      const uint32_t a0 = line + ((((c0 & 63) >> 3) ^ (row & 7)) << 4);
-      const uint32_t a1 = line + (((((c0 & 63) >> 3) + 1) ^ (row & 7)) << 4);
-      uint32_t rr[8];
-      if (HAS_RES) {
-        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                     : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]) : "r"(a0));
-        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                     : "=r"(rr[4]), "=r"(rr[5]), "=r"(rr[6]), "=r"(rr[7]) : "r"(a1));
-      }
-      uint32_t out[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        // the reference rounds the conv output to fp16 before its (separate) activation kernel
-        const __half2 pre = __floats2half2_rn(__uint_as_float(v[2 * i]) + bb[2 * i],
-                                              __uint_as_float(v[2 * i + 1]) + bb[2 * i + 1]);
-        const float2 pf = __half22float2(pre);
-        float f0 = apply_act<ACT>(pf.x), f1 = apply_act<ACT>(pf.y);
-        if (HAS_RES) {  // half + half as torch computes it: exact fp32 sum of the two halves, rounded once
-          const float2 af = __half22float2(__floats2half2_rn(f0, f1));
-          const float2 rf = __half22float2(*reinterpret_cast<const __half2*>(&rr[i]));
-          f0 = af.x + rf.x;
-          f1 = af.y + rf.y;
-        }
-        const __half2 o = __floats2half2_rn(f0, f1);
-        out[i] = *reinterpret_cast<const uint32_t*>(&o);
-      }
-      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "r"(out[0]), "r"(out[1]), "r"(out[2]),
-                   "r"(out[3]) : "memory");
-      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a1), "r"(out[4]), "r"(out[5]), "r"(out[6]),
-                   "r"(out[7]) : "memory");
+      convert16<ACT, HAS_RES>(v0, j * 16, row, sStage, sBiasTile);
+      if (two) convert16<ACT, HAS_RES>(v1, j2 * 16, row, sStage, sBiasTile);
     }
   }
 }
 
 // optional per-tile timeline (diagnostics): trace[tile_local * 8 + event] = clock64(), CTA 0 only
-#define YX_TRACE(ev, tl)                                                                   \
-  do {                                                                                     \
+#define YX_TRACE(ev, tl)                                                                          \
+  do {                                                                                            \
     if (p.trace != nullptr && blockIdx.x == 0 && (tl) < 32) p.trace[(tl) * 8 + (ev)] = clock64(); \
   } while (0)
 
-template <int ACT, bool HAS_RES>
-__global__ void __launch_bounds__(kThreads, 2) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  const int groups = (p.BN + 63) >> 6;  // 64-channel output groups per tile
-  const uint32_t sA = smem_base;
-  const uint32_t sB = sA + p.stages * kAStageBytes;
-  const uint32_t sStage = sB + p.stages * p.b_stage_bytes;
-  const uint32_t sBar = sStage + groups * kAStageBytes;
-  // barrier layout (8 bytes each): full[8], empty[8], tmem_full[2], tmem_empty[2], res_full, then tmem ptr
-  const uint32_t bar_full = sBar, bar_empty = sBar + 64, bar_tfull = sBar + 128, bar_tempty = sBar + 144;
-  const uint32_t bar_res = sBar + 160, tmem_slot = sBar + 168;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.tmA[0]);
-    tma_prefetch_desc(&p.tmW);
-    tma_prefetch_desc(&p.tmOut);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < p.stages; ++s) {
-      mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, 4);  // one arrive per epilogue warp
-    }
-    mbar_init(bar_res, 1);
-    fence_mbar_init();
-  }
-  if (warp == 2) tmem_alloc(tmem_slot, p.tmem_cols);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-
-  const int n_tiles = p.n_tiles_m * p.n_tiles_n;
+struct TileCoord {
+  int img, y0, x0, n0;
+};
+__device__ __forceinline__ TileCoord tile_coord(const ConvParams& p, int tile) {
+  const int nt = tile % p.n_tiles_n, mt = tile / p.n_tiles_n;
   const int tiles_per_img = p.tiles_h * p.tiles_w;
-  const int taps = p.ky * p.kx;
-
-  if (warp == 0) {
-    // ================================ TMA producer ================================
-    if (lane == 0) {
-      uint32_t it = 0, s = 0, ph = 0;  // ring slot / phase kept incrementally (no div/mod on the issue path)
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles_n, mt = tile / p.n_tiles_n;
-        const int img = mt / tiles_per_img, r = mt % tiles_per_img;
-        const int y0 = (r / p.tiles_w) * p.TH, x0 = (r % p.tiles_w) * p.TW;
-        const int n0 = nt * p.BN;
-        int dy = 0, dx = 0;
-        for (int tap = 0; tap < taps; ++tap) {
-          int mi = 0, cx, cy;
-          if (p.stride == 1) {
-            cx = x0 + dx - p.pad_x;
-            cy = y0 + dy - p.pad_y;
-          } else {
-            // input row 2*y + dy - pad.  For k=3,pad=1: dy=0 -> odd row of cell y-1; dy=1 -> even row
-            // of cell y; dy=2 -> odd row of cell y.  k=1 (pad 0): even row/col of cell y.
-            const int oy = dy - p.pad_y, ox = dx - p.pad_y;
-            const int py = oy & 1, px = ox & 1;
-            mi = py * 2 + px;
-            cy = y0 + ((oy - py) >> 1);
-            cx = x0 + ((ox - px) >> 1);
-          }
-          for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
-            mbar_wait(bar_empty + 8 * s, ph ^ 1);
-            if (p.noload && it >= (uint32_t)p.stages) {  // diagnostics: MMA rate with operands already resident
-              mbar_arrive(bar_full + 8 * s);
-            } else {
-              mbar_expect_tx(bar_full + 8 * s, p.a_box_bytes + p.b_stage_bytes);
-              tma_load_4d(sA + s * kAStageBytes, &p.tmA[mi], bar_full + 8 * s, kc * 64, cx, cy, img);
-              tma_load_3d(sB + s * p.b_stage_bytes, &p.tmW, bar_full + 8 * s, kc * 64, tap, n0);
-            }
-            if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
-          }
-          if (++dx == p.kx) { dx = 0; ++dy; }
-        }
-        YX_TRACE(0, (tile - (int)blockIdx.x) / (int)gridDim.x);
-      }
-    }
-  } else if (warp == 1) {
-    // ================================ MMA issuer ================================
-    if (lane == 0) {
-      // The whole tensor pipe is fed by THIS thread: everything per k-iteration is incremental 32-bit math
-      // (a div/mod + 64-bit descriptor rebuild per iteration cost ~830 cycles per 4 MMAs, 2x their execution
-      // time — profiles/r01_conv_tile_trace.txt).
-      uint32_t t = 0, s = 0, ph = 0;
-      const uint32_t hi = sdesc_hi(1024);
-      const uint32_t a_lo0 = sdesc_lo(sA), b_lo0 = sdesc_lo(sB);
-      const uint32_t a_step = kAStageBytes >> 4, b_step = p.b_stage_bytes >> 4;
-      uint32_t a_lo = a_lo0, b_lo = b_lo0;
-      const int ks_last = (p.cin - (p.k_chunks - 1) * 64) >> 4;
-      const int k_iters = taps * p.k_chunks;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
-        const int nt = tile % p.n_tiles_n;
-        const int n0 = nt * p.BN;
-        const int bn_cur = min(p.BN, p.cout16 - n0);
-        const uint32_t idesc = make_idesc_f16(bn_cur);
-        const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
-        mbar_wait(bar_tempty + 8 * acc, acc_ph ^ 1);
-        tc_fence_after();
-        YX_TRACE(1, t);
-        const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
-        uint32_t accum = 0;
-        int kc = 0;
-        for (int i = 0; i < k_iters; ++i) {
-          mbar_wait(bar_full + 8 * s, ph);
-          tc_fence_after();
-          const int ksteps = (kc == p.k_chunks - 1) ? ks_last : 4;
-          umma_f16_ss_lohi(d_tmem, a_lo, hi, b_lo, hi, idesc, accum);
-          if (ksteps > 1) umma_f16_ss_lohi(d_tmem, a_lo + 2, hi, b_lo + 2, hi, idesc, 1u);
-          if (ksteps > 2) umma_f16_ss_lohi(d_tmem, a_lo + 4, hi, b_lo + 4, hi, idesc, 1u);
-          if (ksteps > 3) umma_f16_ss_lohi(d_tmem, a_lo + 6, hi, b_lo + 6, hi, idesc, 1u);
-          accum = 1;
-          umma_commit(bar_empty + 8 * s);  // frees the smem stage when these MMAs retire
-          a_lo += a_step; b_lo += b_step;
-          if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; a_lo = a_lo0; b_lo = b_lo0; }
-          if (++kc == p.k_chunks) kc = 0;
-        }
-        umma_commit(bar_tfull + 8 * acc);  // accumulator complete -> epilogue
-        YX_TRACE(2, t);
-      }
-    }
-  } else {
-    // ================================ epilogue (warps 2..5) ================================
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
-    const int row = q * 32 + lane;
-    const bool row_valid = row < p.TH * p.TW;
-    const bool leader = (warp == 2 && lane == 0);
-    uint32_t t = 0, res_cnt = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
-      const int nt = tile % p.n_tiles_n, mt = tile / p.n_tiles_n;
-      const int img = mt / tiles_per_img, r = mt % tiles_per_img;
-      const int y0 = (r / p.tiles_w) * p.TH, x0 = (r % p.tiles_w) * p.TW;
-      const int n0 = nt * p.BN;
-      const int bn_cur = min(p.BN, p.cout16 - n0);
-      const int groups_cur = (bn_cur + 63) >> 6;
-      const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
-
-      if (HAS_RES && leader) {
-        mbar_expect_tx(bar_res, groups_cur * p.a_box_bytes);
-        for (int g = 0; g < groups_cur; ++g)
-          tma_load_4d(sStage + g * kAStageBytes, &p.tmRes, bar_res, n0 + g * 64, x0, y0, img);
-      }
-      mbar_wait(bar_tfull + 8 * acc, acc_ph);
-      tc_fence_after();
-      if (leader) YX_TRACE(3, t);
-      if (HAS_RES) {
-        mbar_wait(bar_res, res_cnt & 1);
-        ++res_cnt;
-      }
-      const uint32_t taddr = tmem_base + acc * p.acc_stride + (static_cast<uint32_t>(q * 32) << 16);
-      epilogue_convert<ACT, HAS_RES>(taddr, bn_cur, row, row_valid, sStage, p.bias + n0);
-      // accumulator drained -> MMA warp may overwrite it
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
-      // publish the staged tile to the async proxy and store it
-      fence_proxy_async_smem();
-      if (leader) YX_TRACE(4, t);
-      named_bar_sync(1, 128);
-      if (leader) {
-        YX_TRACE(5, t);
-        for (int g = 0; g < groups_cur; ++g)
-          tma_store_4d(&p.tmOut, sStage + g * kAStageBytes, n0 + g * 64, x0, y0, img);
-        tma_store_commit();
-        tma_store_wait_read0();
-        YX_TRACE(6, t);
-      }
-      named_bar_sync(1, 128);  // staging buffer reusable
-    }
-    if (leader) tma_store_wait_all0();
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, p.tmem_cols);
+  const int img = mt / tiles_per_img, r = mt % tiles_per_img;
+  TileCoord c;
+  c.img = img;
+  c.y0 = (r / p.tiles_w) * p.TH;
+  c.x0 = (r % p.tiles_w) * p.TW;
+  c.n0 = nt * p.BN;
+  return c;
 }
 
-// --------------------------------------------------------------------------------------------
-// 3x3 / stride-1 variant with HALO REUSE.
-// The generic kernel re-fetches every activation byte 9x (one shifted box per tap) and each of those
-// fetches is also a 16 KB shared-memory write; ncu shows the tensor-bound layers limited by exactly that
-// (shared-memory fill + operand reads ~ 200 B/cycle/SM against 128).  Here ONE (TH+2)x(TW+2) halo box is
-// loaded per 64-channel chunk and the nine taps are nine DESCRIPTORS into it: with TW = 8 every tile row
-// is one 8-row swizzle atom, atoms are (TW+2)*128 = 1280 B apart (SBO), and a tap shift moves the start
-// address by (dy*10+dx)*128 B.  Such starts are not 1024-B aligned; measured on B200: the MMA unit applies the
-// 128-B swizzle XOR to ABSOLUTE shared-memory address bits (like TMA when it wrote the 1024-B aligned box), so
-// the descriptor's base_offset field must stay 0 — setting it to (addr >> 7) & 7 reads garbage
-// (profiles/r01_halo_descriptor_experiment.txt).
-// MH = 1 or 2 stacked 128-pixel halves per CTA share every weight tile (halves the weight stream).
-// Rings: A (halo, one slot per chunk) and B (one slot per (tap, chunk)) are pipelined independently.
-// --------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t make_sdesc_sw128_halo(uint32_t smem_addr, uint32_t sbo_bytes, bool with_base_offset) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
-  d |= static_cast<uint64_t>(1) << 16;
-  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  if (with_base_offset) d |= static_cast<uint64_t>((smem_addr >> 7) & 7u) << 49;  // swizzle phase of the start row
-  d |= static_cast<uint64_t>(2) << 61;
-  return d;
-}
-
-template <int ACT, bool HAS_RES>
-__global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_constant__ ConvParams p) {
+template <int ACT, bool HAS_RES, bool HALO>
+__global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // tells ptxas the warp index is warp-uniform
   const int lane = threadIdx.x & 31;
-  const int MH = p.mh;
-  constexpr int HW = 10;  // halo row width in pixels (TW = 8)
 
-  const int groups = (p.BN + 63) >> 6;
+  const int groups64 = (p.BN + 63) >> 6;  // 64-channel output groups per N tile
   const uint32_t sA = smem_base;
   const uint32_t sB = sA + p.stages_a * p.a_stage_bytes;
-  const uint32_t sStage = sB + p.stages * p.b_stage_bytes;
-  const uint32_t sBar = sStage + groups * kAStageBytes;
-  // barriers: fullA[4] emptyA[4] fullB[8] emptyB[8] tfull[2] tempty[2] res, tmem slot
-  const uint32_t bar_fa = sBar, bar_ea = sBar + 32, bar_fb = sBar + 64, bar_eb = sBar + 128;
-  const uint32_t bar_tfull = sBar + 192, bar_tempty = sBar + 208, bar_res = sBar + 224, tmem_slot = sBar + 232;
+  const uint32_t sStage0 = sB + p.b_slots * p.b_stage_bytes;
+  const uint32_t stage_buf_bytes = groups64 * kTileBytes;
+  const uint32_t sBias = sStage0 + p.stage_bufs * stage_buf_bytes;
+  const uint32_t sBar = sBias + p.bias_bytes;
+  // barriers (8 bytes each): fullA[8] emptyA[8] fullB[32] emptyB[32] tfull[2] tempty[2] res[2], then the TMEM slot
+  const uint32_t bar_fa = sBar, bar_ea = sBar + 64, bar_fb = sBar + 128, bar_eb = sBar + 384;
+  const uint32_t bar_tfull = sBar + 640, bar_tempty = sBar + 656, bar_res = sBar + 672, tmem_slot = sBar + 688;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA[0]);
@@ -349,12 +169,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages_a; ++s) { mbar_init(bar_fa + 8 * s, 1); mbar_init(bar_ea + 8 * s, 1); }
-    for (int s = 0; s < p.stages; ++s) { mbar_init(bar_fb + 8 * s, 1); mbar_init(bar_eb + 8 * s, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 4); }
-    mbar_init(bar_res, 1);
+    for (int s = 0; s < p.b_slots; ++s) { mbar_init(bar_fb + 8 * s, 1); mbar_init(bar_eb + 8 * s, 1); }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, 4 * p.epi_groups);  // one arrive per epilogue warp
+      mbar_init(bar_res + 8 * a, 1);
+    }
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, p.tmem_cols);
+  for (int i = threadIdx.x; i < p.cout16; i += blockDim.x) {
+    const float b = __ldg(p.bias + i);
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(sBias + i * 4), "f"(b) : "memory");
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -362,130 +189,230 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   const int n_tiles = p.n_tiles_m * p.n_tiles_n;
-  const int tiles_per_img = p.tiles_h * p.tiles_w;
-  const int TH = 16 * MH;
+  const int taps = p.ky * p.kx;
+  const int MH = HALO ? p.mh : 1;
 
-  if (warp == 0) {
-    if (lane == 0) {  // ---------------- TMA producer ----------------
-      uint32_t sa = 0, pha = 0, sb = 0, phb = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles_n, mt = tile / p.n_tiles_n;
-        const int img = mt / tiles_per_img, r = mt % tiles_per_img;
-        const int y0 = (r / p.tiles_w) * TH, x0 = (r % p.tiles_w) * 8;
-        const int n0 = nt * p.BN;
+  const bool is_a_prod = (warp == 0) || (warp == 3 && p.w3_role == 1);
+  const bool is_b_prod = (warp == 2) || (warp == 3 && p.w3_role == 2);
+
+  // Producer and MMA warps run their loops WARP-UNIFORMLY (all 32 lanes, uniform values) and elect one lane only
+  // around the issue itself: under `if (lane == 0)` ptxas cannot prove uniformity and wraps every UTMALDG / UTCHMMA
+  // in an ELECT + 8x R2UR.BROADCAST loop (~200 cycles per TMA instruction, profiles/r01_tma_issue_probe.txt).
+  if (is_a_prod) {
+    // ================================ A producer(s) ================================
+    const uint32_t nprod = p.w3_role == 1 ? 2u : 1u, mine = warp == 0 ? 0u : 1u;
+    uint32_t s = 0, ph = 0, turn = 0;  // ring slot / phase / whose turn, all incremental
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const TileCoord tc = tile_coord(p, tile);
+      if (HALO) {
         for (int kc = 0; kc < p.k_chunks; ++kc) {
-          mbar_wait(bar_ea + 8 * sa, pha ^ 1);
-          mbar_expect_tx(bar_fa + 8 * sa, p.a_box_bytes);
-          tma_load_4d(sA + sa * p.a_stage_bytes, &p.tmA[0], bar_fa + 8 * sa, kc * 64, x0 - 1, y0 - 1, img);
-          if (++sa == (uint32_t)p.stages_a) { sa = 0; pha ^= 1; }
-          for (int tap = 0; tap < 9; ++tap) {
-            mbar_wait(bar_eb + 8 * sb, phb ^ 1);
-            mbar_expect_tx(bar_fb + 8 * sb, p.b_stage_bytes);
-            tma_load_3d(sB + sb * p.b_stage_bytes, &p.tmW, bar_fb + 8 * sb, kc * 64, tap, n0);
-            if (++sb == (uint32_t)p.stages) { sb = 0; phb ^= 1; }
+          if (turn == mine) {
+            mbar_wait(bar_ea + 8 * s, ph ^ 1);
+            if (elect_one()) {
+              mbar_expect_tx(bar_fa + 8 * s, p.a_box_bytes);
+              tma_load_4d(sA + s * p.a_stage_bytes, &p.tmA[0], bar_fa + 8 * s, kc * 64, tc.x0 - 1, tc.y0 - 1, tc.img);
+            }
           }
+          if (++turn == nprod) turn = 0;
+          if (++s == (uint32_t)p.stages_a) { s = 0; ph ^= 1; }
         }
-        YX_TRACE(0, (tile - (int)blockIdx.x) / (int)gridDim.x);
+      } else {
+        int dy = 0, dx = 0;
+        for (int tap = 0; tap < taps; ++tap) {
+          int mi = 0, cx, cy;
+          if (p.stride == 1) {
+            cx = tc.x0 + dx - p.pad_x;
+            cy = tc.y0 + dy - p.pad_y;
+          } else {
+            // input row 2*y + dy - pad.  For k=3,pad=1: dy=0 -> odd row of cell y-1; dy=1 -> even row
+            // of cell y; dy=2 -> odd row of cell y.  k=1 (pad 0): even row/col of cell y.
+            const int oy = dy - p.pad_y, ox = dx - p.pad_y;
+            const int py = oy & 1, px = ox & 1;
+            mi = py * 2 + px;
+            cy = tc.y0 + ((oy - py) >> 1);
+            cx = tc.x0 + ((ox - px) >> 1);
+          }
+          for (int kc = 0; kc < p.k_chunks; ++kc) {
+            if (turn == mine) {
+              mbar_wait(bar_ea + 8 * s, ph ^ 1);
+              if (elect_one()) {
+                mbar_expect_tx(bar_fa + 8 * s, p.a_box_bytes);
+                tma_load_4d(sA + s * p.a_stage_bytes, &p.tmA[mi], bar_fa + 8 * s, kc * 64, cx, cy, tc.img);
+              }
+            }
+            if (++turn == nprod) turn = 0;
+            if (++s == (uint32_t)p.stages_a) { s = 0; ph ^= 1; }
+          }
+          if (++dx == p.kx) { dx = 0; ++dy; }
+        }
       }
+      if (warp == 0 && lane == 0) YX_TRACE(0, (tile - (int)blockIdx.x) / (int)gridDim.x);
+    }
+  } else if (is_b_prod) {
+    // ================================ B (weight) producer(s) ================================
+    const uint32_t nprod = p.w3_role == 2 ? 2u : 1u, mine = warp == 2 ? 0u : 1u;
+    uint32_t s = 0, ph = 0, turn = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int n0 = (tile % p.n_tiles_n) * p.BN;
+      // ring order must match the MMA issuer: halo = (chunk, tap), generic = (tap, chunk)
+      const int outer = HALO ? p.k_chunks : taps, inner = HALO ? taps : p.k_chunks;
+      for (int o = 0; o < outer; ++o)
+        for (int i = 0; i < inner; ++i) {
+          const int kc = HALO ? o : i, tap = HALO ? i : o;
+          if (turn == mine) {
+            if (!p.b_resident) mbar_wait(bar_eb + 8 * s, ph ^ 1);
+            if (elect_one()) {
+              mbar_expect_tx(bar_fb + 8 * s, p.b_stage_bytes);
+              tma_load_3d(sB + s * p.b_stage_bytes, &p.tmW, bar_fb + 8 * s, kc * 64, tap, n0);
+            }
+          }
+          if (++turn == nprod) turn = 0;
+          if (++s == (uint32_t)p.b_slots) { s = 0; ph ^= 1; }
+        }
+      if (p.b_resident) break;  // one N tile per layer: the weights stay in smem for every later tile
     }
   } else if (warp == 1) {
-    if (lane == 0) {  // ---------------- MMA issuer (all per-iteration state incremental, 32-bit) ----------------
-      uint32_t t = 0, sa = 0, pha = 0, sb = 0, phb = 0;
-      const uint32_t a_hi = sdesc_hi(HW * 128), b_hi = sdesc_hi(1024);
-      const uint32_t b_lo0 = sdesc_lo(sB), b_step = p.b_stage_bytes >> 4;
-      uint32_t b_lo = b_lo0;
-      const int ks_last = (p.cin - (p.k_chunks - 1) * 64) >> 4;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
-        const int nt = tile % p.n_tiles_n;
-        const int n0 = nt * p.BN;
-        const int bn_cur = min(p.BN, p.cout16 - n0);
-        const uint32_t idesc = make_idesc_f16(bn_cur);
-        const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
-        mbar_wait(bar_tempty + 8 * acc, acc_ph ^ 1);
-        tc_fence_after();
-        YX_TRACE(1, t);
-        const uint32_t d0 = tmem_base + (acc * MH) * p.acc_stride, d1 = d0 + p.acc_stride;
-        uint32_t accum = 0;
+    // ================================ MMA issuer ================================
+    // The whole tensor pipe is fed by this warp: everything per iteration is incremental 32-bit uniform math.
+    uint32_t t = 0, sa = 0, pha = 0, sb = 0, phb = 0;
+    const uint32_t a_hi = sdesc_hi(HALO ? kHaloW * 128 : 1024), b_hi = sdesc_hi(1024);
+    const uint32_t b_lo0 = sdesc_lo(sB), b_step = p.b_stage_bytes >> 4;
+    uint32_t b_lo = b_lo0;
+    const int ks_last = (p.cin - (p.k_chunks - 1) * 64) >> 4;
+    bool b_ready = false;  // resident weights: wait for them during the first tile only
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+      const int n0 = (tile % p.n_tiles_n) * p.BN;
+      const int bn_cur = min(p.BN, p.cout16 - n0);
+      const uint32_t idesc = make_idesc_f16(bn_cur);
+      const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
+      mbar_wait(bar_tempty + 8 * acc, acc_ph ^ 1);
+      tc_fence_after();
+      if (lane == 0) YX_TRACE(1, t);
+      const uint32_t d0 = tmem_base + (acc * MH) * p.acc_stride, d1 = d0 + p.acc_stride;
+      uint32_t accum = 0;
+      if (p.b_resident) { sb = 0; b_lo = b_lo0; }
+      if (HALO) {
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           mbar_wait(bar_fa + 8 * sa, pha);
           const int ksteps = (kc == p.k_chunks - 1) ? ks_last : 4;
           // tap (dy,dx) of half h starts (16h + dy) halo rows down and dx pixels right: rows are 128 B = 8 units
           uint32_t a_tap = sdesc_lo(sA + sa * p.a_stage_bytes);
-          for (int dy = 0; dy < 3; ++dy, a_tap += (HW - 3) * 8) {
+          for (int dy = 0; dy < 3; ++dy, a_tap += (kHaloW - 3) * 8) {
             for (int dx = 0; dx < 3; ++dx, a_tap += 8) {
-              mbar_wait(bar_fb + 8 * sb, phb);
+              if (!b_ready) mbar_wait(bar_fb + 8 * sb, phb);
               tc_fence_after();
+              if (elect_one()) {
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks)
-                if (ks < ksteps) {
-                  umma_f16_ss_lohi(d0, a_tap + 2 * ks, a_hi, b_lo + 2 * ks, b_hi, idesc, accum | (ks > 0));
-                  if (MH == 2)
-                    umma_f16_ss_lohi(d1, a_tap + 16 * HW * 8 + 2 * ks, a_hi, b_lo + 2 * ks, b_hi, idesc, accum | (ks > 0));
-                }
+                for (int ks = 0; ks < 4; ++ks)
+                  if (ks < ksteps) {
+                    umma_f16_ss_lohi(d0, a_tap + 2 * ks, a_hi, b_lo + 2 * ks, b_hi, idesc, accum | (ks > 0));
+                    if (MH == 2)
+                      umma_f16_ss_lohi(d1, a_tap + 16 * kHaloW * 8 + 2 * ks, a_hi, b_lo + 2 * ks, b_hi, idesc, accum | (ks > 0));
+                  }
+                if (!p.b_resident) umma_commit(bar_eb + 8 * sb);
+              }
               accum = 1;
-              umma_commit(bar_eb + 8 * sb);
               b_lo += b_step;
-              if (++sb == (uint32_t)p.stages) { sb = 0; phb ^= 1; b_lo = b_lo0; }
+              if (++sb == (uint32_t)p.b_slots) { sb = 0; phb ^= 1; b_lo = b_lo0; }
             }
           }
-          umma_commit(bar_ea + 8 * sa);
+          if (elect_one()) umma_commit(bar_ea + 8 * sa);
           if (++sa == (uint32_t)p.stages_a) { sa = 0; pha ^= 1; }
         }
-        umma_commit(bar_tfull + 8 * acc);
-        YX_TRACE(2, t);
+      } else {
+        const uint32_t a_lo0 = sdesc_lo(sA), a_step = p.a_stage_bytes >> 4;
+        const int k_iters = taps * p.k_chunks;
+        int kc = 0;
+        uint32_t a_lo = a_lo0 + sa * a_step;
+        for (int i = 0; i < k_iters; ++i) {
+          mbar_wait(bar_fa + 8 * sa, pha);
+          if (!b_ready) mbar_wait(bar_fb + 8 * sb, phb);
+          tc_fence_after();
+          const int ksteps = (kc == p.k_chunks - 1) ? ks_last : 4;
+          if (elect_one()) {
+            umma_f16_ss_lohi(d0, a_lo, a_hi, b_lo, b_hi, idesc, accum);
+            if (ksteps > 1) umma_f16_ss_lohi(d0, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
+            if (ksteps > 2) umma_f16_ss_lohi(d0, a_lo + 4, a_hi, b_lo + 4, b_hi, idesc, 1u);
+            if (ksteps > 3) umma_f16_ss_lohi(d0, a_lo + 6, a_hi, b_lo + 6, b_hi, idesc, 1u);
+            umma_commit(bar_ea + 8 * sa);  // frees the A stage when these MMAs retire
+            if (!p.b_resident) umma_commit(bar_eb + 8 * sb);
+          }
+          accum = 1;
+          a_lo += a_step;
+          b_lo += b_step;
+          if (++sa == (uint32_t)p.stages_a) { sa = 0; pha ^= 1; a_lo = a_lo0; }
+          if (++sb == (uint32_t)p.b_slots) { sb = 0; phb ^= 1; b_lo = b_lo0; }
+          if (++kc == p.k_chunks) kc = 0;
+        }
       }
+      if (p.b_resident) b_ready = true;
+      if (elect_one()) umma_commit(bar_tfull + 8 * acc);  // accumulator complete -> epilogue
+      if (lane == 0) YX_TRACE(2, t);
     }
-  } else {
-    // ---------------- epilogue (warps 2..5) ----------------
-    const int q = warp & 3;
+  } else if (warp >= 4) {
+    // ================================ epilogue (warps 4..7 [, 8..11]) ================================
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int group = (warp - 4) >> 2;
     const int row = q * 32 + lane;
-    const bool leader = (warp == 2 && lane == 0);
-    uint32_t t = 0, res_cnt = 0;
+    const bool row_valid = HALO ? true : (row < p.TH * p.TW);
+    const bool lead_warp = warp == 4;  // issues the residual loads and the stores (one elected lane)
+    const uint32_t n_epi = 128u * p.epi_groups;
+    const int store_th = HALO ? 16 : p.TH;
+    uint32_t t = 0, u = 0;  // tile counter, staging-unit counter (MH units per tile)
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
-      const int nt = tile % p.n_tiles_n, mt = tile / p.n_tiles_n;
-      const int img = mt / tiles_per_img, r = mt % tiles_per_img;
-      const int y0 = (r / p.tiles_w) * TH, x0 = (r % p.tiles_w) * 8;
-      const int n0 = nt * p.BN;
-      const int bn_cur = min(p.BN, p.cout16 - n0);
+      const TileCoord tc = tile_coord(p, tile);
+      const int bn_cur = min(p.BN, p.cout16 - tc.n0);
       const int groups_cur = (bn_cur + 63) >> 6;
       const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
-      for (int h = 0; h < MH; ++h) {
-        const int yh = y0 + 16 * h;
-        if (HAS_RES && leader) {
-          mbar_expect_tx(bar_res, groups_cur * kAStageBytes);
-          for (int g = 0; g < groups_cur; ++g)
-            tma_load_4d(sStage + g * kAStageBytes, &p.tmRes, bar_res, n0 + g * 64, x0, yh, img);
+      for (int h = 0; h < MH; ++h, ++u) {
+        const int yh = tc.y0 + store_th * h;
+        const uint32_t buf = p.stage_bufs == 2 ? (u & 1) : 0;
+        const uint32_t sStage = sStage0 + buf * stage_buf_bytes;
+        // staging buffer `buf` is free once the store issued stage_bufs units ago has read it
+        // (elect.sync picks the same lane for the same mask every time, so the bulk-group state stays with one thread)
+        if (lead_warp) {
+          if (elect_one()) {
+            if (p.stage_bufs == 2) tma_store_wait_read1(); else tma_store_wait_read0();
+          }
+        }
+        named_bar_sync(1, n_epi);
+        if (HAS_RES && lead_warp) {
+          if (elect_one()) {
+            mbar_expect_tx(bar_res + 8 * buf, groups_cur * p.out_box_bytes);
+            for (int g = 0; g < groups_cur; ++g)
+              tma_load_4d(sStage + g * kTileBytes, &p.tmRes, bar_res + 8 * buf, tc.n0 + g * 64, tc.x0, yh, tc.img);
+          }
         }
         if (h == 0) {
           mbar_wait(bar_tfull + 8 * acc, acc_ph);
           tc_fence_after();
-          if (leader) YX_TRACE(3, t);
+          if (lead_warp && lane == 0) YX_TRACE(3, t);
         }
-        if (HAS_RES) {
-          mbar_wait(bar_res, res_cnt & 1);
-          ++res_cnt;
-        }
+        if (HAS_RES) mbar_wait(bar_res + 8 * buf, (p.stage_bufs == 2 ? (u >> 1) : u) & 1);
         const uint32_t taddr = tmem_base + (acc * MH + h) * p.acc_stride + (static_cast<uint32_t>(q * 32) << 16);
-        epilogue_convert<ACT, HAS_RES>(taddr, bn_cur, row, true, sStage, p.bias + n0);
-        if (h == MH - 1) {
+        epilogue_convert<ACT, HAS_RES>(taddr, bn_cur, row, row_valid, sStage, sBias + tc.n0 * 4, group, p.epi_groups);
+        if (h == MH - 1) {  // accumulator drained -> MMA warp may overwrite it
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
         }
+        // publish the staged tile to the async proxy and store it
         fence_proxy_async_smem();
-        if (leader && h == MH - 1) YX_TRACE(4, t);
-        named_bar_sync(1, 128);
-        if (leader) {
-          for (int g = 0; g < groups_cur; ++g)
-            tma_store_4d(&p.tmOut, sStage + g * kAStageBytes, n0 + g * 64, x0, yh, img);
-          tma_store_commit();
-          tma_store_wait_read0();
-          if (h == MH - 1) YX_TRACE(6, t);
+        if (lead_warp && lane == 0 && h == MH - 1) YX_TRACE(4, t);
+        named_bar_sync(2, n_epi);
+        if (lead_warp) {
+          if (elect_one()) {
+            for (int g = 0; g < groups_cur; ++g)
+              tma_store_4d(&p.tmOut, sStage + g * kTileBytes, tc.n0 + g * 64, tc.x0, yh, tc.img);
+            tma_store_commit();
+            if (h == MH - 1) YX_TRACE(5, t);
+          }
         }
-        named_bar_sync(1, 128);
       }
     }
-    if (leader) tma_store_wait_all0();
+    if (lead_warp) {
+      if (elect_one()) tma_store_wait_all0();
+    }
   }
 
   tc_fence_before();
@@ -563,7 +490,6 @@ static void choose_tile(int H, int W, int* th, int* tw) {
   for (int w = 1; w <= std::min(W, 128); ++w) {
     int h = std::min(H, 128 / w);
     if (h < 1) continue;
-    if (w > 256 || h > 256) continue;
     double tiles = (double)ceil_div(H, h) * ceil_div(W, w);
     double cost = tiles * 1000.0 + std::abs(h - w) * 0.01;
     if (cost < best) { best = cost; bh = h; bw = w; }
@@ -572,7 +498,13 @@ static void choose_tile(int H, int W, int* th, int* tw) {
   *tw = bw;
 }
 
-int conv_plan(const yx_op& op, void* base, const void* weights, const void* biases, int num_sms, ConvPlan* out) {
+struct ConvGeom {
+  bool rowpack, has_res;
+  int Hout, Wout, taps, cin_real;
+  double flops, act_bytes;
+};
+
+static int conv_geom(const yx_op& op, ConvGeom* g) {
   const yx_view& s = op.src;
   const yx_view& d = op.dst;
   YX_REQUIRE(op.ksize == 1 || op.ksize == 3, "conv ksize must be 1 or 3");
@@ -588,138 +520,237 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
   // the right (the s2d output).  TMA reads it through an OVERLAPPING view (64 channels per pixel, pixel pitch 16),
   // so the 128-byte smem row of pixel x holds pixels x-1..x+2 = the three horizontal taps (+1 ignored): the
   // conv becomes 3 vertical taps with K = 48 instead of 9 taps with K = 16, and every TMA row is a full line.
-  const bool rowpack = op.aux == 1;
-  if (rowpack)
-    YX_REQUIRE(op.ksize == 3 && op.stride == 1 && s.c == 16 && s.pitch == 16 && op.cin_pad == 48 && s.w > 4 &&
-                   op.res.c == 0,
+  g->rowpack = op.aux == 1;
+  if (g->rowpack)
+    YX_REQUIRE(op.ksize == 3 && op.stride == 1 && s.c == 16 && s.pitch == 16 && op.cin_pad == 48 && s.w > 4 && op.res.c == 0,
                "row-packed conv needs k=3, s=1, a padded 16-channel source and cin_pad = 48");
   const int pad = op.ksize / 2;
-  const int Hout = rowpack ? s.h : (s.h + 2 * pad - op.ksize) / op.stride + 1;
-  const int Wout = rowpack ? s.w - 4 : (s.w + 2 * pad - op.ksize) / op.stride + 1;
-  YX_REQUIRE(d.h == Hout && d.w == Wout && d.n == s.n, "dst spatial dims do not match the conv geometry");
-  const bool has_res = op.res.c > 0;
-  if (has_res)
+  g->Hout = g->rowpack ? s.h : (s.h + 2 * pad - op.ksize) / op.stride + 1;
+  g->Wout = g->rowpack ? s.w - 4 : (s.w + 2 * pad - op.ksize) / op.stride + 1;
+  YX_REQUIRE(d.h == g->Hout && d.w == g->Wout && d.n == s.n, "dst spatial dims do not match the conv geometry");
+  g->has_res = op.res.c > 0;
+  if (g->has_res)
     YX_REQUIRE(op.res.h == d.h && op.res.w == d.w && op.res.c == d.c && op.res.n == d.n && op.res.pitch % 8 == 0 &&
                    op.res.offset % 16 == 0 && op.res.nstride % 8 == 0,
                "residual view must match dst");
+  g->taps = g->rowpack ? 3 : op.ksize * op.ksize;
+  g->cin_real = g->rowpack ? 12 : s.c;
+  const double px_out = (double)d.n * g->Hout * g->Wout;
+  g->flops = 2.0 * px_out * d.c * g->cin_real * op.ksize * op.ksize;
+  g->act_bytes = 2.0 * ((double)s.n * s.h * s.w * (g->rowpack ? 12 : s.c) + px_out * d.c * (g->has_res ? 2 : 1));
+  return YX_OK;
+}
+
+static bool halo_ok(const yx_op& op, const ConvGeom& g) {
+  if (!(op.ksize == 3 && op.stride == 1 && !g.rowpack && g.Hout >= 16 && g.Wout >= 8)) return false;
+  const double eff16 = (double)(ceil_div(g.Hout, 16) * 16) * (ceil_div(g.Wout, 8) * 8) / ((double)g.Hout * g.Wout);
+  return eff16 <= 1.25;
+}
+
+// The heuristic (untuned) launch shape.
+static ConvTune default_tune(const yx_op& op, const ConvGeom& g) {
+  static const int halo_env = getenv("YX_HALO") ? atoi(getenv("YX_HALO")) : 1;
+  ConvTune t;
+  memset(&t, 0, sizeof t);
+  const int cout16 = op.cout_pad;
+  const bool mem_bound = g.flops / g.act_bytes < mem_bound_ai();
+  t.epi_groups = 1;
+  t.stage_bufs = 2;
+  if (halo_env && halo_ok(op, g) && op.src.c <= 96) {
+    t.variant = 2;
+    t.bn = cout16 <= 256 ? cout16 : round_up(ceil_div(cout16, ceil_div(cout16, 256)), 64);
+    t.mh = (cout16 <= 128 && ceil_div(g.Hout, 32) * 32 <= 1.2 * ceil_div(g.Hout, 16) * 16) ? 2 : 1;
+    t.ctas = 1;
+    t.w3 = 2;
+    return t;
+  }
+  t.variant = 1;
+  if (mem_bound) {
+    t.bn = cout16 <= 128 ? cout16 : 128;
+    t.ctas = 2;
+  } else {
+    t.bn = cout16 <= 256 ? cout16 : round_up(ceil_div(cout16, ceil_div(cout16, 256)), 64);
+    t.ctas = 1;
+  }
+  t.w3 = 1;
+  return t;
+}
+
+void conv_candidates(const yx_op& op, std::vector<ConvTune>* out) {
+  out->clear();
+  ConvGeom g;
+  if (conv_geom(op, &g) != YX_OK) return;
+  out->push_back(default_tune(op, g));
+  const int cout16 = op.cout_pad;
+  std::vector<int> bns;
+  auto add_bn = [&](int b) {
+    if (b >= 16 && b <= 256 && b % 16 == 0 && b <= cout16 && (b % 64 == 0 || b == cout16) &&
+        std::find(bns.begin(), bns.end(), b) == bns.end())
+      bns.push_back(b);
+  };
+  add_bn(std::min(cout16, 256));
+  if (cout16 > 256) add_bn(round_up(ceil_div(cout16, ceil_div(cout16, 256)), 64));
+  if (cout16 > 128) add_bn(128);
+  if (cout16 > 192) add_bn(192);
+  if (cout16 > 64 && cout16 % 64 == 0 && cout16 <= 128) add_bn(64);
+  auto push = [&](ConvTune t) {
+    for (const ConvTune& o : *out)
+      if (memcmp(&o, &t, sizeof t) == 0) return;
+    out->push_back(t);
+  };
+  for (int bn : bns) {
+    for (int ctas = 1; ctas <= 2; ++ctas)
+      for (int eg = 1; eg <= 2; ++eg)
+        for (int sb = 2; sb >= 1; --sb) {
+          if (ctas == 2 && (bn > 128 || sb == 1 || eg == 2)) continue;  // 2 x 384 threads x ~90 regs exceed the register file
+          if (sb == 1 && bn < 128) continue;  // small tiles: the second staging buffer is cheap, keep it
+          ConvTune t;
+          memset(&t, 0, sizeof t);
+          t.variant = 1; t.bn = bn; t.ctas = ctas; t.epi_groups = eg; t.stage_bufs = sb; t.w3 = 1;
+          push(t);
+        }
+    if (halo_ok(op, g))
+      for (int mh = 1; mh <= 2; ++mh)
+        for (int eg = 1; eg <= 2; ++eg)
+          for (int sb = 2; sb >= 1; --sb) {
+            if (sb == 1 && bn < 128) continue;
+            if (mh == 2 && bn > 128) continue;  // 2 halves x 2 accumulators x BN columns must fit 512
+            ConvTune t;
+            memset(&t, 0, sizeof t);
+            t.variant = 2; t.bn = bn; t.ctas = 1; t.mh = mh; t.epi_groups = eg; t.stage_bufs = sb; t.w3 = 2;
+            push(t);
+          }
+  }
+}
+
+int conv_plan(const yx_op& op, void* base, const void* weights, const void* biases, int num_sms, const ConvTune* tune,
+              ConvPlan* out) {
+  const yx_view& s = op.src;
+  const yx_view& d = op.dst;
+  ConvGeom g;
+  int rc = conv_geom(op, &g);
+  if (rc != YX_OK) return rc;
+  const ConvTune t = tune ? *tune : default_tune(op, g);
+  const bool halo = t.variant == 2;
+  YX_REQUIRE(t.variant == 1 || t.variant == 2, "conv tune: variant must be 1 (generic) or 2 (halo)");
+  YX_REQUIRE(!halo || halo_ok(op, g), "conv tune: halo variant needs a 3x3 stride-1 conv on a map of at least 16x8");
+  YX_REQUIRE(t.bn >= 16 && t.bn <= 256 && t.bn % 16 == 0 && (t.bn % 64 == 0 || t.bn >= op.cout_pad),
+             "conv tune: N tile must be a multiple of 64 (or the whole padded Cout), at most 256");
+  YX_REQUIRE(t.ctas == 1 || t.ctas == 2, "conv tune: ctas per SM must be 1 or 2");
+  YX_REQUIRE(t.epi_groups == 1 || t.epi_groups == 2, "conv tune: epilogue groups must be 1 or 2");
+  YX_REQUIRE(op.cout_pad <= 4096, "cout too large");
 
   ConvPlan pl;
   memset(&pl, 0, sizeof pl);
+  pl.tune = t;
   ConvParams& p = pl.p;
-  p.ksize = op.ksize; p.stride = op.stride; p.act = op.act; p.has_res = has_res;
-  p.ky = op.ksize; p.kx = rowpack ? 1 : op.ksize;
-  p.pad_y = pad; p.pad_x = rowpack ? 0 : pad;
+  const int pad = op.ksize / 2;
+  p.ksize = op.ksize; p.stride = op.stride; p.act = op.act; p.has_res = g.has_res;
+  p.ky = op.ksize; p.kx = g.rowpack ? 1 : op.ksize;
+  p.pad_y = pad; p.pad_x = g.rowpack ? 0 : pad;
   p.cin = op.cin_pad;
   p.cout16 = op.cout_pad;
   p.k_chunks = ceil_div(p.cin, 64);
-  choose_tile(Hout, Wout, &p.TH, &p.TW);
-  p.tiles_h = ceil_div(Hout, p.TH);
-  p.tiles_w = ceil_div(Wout, p.TW);
-  p.n_tiles_m = d.n * p.tiles_h * p.tiles_w;
-  // Algorithmic work decides the launch shape.  Layers below the ridge (HBM-bound: all 1x1 convs at
-  // these channel counts, the 48/96-channel 3x3 convs) run TWO CTAs per SM with narrow N tiles so one
-  // CTA's epilogue / TMA-store latency hides behind the other's loads; tensor-bound layers keep one CTA
-  // per SM with the widest N tile (fewest re-reads of A) and the deepest smem pipeline.
-  const double px_out_ = (double)d.n * Hout * Wout;
-  const int cin_real = rowpack ? 12 : s.c;
-  const double flops_ = 2.0 * px_out_ * d.c * cin_real * op.ksize * op.ksize;
-  const double bytes_ = 2.0 * ((double)s.n * s.h * s.w * s.c + px_out_ * d.c * (has_res ? 2 : 1));
-  const bool mem_bound = flops_ / bytes_ < mem_bound_ai();
-  int ctas_per_sm = 1;
-  if (mem_bound) {
-    if (p.cout16 <= 128) {
-      p.BN = p.cout16;
-      p.n_tiles_n = 1;
-    } else {
-      p.BN = 128;
-      p.n_tiles_n = ceil_div(p.cout16, 128);
-    }
-    ctas_per_sm = 2;
-  } else if (p.cout16 <= 256) {
-    p.BN = p.cout16;
-    p.n_tiles_n = 1;
-  } else {
-    int nt = ceil_div(p.cout16, 256);
-    p.BN = round_up(ceil_div(p.cout16, nt), 64);
-    p.n_tiles_n = ceil_div(p.cout16, p.BN);
-  }
-  p.tmem_cols = 32;
-  while (p.tmem_cols < 2 * p.BN) p.tmem_cols <<= 1;
-  p.acc_stride = p.tmem_cols / 2;
+  p.BN = std::min(t.bn, p.cout16);
+  p.n_tiles_n = ceil_div(p.cout16, p.BN);
+  p.halo = halo ? 1 : 0;
+  p.epi_groups = t.epi_groups;
+  p.bias_bytes = round_up(p.cout16 * 4, 128);
   p.b_stage_bytes = p.BN * 128;
-  p.a_box_bytes = p.TH * p.TW * 128;
-  const int groups = ceil_div(p.BN, 64);
-  const int fixed = groups * kAStageBytes + kBarBytes + 1024;  // staging + barriers + alignment slack
-  const int budget = ctas_per_sm == 2 ? kSmemTwoCtas : kSmemLimit;
-  p.stages = std::min(kMaxStages, (budget - fixed) / (kAStageBytes + p.b_stage_bytes));
-  YX_REQUIRE(p.stages >= 2, "not enough shared memory for a 2-stage pipeline");
-  pl.smem_bytes = fixed + p.stages * (kAStageBytes + p.b_stage_bytes);
-  // never let a third CTA (which would stall in tcgen05.alloc) fit on an SM
-  if (ctas_per_sm == 2) pl.smem_bytes = std::max(pl.smem_bytes, 80 * 1024);
-  pl.grid = std::min(p.n_tiles_m * p.n_tiles_n, ctas_per_sm * num_sms);
   p.bias = reinterpret_cast<const float*>(static_cast<const uint8_t*>(biases) + op.b_offset);
+  const int taps = g.taps;
+  const int groups64 = ceil_div(p.BN, 64);
+  int stride_cols = 32;
+  while (stride_cols < p.BN) stride_cols <<= 1;
+  int budget = t.ctas == 2 ? kSmemTwoCtas : kSmemLimit;
 
-  // ---- halo-reuse shape for 3x3 / stride 1 (see conv3x3_halo_kernel) ------------------------------
-  // YX_HALO=0 disables it (2 = diagnostic: set the descriptor base_offset); YX_HALO_MH / YX_HALO_BN force the stacked halves / N tile for experiments.
-  static const int halo_env = getenv("YX_HALO") ? atoi(getenv("YX_HALO")) : 1;
-  static const int halo_mh_env = getenv("YX_HALO_MH") ? atoi(getenv("YX_HALO_MH")) : 0;
-  static const int halo_bn_env = getenv("YX_HALO_BN") ? atoi(getenv("YX_HALO_BN")) : 0;
-  p.halo = 0;
-  if (halo_env && op.ksize == 3 && op.stride == 1 && !rowpack && Hout >= 16 && Wout >= 8) {
-    const double eff16 = (double)(ceil_div(Hout, 16) * 16) * (ceil_div(Wout, 8) * 8) / ((double)Hout * Wout);
-    if (eff16 <= 1.25) {
-      int bn, mh;
-      if (p.cout16 <= 128) { bn = p.cout16; mh = 2; }
-      else if (p.cout16 % 128 == 0) { bn = 128; mh = 2; }
-      else if (p.cout16 <= 256) { bn = p.cout16; mh = 1; }
-      else { bn = round_up(ceil_div(p.cout16, ceil_div(p.cout16, 256)), 64); mh = 1; }
-      if (halo_bn_env > 0 && halo_bn_env % 16 == 0 && halo_bn_env <= 256 && (halo_bn_env % 64 == 0 || halo_bn_env >= p.cout16))
-        bn = std::min(halo_bn_env, p.cout16);
-      if (halo_mh_env == 1 || halo_mh_env == 2) mh = halo_mh_env;
-      int stride_cols = 32;
-      while (stride_cols < bn) stride_cols <<= 1;
-      if (2 * mh * stride_cols > 512) mh = 1;
-      const double eff32 = (double)(ceil_div(Hout, 32) * 32) / (ceil_div(Hout, 16) * 16);
-      if (mh == 2 && eff32 > 1.2) mh = 1;
-      p.halo = halo_env == 2 ? 2 : 1; p.mh = mh; p.BN = bn;
-      p.n_tiles_n = ceil_div(p.cout16, bn);
-      p.TH = 16 * mh; p.TW = 8;
-      p.tiles_h = ceil_div(Hout, p.TH);
-      p.tiles_w = ceil_div(Wout, 8);
-      p.n_tiles_m = d.n * p.tiles_h * p.tiles_w;
-      p.acc_stride = stride_cols;
-      p.tmem_cols = 2 * mh * stride_cols;
-      p.b_stage_bytes = bn * 128;
-      p.a_box_bytes = (p.TH + 2) * 10 * 128;
-      p.a_stage_bytes = round_up(p.a_box_bytes, 1024);
-      p.stages_a = 2;
-      const int hfixed = ceil_div(bn, 64) * kAStageBytes + kBarBytes + 1024 + p.stages_a * p.a_stage_bytes;
-      p.stages = std::min(kMaxStages, (kSmemLimit - hfixed) / p.b_stage_bytes);
-      YX_REQUIRE(p.stages >= 3, "halo conv: not enough shared memory for the weight ring");
-      pl.smem_bytes = hfixed + p.stages * p.b_stage_bytes;
-      pl.smem_bytes = std::max(pl.smem_bytes, 120 * 1024);  // one CTA per SM (it may own all 512 TMEM columns)
-      pl.grid = std::min(p.n_tiles_m * p.n_tiles_n, num_sms);
-    }
+  if (halo) {
+    int mh = t.mh == 2 ? 2 : 1;
+    if (2 * mh * stride_cols > 512) mh = 1;
+    p.mh = mh;
+    p.TH = 16 * mh; p.TW = 8;
+    p.a_box_bytes = (p.TH + 2) * kHaloW * 128;
+    p.a_stage_bytes = round_up(p.a_box_bytes, 1024);
+    p.out_box_bytes = kTileBytes;
+    p.acc_stride = stride_cols;
+    p.tmem_cols = 32;
+    while (p.tmem_cols < 2 * mh * stride_cols) p.tmem_cols <<= 1;
+  } else {
+    p.mh = 1;
+    choose_tile(g.Hout, g.Wout, &p.TH, &p.TW);
+    p.a_box_bytes = p.TH * p.TW * 128;
+    p.a_stage_bytes = kTileBytes;
+    p.out_box_bytes = p.a_box_bytes;
+    p.tmem_cols = 32;
+    while (p.tmem_cols < 2 * stride_cols) p.tmem_cols <<= 1;
+    p.acc_stride = p.tmem_cols / 2;
   }
+  YX_REQUIRE(t.ctas == 1 || p.tmem_cols <= 256, "conv tune: two CTAs per SM need <= 256 TMEM columns each");
+  p.tiles_h = ceil_div(g.Hout, p.TH);
+  p.tiles_w = ceil_div(g.Wout, p.TW);
+  p.n_tiles_m = d.n * p.tiles_h * p.tiles_w;
 
-  int rc;
-  if (p.halo) {
+  // ---- shared-memory budget: [A ring][B ring or resident B][staging x stage_bufs][bias][barriers] ----
+  p.stage_bufs = t.stage_bufs == 1 ? 1 : 2;
+  const int k_loads_b = taps * p.k_chunks;  // B tiles per output tile
+  for (;;) {
+    const int fixed = 1024 + kBarBytes + p.bias_bytes + p.stage_bufs * groups64 * kTileBytes;
+    const int avail = budget - fixed;
+    const int min_a = (halo ? 2 : 2) * p.a_stage_bytes;
+    const bool can_res = p.n_tiles_n == 1 && k_loads_b <= kMaxBRing && t.no_resident == 0 &&
+                         k_loads_b * p.b_stage_bytes + min_a <= avail;
+    if (can_res) {
+      p.b_resident = 1;
+      p.b_slots = k_loads_b;
+      p.stages_a = std::min(halo ? 3 : kMaxARing, (avail - k_loads_b * p.b_stage_bytes) / p.a_stage_bytes);
+    } else if (halo) {
+      p.b_resident = 0;
+      p.stages_a = (avail - 3 * p.a_stage_bytes >= 4 * p.b_stage_bytes) ? 3 : 2;
+      p.b_slots = std::min(12, (avail - p.stages_a * p.a_stage_bytes) / p.b_stage_bytes);
+    } else {
+      p.b_resident = 0;
+      const int st = std::min(kMaxARing, avail / (p.a_stage_bytes + p.b_stage_bytes));
+      p.stages_a = st;
+      p.b_slots = st;
+    }
+    const bool fits = p.stages_a >= 2 && p.b_slots >= (p.b_resident ? 1 : (halo ? 3 : 2));
+    if (fits) {
+      pl.smem_bytes = fixed + p.stages_a * p.a_stage_bytes + p.b_slots * p.b_stage_bytes;
+      break;
+    }
+    if (p.stage_bufs == 2) { p.stage_bufs = 1; continue; }
+    set_error("conv plan: launch shape does not fit in shared memory");
+    return YX_ERR_INVALID;
+  }
+  // never let an extra CTA (which would stall in tcgen05.alloc) fit on an SM
+  if (t.ctas == 2) pl.smem_bytes = std::max(pl.smem_bytes, 80 * 1024);
+  else if (p.tmem_cols > 256) pl.smem_bytes = std::max(pl.smem_bytes, 120 * 1024);
+  else pl.smem_bytes = std::max(pl.smem_bytes, 80 * 1024);
+  pl.grid = std::min(p.n_tiles_m * p.n_tiles_n, t.ctas * num_sms);
+  pl.threads = 128 + 128 * p.epi_groups;
+  // warp 3: second producer for the operand with more loads per tile (none when B is resident and A is one load)
+  const int a_loads = halo ? p.k_chunks : k_loads_b;
+  const int b_loads = p.b_resident ? 0 : k_loads_b;
+  p.w3_role = t.w3 == 0 ? 0 : (b_loads > a_loads ? 2 : 1);
+  if (p.w3_role == 1 && p.stages_a < 2) p.w3_role = 0;
+  if (p.w3_role == 2 && p.b_slots < 2) p.w3_role = 0;
+
+  if (halo) {
     uint64_t dims[4] = {(uint64_t)s.c, (uint64_t)s.w, (uint64_t)s.h, (uint64_t)s.n};
     uint64_t st[4] = {2, (uint64_t)s.pitch * 2, (uint64_t)s.pitch * 2 * s.w, (uint64_t)s.nstride * 2};
-    uint32_t box[4] = {64, 10, (uint32_t)(p.TH + 2), 1};
+    uint32_t box[4] = {64, (uint32_t)kHaloW, (uint32_t)(p.TH + 2), 1};
     if ((rc = encode_map(&p.tmA[0], static_cast<uint8_t*>(base) + s.offset, 4, dims, st, box, true, "A-halo")) != YX_OK)
       return rc;
     for (int i = 1; i < 4; ++i) p.tmA[i] = p.tmA[0];
-  } else if (rowpack) {
-    uint64_t dims[4] = {64, (uint64_t)Wout, (uint64_t)s.h, (uint64_t)s.n};
+  } else if (g.rowpack) {
+    uint64_t dims[4] = {64, (uint64_t)g.Wout, (uint64_t)s.h, (uint64_t)s.n};
     uint64_t st[4] = {2, 32, (uint64_t)s.w * 32, (uint64_t)s.nstride * 2};
     uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)p.TH, 1};
     if ((rc = encode_map(&p.tmA[0], static_cast<uint8_t*>(base) + s.offset, 4, dims, st, box, true, "A-rowpack")) != YX_OK)
       return rc;
     for (int i = 1; i < 4; ++i) p.tmA[i] = p.tmA[0];
   } else if (op.stride == 1) {
-    yx_view sv = s;
-    if ((rc = encode_view(&p.tmA[0], base, sv, p.TW, p.TH, "A")) != YX_OK) return rc;
+    if ((rc = encode_view(&p.tmA[0], base, s, p.TW, p.TH, "A")) != YX_OK) return rc;
     for (int i = 1; i < 4; ++i) p.tmA[i] = p.tmA[0];
   } else {
     for (int py = 0; py < 2; ++py)
@@ -734,7 +765,6 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
       }
   }
   {
-    const int taps = p.ky * p.kx;
     uint64_t dims[3] = {(uint64_t)op.cin_pad, (uint64_t)taps, (uint64_t)op.cout_pad};
     uint64_t st[3] = {2, (uint64_t)op.cin_pad * 2, (uint64_t)op.cin_pad * 2 * taps};
     uint32_t box[3] = {64, 1, (uint32_t)p.BN};
@@ -742,45 +772,39 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
     YX_REQUIRE(op.w_offset % 16 == 0, "weight offset must be 16-byte aligned");
     if ((rc = encode_map(&p.tmW, addr, 3, dims, st, box, true, "W")) != YX_OK) return rc;
   }
-  const int store_th = p.halo ? 16 : p.TH;  // the halo kernel stores one 16x8 half at a time
+  const int store_th = halo ? 16 : p.TH;  // the halo variant stores one 16x8 half at a time
   if ((rc = encode_view(&p.tmOut, base, d, p.TW, store_th, "out")) != YX_OK) return rc;
-  if (has_res) {
+  if (g.has_res) {
     if ((rc = encode_view(&p.tmRes, base, op.res, p.TW, store_th, "res")) != YX_OK) return rc;
   } else {
     p.tmRes = p.tmOut;
   }
-  const double px_out = (double)d.n * Hout * Wout;
-  pl.flops = 2.0 * px_out * d.c * cin_real * op.ksize * op.ksize;
-  pl.bytes = 2.0 * ((double)s.n * s.h * s.w * s.c + px_out * d.c * (has_res ? 2 : 1)) +
-             2.0 * (double)d.c * cin_real * op.ksize * op.ksize;
+  pl.flops = g.flops;
+  pl.bytes = g.act_bytes + 2.0 * (double)d.c * g.cin_real * op.ksize * op.ksize;
+  snprintf(pl.desc, sizeof pl.desc, "%s BN%d%s mh%d ctas%d epi%d sbuf%d A%dx%dK B%d%s w3:%d grid%d smem%dK", halo ? "halo" : "generic",
+           p.BN, p.n_tiles_n > 1 ? "*" : "", p.mh, t.ctas, p.epi_groups, p.stage_bufs, p.stages_a, p.a_stage_bytes >> 10, p.b_slots,
+           p.b_resident ? "res" : "", p.w3_role, pl.grid, pl.smem_bytes >> 10);
   *out = pl;
   return YX_OK;
 }
 
-template <int ACT, bool HAS_RES>
+template <int ACT, bool HAS_RES, bool HALO>
 static int launch_variant(const ConvPlan& plan, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    YX_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<ACT, HAS_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    YX_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<ACT, HAS_RES, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     attr_set = true;
   }
-  if (plan.p.halo) {
-    static bool halo_attr_set = false;
-    if (!halo_attr_set) {
-      YX_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<ACT, HAS_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-      halo_attr_set = true;
-    }
-    conv3x3_halo_kernel<ACT, HAS_RES><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.p);
-  } else {
-    conv_igemm_kernel<ACT, HAS_RES><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.p);
-  }
+  conv_gemm_kernel<ACT, HAS_RES, HALO><<<plan.grid, plan.threads, plan.smem_bytes, stream>>>(plan.p);
   YX_CUDA(cudaGetLastError());
   return YX_OK;
 }
 
 template <int ACT>
 static int launch_act(const ConvPlan& plan, cudaStream_t stream) {
-  return plan.p.has_res ? launch_variant<ACT, true>(plan, stream) : launch_variant<ACT, false>(plan, stream);
+  if (plan.p.halo)
+    return plan.p.has_res ? launch_variant<ACT, true, true>(plan, stream) : launch_variant<ACT, false, true>(plan, stream);
+  return plan.p.has_res ? launch_variant<ACT, true, false>(plan, stream) : launch_variant<ACT, false, false>(plan, stream);
 }
 
 int conv_launch(const ConvPlan& plan, cudaStream_t stream) {

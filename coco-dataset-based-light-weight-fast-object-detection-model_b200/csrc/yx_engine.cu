@@ -41,6 +41,7 @@ struct yx_engine {
   int num_sms = 148;
   cudaGraphExec_t graph_exec = nullptr;
   cudaStream_t graph_stream = nullptr;  // private stream used only to capture the graph
+  bool tuned = false;
 };
 
 using namespace yx;
@@ -108,7 +109,7 @@ extern "C" int yx_engine_create(const yx_op* ops, int n_ops, void* arena, size_t
         set_error(std::string(where) + "weight/bias range outside the blobs");
         rc = YX_ERR_INVALID;
       } else {
-        rc = conv_plan(op, arena, weights, biases, sms, &s.conv);
+        rc = conv_plan(op, arena, weights, biases, sms, nullptr, &s.conv);
         s.flops = s.conv.flops; s.bytes = s.conv.bytes;
         if (rc != YX_OK) set_error(std::string(where) + g_last_error);
       }
@@ -180,6 +181,75 @@ extern "C" int yx_engine_run_ops(yx_engine* e, const void* image, int image_dtyp
   return YX_OK;
 }
 
+
+// Per-layer launch-shape selection (the engine's cudnn.benchmark): runs the network ONCE in order on `image`, and for
+// every conv times each candidate shape (generic / halo, N tile, CTAs per SM, epilogue groups, staging buffers) on
+// the layer's real inputs, keeping the fastest.  All candidates compute the same function, so the arena holds a valid
+// forward result afterwards.  Host-synchronising; call it once after create (yx_engine_run works without it, with the
+// heuristic shapes).
+extern "C" int yx_engine_tune(yx_engine* e, const void* image, int image_dtype, float in_scale, float in_shift, int iters,
+                              void* stream) {
+  YX_REQUIRE(e && image && iters >= 1, "bad tune arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaEvent_t ev0, ev1;
+  YX_CUDA(cudaEventCreate(&ev0));
+  YX_CUDA(cudaEventCreate(&ev1));
+  int rc = YX_OK;
+  const bool verbose = getenv("YX_TUNE_VERBOSE") != nullptr;
+  std::vector<ConvTune> cands;
+  for (size_t i = 0; i < e->steps.size() && rc == YX_OK; ++i) {
+    Step& s = e->steps[i];
+    if (s.op.kind != YX_OP_CONV) {
+      rc = run_step(e, s, image, image_dtype, in_scale, in_shift, st);
+      continue;
+    }
+    conv_candidates(s.op, &cands);
+    float best_ms = 1e30f;
+    ConvPlan best = s.conv;
+    for (const ConvTune& t : cands) {
+      ConvPlan pl;
+      if (conv_plan(s.op, e->arena, e->weights, e->biases, e->num_sms, &t, &pl) != YX_OK) continue;  // shape does not fit
+      if ((rc = conv_launch(pl, st)) != YX_OK) break;  // warm-up (also sets the smem attribute)
+      float ms_min = 1e30f;
+      for (int k = 0; k < iters && rc == YX_OK; ++k) {
+        cudaEventRecord(ev0, st);
+        rc = conv_launch(pl, st);
+        cudaEventRecord(ev1, st);
+        if (cudaEventSynchronize(ev1) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "tune sync", __FILE__, __LINE__); break; }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev0, ev1);
+        ms_min = ms < ms_min ? ms : ms_min;
+      }
+      if (rc != YX_OK) break;
+      if (verbose) fprintf(stderr, "  tune op %zu  %-90s %.4f ms\n", i, pl.desc, ms_min);
+      if (ms_min < best_ms) { best_ms = ms_min; best = pl; }
+    }
+    if (rc != YX_OK) break;
+    s.conv = best;
+    if (verbose) fprintf(stderr, "tune op %zu -> %s  %.4f ms\n", i, best.desc, best_ms);
+    rc = conv_launch(s.conv, st);  // leave the chosen variant's output in the arena
+  }
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+  if (rc == YX_OK && e->graph_exec) {  // a graph captured with the old shapes is stale
+    cudaGraphExecDestroy(e->graph_exec);
+    e->graph_exec = nullptr;
+  }
+  if (rc == YX_OK) YX_CUDA(cudaStreamSynchronize(st));
+  e->tuned = rc == YX_OK;
+  return rc;
+}
+
+extern "C" int yx_engine_op_desc(const yx_engine* e, int i, char* buf_host, int buf_len) {
+  YX_REQUIRE(e && buf_host && buf_len > 0 && i >= 0 && i < (int)e->steps.size(), "bad op index");
+  const Step& s = e->steps[i];
+  static const char* kinds[] = {"conv", "s2d", "spp", "upsample", "dwconv"};
+  if (s.op.kind == YX_OP_CONV) snprintf(buf_host, buf_len, "conv k%d s%d %d->%d @%dx%d: %s", s.op.ksize, s.op.stride, s.op.src.c,
+                                        s.op.dst.c, s.op.dst.h, s.op.dst.w, s.conv.desc);
+  else snprintf(buf_host, buf_len, "%s", s.op.kind >= 0 && s.op.kind <= 4 ? kinds[s.op.kind] : "?");
+  return YX_OK;
+}
+
 extern "C" int yx_engine_profile(yx_engine* e, const void* image, int image_dtype, int iters, void* stream,
                                  float* ms_host, double* flops_host, double* bytes_host, int n_ops) {
   YX_REQUIRE(e && image && ms_host && n_ops == (int)e->steps.size() && iters >= 1, "bad profile arguments");
@@ -209,14 +279,22 @@ extern "C" int yx_engine_profile(yx_engine* e, const void* image, int image_dtyp
   return rc;
 }
 
-extern "C" int yx_conv2d(const yx_op* op, void* base, const void* weights, const void* biases, void* stream) {
+extern "C" int yx_conv2d_ex(const yx_op* op, void* base, const void* weights, const void* biases, const yx_conv_tune* tune,
+                            void* stream) {
   YX_REQUIRE(op && base && weights && biases, "null argument");
   YX_REQUIRE(op->kind == YX_OP_CONV, "yx_conv2d expects a YX_OP_CONV op");
   int dev = 0, sms = 148;
   YX_CUDA(cudaGetDevice(&dev));
   YX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   ConvPlan plan;
-  int rc = conv_plan(*op, base, weights, biases, sms, &plan);
+  ConvTune t;
+  if (tune) {
+    memset(&t, 0, sizeof t);
+    t.variant = tune->variant; t.bn = tune->n_tile; t.ctas = tune->ctas_per_sm; t.mh = tune->halves;
+    t.epi_groups = tune->epilogue_groups; t.stage_bufs = tune->staging_buffers; t.w3 = tune->second_producer;
+    t.no_resident = tune->no_resident_weights;
+  }
+  int rc = conv_plan(*op, base, weights, biases, sms, tune ? &t : nullptr, &plan);
   if (rc) return rc;
   if (getenv("YX_CONV_TRACE")) {  // diagnostics: print the per-tile timeline of CTA 0 (cycles)
     long long* d = nullptr;
@@ -224,19 +302,22 @@ extern "C" int yx_conv2d(const yx_op* op, void* base, const void* weights, const
     YX_CUDA(cudaMalloc(&d, sizeof h));
     YX_CUDA(cudaMemset(d, 0, sizeof h));
     plan.p.trace = d;
-    plan.p.noload = getenv("YX_CONV_NOLOAD") ? 1 : 0;
     rc = conv_launch(plan, static_cast<cudaStream_t>(stream));
     YX_CUDA(cudaDeviceSynchronize());
     YX_CUDA(cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost));
     cudaFree(d);
-    fprintf(stderr, "trace: grid %d smem %d stages %d BN %d TH %d TW %d tiles %d x %d  (cycles rel. to first event)\n"
-                    " tile  prod_done  mma_start  mma_commit  epi_tfull  epi_staged  store_issue  store_read\n",
-            plan.grid, plan.smem_bytes, plan.p.stages, plan.p.BN, plan.p.TH, plan.p.TW, plan.p.n_tiles_m, plan.p.n_tiles_n);
+    fprintf(stderr, "trace: %s TH %d TW %d tiles %d x %d  (cycles rel. to the first MMA)\n"
+                    " tile  prodA_done  mma_start  mma_commit  epi_tfull  epi_staged  store_issue\n",
+            plan.desc, plan.p.TH, plan.p.TW, plan.p.n_tiles_m, plan.p.n_tiles_n);
     long long t0 = h[1] ? h[1] : h[0];
-    for (int t = 0; t < 32 && (h[t * 8 + 3] || t == 0); ++t)
-      fprintf(stderr, " %4d %10lld %10lld %10lld %10lld %10lld %10lld %10lld\n", t, h[t * 8 + 0] - t0, h[t * 8 + 1] - t0,
-              h[t * 8 + 2] - t0, h[t * 8 + 3] - t0, h[t * 8 + 4] - t0, h[t * 8 + 5] - t0, h[t * 8 + 6] - t0);
+    for (int t2 = 0; t2 < 32 && (h[t2 * 8 + 3] || t2 == 0); ++t2)
+      fprintf(stderr, " %4d %10lld %10lld %10lld %10lld %10lld %10lld\n", t2, h[t2 * 8 + 0] - t0, h[t2 * 8 + 1] - t0,
+              h[t2 * 8 + 2] - t0, h[t2 * 8 + 3] - t0, h[t2 * 8 + 4] - t0, h[t2 * 8 + 5] - t0);
     return rc;
   }
   return conv_launch(plan, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int yx_conv2d(const yx_op* op, void* base, const void* weights, const void* biases, void* stream) {
+  return yx_conv2d_ex(op, base, weights, biases, nullptr, stream);
 }

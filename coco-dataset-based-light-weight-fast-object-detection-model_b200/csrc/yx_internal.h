@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <vector>
 
 #include "../../include/yolox_b200.h"
 
@@ -32,33 +33,52 @@ inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
 
 // ------------------------------------------------------------------ conv (yx_conv.cu)
 struct ConvParams {
-  CUtensorMap tmA[4];  // activation source(s): [0] for stride 1, [py*2+px] parity views for stride 2
-  CUtensorMap tmW;     // weights  (cin_pad, k*k, cout_pad), box (64, 1, BN)
-  CUtensorMap tmOut;   // output   (c, W, H, N),             box (64, TW, TH, 1)
+  CUtensorMap tmA[4];  // activation source(s): [0] for stride 1 / halo, [py*2+px] parity views for stride 2
+  CUtensorMap tmW;     // weights  (cin_pad, taps, cout_pad), box (64, 1, BN)
+  CUtensorMap tmOut;   // output   (c, W, H, N),             box (64, TW, TH or 16, 1)
   CUtensorMap tmRes;   // residual, same geometry as tmOut
   const float* bias;
   int ksize, stride, act, has_res;
-  int ky, kx, pad_y, pad_x;     // tap grid actually iterated (3x1 for the row-packed stem conv)
-  int TH, TW, tiles_h, tiles_w;  // spatial tiling of the output
+  int ky, kx, pad_y, pad_x;      // tap grid actually iterated (3x1 for the row-packed stem conv)
+  int TH, TW, tiles_h, tiles_w;  // spatial tiling of the output (halo: TH = 16*mh, TW = 8)
   int n_tiles_m, n_tiles_n, BN;
   int cin, cout16;
   int k_chunks;
-  int stages, b_stage_bytes, a_box_bytes;
-  int halo, mh, stages_a, a_stage_bytes;  // conv3x3_halo_kernel: stacked 128-pixel halves, halo ring
-  int tmem_cols, acc_stride;
-  int noload;                 // diagnostics: skip TMA loads after the ring is primed (results are garbage)
-  long long* trace;           // diagnostics: per-tile timeline of CTA 0 (nullptr = off)  // TMEM columns allocated (power of two) and offset of accumulator 1
+  int halo, mh;                  // halo variant: mh stacked 128-pixel halves per CTA
+  int stages_a, a_stage_bytes, a_box_bytes;  // A ring
+  int b_slots, b_stage_bytes, b_resident;    // B ring (or the whole weight tile, loaded once)
+  int stage_bufs, out_box_bytes, bias_bytes; // output staging buffers (1 or 2), bytes per 64-ch residual box
+  int epi_groups;                // epilogue warpgroups (1 or 2)
+  int w3_role;                   // warp 3: 0 idle, 1 second A producer, 2 second B producer
+  int tmem_cols, acc_stride;     // TMEM columns allocated (power of two) and columns per accumulator
+  long long* trace;              // diagnostics: per-tile timeline of CTA 0 (nullptr = off)
+};
+
+// Launch-shape knobs of one conv (chosen by default_tune() or by yx_engine_tune()).
+struct ConvTune {
+  int variant;      // 1 generic (one A box per tap), 2 halo (3x3/s1: one halo box per chunk, 9 descriptors)
+  int bn;           // N tile
+  int ctas;         // CTAs per SM (1 or 2)
+  int mh;           // halo: stacked halves (1 or 2)
+  int epi_groups;   // 1 or 2
+  int stage_bufs;   // 1 or 2
+  int w3;           // 0: no second producer warp, otherwise pick automatically
+  int no_resident;  // 1: never keep the weights resident (experiments)
 };
 
 struct ConvPlan {
   ConvParams p;
-  int grid;
+  ConvTune tune;
+  int grid, threads;
   int smem_bytes;
   double flops;  // algorithmic: 2*N*Hout*Wout*Cout*Cin*k*k (real channel counts)
   double bytes;  // algorithmic: fp16 in + out (+ residual) + weights
+  char desc[160];
 };
 
-int conv_plan(const yx_op& op, void* base, const void* weights, const void* biases, int num_sms, ConvPlan* out);
+int conv_plan(const yx_op& op, void* base, const void* weights, const void* biases, int num_sms, const ConvTune* tune,
+              ConvPlan* out);
+void conv_candidates(const yx_op& op, std::vector<ConvTune>* out);
 int conv_launch(const ConvPlan& plan, cudaStream_t stream);
 
 // ------------------------------------------------------------------ aux ops (yx_aux.cu)

@@ -9,6 +9,7 @@ The builder implements the fusions that need no kernel support:
   * reg_pred + obj_pred merged into one 1x1 conv writing a packed [B,A,8] tensor.
 Buffers get arena offsets from a liveness-based first-fit allocator.
 """
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
 
@@ -281,6 +282,9 @@ class Engine:
                                                   graph.in_h, graph.in_w, graph.batch, handle), "yx_engine_create")
             self.handle = handle
         self.n_launches = self.lib.yx_engine_num_launches(self.handle)
+        # per-layer launch shapes are picked by measurement on the first real input (like cudnn.benchmark);
+        # YX_TUNE=0 keeps the heuristic shapes
+        self.tuned = os.environ.get("YX_TUNE", "1") == "0"
 
     def tensor_of(self, buf: Buf):
         """fp16 torch view [n, h, w, c] of an arena buffer (no copy)."""
@@ -302,6 +306,11 @@ class Engine:
         else:
             raise RuntimeError(f"unsupported image dtype {image.dtype}")
         image = image.contiguous()
+        if not self.tuned:
+            self.tuned = True
+            _capi.check(self.lib.yx_engine_tune(self.handle, image.data_ptr(), dt, float(in_scale), float(in_shift),
+                                                int(os.environ.get("YX_TUNE_ITERS", "3")), _capi.current_stream_ptr()),
+                        "yx_engine_tune")
         _capi.check(self.lib.yx_engine_run(self.handle, image.data_ptr(), dt, float(in_scale), float(in_shift),
                                            int(use_graph), _capi.current_stream_ptr()), "yx_engine_run")
 
@@ -328,7 +337,14 @@ class Engine:
         dt = _capi.YX_F16 if image.dtype == torch.float16 else _capi.YX_F32
         _capi.check(self.lib.yx_engine_profile(self.handle, image.contiguous().data_ptr(), dt, iters,
                                                _capi.current_stream_ptr(), ms, fl, by, n), "yx_engine_profile")
-        return [dict(name=op.name, kind=op.kind, ms=ms[i], flops=fl[i], bytes=by[i]) for i, op in enumerate(self.graph.ops)]
+        return [dict(name=op.name, kind=op.kind, ms=ms[i], flops=fl[i], bytes=by[i], shape=self.op_desc(i))
+                for i, op in enumerate(self.graph.ops)]
+
+    def op_desc(self, i: int) -> str:
+        import ctypes
+        buf = ctypes.create_string_buffer(320)
+        _capi.check(self.lib.yx_engine_op_desc(self.handle, i, buf, 320), "yx_engine_op_desc")
+        return buf.value.decode()
 
     def __del__(self):
         try:

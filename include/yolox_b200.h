@@ -116,10 +116,34 @@ int yx_engine_profile(yx_engine* e, const void* image, int image_dtype, int iter
                       float* ms_host, double* flops_host, double* bytes_host, int n_ops);
 int yx_engine_num_launches(const yx_engine* e); /* kernels launched by one yx_engine_run */
 
+/* Per-layer launch-shape selection by measurement (the counterpart of torch.backends.cudnn.benchmark = True, which
+ * the reference sets in tools/eval.py:122).  Runs the network once on `image`, timing every candidate shape of every
+ * conv on its real inputs (min of `iters` CUDA-event timings) and keeping the fastest; the arena holds a valid forward
+ * result afterwards.  Host-synchronising setup call. */
+int yx_engine_tune(yx_engine* e, const void* image, int image_dtype, float in_scale, float in_shift, int iters,
+                   void* stream);
+/* Human-readable description of op i and of the launch shape chosen for it (diagnostics / profiles). */
+int yx_engine_op_desc(const yx_engine* e, int i, char* buf_host, int buf_len);
+
 /* ---- stand-alone operators (used by tests and by the reference-style Python functions) ---------- */
 
 /* One conv op outside an engine (same kernel the engine launches). Views are relative to `base`. */
 int yx_conv2d(const yx_op* op_host, void* base, const void* weights, const void* biases, void* stream);
+
+/* Launch-shape knobs of the conv kernel (see csrc/yx_conv.cu).  yx_engine_tune picks them per layer by timing;
+ * yx_conv2d_ex lets the parity tests force every shape.  A shape that does not fit the layer is YX_ERR_INVALID. */
+typedef struct yx_conv_tune {
+  int32_t variant;             /* 1 = one TMA box per filter tap, 2 = 3x3/stride-1 halo tile + nine descriptors */
+  int32_t n_tile;              /* output channels per tile: multiple of 64, or the whole padded Cout; <= 256 */
+  int32_t ctas_per_sm;         /* 1 or 2 */
+  int32_t halves;              /* variant 2: 128-pixel halves stacked per CTA (1 or 2) */
+  int32_t epilogue_groups;     /* 1 or 2 epilogue warpgroups */
+  int32_t staging_buffers;     /* 1 or 2 output staging buffers */
+  int32_t second_producer;     /* 0 = one TMA producer warp per operand, 1 = add a second one */
+  int32_t no_resident_weights; /* 1 = always stream the weights through the ring */
+} yx_conv_tune;
+int yx_conv2d_ex(const yx_op* op_host, void* base, const void* weights, const void* biases, const yx_conv_tune* tune_host,
+                 void* stream);
 
 /* ---- head decode / candidate selection / NMS --------------------------------------------------- */
 

@@ -18,9 +18,10 @@ def _rup(a, b):
 
 
 def run_conv_case(cin, cout, k, stride, H, W, B=2, act="silu", res=False, src_pitch=None, src_off=0,
-                  dst_pitch=None, dst_off=0, seed=0, dst_c=None, device="cuda"):
+                  dst_pitch=None, dst_off=0, seed=0, dst_c=None, device="cuda", tune=None):
     """Returns dict(max_err, ref_scale, out, ref).  src/dst may be channel slices of wider buffers
-    (pitch/off in channels).  dst_c: channels of the dst view (>= cout, e.g. 8 for the 5-channel reg+obj pred)."""
+    (pitch/off in channels).  dst_c: channels of the dst view (>= cout, e.g. 8 for the 5-channel reg+obj pred).
+    tune: dict of yx_conv_tune fields forcing one launch shape (None = the library's heuristic)."""
     lib = _capi.load()
     g = torch.Generator().manual_seed(seed)
     pad = k // 2
@@ -62,8 +63,13 @@ def run_conv_case(cin, cout, k, stride, H, W, B=2, act="silu", res=False, src_pi
         op.res.offset, op.res.nstride = sb + db + dst_off * 2, Ho * Wo * dst_pitch
         op.res.n, op.res.h, op.res.w, op.res.c, op.res.pitch = B, Ho, Wo, dst_c, dst_pitch
     op.w_offset, op.b_offset, op.cin_pad, op.cout_pad = 0, 0, cin_pad, cout_pad
-    _capi.check(lib.yx_conv2d(ctypes.byref(op), base, wd.data_ptr(), bd.data_ptr(),
-                              torch.cuda.current_stream().cuda_stream), "yx_conv2d")
+    if tune is None:
+        _capi.check(lib.yx_conv2d(ctypes.byref(op), base, wd.data_ptr(), bd.data_ptr(),
+                                  torch.cuda.current_stream().cuda_stream), "yx_conv2d")
+    else:
+        ct = _capi.ConvTune(**tune)
+        _capi.check(lib.yx_conv2d_ex(ctypes.byref(op), base, wd.data_ptr(), bd.data_ptr(), ctypes.byref(ct),
+                                     torch.cuda.current_stream().cuda_stream), "yx_conv2d_ex")
     torch.cuda.synchronize()
     out_full = region(sb, B * Ho * Wo * dst_pitch).view(B, Ho, Wo, dst_pitch).float().cpu()
     out = out_full[..., dst_off:dst_off + cout]
@@ -106,6 +112,34 @@ CASES = [
     dict(cin=1152, cout=864, k=1, stride=1, H=40, W=40, act="hard_swish", B=1),  # deep K, 4 N tiles
     dict(cin=576, cout=768, k=3, stride=2, H=40, W=40, act="hard_swish", B=1),
     dict(cin=192, cout=192, k=3, stride=1, H=160, W=160, act="hard_swish", B=2),  # many tiles per CTA
+]
+
+
+def _t(variant, n_tile, ctas=1, halves=1, eg=1, sb=2, w3=1, nores=0):
+    return dict(variant=variant, n_tile=n_tile, ctas_per_sm=ctas, halves=halves, epilogue_groups=eg, staging_buffers=sb,
+                second_producer=w3, no_resident_weights=nores)
+
+
+# every launch shape the tuner may pick, forced on layers it applies to
+TUNED_CASES = [
+    dict(cin=96, cout=96, k=1, stride=1, H=64, W=64, act="hard_swish", tune=_t(1, 96, ctas=2)),               # resident B, 2 CTAs/SM
+    dict(cin=96, cout=96, k=1, stride=1, H=64, W=64, act="hard_swish", tune=_t(1, 96, eg=2)),                  # 2 epilogue groups
+    dict(cin=96, cout=96, k=1, stride=1, H=64, W=64, act="hard_swish", tune=_t(1, 96, sb=1, w3=0, nores=1)),   # streamed B, 1 staging buffer
+    dict(cin=96, cout=96, k=1, stride=1, H=64, W=64, act="hard_swish", res=True, tune=_t(1, 64, ctas=2)),      # 2 N tiles (64+32), residual
+    dict(cin=384, cout=384, k=1, stride=1, H=32, W=32, act="silu", tune=_t(1, 128, ctas=2)),                   # 3 N tiles, streamed
+    dict(cin=384, cout=384, k=1, stride=1, H=32, W=32, act="silu", tune=_t(1, 192, eg=2, sb=1)),
+    dict(cin=48, cout=48, k=3, stride=1, H=64, W=64, act="hard_swish", res=True, tune=_t(2, 48, halves=2)),    # halo, resident B
+    dict(cin=48, cout=48, k=3, stride=1, H=64, W=64, act="hard_swish", res=True, tune=_t(2, 48, halves=1, eg=2)),
+    dict(cin=48, cout=48, k=3, stride=1, H=64, W=64, act="hard_swish", res=True, tune=_t(1, 48, ctas=2)),      # generic 3x3, resident B
+    dict(cin=96, cout=96, k=3, stride=1, H=48, W=40, act="hard_swish", res=True, tune=_t(2, 96, halves=2)),
+    dict(cin=192, cout=192, k=3, stride=1, H=80, W=80, act="hard_swish", tune=_t(2, 192, halves=1)),
+    dict(cin=192, cout=192, k=3, stride=1, H=80, W=80, act="hard_swish", tune=_t(2, 128, halves=2, eg=2)),     # N tiles 128+64
+    dict(cin=192, cout=192, k=3, stride=1, H=80, W=80, act="hard_swish", tune=_t(1, 192, eg=2)),
+    dict(cin=192, cout=384, k=3, stride=1, H=32, W=32, act="silu", tune=_t(2, 192, halves=1, sb=1)),
+    dict(cin=288, cout=288, k=3, stride=1, H=40, W=40, act="hard_swish", tune=_t(2, 192, halves=1)),  # N tiles 192 + 96
+    dict(cin=48, cout=96, k=3, stride=2, H=64, W=64, act="hard_swish", tune=_t(1, 96, ctas=2)),
+    dict(cin=48, cout=96, k=3, stride=2, H=64, W=64, act="hard_swish", tune=_t(1, 96, eg=2)),
+    dict(cin=96, cout=192, k=3, stride=2, H=64, W=64, act="hard_swish", tune=_t(1, 192, w3=0)),
 ]
 
 

@@ -4,7 +4,7 @@ O(1..8) values) after fp32 accumulation in a different order => abs 1.5e-2."""
 import pytest
 import torch
 
-from tests.conv_util import CASES, run_conv_case, tolerance
+from tests.conv_util import CASES, TUNED_CASES, run_conv_case, tolerance
 
 pytestmark = pytest.mark.gpu
 
@@ -20,6 +20,28 @@ def test_conv_matches_torch(case):
     assert r["max_err"] <= tolerance(case), r["max_err"]
     assert not r["clobbered"], "conv wrote outside its channel slice"
     assert not r["pad_nonzero"], "padded output channels must be zero"
+
+
+def _tid(c):
+    t = c["tune"]
+    return _id(c) + f"_v{t['variant']}bn{t['n_tile']}c{t['ctas_per_sm']}h{t['halves']}e{t['epilogue_groups']}s{t['staging_buffers']}" + \
+        ("_nores" if t["no_resident_weights"] else "")
+
+
+@pytest.mark.parametrize("case", TUNED_CASES, ids=[_tid(c) for c in TUNED_CASES])
+def test_conv_forced_launch_shapes(case):
+    """Every launch shape yx_engine_tune may choose (generic / halo, N tile, CTAs per SM, epilogue groups, staging
+    buffers, resident or streamed weights) computes the same function."""
+    r = run_conv_case(B=3, **case)
+    assert r["max_err"] <= tolerance(case), r["max_err"]
+    assert not r["clobbered"]
+
+
+def test_conv_rejects_unfit_shape():
+    import ctypes
+    from tests.conv_util import _t
+    with pytest.raises(RuntimeError, match="halo"):
+        run_conv_case(cin=64, cout=64, k=1, stride=1, H=16, W=16, tune=_t(2, 64))
 
 
 def test_conv_rejects_bad_geometry():
