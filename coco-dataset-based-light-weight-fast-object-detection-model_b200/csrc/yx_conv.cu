@@ -129,23 +129,124 @@ __device__ __forceinline__ void epilogue_convert(uint32_t taddr, int bn_cur, int
     if (p.trace != nullptr && blockIdx.x == 0 && (tl) < 32) p.trace[(tl) * 8 + (ev)] = clock64(); \
   } while (0)
 
-struct TileCoord {
-  int img, y0, x0, n0;
+// mbarrier wait that, in trace mode, also accumulates the cycles this role spent blocked (who is the bottleneck?)
+__device__ __forceinline__ void mbar_wait_acc(uint32_t bar, uint32_t parity, bool tracing, long long& acc) {
+  if (tracing) {
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    acc += clock64() - t0;
+  } else {
+    mbar_wait(bar, parity);
+  }
+}
+// trace[256 + slot]: blocked cycles per role of CTA 0
+enum { TW_APROD_EMPTY = 0, TW_BPROD_EMPTY = 1, TW_MMA_FULLA = 2, TW_MMA_FULLB = 3, TW_MMA_TEMPTY = 4, TW_EPI_TFULL = 5,
+       TW_EPI_STAGE = 6, TW_TOTAL = 7 };
+#define YX_TRACE_SUM(slot, v)                                                              \
+  do {                                                                                     \
+    if (tracing && blockIdx.x == 0 && lane == 0) p.trace[256 + (slot)] = (v);              \
+  } while (0)
+
+// Tile index = ((img * tiles_h + ty) * tiles_w + tx) * n_tiles_n + nt.  Each role walks tiles blockIdx.x, +gridDim.x, ...;
+// the coordinates are kept as mixed-radix digits and advanced by the (host-decomposed) step with carries, because the
+// three runtime integer divisions of a plain decode cost ~450 cycles of dependent latency per tile in EVERY role.
+struct TileIter {
+  int nt, tx, ty, img;
+  __device__ __forceinline__ void init(const ConvParams& p, int tile) {
+    nt = tile % p.n_tiles_n;
+    int r = tile / p.n_tiles_n;
+    tx = r % p.tiles_w; r /= p.tiles_w;
+    ty = r % p.tiles_h;
+    img = r / p.tiles_h;
+  }
+  __device__ __forceinline__ void next(int n_tiles_n, int tiles_w, int tiles_h, int s_nt, int s_x, int s_y, int s_img) {
+    nt += s_nt;
+    int c = nt >= n_tiles_n ? 1 : 0;
+    nt -= c ? n_tiles_n : 0;
+    tx += s_x + c;
+    c = tx >= tiles_w ? 1 : 0;
+    tx -= c ? tiles_w : 0;
+    ty += s_y + c;
+    c = ty >= tiles_h ? 1 : 0;
+    ty -= c ? tiles_h : 0;
+    img += s_img + c;
+  }
 };
-__device__ __forceinline__ TileCoord tile_coord(const ConvParams& p, int tile) {
-  const int nt = tile % p.n_tiles_n, mt = tile / p.n_tiles_n;
-  const int tiles_per_img = p.tiles_h * p.tiles_w;
-  const int img = mt / tiles_per_img, r = mt % tiles_per_img;
-  TileCoord c;
-  c.img = img;
-  c.y0 = (r / p.tiles_w) * p.TH;
-  c.x0 = (r % p.tiles_w) * p.TW;
-  c.n0 = nt * p.BN;
-  return c;
+#define YX_TILE_NEXT(it) (it).next(n_tiles_n, tiles_w, tiles_h, p.step_nt, p.step_x, p.step_y, p.step_img)
+
+// ---- MMA issue helpers.  Everything here runs in the single MMA warp, warp-uniformly; the tensor pipe can only be as
+// busy as this warp is fast (ncu: with ~85 SASS instructions per tap the warp, not the tensor core, was the limiter
+// of every layer with N <= 192), so the tap sequence is fully unrolled and all loop state lives in locals.
+template <int MH, bool RING>
+__device__ __forceinline__ void halo_chunk_mma(uint32_t d0, uint32_t d1, uint32_t a0, uint32_t a_hi, uint32_t& b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t& accum, int ksteps, uint32_t bar_fb, uint32_t bar_eb,
+                                               uint32_t& sb, uint32_t& phb, uint32_t b_slots, uint32_t b_lo0, uint32_t b_step,
+                                               bool wait_b, bool tracing, long long& w_acc, bool skip_mma) {
+  if (!RING && !wait_b) {
+    // resident weights already in shared memory: nothing to wait for inside the chunk, so the whole 9-tap sequence
+    // is ONE elected straight-line block (no per-tap elect / branch / reconvergence)
+    if (elect_one() && !skip_mma) {
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const uint32_t a_tap = a0 + ((tap / 3) * kHaloW + (tap % 3)) * 8;
+        const uint32_t b_tap = b_lo + tap * b_step;
+        if (ksteps == 4) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            umma_f16_ss_lohi(d0, a_tap + 2 * ks, a_hi, b_tap + 2 * ks, b_hi, idesc, (tap | ks) == 0 ? accum : 1u);
+            if (MH == 2) umma_f16_ss_lohi(d1, a_tap + 16 * kHaloW * 8 + 2 * ks, a_hi, b_tap + 2 * ks, b_hi, idesc, (tap | ks) == 0 ? accum : 1u);
+          }
+        } else {
+#pragma unroll
+          for (int ks = 0; ks < 3; ++ks)
+            if (ks < ksteps) {
+              umma_f16_ss_lohi(d0, a_tap + 2 * ks, a_hi, b_tap + 2 * ks, b_hi, idesc, (tap | ks) == 0 ? accum : 1u);
+              if (MH == 2) umma_f16_ss_lohi(d1, a_tap + 16 * kHaloW * 8 + 2 * ks, a_hi, b_tap + 2 * ks, b_hi, idesc, (tap | ks) == 0 ? accum : 1u);
+            }
+        }
+      }
+    }
+    accum = 1;
+    b_lo += 9 * b_step;
+    return;
+  }
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    // tap (dy,dx) of half h starts (16h + dy) halo rows down and dx pixels right: rows are 128 B = 8 descriptor units
+    const uint32_t a_tap = a0 + ((tap / 3) * kHaloW + (tap % 3)) * 8;
+    if (wait_b) {
+      mbar_wait_acc(bar_fb + 8 * sb, phb, tracing, w_acc);
+      tc_fence_after();
+    }
+    if (elect_one()) {
+      if (skip_mma) {
+      } else if (ksteps == 4) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          umma_f16_ss_lohi(d0, a_tap + 2 * ks, a_hi, b_lo + 2 * ks, b_hi, idesc, ks == 0 ? accum : 1u);
+          if (MH == 2) umma_f16_ss_lohi(d1, a_tap + 16 * kHaloW * 8 + 2 * ks, a_hi, b_lo + 2 * ks, b_hi, idesc, ks == 0 ? accum : 1u);
+        }
+      } else {
+        for (int ks = 0; ks < ksteps; ++ks) {
+          umma_f16_ss_lohi(d0, a_tap + 2 * ks, a_hi, b_lo + 2 * ks, b_hi, idesc, ks == 0 ? accum : 1u);
+          if (MH == 2) umma_f16_ss_lohi(d1, a_tap + 16 * kHaloW * 8 + 2 * ks, a_hi, b_lo + 2 * ks, b_hi, idesc, ks == 0 ? accum : 1u);
+        }
+      }
+      if (RING) umma_commit(bar_eb + 8 * sb);
+    }
+    accum = 1;
+    b_lo += b_step;
+    if (RING) {
+      if (++sb == b_slots) { sb = 0; phb ^= 1; b_lo = b_lo0; }
+    }
+  }
 }
 
-template <int ACT, bool HAS_RES, bool HALO>
+// MODE: 0 = generic (one A box per tap), 1 = halo with one 128-pixel half per CTA, 2 = halo with two stacked halves
+template <int ACT, bool HAS_RES, int MODE>
 __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant__ ConvParams p) {
+  constexpr bool HALO = MODE > 0;
+  constexpr int MH = MODE == 2 ? 2 : 1;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // tells ptxas the warp index is warp-uniform
@@ -158,8 +259,11 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
   const uint32_t stage_buf_bytes = groups64 * kTileBytes;
   const uint32_t sBias = sStage0 + p.stage_bufs * stage_buf_bytes;
   const uint32_t sBar = sBias + p.bias_bytes;
-  // barriers (8 bytes each): fullA[8] emptyA[8] fullB[32] emptyB[32] tfull[2] tempty[2] res[2], then the TMEM slot
-  const uint32_t bar_fa = sBar, bar_ea = sBar + 64, bar_fb = sBar + 128, bar_eb = sBar + 384;
+  // barriers (8 bytes each): fullA[8] emptyA[8] fullB[32] emptyB[32] tfull[2] tempty[2] res[2], then the TMEM slot.
+  // shared_ring (generic, streamed weights): A and B of a k-iteration share fullA/emptyA (two producer arrivals), so
+  // the MMA warp waits and commits once per k-iteration.
+  const uint32_t bar_fa = sBar, bar_ea = sBar + 64;
+  const uint32_t bar_fb = p.shared_ring ? bar_fa : sBar + 128, bar_eb = p.shared_ring ? bar_ea : sBar + 384;
   const uint32_t bar_tfull = sBar + 640, bar_tempty = sBar + 656, bar_res = sBar + 672, tmem_slot = sBar + 688;
 
   if (warp == 0 && lane == 0) {
@@ -168,8 +272,9 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
     tma_prefetch_desc(&p.tmOut);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < p.stages_a; ++s) { mbar_init(bar_fa + 8 * s, 1); mbar_init(bar_ea + 8 * s, 1); }
-    for (int s = 0; s < p.b_slots; ++s) { mbar_init(bar_fb + 8 * s, 1); mbar_init(bar_eb + 8 * s, 1); }
+    for (int s = 0; s < p.stages_a; ++s) { mbar_init(bar_fa + 8 * s, p.shared_ring ? 2 : 1); mbar_init(bar_ea + 8 * s, 1); }
+    if (!p.shared_ring)
+      for (int s = 0; s < p.b_slots; ++s) { mbar_init(bar_fb + 8 * s, 1); mbar_init(bar_eb + 8 * s, 1); }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
       mbar_init(bar_tempty + 8 * a, 4 * p.epi_groups);  // one arrive per epilogue warp
@@ -189,9 +294,16 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   const int n_tiles = p.n_tiles_m * p.n_tiles_n;
+  const int tile_step = gridDim.x;
+  const int n_tiles_n = p.n_tiles_n, tiles_w = p.tiles_w, tiles_h = p.tiles_h;
   const int taps = p.ky * p.kx;
-  const int MH = HALO ? p.mh : 1;
+  const int k_chunks = p.k_chunks;
+  const uint32_t stages_a = p.stages_a, b_slots = p.b_slots;
+  const bool resident = p.b_resident != 0;
 
+  const bool tracing = p.trace != nullptr;
+  long long w_acc0 = 0, w_acc1 = 0, w_acc2 = 0;
+  const long long t_begin = tracing ? clock64() : 0;
   const bool is_a_prod = (warp == 0) || (warp == 3 && p.w3_role == 1);
   const bool is_b_prod = (warp == 2) || (warp == 3 && p.w3_role == 2);
 
@@ -201,154 +313,176 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
   if (is_a_prod) {
     // ================================ A producer(s) ================================
     const uint32_t nprod = p.w3_role == 1 ? 2u : 1u, mine = warp == 0 ? 0u : 1u;
+    const uint32_t a_stage_bytes = p.a_stage_bytes, a_box_bytes = p.a_box_bytes;
     uint32_t s = 0, ph = 0, turn = 0;  // ring slot / phase / whose turn, all incremental
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const TileCoord tc = tile_coord(p, tile);
+    const int TH = p.TH, TW = p.TW;
+    TileIter ti;
+    ti.init(p, blockIdx.x);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += tile_step) {
+      const int x0 = ti.tx * TW, y0 = ti.ty * TH, img = ti.img;
+      YX_TILE_NEXT(ti);
       if (HALO) {
-        for (int kc = 0; kc < p.k_chunks; ++kc) {
+        for (int kc = 0; kc < k_chunks; ++kc) {
           if (turn == mine) {
-            mbar_wait(bar_ea + 8 * s, ph ^ 1);
+            mbar_wait_acc(bar_ea + 8 * s, ph ^ 1, tracing, w_acc0);
             if (elect_one()) {
-              mbar_expect_tx(bar_fa + 8 * s, p.a_box_bytes);
-              tma_load_4d(sA + s * p.a_stage_bytes, &p.tmA[0], bar_fa + 8 * s, kc * 64, tc.x0 - 1, tc.y0 - 1, tc.img);
+              if (p.diag & 2) {
+                mbar_arrive(bar_fa + 8 * s);
+              } else {
+                mbar_expect_tx(bar_fa + 8 * s, a_box_bytes);
+                tma_load_4d(sA + s * a_stage_bytes, &p.tmA[0], bar_fa + 8 * s, kc * 64, x0 - 1, y0 - 1, img);
+              }
             }
           }
           if (++turn == nprod) turn = 0;
-          if (++s == (uint32_t)p.stages_a) { s = 0; ph ^= 1; }
+          if (++s == stages_a) { s = 0; ph ^= 1; }
         }
       } else {
+        const int stride = p.stride, kx = p.kx, pad_x = p.pad_x, pad_y = p.pad_y;
         int dy = 0, dx = 0;
         for (int tap = 0; tap < taps; ++tap) {
           int mi = 0, cx, cy;
-          if (p.stride == 1) {
-            cx = tc.x0 + dx - p.pad_x;
-            cy = tc.y0 + dy - p.pad_y;
+          if (stride == 1) {
+            cx = x0 + dx - pad_x;
+            cy = y0 + dy - pad_y;
           } else {
             // input row 2*y + dy - pad.  For k=3,pad=1: dy=0 -> odd row of cell y-1; dy=1 -> even row
             // of cell y; dy=2 -> odd row of cell y.  k=1 (pad 0): even row/col of cell y.
-            const int oy = dy - p.pad_y, ox = dx - p.pad_y;
+            const int oy = dy - pad_y, ox = dx - pad_y;
             const int py = oy & 1, px = ox & 1;
             mi = py * 2 + px;
-            cy = tc.y0 + ((oy - py) >> 1);
-            cx = tc.x0 + ((ox - px) >> 1);
+            cy = y0 + ((oy - py) >> 1);
+            cx = x0 + ((ox - px) >> 1);
           }
-          for (int kc = 0; kc < p.k_chunks; ++kc) {
+          for (int kc = 0; kc < k_chunks; ++kc) {
             if (turn == mine) {
-              mbar_wait(bar_ea + 8 * s, ph ^ 1);
+              mbar_wait_acc(bar_ea + 8 * s, ph ^ 1, tracing, w_acc0);
               if (elect_one()) {
-                mbar_expect_tx(bar_fa + 8 * s, p.a_box_bytes);
-                tma_load_4d(sA + s * p.a_stage_bytes, &p.tmA[mi], bar_fa + 8 * s, kc * 64, cx, cy, tc.img);
+                if (p.diag & 2) {
+                  mbar_arrive(bar_fa + 8 * s);
+                } else {
+                  mbar_expect_tx(bar_fa + 8 * s, a_box_bytes);
+                  tma_load_4d(sA + s * a_stage_bytes, &p.tmA[mi], bar_fa + 8 * s, kc * 64, cx, cy, img);
+                }
               }
             }
             if (++turn == nprod) turn = 0;
-            if (++s == (uint32_t)p.stages_a) { s = 0; ph ^= 1; }
+            if (++s == stages_a) { s = 0; ph ^= 1; }
           }
-          if (++dx == p.kx) { dx = 0; ++dy; }
+          if (++dx == kx) { dx = 0; ++dy; }
         }
       }
-      if (warp == 0 && lane == 0) YX_TRACE(0, (tile - (int)blockIdx.x) / (int)gridDim.x);
+      if (warp == 0 && lane == 0) YX_TRACE(0, (tile - (int)blockIdx.x) / tile_step);
     }
+    if (warp == 0) YX_TRACE_SUM(TW_APROD_EMPTY, w_acc0);
   } else if (is_b_prod) {
     // ================================ B (weight) producer(s) ================================
     const uint32_t nprod = p.w3_role == 2 ? 2u : 1u, mine = warp == 2 ? 0u : 1u;
+    const uint32_t b_stage_bytes = p.b_stage_bytes;
+    const int BN = p.BN;
     uint32_t s = 0, ph = 0, turn = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int n0 = (tile % p.n_tiles_n) * p.BN;
+    int nt = blockIdx.x % n_tiles_n;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += tile_step) {
+      const int n0 = nt * BN;
+      nt += p.step_nt;
+      if (nt >= n_tiles_n) nt -= n_tiles_n;
       // ring order must match the MMA issuer: halo = (chunk, tap), generic = (tap, chunk)
-      const int outer = HALO ? p.k_chunks : taps, inner = HALO ? taps : p.k_chunks;
+      const int outer = HALO ? k_chunks : taps, inner = HALO ? taps : k_chunks;
       for (int o = 0; o < outer; ++o)
         for (int i = 0; i < inner; ++i) {
           const int kc = HALO ? o : i, tap = HALO ? i : o;
           if (turn == mine) {
-            if (!p.b_resident) mbar_wait(bar_eb + 8 * s, ph ^ 1);
+            if (!resident) mbar_wait_acc(bar_eb + 8 * s, ph ^ 1, tracing, w_acc0);
             if (elect_one()) {
-              mbar_expect_tx(bar_fb + 8 * s, p.b_stage_bytes);
-              tma_load_3d(sB + s * p.b_stage_bytes, &p.tmW, bar_fb + 8 * s, kc * 64, tap, n0);
+              mbar_expect_tx(bar_fb + 8 * s, b_stage_bytes);
+              tma_load_3d(sB + s * b_stage_bytes, &p.tmW, bar_fb + 8 * s, kc * 64, tap, n0);
             }
           }
           if (++turn == nprod) turn = 0;
-          if (++s == (uint32_t)p.b_slots) { s = 0; ph ^= 1; }
+          if (++s == b_slots) { s = 0; ph ^= 1; }
         }
-      if (p.b_resident) break;  // one N tile per layer: the weights stay in smem for every later tile
+      if (resident) break;  // one N tile per layer: the weights stay in smem for every later tile
     }
+    if (warp == 2) YX_TRACE_SUM(TW_BPROD_EMPTY, w_acc0);
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    // The whole tensor pipe is fed by this warp: everything per iteration is incremental 32-bit uniform math.
     uint32_t t = 0, sa = 0, pha = 0, sb = 0, phb = 0;
     const uint32_t a_hi = sdesc_hi(HALO ? kHaloW * 128 : 1024), b_hi = sdesc_hi(1024);
+    const uint32_t a_lo0 = sdesc_lo(sA), a_step = p.a_stage_bytes >> 4;
     const uint32_t b_lo0 = sdesc_lo(sB), b_step = p.b_stage_bytes >> 4;
-    uint32_t b_lo = b_lo0;
-    const int ks_last = (p.cin - (p.k_chunks - 1) * 64) >> 4;
+    uint32_t a_lo = a_lo0, b_lo = b_lo0;
+    const int ks_last = (p.cin - (k_chunks - 1) * 64) >> 4;
+    const int BN = p.BN, cout16 = p.cout16;
+    const uint32_t acc_stride = p.acc_stride;
+    const bool shared_ring = p.shared_ring != 0;
     bool b_ready = false;  // resident weights: wait for them during the first tile only
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
-      const int n0 = (tile % p.n_tiles_n) * p.BN;
-      const int bn_cur = min(p.BN, p.cout16 - n0);
+    int nt = blockIdx.x % n_tiles_n;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += tile_step, ++t) {
+      const int n0 = nt * BN;
+      nt += p.step_nt;
+      if (nt >= n_tiles_n) nt -= n_tiles_n;
+      const int bn_cur = min(BN, cout16 - n0);
       const uint32_t idesc = make_idesc_f16(bn_cur);
       const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
-      mbar_wait(bar_tempty + 8 * acc, acc_ph ^ 1);
+      mbar_wait_acc(bar_tempty + 8 * acc, acc_ph ^ 1, tracing, w_acc2);
       tc_fence_after();
       if (lane == 0) YX_TRACE(1, t);
-      const uint32_t d0 = tmem_base + (acc * MH) * p.acc_stride, d1 = d0 + p.acc_stride;
+      const uint32_t d0 = tmem_base + (acc * MH) * acc_stride, d1 = d0 + acc_stride;
       uint32_t accum = 0;
-      if (p.b_resident) { sb = 0; b_lo = b_lo0; }
+      if (resident) { sb = 0; b_lo = b_lo0; }
       if (HALO) {
-        for (int kc = 0; kc < p.k_chunks; ++kc) {
-          mbar_wait(bar_fa + 8 * sa, pha);
-          const int ksteps = (kc == p.k_chunks - 1) ? ks_last : 4;
-          // tap (dy,dx) of half h starts (16h + dy) halo rows down and dx pixels right: rows are 128 B = 8 units
-          uint32_t a_tap = sdesc_lo(sA + sa * p.a_stage_bytes);
-          for (int dy = 0; dy < 3; ++dy, a_tap += (kHaloW - 3) * 8) {
-            for (int dx = 0; dx < 3; ++dx, a_tap += 8) {
-              if (!b_ready) mbar_wait(bar_fb + 8 * sb, phb);
-              tc_fence_after();
-              if (elect_one()) {
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                  if (ks < ksteps) {
-                    umma_f16_ss_lohi(d0, a_tap + 2 * ks, a_hi, b_lo + 2 * ks, b_hi, idesc, accum | (ks > 0));
-                    if (MH == 2)
-                      umma_f16_ss_lohi(d1, a_tap + 16 * kHaloW * 8 + 2 * ks, a_hi, b_lo + 2 * ks, b_hi, idesc, accum | (ks > 0));
-                  }
-                if (!p.b_resident) umma_commit(bar_eb + 8 * sb);
-              }
-              accum = 1;
-              b_lo += b_step;
-              if (++sb == (uint32_t)p.b_slots) { sb = 0; phb ^= 1; b_lo = b_lo0; }
-            }
-          }
+        for (int kc = 0; kc < k_chunks; ++kc) {
+          mbar_wait_acc(bar_fa + 8 * sa, pha, tracing, w_acc0);
+          tc_fence_after();
+          const int ksteps = (kc == k_chunks - 1) ? ks_last : 4;
+          if (resident)
+            halo_chunk_mma<MH, false>(d0, d1, a_lo, a_hi, b_lo, b_hi, idesc, accum, ksteps, bar_fb, bar_eb, sb, phb, b_slots, b_lo0,
+                                      b_step, !b_ready, tracing, w_acc1, (p.diag & 4) != 0);
+          else
+            halo_chunk_mma<MH, true>(d0, d1, a_lo, a_hi, b_lo, b_hi, idesc, accum, ksteps, bar_fb, bar_eb, sb, phb, b_slots, b_lo0,
+                                     b_step, true, tracing, w_acc1, (p.diag & 4) != 0);
           if (elect_one()) umma_commit(bar_ea + 8 * sa);
-          if (++sa == (uint32_t)p.stages_a) { sa = 0; pha ^= 1; }
+          a_lo += a_step;
+          if (++sa == stages_a) { sa = 0; pha ^= 1; a_lo = a_lo0; }
         }
       } else {
-        const uint32_t a_lo0 = sdesc_lo(sA), a_step = p.a_stage_bytes >> 4;
-        const int k_iters = taps * p.k_chunks;
+        const int k_iters = taps * k_chunks;
         int kc = 0;
-        uint32_t a_lo = a_lo0 + sa * a_step;
         for (int i = 0; i < k_iters; ++i) {
-          mbar_wait(bar_fa + 8 * sa, pha);
-          if (!b_ready) mbar_wait(bar_fb + 8 * sb, phb);
+          mbar_wait_acc(bar_fa + 8 * sa, pha, tracing, w_acc0);   // shared ring: covers the weights of this k-iteration too
+          if (resident && !b_ready) mbar_wait_acc(bar_fb + 8 * sb, phb, tracing, w_acc1);
           tc_fence_after();
-          const int ksteps = (kc == p.k_chunks - 1) ? ks_last : 4;
+          const bool last = ++kc == k_chunks;
+          if (last) kc = 0;
           if (elect_one()) {
-            umma_f16_ss_lohi(d0, a_lo, a_hi, b_lo, b_hi, idesc, accum);
-            if (ksteps > 1) umma_f16_ss_lohi(d0, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
-            if (ksteps > 2) umma_f16_ss_lohi(d0, a_lo + 4, a_hi, b_lo + 4, b_hi, idesc, 1u);
-            if (ksteps > 3) umma_f16_ss_lohi(d0, a_lo + 6, a_hi, b_lo + 6, b_hi, idesc, 1u);
-            umma_commit(bar_ea + 8 * sa);  // frees the A stage when these MMAs retire
-            if (!p.b_resident) umma_commit(bar_eb + 8 * sb);
+            if (p.diag & 4) {
+            } else if (!last || ks_last == 4) {
+              umma_f16_ss_lohi(d0, a_lo, a_hi, b_lo, b_hi, idesc, accum);
+              umma_f16_ss_lohi(d0, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
+              umma_f16_ss_lohi(d0, a_lo + 4, a_hi, b_lo + 4, b_hi, idesc, 1u);
+              umma_f16_ss_lohi(d0, a_lo + 6, a_hi, b_lo + 6, b_hi, idesc, 1u);
+            } else {
+              umma_f16_ss_lohi(d0, a_lo, a_hi, b_lo, b_hi, idesc, accum);
+              if (ks_last > 1) umma_f16_ss_lohi(d0, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
+              if (ks_last > 2) umma_f16_ss_lohi(d0, a_lo + 4, a_hi, b_lo + 4, b_hi, idesc, 1u);
+            }
+            umma_commit(bar_ea + 8 * sa);  // frees the stage (A, and B when the ring is shared) when these MMAs retire
           }
           accum = 1;
           a_lo += a_step;
           b_lo += b_step;
-          if (++sa == (uint32_t)p.stages_a) { sa = 0; pha ^= 1; a_lo = a_lo0; }
-          if (++sb == (uint32_t)p.b_slots) { sb = 0; phb ^= 1; b_lo = b_lo0; }
-          if (++kc == p.k_chunks) kc = 0;
+          if (++sa == stages_a) { sa = 0; pha ^= 1; a_lo = a_lo0; if (shared_ring) b_lo = b_lo0; }
+          if (resident) ++sb;
         }
       }
-      if (p.b_resident) b_ready = true;
+      if (resident) b_ready = true;
       if (elect_one()) umma_commit(bar_tfull + 8 * acc);  // accumulator complete -> epilogue
       if (lane == 0) YX_TRACE(2, t);
     }
+    YX_TRACE_SUM(TW_MMA_FULLA, w_acc0);
+    YX_TRACE_SUM(TW_MMA_FULLB, w_acc1);
+    YX_TRACE_SUM(TW_MMA_TEMPTY, w_acc2);
+    YX_TRACE_SUM(TW_TOTAL, clock64() - t_begin);
   } else if (warp >= 4) {
     // ================================ epilogue (warps 4..7 [, 8..11]) ================================
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
@@ -356,26 +490,36 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
     const int row = q * 32 + lane;
     const bool row_valid = HALO ? true : (row < p.TH * p.TW);
     const bool lead_warp = warp == 4;  // issues the residual loads and the stores (one elected lane)
-    const uint32_t n_epi = 128u * p.epi_groups;
+    const int epi_groups = p.epi_groups, stage_bufs = p.stage_bufs;
+    const uint32_t n_epi = 128u * epi_groups;
     const int store_th = HALO ? 16 : p.TH;
+    const int BN = p.BN, cout16 = p.cout16;
+    const uint32_t acc_stride = p.acc_stride;
     uint32_t t = 0, u = 0;  // tile counter, staging-unit counter (MH units per tile)
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
-      const TileCoord tc = tile_coord(p, tile);
-      const int bn_cur = min(p.BN, p.cout16 - tc.n0);
+    const int TH = p.TH, TW = p.TW;
+    TileIter ti;
+    ti.init(p, blockIdx.x);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += tile_step, ++t) {
+      struct { int x0, y0, img, n0; } tc = {ti.tx * TW, ti.ty * TH, ti.img, ti.nt * BN};
+      YX_TILE_NEXT(ti);
+      const int bn_cur = min(BN, cout16 - tc.n0);
       const int groups_cur = (bn_cur + 63) >> 6;
       const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
+#pragma unroll
       for (int h = 0; h < MH; ++h, ++u) {
         const int yh = tc.y0 + store_th * h;
-        const uint32_t buf = p.stage_bufs == 2 ? (u & 1) : 0;
+        const uint32_t buf = stage_bufs == 2 ? (u & 1) : 0;
         const uint32_t sStage = sStage0 + buf * stage_buf_bytes;
         // staging buffer `buf` is free once the store issued stage_bufs units ago has read it
         // (elect.sync picks the same lane for the same mask every time, so the bulk-group state stays with one thread)
+        const long long ts0 = tracing ? clock64() : 0;
         if (lead_warp) {
           if (elect_one()) {
-            if (p.stage_bufs == 2) tma_store_wait_read1(); else tma_store_wait_read0();
+            if (stage_bufs == 2) tma_store_wait_read1(); else tma_store_wait_read0();
           }
         }
         named_bar_sync(1, n_epi);
+        if (tracing) w_acc1 += clock64() - ts0;
         if (HAS_RES && lead_warp) {
           if (elect_one()) {
             mbar_expect_tx(bar_res + 8 * buf, groups_cur * p.out_box_bytes);
@@ -384,13 +528,13 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
           }
         }
         if (h == 0) {
-          mbar_wait(bar_tfull + 8 * acc, acc_ph);
+          mbar_wait_acc(bar_tfull + 8 * acc, acc_ph, tracing, w_acc0);
           tc_fence_after();
           if (lead_warp && lane == 0) YX_TRACE(3, t);
         }
-        if (HAS_RES) mbar_wait(bar_res + 8 * buf, (p.stage_bufs == 2 ? (u >> 1) : u) & 1);
-        const uint32_t taddr = tmem_base + (acc * MH + h) * p.acc_stride + (static_cast<uint32_t>(q * 32) << 16);
-        epilogue_convert<ACT, HAS_RES>(taddr, bn_cur, row, row_valid, sStage, sBias + tc.n0 * 4, group, p.epi_groups);
+        if (HAS_RES) mbar_wait(bar_res + 8 * buf, (stage_bufs == 2 ? (u >> 1) : u) & 1);
+        const uint32_t taddr = tmem_base + (acc * MH + h) * acc_stride + (static_cast<uint32_t>(q * 32) << 16);
+        if (!(p.diag & 1)) epilogue_convert<ACT, HAS_RES>(taddr, bn_cur, row, row_valid, sStage, sBias + tc.n0 * 4, group, epi_groups);
         if (h == MH - 1) {  // accumulator drained -> MMA warp may overwrite it
           tc_fence_before();
           __syncwarp();
@@ -400,7 +544,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
         fence_proxy_async_smem();
         if (lead_warp && lane == 0 && h == MH - 1) YX_TRACE(4, t);
         named_bar_sync(2, n_epi);
-        if (lead_warp) {
+        if (lead_warp && !(p.diag & 1)) {
           if (elect_one()) {
             for (int g = 0; g < groups_cur; ++g)
               tma_store_4d(&p.tmOut, sStage + g * kTileBytes, tc.n0 + g * 64, tc.x0, yh, tc.img);
@@ -412,6 +556,8 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
     }
     if (lead_warp) {
       if (elect_one()) tma_store_wait_all0();
+      YX_TRACE_SUM(TW_EPI_TFULL, w_acc0);
+      YX_TRACE_SUM(TW_EPI_STAGE, w_acc1);
     }
   }
 
@@ -658,6 +804,8 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
   p.bias_bytes = round_up(p.cout16 * 4, 128);
   p.b_stage_bytes = p.BN * 128;
   p.bias = reinterpret_cast<const float*>(static_cast<const uint8_t*>(biases) + op.b_offset);
+  static const int diag_env = getenv("YX_CONV_DIAG") ? atoi(getenv("YX_CONV_DIAG")) : 0;  // experiments only (results are garbage)
+  p.diag = diag_env;
   const int taps = g.taps;
   const int groups64 = ceil_div(p.BN, 64);
   int stride_cols = 32;
@@ -713,6 +861,7 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
       p.stages_a = st;
       p.b_slots = st;
     }
+    p.shared_ring = (!halo && !p.b_resident) ? 1 : 0;
     const bool fits = p.stages_a >= 2 && p.b_slots >= (p.b_resident ? 1 : (halo ? 3 : 2));
     if (fits) {
       pl.smem_bytes = fixed + p.stages_a * p.a_stage_bytes + p.b_slots * p.b_stage_bytes;
@@ -727,6 +876,13 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
   else if (p.tmem_cols > 256) pl.smem_bytes = std::max(pl.smem_bytes, 120 * 1024);
   else pl.smem_bytes = std::max(pl.smem_bytes, 80 * 1024);
   pl.grid = std::min(p.n_tiles_m * p.n_tiles_n, t.ctas * num_sms);
+  {  // mixed-radix digits of the persistent-tile step (see TileIter)
+    int st = pl.grid;
+    p.step_nt = st % p.n_tiles_n; st /= p.n_tiles_n;
+    p.step_x = st % p.tiles_w; st /= p.tiles_w;
+    p.step_y = st % p.tiles_h;
+    p.step_img = st / p.tiles_h;
+  }
   pl.threads = 128 + 128 * p.epi_groups;
   // warp 3: second producer for the operand with more loads per tile (none when B is resident and A is one load)
   const int a_loads = halo ? p.k_chunks : k_loads_b;
@@ -788,23 +944,25 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
   return YX_OK;
 }
 
-template <int ACT, bool HAS_RES, bool HALO>
+template <int ACT, bool HAS_RES, int MODE>
 static int launch_variant(const ConvPlan& plan, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    YX_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<ACT, HAS_RES, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    YX_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<ACT, HAS_RES, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     attr_set = true;
   }
-  conv_gemm_kernel<ACT, HAS_RES, HALO><<<plan.grid, plan.threads, plan.smem_bytes, stream>>>(plan.p);
+  conv_gemm_kernel<ACT, HAS_RES, MODE><<<plan.grid, plan.threads, plan.smem_bytes, stream>>>(plan.p);
   YX_CUDA(cudaGetLastError());
   return YX_OK;
 }
 
 template <int ACT>
 static int launch_act(const ConvPlan& plan, cudaStream_t stream) {
+  if (plan.p.halo && plan.p.mh == 2)
+    return plan.p.has_res ? launch_variant<ACT, true, 2>(plan, stream) : launch_variant<ACT, false, 2>(plan, stream);
   if (plan.p.halo)
-    return plan.p.has_res ? launch_variant<ACT, true, true>(plan, stream) : launch_variant<ACT, false, true>(plan, stream);
-  return plan.p.has_res ? launch_variant<ACT, true, false>(plan, stream) : launch_variant<ACT, false, false>(plan, stream);
+    return plan.p.has_res ? launch_variant<ACT, true, 1>(plan, stream) : launch_variant<ACT, false, 1>(plan, stream);
+  return plan.p.has_res ? launch_variant<ACT, true, 0>(plan, stream) : launch_variant<ACT, false, 0>(plan, stream);
 }
 
 int conv_launch(const ConvPlan& plan, cudaStream_t stream) {

@@ -298,7 +298,7 @@ extern "C" int yx_conv2d_ex(const yx_op* op, void* base, const void* weights, co
   if (rc) return rc;
   if (getenv("YX_CONV_TRACE")) {  // diagnostics: print the per-tile timeline of CTA 0 (cycles)
     long long* d = nullptr;
-    long long h[32 * 8];
+    long long h[32 * 8 + 8];
     YX_CUDA(cudaMalloc(&d, sizeof h));
     YX_CUDA(cudaMemset(d, 0, sizeof h));
     plan.p.trace = d;
@@ -313,6 +313,12 @@ extern "C" int yx_conv2d_ex(const yx_op* op, void* base, const void* weights, co
     for (int t2 = 0; t2 < 32 && (h[t2 * 8 + 3] || t2 == 0); ++t2)
       fprintf(stderr, " %4d %10lld %10lld %10lld %10lld %10lld %10lld\n", t2, h[t2 * 8 + 0] - t0, h[t2 * 8 + 1] - t0,
               h[t2 * 8 + 2] - t0, h[t2 * 8 + 3] - t0, h[t2 * 8 + 4] - t0, h[t2 * 8 + 5] - t0);
+    const long long* w = h + 256;
+    const double tot = w[7] > 0 ? (double)w[7] : 1.0;
+    fprintf(stderr, "blocked cycles of CTA 0 (%% of %lld): A-producer on empty %.0f%% | B-producer on empty %.0f%% | MMA on fullA %.0f%% "
+                    "fullB %.0f%% tmem-empty %.0f%% | epilogue on tmem-full %.0f%% staging/barrier %.0f%%\n",
+            w[7], 100.0 * w[0] / tot, 100.0 * w[1] / tot, 100.0 * w[2] / tot, 100.0 * w[3] / tot, 100.0 * w[4] / tot,
+            100.0 * w[5] / tot, 100.0 * w[6] / tot);
     return rc;
   }
   return conv_launch(plan, static_cast<cudaStream_t>(stream));

@@ -42,15 +42,18 @@ struct ConvParams {
   int ky, kx, pad_y, pad_x;      // tap grid actually iterated (3x1 for the row-packed stem conv)
   int TH, TW, tiles_h, tiles_w;  // spatial tiling of the output (halo: TH = 16*mh, TW = 8)
   int n_tiles_m, n_tiles_n, BN;
+  int step_nt, step_x, step_y, step_img;  // mixed-radix digits of the persistent-tile step (= grid size)
   int cin, cout16;
   int k_chunks;
   int halo, mh;                  // halo variant: mh stacked 128-pixel halves per CTA
   int stages_a, a_stage_bytes, a_box_bytes;  // A ring
   int b_slots, b_stage_bytes, b_resident;    // B ring (or the whole weight tile, loaded once)
+  int shared_ring;               // generic + streamed weights: A and B share one full/empty barrier pair per stage
   int stage_bufs, out_box_bytes, bias_bytes; // output staging buffers (1 or 2), bytes per 64-ch residual box
   int epi_groups;                // epilogue warpgroups (1 or 2)
   int w3_role;                   // warp 3: 0 idle, 1 second A producer, 2 second B producer
   int tmem_cols, acc_stride;     // TMEM columns allocated (power of two) and columns per accumulator
+  int diag;                      // experiments (YX_CONV_DIAG): 1 no epilogue work, 2 no A loads, 4 no MMAs
   long long* trace;              // diagnostics: per-tile timeline of CTA 0 (nullptr = off)
 };
 
