@@ -31,7 +31,7 @@ class View(ctypes.Structure):
 
 class Op(ctypes.Structure):
     _fields_ = [("kind", c_i32), ("ksize", c_i32), ("stride", c_i32), ("act", c_i32),
-                ("src", View), ("dst", View), ("res", View),
+                ("src", View), ("dst", View), ("res", View), ("up", View),
                 ("w_offset", c_i64), ("b_offset", c_i64), ("cin_pad", c_i32), ("cout_pad", c_i32),
                 ("aux", c_i32), ("_pad", c_i32)]
 
@@ -40,7 +40,7 @@ class ConvTune(ctypes.Structure):
     """Mirror of yx_conv_tune (include/yolox_b200.h)."""
     _fields_ = [("variant", c_i32), ("n_tile", c_i32), ("ctas_per_sm", c_i32), ("halves", c_i32),
                 ("epilogue_groups", c_i32), ("staging_buffers", c_i32), ("second_producer", c_i32),
-                ("no_resident_weights", c_i32)]
+                ("no_resident_weights", c_i32), ("cta_pair", c_i32)]
 
 
 class Levels(ctypes.Structure):
@@ -106,7 +106,7 @@ def load():
     lib.yx_decode_outputs.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, ctypes.POINTER(Levels), c_vp]
     lib.yx_postprocess_yolox.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_f32, c_i32, c_vp, c_sz, c_vp, c_vp,
                                          c_vp, c_vp]
-    if lib.yx_abi_version() != 1:
+    if lib.yx_abi_version() != 2:
         raise RuntimeError("libyolox_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -148,14 +148,17 @@ class CSPLayer(nn.Module):
         self.conv3 = BaseConv(hidden + c2, out_channels, 1, 1, act=act, bn=bn)
         self.hidden, self.c2 = hidden, c2
 
-    def emit(self, g, name, x, out=None):
+    def emit(self, g, name, x, out=None, up=None):
+        """up: the layer's input is torch.cat([upsample2x(up), x], 1) (PAFPN top-down path); neither the upsampled
+        tensor nor the concatenation is materialised."""
         h, c2 = self.hidden, self.c2
         cat = g.new_buf(name + ".cat", x.H, x.W, h + c2)  # [x_1 | x_2]
         # conv1 and conv2 read the same tensor: one GEMM with Cout = h + c2 writes [x_0 | x_2]
         w1, b1 = self.conv1.folded()
         w2, b2 = self.conv2.folded()
         assert self.conv1.act_type == self.conv2.act_type
-        g.conv(name + ".conv1+2", x, cat.view(), torch.cat([w1, w2], 0), torch.cat([b1, b2], 0), 1, self.conv1.act_type)
+        g.conv(name + ".conv1+2", x, cat.view(), torch.cat([w1, w2], 0), torch.cat([b1, b2], 0), 1, self.conv1.act_type,
+               up=up)
         cur = cat.view(0, h)
         n = len(self.m)
         for i, m in enumerate(self.m):

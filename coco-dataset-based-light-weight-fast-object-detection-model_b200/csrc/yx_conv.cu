@@ -177,7 +177,19 @@ struct TileIter {
 // ---- MMA issue helpers.  Everything here runs in the single MMA warp, warp-uniformly; the tensor pipe can only be as
 // busy as this warp is fast (ncu: with ~85 SASS instructions per tap the warp, not the tensor core, was the limiter
 // of every layer with N <= 192), so the tap sequence is fully unrolled and all loop state lives in locals.
-template <int MH, bool RING>
+template <bool PAIR>
+__device__ __forceinline__ void umma_x(uint32_t d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                       uint32_t accumulate) {
+  if (PAIR) umma_f16_ss_lohi_2sm(d, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
+  else umma_f16_ss_lohi(d, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
+}
+template <bool PAIR>
+__device__ __forceinline__ void commit_x(uint32_t bar) {
+  if (PAIR) umma_commit_2sm(bar);
+  else umma_commit(bar);
+}
+
+template <int MH, bool RING, bool PAIR>
 __device__ __forceinline__ void halo_chunk_mma(uint32_t d0, uint32_t d1, uint32_t a0, uint32_t a_hi, uint32_t& b_lo, uint32_t b_hi,
                                                uint32_t idesc, uint32_t& accum, int ksteps, uint32_t bar_fb, uint32_t bar_eb,
                                                uint32_t& sb, uint32_t& phb, uint32_t b_slots, uint32_t b_lo0, uint32_t b_step,
@@ -193,15 +205,15 @@ __device__ __forceinline__ void halo_chunk_mma(uint32_t d0, uint32_t d1, uint32_
         if (ksteps == 4) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
-            umma_f16_ss_lohi(d0, a_tap + 2 * ks, a_hi, b_tap + 2 * ks, b_hi, idesc, (tap | ks) == 0 ? accum : 1u);
-            if (MH == 2) umma_f16_ss_lohi(d1, a_tap + 16 * kHaloW * 8 + 2 * ks, a_hi, b_tap + 2 * ks, b_hi, idesc, (tap | ks) == 0 ? accum : 1u);
+            umma_x<PAIR>(d0, a_tap + 2 * ks, a_hi, b_tap + 2 * ks, b_hi, idesc, (tap | ks) == 0 ? accum : 1u);
+            if (MH == 2) umma_x<PAIR>(d1, a_tap + 16 * kHaloW * 8 + 2 * ks, a_hi, b_tap + 2 * ks, b_hi, idesc, (tap | ks) == 0 ? accum : 1u);
           }
         } else {
 #pragma unroll
           for (int ks = 0; ks < 3; ++ks)
             if (ks < ksteps) {
-              umma_f16_ss_lohi(d0, a_tap + 2 * ks, a_hi, b_tap + 2 * ks, b_hi, idesc, (tap | ks) == 0 ? accum : 1u);
-              if (MH == 2) umma_f16_ss_lohi(d1, a_tap + 16 * kHaloW * 8 + 2 * ks, a_hi, b_tap + 2 * ks, b_hi, idesc, (tap | ks) == 0 ? accum : 1u);
+              umma_x<PAIR>(d0, a_tap + 2 * ks, a_hi, b_tap + 2 * ks, b_hi, idesc, (tap | ks) == 0 ? accum : 1u);
+              if (MH == 2) umma_x<PAIR>(d1, a_tap + 16 * kHaloW * 8 + 2 * ks, a_hi, b_tap + 2 * ks, b_hi, idesc, (tap | ks) == 0 ? accum : 1u);
             }
         }
       }
@@ -223,16 +235,16 @@ __device__ __forceinline__ void halo_chunk_mma(uint32_t d0, uint32_t d1, uint32_
       } else if (ksteps == 4) {
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-          umma_f16_ss_lohi(d0, a_tap + 2 * ks, a_hi, b_lo + 2 * ks, b_hi, idesc, ks == 0 ? accum : 1u);
-          if (MH == 2) umma_f16_ss_lohi(d1, a_tap + 16 * kHaloW * 8 + 2 * ks, a_hi, b_lo + 2 * ks, b_hi, idesc, ks == 0 ? accum : 1u);
+          umma_x<PAIR>(d0, a_tap + 2 * ks, a_hi, b_lo + 2 * ks, b_hi, idesc, ks == 0 ? accum : 1u);
+          if (MH == 2) umma_x<PAIR>(d1, a_tap + 16 * kHaloW * 8 + 2 * ks, a_hi, b_lo + 2 * ks, b_hi, idesc, ks == 0 ? accum : 1u);
         }
       } else {
         for (int ks = 0; ks < ksteps; ++ks) {
-          umma_f16_ss_lohi(d0, a_tap + 2 * ks, a_hi, b_lo + 2 * ks, b_hi, idesc, ks == 0 ? accum : 1u);
-          if (MH == 2) umma_f16_ss_lohi(d1, a_tap + 16 * kHaloW * 8 + 2 * ks, a_hi, b_lo + 2 * ks, b_hi, idesc, ks == 0 ? accum : 1u);
+          umma_x<PAIR>(d0, a_tap + 2 * ks, a_hi, b_lo + 2 * ks, b_hi, idesc, ks == 0 ? accum : 1u);
+          if (MH == 2) umma_x<PAIR>(d1, a_tap + 16 * kHaloW * 8 + 2 * ks, a_hi, b_lo + 2 * ks, b_hi, idesc, ks == 0 ? accum : 1u);
         }
       }
-      if (RING) umma_commit(bar_eb + 8 * sb);
+      if (RING) commit_x<PAIR>(bar_eb + 8 * sb);
     }
     accum = 1;
     b_lo += b_step;
@@ -243,10 +255,12 @@ __device__ __forceinline__ void halo_chunk_mma(uint32_t d0, uint32_t d1, uint32_
 }
 
 // MODE: 0 = generic (one A box per tap), 1 = halo with one 128-pixel half per CTA, 2 = halo with two stacked halves
-template <int ACT, bool HAS_RES, int MODE>
+// PAIR: two CTAs of a cluster share every MMA (cta_group::2, M = 256): half of the weight tile per CTA
+template <int ACT, bool HAS_RES, int MODE, bool PAIR>
 __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant__ ConvParams p) {
   constexpr bool HALO = MODE > 0;
   constexpr int MH = MODE == 2 ? 2 : 1;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;  // position in the CTA pair; rank 0 = leader (issues the MMAs)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // tells ptxas the warp index is warp-uniform
@@ -277,24 +291,29 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
       for (int s = 0; s < p.b_slots; ++s) { mbar_init(bar_fb + 8 * s, 1); mbar_init(bar_eb + 8 * s, 1); }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, 4 * p.epi_groups);  // one arrive per epilogue warp
+      mbar_init(bar_tempty + 8 * a, (PAIR ? 8 : 4) * p.epi_groups);  // one arrive per epilogue warp (of both CTAs)
       mbar_init(bar_res + 8 * a, 1);
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, p.tmem_cols);
+  if (warp == 2) {
+    if (PAIR) tmem_alloc_2sm(tmem_slot, p.tmem_cols); else tmem_alloc(tmem_slot, p.tmem_cols);
+  }
   for (int i = threadIdx.x; i < p.cout16; i += blockDim.x) {
     const float b = __ldg(p.bias + i);
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(sBias + i * 4), "f"(b) : "memory");
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer's barriers must be initialised before anything is signalled across the pair
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
+  // PAIR: the tile space is walked in units of CTA pairs; CTA `rank` owns the x-tile 2*tx + rank of every pair tile
   const int n_tiles = p.n_tiles_m * p.n_tiles_n;
-  const int tile_step = gridDim.x;
+  const int tile_step = PAIR ? (gridDim.x >> 1) : gridDim.x;
+  const int tile_first = PAIR ? (blockIdx.x >> 1) : blockIdx.x;
   const int n_tiles_n = p.n_tiles_n, tiles_w = p.tiles_w, tiles_h = p.tiles_h;
   const int taps = p.ky * p.kx;
   const int k_chunks = p.k_chunks;
@@ -317,9 +336,9 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
     uint32_t s = 0, ph = 0, turn = 0;  // ring slot / phase / whose turn, all incremental
     const int TH = p.TH, TW = p.TW;
     TileIter ti;
-    ti.init(p, blockIdx.x);
-    for (int tile = blockIdx.x; tile < n_tiles; tile += tile_step) {
-      const int x0 = ti.tx * TW, y0 = ti.ty * TH, img = ti.img;
+    ti.init(p, tile_first);
+    for (int tile = tile_first; tile < n_tiles; tile += tile_step) {
+      const int x0 = (PAIR ? 2 * ti.tx + (int)rank : ti.tx) * TW, y0 = ti.ty * TH, img = ti.img;
       YX_TILE_NEXT(ti);
       if (HALO) {
         for (int kc = 0; kc < k_chunks; ++kc) {
@@ -328,6 +347,9 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
             if (elect_one()) {
               if (p.diag & 2) {
                 mbar_arrive(bar_fa + 8 * s);
+              } else if (PAIR) {  // the leader's barrier collects the bytes of both CTAs' tiles
+                if (rank == 0) mbar_expect_tx(bar_fa + 8 * s, 2 * a_box_bytes);
+                tma_load_4d_2sm(sA + s * a_stage_bytes, &p.tmA[0], bar_fa + 8 * s, kc * 64, x0 - 1, y0 - 1, img);
               } else {
                 mbar_expect_tx(bar_fa + 8 * s, a_box_bytes);
                 tma_load_4d(sA + s * a_stage_bytes, &p.tmA[0], bar_fa + 8 * s, kc * 64, x0 - 1, y0 - 1, img);
@@ -338,7 +360,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
           if (++s == stages_a) { s = 0; ph ^= 1; }
         }
       } else {
-        const int stride = p.stride, kx = p.kx, pad_x = p.pad_x, pad_y = p.pad_y;
+        const int stride = p.stride, kx = p.kx, pad_x = p.pad_x, pad_y = p.pad_y, up_chunks = p.up_chunks, up_h = p.up_h;
         int dy = 0, dx = 0;
         for (int tap = 0; tap < taps; ++tap) {
           int mi = 0, cx, cy;
@@ -360,9 +382,22 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
               if (elect_one()) {
                 if (p.diag & 2) {
                   mbar_arrive(bar_fa + 8 * s);
+                } else if (kc < up_chunks) {
+                  // fused nearest x2 upsample + concat: these K chunks come from the low-resolution tensor, each
+                  // pixel repeated 2x2 by the tensor map's stride-0 dimensions
+                  if (PAIR) {
+                    if (rank == 0) mbar_expect_tx(bar_fa + 8 * s, 2 * a_box_bytes);
+                    tma_load_5d_2sm(sA + s * a_stage_bytes, &p.tmUp, bar_fa + 8 * s, kc * 64, 0, cx >> 1, 0, img * up_h + (cy >> 1));
+                  } else {
+                    mbar_expect_tx(bar_fa + 8 * s, a_box_bytes);
+                    tma_load_5d(sA + s * a_stage_bytes, &p.tmUp, bar_fa + 8 * s, kc * 64, 0, cx >> 1, 0, img * up_h + (cy >> 1));
+                  }
+                } else if (PAIR) {
+                  if (rank == 0) mbar_expect_tx(bar_fa + 8 * s, 2 * a_box_bytes);
+                  tma_load_4d_2sm(sA + s * a_stage_bytes, &p.tmA[mi], bar_fa + 8 * s, (kc - up_chunks) * 64, cx, cy, img);
                 } else {
                   mbar_expect_tx(bar_fa + 8 * s, a_box_bytes);
-                  tma_load_4d(sA + s * a_stage_bytes, &p.tmA[mi], bar_fa + 8 * s, kc * 64, cx, cy, img);
+                  tma_load_4d(sA + s * a_stage_bytes, &p.tmA[mi], bar_fa + 8 * s, (kc - up_chunks) * 64, cx, cy, img);
                 }
               }
             }
@@ -372,18 +407,19 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
           if (++dx == kx) { dx = 0; ++dy; }
         }
       }
-      if (warp == 0 && lane == 0) YX_TRACE(0, (tile - (int)blockIdx.x) / tile_step);
+      if (warp == 0 && lane == 0) YX_TRACE(0, (tile - tile_first) / tile_step);
     }
     if (warp == 0) YX_TRACE_SUM(TW_APROD_EMPTY, w_acc0);
   } else if (is_b_prod) {
     // ================================ B (weight) producer(s) ================================
     const uint32_t nprod = p.w3_role == 2 ? 2u : 1u, mine = warp == 2 ? 0u : 1u;
     const uint32_t b_stage_bytes = p.b_stage_bytes;
-    const int BN = p.BN;
+    const int BN = p.BN, cout16 = p.cout16;
     uint32_t s = 0, ph = 0, turn = 0;
-    int nt = blockIdx.x % n_tiles_n;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += tile_step) {
-      const int n0 = nt * BN;
+    int nt = tile_first % n_tiles_n;
+    for (int tile = tile_first; tile < n_tiles; tile += tile_step) {
+      int n0 = nt * BN;
+      if (PAIR) n0 += (int)rank * (min(BN, cout16 - n0) >> 1);  // this CTA's half of the N tile
       nt += p.step_nt;
       if (nt >= n_tiles_n) nt -= n_tiles_n;
       // ring order must match the MMA issuer: halo = (chunk, tap), generic = (tap, chunk)
@@ -394,8 +430,13 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
           if (turn == mine) {
             if (!resident) mbar_wait_acc(bar_eb + 8 * s, ph ^ 1, tracing, w_acc0);
             if (elect_one()) {
-              mbar_expect_tx(bar_fb + 8 * s, b_stage_bytes);
-              tma_load_3d(sB + s * b_stage_bytes, &p.tmW, bar_fb + 8 * s, kc * 64, tap, n0);
+              if (PAIR) {
+                if (rank == 0) mbar_expect_tx(bar_fb + 8 * s, 2 * b_stage_bytes);
+                tma_load_3d_2sm(sB + s * b_stage_bytes, &p.tmW, bar_fb + 8 * s, kc * 64, tap, n0);
+              } else {
+                mbar_expect_tx(bar_fb + 8 * s, b_stage_bytes);
+                tma_load_3d(sB + s * b_stage_bytes, &p.tmW, bar_fb + 8 * s, kc * 64, tap, n0);
+              }
             }
           }
           if (++turn == nprod) turn = 0;
@@ -404,8 +445,8 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
       if (resident) break;  // one N tile per layer: the weights stay in smem for every later tile
     }
     if (warp == 2) YX_TRACE_SUM(TW_BPROD_EMPTY, w_acc0);
-  } else if (warp == 1) {
-    // ================================ MMA issuer ================================
+  } else if (warp == 1 && rank == 0) {
+    // ================================ MMA issuer (leader CTA only in PAIR mode) ================================
     uint32_t t = 0, sa = 0, pha = 0, sb = 0, phb = 0;
     const uint32_t a_hi = sdesc_hi(HALO ? kHaloW * 128 : 1024), b_hi = sdesc_hi(1024);
     const uint32_t a_lo0 = sdesc_lo(sA), a_step = p.a_stage_bytes >> 4;
@@ -416,13 +457,13 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
     const uint32_t acc_stride = p.acc_stride;
     const bool shared_ring = p.shared_ring != 0;
     bool b_ready = false;  // resident weights: wait for them during the first tile only
-    int nt = blockIdx.x % n_tiles_n;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += tile_step, ++t) {
+    int nt = tile_first % n_tiles_n;
+    for (int tile = tile_first; tile < n_tiles; tile += tile_step, ++t) {
       const int n0 = nt * BN;
       nt += p.step_nt;
       if (nt >= n_tiles_n) nt -= n_tiles_n;
       const int bn_cur = min(BN, cout16 - n0);
-      const uint32_t idesc = make_idesc_f16(bn_cur);
+      const uint32_t idesc = PAIR ? make_idesc_f16_m256(bn_cur) : make_idesc_f16(bn_cur);
       const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
       mbar_wait_acc(bar_tempty + 8 * acc, acc_ph ^ 1, tracing, w_acc2);
       tc_fence_after();
@@ -436,12 +477,12 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
           tc_fence_after();
           const int ksteps = (kc == k_chunks - 1) ? ks_last : 4;
           if (resident)
-            halo_chunk_mma<MH, false>(d0, d1, a_lo, a_hi, b_lo, b_hi, idesc, accum, ksteps, bar_fb, bar_eb, sb, phb, b_slots, b_lo0,
+            halo_chunk_mma<MH, false, PAIR>(d0, d1, a_lo, a_hi, b_lo, b_hi, idesc, accum, ksteps, bar_fb, bar_eb, sb, phb, b_slots, b_lo0,
                                       b_step, !b_ready, tracing, w_acc1, (p.diag & 4) != 0);
           else
-            halo_chunk_mma<MH, true>(d0, d1, a_lo, a_hi, b_lo, b_hi, idesc, accum, ksteps, bar_fb, bar_eb, sb, phb, b_slots, b_lo0,
+            halo_chunk_mma<MH, true, PAIR>(d0, d1, a_lo, a_hi, b_lo, b_hi, idesc, accum, ksteps, bar_fb, bar_eb, sb, phb, b_slots, b_lo0,
                                      b_step, true, tracing, w_acc1, (p.diag & 4) != 0);
-          if (elect_one()) umma_commit(bar_ea + 8 * sa);
+          if (elect_one()) commit_x<PAIR>(bar_ea + 8 * sa);
           a_lo += a_step;
           if (++sa == stages_a) { sa = 0; pha ^= 1; a_lo = a_lo0; }
         }
@@ -457,16 +498,16 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
           if (elect_one()) {
             if (p.diag & 4) {
             } else if (!last || ks_last == 4) {
-              umma_f16_ss_lohi(d0, a_lo, a_hi, b_lo, b_hi, idesc, accum);
-              umma_f16_ss_lohi(d0, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
-              umma_f16_ss_lohi(d0, a_lo + 4, a_hi, b_lo + 4, b_hi, idesc, 1u);
-              umma_f16_ss_lohi(d0, a_lo + 6, a_hi, b_lo + 6, b_hi, idesc, 1u);
+              umma_x<PAIR>(d0, a_lo, a_hi, b_lo, b_hi, idesc, accum);
+              umma_x<PAIR>(d0, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
+              umma_x<PAIR>(d0, a_lo + 4, a_hi, b_lo + 4, b_hi, idesc, 1u);
+              umma_x<PAIR>(d0, a_lo + 6, a_hi, b_lo + 6, b_hi, idesc, 1u);
             } else {
-              umma_f16_ss_lohi(d0, a_lo, a_hi, b_lo, b_hi, idesc, accum);
-              if (ks_last > 1) umma_f16_ss_lohi(d0, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
-              if (ks_last > 2) umma_f16_ss_lohi(d0, a_lo + 4, a_hi, b_lo + 4, b_hi, idesc, 1u);
+              umma_x<PAIR>(d0, a_lo, a_hi, b_lo, b_hi, idesc, accum);
+              if (ks_last > 1) umma_x<PAIR>(d0, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
+              if (ks_last > 2) umma_x<PAIR>(d0, a_lo + 4, a_hi, b_lo + 4, b_hi, idesc, 1u);
             }
-            umma_commit(bar_ea + 8 * sa);  // frees the stage (A, and B when the ring is shared) when these MMAs retire
+            commit_x<PAIR>(bar_ea + 8 * sa);  // frees the stage (A, and B when the ring is shared) when these MMAs retire
           }
           accum = 1;
           a_lo += a_step;
@@ -476,7 +517,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
         }
       }
       if (resident) b_ready = true;
-      if (elect_one()) umma_commit(bar_tfull + 8 * acc);  // accumulator complete -> epilogue
+      if (elect_one()) commit_x<PAIR>(bar_tfull + 8 * acc);  // accumulator complete -> epilogue (of both CTAs)
       if (lane == 0) YX_TRACE(2, t);
     }
     YX_TRACE_SUM(TW_MMA_FULLA, w_acc0);
@@ -498,9 +539,9 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
     uint32_t t = 0, u = 0;  // tile counter, staging-unit counter (MH units per tile)
     const int TH = p.TH, TW = p.TW;
     TileIter ti;
-    ti.init(p, blockIdx.x);
-    for (int tile = blockIdx.x; tile < n_tiles; tile += tile_step, ++t) {
-      struct { int x0, y0, img, n0; } tc = {ti.tx * TW, ti.ty * TH, ti.img, ti.nt * BN};
+    ti.init(p, tile_first);
+    for (int tile = tile_first; tile < n_tiles; tile += tile_step, ++t) {
+      struct { int x0, y0, img, n0; } tc = {(PAIR ? 2 * ti.tx + (int)rank : ti.tx) * TW, ti.ty * TH, ti.img, ti.nt * BN};
       YX_TILE_NEXT(ti);
       const int bn_cur = min(BN, cout16 - tc.n0);
       const int groups_cur = (bn_cur + 63) >> 6;
@@ -538,7 +579,9 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
         if (h == MH - 1) {  // accumulator drained -> MMA warp may overwrite it
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+          if (lane == 0) {
+            if (PAIR) mbar_arrive_cluster(mapa_shared(bar_tempty + 8 * acc, 0)); else mbar_arrive(bar_tempty + 8 * acc);
+          }
         }
         // publish the staged tile to the async proxy and store it
         fence_proxy_async_smem();
@@ -563,7 +606,10 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, p.tmem_cols);
+  if (PAIR) cluster_sync_all();  // neither CTA may exit (or free TMEM) while the other can still touch it
+  if (warp == 2) {
+    if (PAIR) tmem_dealloc_2sm(tmem_base, p.tmem_cols); else tmem_dealloc(tmem_base, p.tmem_cols);
+  }
 }
 
 // --------------------------------------------------------------------------------------------
@@ -629,12 +675,14 @@ static int encode_view(CUtensorMap* m, void* base, const yx_view& v, int tw, int
   return encode_map(m, static_cast<uint8_t*>(base) + v.offset, 4, dims, st, box, true, what);
 }
 
-static void choose_tile(int H, int W, int* th, int* tw) {
+static void choose_tile(int H, int W, int* th, int* tw, bool even = false) {
   // minimise padded MMA rows; ties -> squarer tile (fewer halo re-reads from L2)
   double best = 1e30;
-  int bh = 1, bw = 1;
+  int bh = even ? 2 : 1, bw = even ? 2 : 1;
   for (int w = 1; w <= std::min(W, 128); ++w) {
     int h = std::min(H, 128 / w);
+    if (even) h &= ~1;
+    if (even && (w & 1)) continue;
     if (h < 1) continue;
     double tiles = (double)ceil_div(H, h) * ceil_div(W, w);
     double cost = tiles * 1000.0 + std::abs(h - w) * 0.01;
@@ -645,7 +693,7 @@ static void choose_tile(int H, int W, int* th, int* tw) {
 }
 
 struct ConvGeom {
-  bool rowpack, has_res;
+  bool rowpack, has_res, has_up;
   int Hout, Wout, taps, cin_real;
   double flops, act_bytes;
 };
@@ -656,7 +704,7 @@ static int conv_geom(const yx_op& op, ConvGeom* g) {
   YX_REQUIRE(op.ksize == 1 || op.ksize == 3, "conv ksize must be 1 or 3");
   YX_REQUIRE(op.stride == 1 || op.stride == 2, "conv stride must be 1 or 2");
   YX_REQUIRE(op.cin_pad % 16 == 0 && op.cout_pad % 16 == 0, "cin_pad/cout_pad must be multiples of 16");
-  YX_REQUIRE(s.c <= op.cin_pad && s.c % 8 == 0, "src channels must be a multiple of 8 and <= cin_pad");
+  YX_REQUIRE(s.c % 8 == 0, "src channels must be a multiple of 8");
   YX_REQUIRE(op.aux == 0 || op.aux == 1, "conv aux must be 0 or 1 (row-packed)");
   YX_REQUIRE(d.c % 8 == 0 && d.c <= op.cout_pad, "dst channels must be a multiple of 8 and <= cout_pad");
   YX_REQUIRE(s.pitch % 8 == 0 && d.pitch % 8 == 0 && s.offset % 16 == 0 && d.offset % 16 == 0 && s.nstride % 8 == 0 &&
@@ -679,11 +727,23 @@ static int conv_geom(const yx_op& op, ConvGeom* g) {
     YX_REQUIRE(op.res.h == d.h && op.res.w == d.w && op.res.c == d.c && op.res.n == d.n && op.res.pitch % 8 == 0 &&
                    op.res.offset % 16 == 0 && op.res.nstride % 8 == 0,
                "residual view must match dst");
+  g->has_up = op.up.c > 0;
+  if (g->has_up) {
+    YX_REQUIRE(op.ksize == 1 && op.stride == 1 && !g->rowpack, "fused upsample needs a 1x1 stride-1 conv");
+    YX_REQUIRE(op.up.c % 64 == 0 && op.up.n == s.n && op.up.h * 2 == s.h && op.up.w * 2 == s.w && s.h % 2 == 0 && s.w % 2 == 0,
+               "fused upsample: up must be [n, h/2, w/2, 64*k]");
+    YX_REQUIRE(op.up.pitch % 8 == 0 && op.up.offset % 16 == 0 && op.up.nstride == (int64_t)op.up.h * op.up.w * op.up.pitch,
+               "fused upsample: the low-resolution tensor must be 16-byte aligned with contiguous images");
+    YX_REQUIRE(op.cin_pad == op.up.c + round_up(s.c, 16), "fused upsample: cin_pad must be up.c + padded src.c");
+  } else {
+    YX_REQUIRE(s.c <= op.cin_pad, "src channels must be <= cin_pad");
+  }
   g->taps = g->rowpack ? 3 : op.ksize * op.ksize;
-  g->cin_real = g->rowpack ? 12 : s.c;
+  g->cin_real = g->rowpack ? 12 : s.c + (g->has_up ? op.up.c : 0);
   const double px_out = (double)d.n * g->Hout * g->Wout;
   g->flops = 2.0 * px_out * d.c * g->cin_real * op.ksize * op.ksize;
   g->act_bytes = 2.0 * ((double)s.n * s.h * s.w * (g->rowpack ? 12 : s.c) + px_out * d.c * (g->has_res ? 2 : 1));
+  if (g->has_up) g->act_bytes += 2.0 * (double)op.up.n * op.up.h * op.up.w * op.up.c;  // read once at LOW resolution
   return YX_OK;
 }
 
@@ -755,6 +815,14 @@ void conv_candidates(const yx_op& op, std::vector<ConvTune>* out) {
           t.variant = 1; t.bn = bn; t.ctas = ctas; t.epi_groups = eg; t.stage_bufs = sb; t.w3 = 1;
           push(t);
         }
+    if (bn >= 64 && cout16 >= 96)  // CTA-pair shapes: half of the weight tile per CTA
+      for (int v = 1; v <= (halo_ok(op, g) ? 2 : 1); ++v)
+        for (int sb = 2; sb >= 1; --sb) {
+          ConvTune t;
+          memset(&t, 0, sizeof t);
+          t.variant = v; t.bn = bn; t.ctas = 1; t.mh = 1; t.epi_groups = 1; t.stage_bufs = sb; t.w3 = v == 2 ? 2 : 1; t.pair = 1;
+          push(t);
+        }
     if (halo_ok(op, g))
       for (int mh = 1; mh <= 2; ++mh)
         for (int eg = 1; eg <= 2; ++eg)
@@ -778,8 +846,11 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
   if (rc != YX_OK) return rc;
   const ConvTune t = tune ? *tune : default_tune(op, g);
   const bool halo = t.variant == 2;
+  const bool pair = t.pair != 0;
   YX_REQUIRE(t.variant == 1 || t.variant == 2, "conv tune: variant must be 1 (generic) or 2 (halo)");
+  YX_REQUIRE(!pair || (t.ctas == 1 && (!halo || t.mh != 2)), "conv tune: CTA-pair mode runs one CTA per SM and one 128-pixel half per CTA");
   YX_REQUIRE(!halo || halo_ok(op, g), "conv tune: halo variant needs a 3x3 stride-1 conv on a map of at least 16x8");
+  YX_REQUIRE(!g.has_up || !halo, "fused upsample is a 1x1 conv: generic variant only");
   YX_REQUIRE(t.bn >= 16 && t.bn <= 256 && t.bn % 16 == 0 && (t.bn % 64 == 0 || t.bn >= op.cout_pad),
              "conv tune: N tile must be a multiple of 64 (or the whole padded Cout), at most 256");
   YX_REQUIRE(t.ctas == 1 || t.ctas == 2, "conv tune: ctas per SM must be 1 or 2");
@@ -796,13 +867,16 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
   p.pad_y = pad; p.pad_x = g.rowpack ? 0 : pad;
   p.cin = op.cin_pad;
   p.cout16 = op.cout_pad;
-  p.k_chunks = ceil_div(p.cin, 64);
+  p.up_chunks = g.has_up ? op.up.c / 64 : 0;
+  p.up_h = g.has_up ? op.up.h : 0;
+  p.k_chunks = p.up_chunks + ceil_div(p.cin - p.up_chunks * 64, 64);
   p.BN = std::min(t.bn, p.cout16);
   p.n_tiles_n = ceil_div(p.cout16, p.BN);
   p.halo = halo ? 1 : 0;
+  p.pair = pair ? 1 : 0;
   p.epi_groups = t.epi_groups;
   p.bias_bytes = round_up(p.cout16 * 4, 128);
-  p.b_stage_bytes = p.BN * 128;
+  p.b_stage_bytes = (pair ? p.BN / 2 : p.BN) * 128;  // pair: each CTA holds half of the N tile's weight rows
   p.bias = reinterpret_cast<const float*>(static_cast<const uint8_t*>(biases) + op.b_offset);
   static const int diag_env = getenv("YX_CONV_DIAG") ? atoi(getenv("YX_CONV_DIAG")) : 0;  // experiments only (results are garbage)
   p.diag = diag_env;
@@ -825,7 +899,7 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
     while (p.tmem_cols < 2 * mh * stride_cols) p.tmem_cols <<= 1;
   } else {
     p.mh = 1;
-    choose_tile(g.Hout, g.Wout, &p.TH, &p.TW);
+    choose_tile(g.Hout, g.Wout, &p.TH, &p.TW, g.has_up);
     p.a_box_bytes = p.TH * p.TW * 128;
     p.a_stage_bytes = kTileBytes;
     p.out_box_bytes = p.a_box_bytes;
@@ -836,6 +910,7 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
   YX_REQUIRE(t.ctas == 1 || p.tmem_cols <= 256, "conv tune: two CTAs per SM need <= 256 TMEM columns each");
   p.tiles_h = ceil_div(g.Hout, p.TH);
   p.tiles_w = ceil_div(g.Wout, p.TW);
+  if (pair) p.tiles_w = ceil_div(p.tiles_w, 2);  // iteration space in pair tiles: CTA `rank` owns x-tile 2*tx + rank
   p.n_tiles_m = d.n * p.tiles_h * p.tiles_w;
 
   // ---- shared-memory budget: [A ring][B ring or resident B][staging x stage_bufs][bias][barriers] ----
@@ -845,7 +920,7 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
     const int fixed = 1024 + kBarBytes + p.bias_bytes + p.stage_bufs * groups64 * kTileBytes;
     const int avail = budget - fixed;
     const int min_a = (halo ? 2 : 2) * p.a_stage_bytes;
-    const bool can_res = p.n_tiles_n == 1 && k_loads_b <= kMaxBRing && t.no_resident == 0 &&
+    const bool can_res = !pair && p.n_tiles_n == 1 && k_loads_b <= kMaxBRing && t.no_resident == 0 &&
                          k_loads_b * p.b_stage_bytes + min_a <= avail;
     if (can_res) {
       p.b_resident = 1;
@@ -876,8 +951,9 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
   else if (p.tmem_cols > 256) pl.smem_bytes = std::max(pl.smem_bytes, 120 * 1024);
   else pl.smem_bytes = std::max(pl.smem_bytes, 80 * 1024);
   pl.grid = std::min(p.n_tiles_m * p.n_tiles_n, t.ctas * num_sms);
+  if (pair) pl.grid = 2 * std::min(p.n_tiles_m * p.n_tiles_n, num_sms / 2);
   {  // mixed-radix digits of the persistent-tile step (see TileIter)
-    int st = pl.grid;
+    int st = pair ? pl.grid / 2 : pl.grid;
     p.step_nt = st % p.n_tiles_n; st /= p.n_tiles_n;
     p.step_x = st % p.tiles_w; st /= p.tiles_w;
     p.step_y = st % p.tiles_h;
@@ -908,6 +984,16 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
   } else if (op.stride == 1) {
     if ((rc = encode_view(&p.tmA[0], base, s, p.TW, p.TH, "A")) != YX_OK) return rc;
     for (int i = 1; i < 4; ++i) p.tmA[i] = p.tmA[0];
+    if (g.has_up) {
+      // (c, dup_x, w/2, dup_y, n*h/2): the two stride-0 dimensions repeat every low-resolution pixel 2x2, so the box
+      // (64, 2, TW/2, 2, TH/2) lands in shared memory in exactly the high-resolution pixel order of the tile
+      const yx_view& u = op.up;
+      YX_REQUIRE(p.TW % 2 == 0 && p.TH % 2 == 0, "fused upsample needs an even tile");
+      uint64_t dims[5] = {(uint64_t)u.c, 2, (uint64_t)u.w, 2, (uint64_t)u.n * u.h};
+      uint64_t st[5] = {2, 0, (uint64_t)u.pitch * 2, 0, (uint64_t)u.pitch * 2 * u.w};
+      uint32_t box[5] = {64, 2, (uint32_t)p.TW / 2, 2, (uint32_t)p.TH / 2};
+      if ((rc = encode_map(&p.tmUp, static_cast<uint8_t*>(base) + u.offset, 5, dims, st, box, true, "A-upsample")) != YX_OK) return rc;
+    }
   } else {
     for (int py = 0; py < 2; ++py)
       for (int px = 0; px < 2; ++px) {
@@ -923,7 +1009,7 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
   {
     uint64_t dims[3] = {(uint64_t)op.cin_pad, (uint64_t)taps, (uint64_t)op.cout_pad};
     uint64_t st[3] = {2, (uint64_t)op.cin_pad * 2, (uint64_t)op.cin_pad * 2 * taps};
-    uint32_t box[3] = {64, 1, (uint32_t)p.BN};
+    uint32_t box[3] = {64, 1, (uint32_t)(pair ? p.BN / 2 : p.BN)};
     uint8_t* addr = const_cast<uint8_t*>(static_cast<const uint8_t*>(weights)) + op.w_offset;
     YX_REQUIRE(op.w_offset % 16 == 0, "weight offset must be 16-byte aligned");
     if ((rc = encode_map(&p.tmW, addr, 3, dims, st, box, true, "W")) != YX_OK) return rc;
@@ -937,32 +1023,55 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
   }
   pl.flops = g.flops;
   pl.bytes = g.act_bytes + 2.0 * (double)d.c * g.cin_real * op.ksize * op.ksize;
-  snprintf(pl.desc, sizeof pl.desc, "%s BN%d%s mh%d ctas%d epi%d sbuf%d A%dx%dK B%d%s w3:%d grid%d smem%dK", halo ? "halo" : "generic",
+  snprintf(pl.desc, sizeof pl.desc, "%s%s BN%d%s mh%d ctas%d epi%d sbuf%d A%dx%dK B%d%s w3:%d grid%d smem%dK", pair ? "pair-" : "", halo ? "halo" : "generic",
            p.BN, p.n_tiles_n > 1 ? "*" : "", p.mh, t.ctas, p.epi_groups, p.stage_bufs, p.stages_a, p.a_stage_bytes >> 10, p.b_slots,
            p.b_resident ? "res" : "", p.w3_role, pl.grid, pl.smem_bytes >> 10);
   *out = pl;
   return YX_OK;
 }
 
-template <int ACT, bool HAS_RES, int MODE>
+template <int ACT, bool HAS_RES, int MODE, bool PAIR>
 static int launch_variant(const ConvPlan& plan, cudaStream_t stream) {
   static bool attr_set = false;
+  auto kernel = conv_gemm_kernel<ACT, HAS_RES, MODE, PAIR>;
   if (!attr_set) {
-    YX_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<ACT, HAS_RES, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    YX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     attr_set = true;
   }
-  conv_gemm_kernel<ACT, HAS_RES, MODE><<<plan.grid, plan.threads, plan.smem_bytes, stream>>>(plan.p);
-  YX_CUDA(cudaGetLastError());
+  if (!PAIR) {
+    kernel<<<plan.grid, plan.threads, plan.smem_bytes, stream>>>(plan.p);
+    YX_CUDA(cudaGetLastError());
+    return YX_OK;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(plan.grid, 1, 1);
+  cfg.blockDim = dim3(plan.threads, 1, 1);
+  cfg.dynamicSmemBytes = plan.smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;  // the CTA pair
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  YX_CUDA(cudaLaunchKernelEx(&cfg, kernel, plan.p));
   return YX_OK;
+}
+
+template <int ACT, bool HAS_RES>
+static int launch_mode(const ConvPlan& plan, cudaStream_t stream) {
+  if (plan.p.pair)
+    return plan.p.halo ? launch_variant<ACT, HAS_RES, 1, true>(plan, stream) : launch_variant<ACT, HAS_RES, 0, true>(plan, stream);
+  if (plan.p.halo && plan.p.mh == 2) return launch_variant<ACT, HAS_RES, 2, false>(plan, stream);
+  if (plan.p.halo) return launch_variant<ACT, HAS_RES, 1, false>(plan, stream);
+  return launch_variant<ACT, HAS_RES, 0, false>(plan, stream);
 }
 
 template <int ACT>
 static int launch_act(const ConvPlan& plan, cudaStream_t stream) {
-  if (plan.p.halo && plan.p.mh == 2)
-    return plan.p.has_res ? launch_variant<ACT, true, 2>(plan, stream) : launch_variant<ACT, false, 2>(plan, stream);
-  if (plan.p.halo)
-    return plan.p.has_res ? launch_variant<ACT, true, 1>(plan, stream) : launch_variant<ACT, false, 1>(plan, stream);
-  return plan.p.has_res ? launch_variant<ACT, true, 0>(plan, stream) : launch_variant<ACT, false, 0>(plan, stream);
+  return plan.p.has_res ? launch_mode<ACT, true>(plan, stream) : launch_mode<ACT, false>(plan, stream);
 }
 
 int conv_launch(const ConvPlan& plan, cudaStream_t stream) {

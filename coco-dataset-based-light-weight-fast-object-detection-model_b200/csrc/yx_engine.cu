@@ -98,6 +98,7 @@ extern "C" int yx_engine_create(const yx_op* ops, int n_ops, void* arena, size_t
     bool ok = view_ok(op.dst, arena_bytes);
     if (op.kind != YX_OP_S2D) ok = ok && view_ok(op.src, arena_bytes);
     if (op.kind == YX_OP_CONV && op.res.c > 0) ok = ok && view_ok(op.res, arena_bytes);
+    if (op.kind == YX_OP_CONV && op.up.c > 0) ok = ok && view_ok(op.up, arena_bytes);
     int rc = YX_OK;
     if (!ok) {
       set_error(std::string(where) + "view outside the arena");
@@ -244,8 +245,8 @@ extern "C" int yx_engine_op_desc(const yx_engine* e, int i, char* buf_host, int 
   YX_REQUIRE(e && buf_host && buf_len > 0 && i >= 0 && i < (int)e->steps.size(), "bad op index");
   const Step& s = e->steps[i];
   static const char* kinds[] = {"conv", "s2d", "spp", "upsample", "dwconv"};
-  if (s.op.kind == YX_OP_CONV) snprintf(buf_host, buf_len, "conv k%d s%d %d->%d @%dx%d: %s", s.op.ksize, s.op.stride, s.op.src.c,
-                                        s.op.dst.c, s.op.dst.h, s.op.dst.w, s.conv.desc);
+  if (s.op.kind == YX_OP_CONV) snprintf(buf_host, buf_len, "conv k%d s%d %s%d->%d @%dx%d: %s", s.op.ksize, s.op.stride,
+                                        s.op.up.c > 0 ? "up2x+" : "", s.op.src.c + s.op.up.c, s.op.dst.c, s.op.dst.h, s.op.dst.w, s.conv.desc);
   else snprintf(buf_host, buf_len, "%s", s.op.kind >= 0 && s.op.kind <= 4 ? kinds[s.op.kind] : "?");
   return YX_OK;
 }
@@ -292,7 +293,7 @@ extern "C" int yx_conv2d_ex(const yx_op* op, void* base, const void* weights, co
     memset(&t, 0, sizeof t);
     t.variant = tune->variant; t.bn = tune->n_tile; t.ctas = tune->ctas_per_sm; t.mh = tune->halves;
     t.epi_groups = tune->epilogue_groups; t.stage_bufs = tune->staging_buffers; t.w3 = tune->second_producer;
-    t.no_resident = tune->no_resident_weights;
+    t.no_resident = tune->no_resident_weights; t.pair = tune->cta_pair;
   }
   int rc = conv_plan(*op, base, weights, biases, sms, tune ? &t : nullptr, &plan);
   if (rc) return rc;

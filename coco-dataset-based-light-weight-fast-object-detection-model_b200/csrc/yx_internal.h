@@ -37,6 +37,8 @@ struct ConvParams {
   CUtensorMap tmW;     // weights  (cin_pad, taps, cout_pad), box (64, 1, BN)
   CUtensorMap tmOut;   // output   (c, W, H, N),             box (64, TW, TH or 16, 1)
   CUtensorMap tmRes;   // residual, same geometry as tmOut
+  CUtensorMap tmUp;    // fused upsample source: (c, dup_x, w/2, dup_y, n*h/2) with stride-0 dup dims, box (64, 2, TW/2, 2, TH/2)
+  int up_chunks, up_h;  // leading K chunks that come from tmUp; rows per image of the low-res tensor
   const float* bias;
   int ksize, stride, act, has_res;
   int ky, kx, pad_y, pad_x;      // tap grid actually iterated (3x1 for the row-packed stem conv)
@@ -46,6 +48,7 @@ struct ConvParams {
   int cin, cout16;
   int k_chunks;
   int halo, mh;                  // halo variant: mh stacked 128-pixel halves per CTA
+  int pair;                      // CTA-pair mode (cluster of 2, cta_group::2 MMAs of M = 256)
   int stages_a, a_stage_bytes, a_box_bytes;  // A ring
   int b_slots, b_stage_bytes, b_resident;    // B ring (or the whole weight tile, loaded once)
   int shared_ring;               // generic + streamed weights: A and B share one full/empty barrier pair per stage
@@ -67,6 +70,7 @@ struct ConvTune {
   int stage_bufs;   // 1 or 2
   int w3;           // 0: no second producer warp, otherwise pick automatically
   int no_resident;  // 1: never keep the weights resident (experiments)
+  int pair;         // 1: CTA-pair mode (cta_group::2)
 };
 
 struct ConvPlan {

@@ -13,6 +13,8 @@ runs it; nothing executes in eager PyTorch.
 """
 from typing import Dict, List, Optional, Tuple
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -86,6 +88,17 @@ class CSPDarknetCustomP6(CSPDarknet):
 # ==========================================================================================
 # necks
 # ==========================================================================================
+def _topdown(g: Graph, csp, name: str, lateral: V, cat: "Buf", c_up: int) -> V:
+    """PAFPN top-down merge (yolo_pafpn.py:86-94, yolo_pafpn_p6.py:153-165): CSP(cat([upsample(lateral), feature])).
+    `cat` = [c_up channels reserved for the upsampled tensor | backbone feature, already written by its producer].
+    When the engine can fold the upsample into the consumer's loads the first half of `cat` is never written."""
+    feat = cat.view(c_up, cat.c - c_up)
+    if os.environ.get("YX_FUSE_UPSAMPLE", "1") != "0" and Graph.can_fuse_upsample(lateral):
+        return csp.emit(g, name, feat, up=lateral)
+    g.upsample(lateral, cat.view(0, c_up))
+    return csp.emit(g, name, cat.view())
+
+
 class YOLOPAFPN(nn.Module):
     """yolox/models/yolo_pafpn.py:15-106 / yolox_infer/models/yolo_pafpn.py."""
 
@@ -121,11 +134,9 @@ class YOLOPAFPN(nn.Module):
         f = self.backbone.emit(g, {"dark3": cat_p3.view(c[0], c[0]), "dark4": cat_p4.view(c[1], c[1]), "dark5": None})
         x0 = f["dark5"]
         fpn_out0 = self.lateral_conv0.emit(g, "backbone.lateral_conv0", x0, cat_n4.view(c[1], c[1]))
-        g.upsample(fpn_out0, cat_p4.view(0, c[1]))
-        f_out0 = self.C3_p4.emit(g, "backbone.C3_p4", cat_p4.view())
+        f_out0 = _topdown(g, self.C3_p4, "backbone.C3_p4", fpn_out0, cat_p4, c[1])
         fpn_out1 = self.reduce_conv1.emit(g, "backbone.reduce_conv1", f_out0, cat_n3.view(c[0], c[0]))
-        g.upsample(fpn_out1, cat_p3.view(0, c[0]))
-        pan_out2 = self.C3_p3.emit(g, "backbone.C3_p3", cat_p3.view())
+        pan_out2 = _topdown(g, self.C3_p3, "backbone.C3_p3", fpn_out1, cat_p3, c[0])
         self.bu_conv2.emit(g, "backbone.bu_conv2", pan_out2, cat_n3.view(0, c[0]))
         pan_out1 = self.C3_n3.emit(g, "backbone.C3_n3", cat_n3.view())
         self.bu_conv1.emit(g, "backbone.bu_conv1", pan_out1, cat_n4.view(0, c[1]))
@@ -177,14 +188,11 @@ class YOLOPAFPNCustomP6(nn.Module):
                                    "dark5": cat_p5.view(c[2], c[2]), "dark6": None})
         x0 = f["dark6"]
         fpn_out0 = self.lateral_conv0.emit(g, "backbone.lateral_conv0", x0, cat_n5.view(c[2], c[2]))
-        g.upsample(fpn_out0, cat_p5.view(0, c[2]))
-        f_out0 = self.C3_p5.emit(g, "backbone.C3_p5", cat_p5.view())
+        f_out0 = _topdown(g, self.C3_p5, "backbone.C3_p5", fpn_out0, cat_p5, c[2])
         fpn_out1 = self.lateral_conv1.emit(g, "backbone.lateral_conv1", f_out0, cat_n4.view(c[1], c[1]))
-        g.upsample(fpn_out1, cat_p4.view(0, c[1]))
-        f_out1 = self.C3_p4.emit(g, "backbone.C3_p4", cat_p4.view())
+        f_out1 = _topdown(g, self.C3_p4, "backbone.C3_p4", fpn_out1, cat_p4, c[1])
         fpn_out2 = self.reduce_conv1.emit(g, "backbone.reduce_conv1", f_out1, cat_n3.view(c[0], c[0]))
-        g.upsample(fpn_out2, cat_p3.view(0, c[0]))
-        pan_out3 = self.C3_p3.emit(g, "backbone.C3_p3", cat_p3.view())
+        pan_out3 = _topdown(g, self.C3_p3, "backbone.C3_p3", fpn_out2, cat_p3, c[0])
         self.bu_conv2.emit(g, "backbone.bu_conv2", pan_out3, cat_n3.view(0, c[0]))
         pan_out2 = self.C3_n3.emit(g, "backbone.C3_n3", cat_n3.view())
         self.bu_conv1.emit(g, "backbone.bu_conv1", pan_out2, cat_n4.view(0, c[1]))

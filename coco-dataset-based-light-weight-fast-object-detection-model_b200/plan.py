@@ -92,6 +92,7 @@ class PlannedOp:
     cout_pad: int = 0
     w_offset: int = 0
     b_offset: int = 0
+    up: Optional[V] = None      # low-resolution tensor whose x2 nearest upsampling is concatenated in front of src
 
 
 class Graph:
@@ -121,7 +122,7 @@ class Graph:
 
     def _add(self, op: PlannedOp) -> V:
         idx = len(self.ops)
-        self._touch(op.src, idx); self._touch(op.dst, idx); self._touch(op.res, idx)
+        self._touch(op.src, idx); self._touch(op.dst, idx); self._touch(op.res, idx); self._touch(op.up, idx)
         self.ops.append(op)
         return op.dst
 
@@ -145,10 +146,24 @@ class Graph:
         return self._add(PlannedOp(_capi.OP_CONV, name, src, dst, None, 3, 1, _capi.act_code(act), w48,
                                    bias.detach().float().cpu(), aux=1, cin_pad=48, cout_pad=_rup(cout, 16)))
 
+    @staticmethod
+    def can_fuse_upsample(up: V) -> bool:
+        """The engine folds nearest x2 upsample + concat into a 1x1 conv's loads when the upsampled part is whole
+        64-channel chunks of a plain (not level-windowed) buffer."""
+        return up.c % 64 == 0 and up.lvl_off == 0 and up.nstride == 0
+
     def conv(self, name: str, src: V, dst: V, weight: torch.Tensor, bias: torch.Tensor, stride: int, act: str,
-             res: Optional[V] = None) -> V:
+             res: Optional[V] = None, up: Optional[V] = None) -> V:
+        """up: conv over torch.cat([upsample2x(up), src], channel) without materialising either (1x1 only)."""
         cout, cin, k, k2 = weight.shape
         assert k == k2 and k in (1, 3), f"{name}: unsupported kernel size {k}"
+        if up is not None:
+            assert k == 1 and stride == 1 and self.can_fuse_upsample(up), f"{name}: cannot fuse this upsample"
+            assert (2 * up.H, 2 * up.W) == (src.H, src.W) and cin == up.c + src.c, f"{name}: upsample/concat shape mismatch"
+            assert cout <= dst.c <= _rup(cout, 16) and (dst.H, dst.W) == (src.H, src.W)
+            return self._add(PlannedOp(_capi.OP_CONV, name, src, dst, res, k, stride, _capi.act_code(act),
+                                       weight.detach().float().cpu(), bias.detach().float().cpu(), up=up,
+                                       cin_pad=up.c + _rup(src.c, 16), cout_pad=_rup(cout, 16)))
         assert cin <= src.c <= _rup(cin, 16), f"{name}: src has {src.c} channels, weight expects {cin}"
         assert cout <= dst.c <= _rup(cout, 16), f"{name}: dst has {dst.c} channels, weight gives {cout}"
         pad = k // 2
@@ -234,6 +249,8 @@ class Graph:
             o.dst = op.dst.to_c()
             if op.res is not None:
                 o.res = op.res.to_c()
+            if op.up is not None:
+                o.up = op.up.to_c()
             o.w_offset, o.b_offset, o.cin_pad, o.cout_pad = op.w_offset, op.b_offset, op.cin_pad, op.cout_pad
         return arr
 

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define YX_ABI_VERSION 1
+#define YX_ABI_VERSION 2
 
 typedef enum yx_status {
   YX_OK = 0,
@@ -74,6 +74,11 @@ typedef struct yx_op {
   yx_view src;        /* S2D: ignored (reads the external image) */
   yx_view dst;
   yx_view res;        /* residual added after the activation; res.c == 0 -> none */
+  yx_view up;         /* CONV (1x1, stride 1): low-resolution tensor [n, h/2, w/2, c_up] whose nearest-neighbour x2
+                         upsampling is CONCATENATED IN FRONT of src along channels (yolo_pafpn_p6.py:153-154): the
+                         upsample and the torch.cat are folded into the conv's TMA loads (stride-0 tensor-map
+                         dimensions repeat each pixel 2x2).  up.c == 0 -> none; up.c must be a multiple of 64.
+                         Weights cover [up channels | src channels] in that order */
   int64_t w_offset;   /* byte offset into the weight blob: fp16 [cout_pad][k*k][cin_pad] (DWCONV: [k*k][c]) */
   int64_t b_offset;   /* byte offset into the bias blob: fp32 [cout_pad] */
   int32_t cin_pad;    /* multiple of 16 */
@@ -141,6 +146,7 @@ typedef struct yx_conv_tune {
   int32_t staging_buffers;     /* 1 or 2 output staging buffers */
   int32_t second_producer;     /* 0 = one TMA producer warp per operand, 1 = add a second one */
   int32_t no_resident_weights; /* 1 = always stream the weights through the ring */
+  int32_t cta_pair;            /* 1 = two-CTA clusters issuing cta_group::2 MMAs (M = 256), half of the weights per CTA */
 } yx_conv_tune;
 int yx_conv2d_ex(const yx_op* op_host, void* base, const void* weights, const void* biases, const yx_conv_tune* tune_host,
                  void* stream);

@@ -18,10 +18,12 @@ def _rup(a, b):
 
 
 def run_conv_case(cin, cout, k, stride, H, W, B=2, act="silu", res=False, src_pitch=None, src_off=0,
-                  dst_pitch=None, dst_off=0, seed=0, dst_c=None, device="cuda", tune=None):
+                  dst_pitch=None, dst_off=0, seed=0, dst_c=None, device="cuda", tune=None, up_c=0):
     """Returns dict(max_err, ref_scale, out, ref).  src/dst may be channel slices of wider buffers
     (pitch/off in channels).  dst_c: channels of the dst view (>= cout, e.g. 8 for the 5-channel reg+obj pred).
-    tune: dict of yx_conv_tune fields forcing one launch shape (None = the library's heuristic)."""
+    tune: dict of yx_conv_tune fields forcing one launch shape (None = the library's heuristic).
+    up_c: channels of a low-resolution tensor [B, H/2, W/2, up_c] whose nearest x2 upsampling is concatenated in front of
+    the source (fused into the conv's loads); the weight then has up_c + cin input channels."""
     lib = _capi.load()
     g = torch.Generator().manual_seed(seed)
     pad = k // 2
@@ -30,12 +32,14 @@ def run_conv_case(cin, cout, k, stride, H, W, B=2, act="silu", res=False, src_pi
     dst_c = dst_c or cout
     dst_pitch = dst_pitch or dst_c
     x = (torch.randn(B, H, W, src_pitch, generator=g) * 1.0).half()
-    w = (torch.randn(cout, cin, k, k, generator=g) * (1.0 / np.sqrt(cin * k * k))).half()
+    w = (torch.randn(cout, cin + up_c, k, k, generator=g) * (1.0 / np.sqrt((cin + up_c) * k * k))).half()
+    xu = (torch.randn(B, H // 2, W // 2, max(up_c, 8), generator=g) * 1.0).half()
     b = torch.randn(cout, generator=g) * 0.5
     r = (torch.randn(B, Ho, Wo, dst_pitch, generator=g) * 1.0).half() if res else None
-    # arena: [src | dst | res] each 1024-aligned
+    # arena: [src | dst | res | up] each 1024-aligned
     sb, db = _rup(x.numel() * 2, 1024), _rup(B * Ho * Wo * dst_pitch * 2, 1024)
-    arena = torch.zeros(sb + 2 * db + 1024, dtype=torch.uint8, device=device)
+    ub = _rup(xu.numel() * 2, 1024)
+    arena = torch.zeros(sb + 2 * db + ub + 1024, dtype=torch.uint8, device=device)
     base_off = (-arena.data_ptr()) % 1024
     base = arena.data_ptr() + base_off
 
@@ -46,9 +50,11 @@ def run_conv_case(cin, cout, k, stride, H, W, B=2, act="silu", res=False, src_pi
     region(sb, dst_init.numel()).copy_(dst_init)
     if res:
         region(sb + db, r.numel()).copy_(r.reshape(-1).to(device))
-    cin_pad, cout_pad = _rup(cin, 16), _rup(cout, 16)
+    if up_c:
+        region(sb + 2 * db, xu.numel()).copy_(xu.reshape(-1).to(device))
+    cin_pad, cout_pad = up_c + _rup(cin, 16), _rup(cout, 16)
     wp = torch.zeros(cout_pad, k * k, cin_pad, dtype=torch.float16)
-    wp[:cout, :, :cin] = w.permute(0, 2, 3, 1).reshape(cout, k * k, cin)
+    wp[:cout, :, :cin + up_c] = w.permute(0, 2, 3, 1).reshape(cout, k * k, cin + up_c)
     bp = torch.zeros(cout_pad, dtype=torch.float32)
     bp[:cout] = b
     wd, bd = wp.to(device), bp.to(device)
@@ -62,6 +68,9 @@ def run_conv_case(cin, cout, k, stride, H, W, B=2, act="silu", res=False, src_pi
     if res:
         op.res.offset, op.res.nstride = sb + db + dst_off * 2, Ho * Wo * dst_pitch
         op.res.n, op.res.h, op.res.w, op.res.c, op.res.pitch = B, Ho, Wo, dst_c, dst_pitch
+    if up_c:
+        op.up.offset, op.up.nstride = sb + 2 * db, (H // 2) * (W // 2) * up_c
+        op.up.n, op.up.h, op.up.w, op.up.c, op.up.pitch = B, H // 2, W // 2, up_c, up_c
     op.w_offset, op.b_offset, op.cin_pad, op.cout_pad = 0, 0, cin_pad, cout_pad
     if tune is None:
         _capi.check(lib.yx_conv2d(ctypes.byref(op), base, wd.data_ptr(), bd.data_ptr(),
@@ -75,6 +84,8 @@ def run_conv_case(cin, cout, k, stride, H, W, B=2, act="silu", res=False, src_pi
     out = out_full[..., dst_off:dst_off + cout]
 
     xs = x[..., src_off:src_off + cin].float().permute(0, 3, 1, 2)
+    if up_c:
+        xs = torch.cat([F.interpolate(xu.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest"), xs], 1)
     ref = F.conv2d(xs.to(device), w.float().to(device), b.to(device), stride=stride, padding=pad).cpu()
     ref = activation(ref.half().float(), ACT_NAMES[act]).permute(0, 2, 3, 1)
     if res:
@@ -115,9 +126,9 @@ CASES = [
 ]
 
 
-def _t(variant, n_tile, ctas=1, halves=1, eg=1, sb=2, w3=1, nores=0):
+def _t(variant, n_tile, ctas=1, halves=1, eg=1, sb=2, w3=1, nores=0, pair=0):
     return dict(variant=variant, n_tile=n_tile, ctas_per_sm=ctas, halves=halves, epilogue_groups=eg, staging_buffers=sb,
-                second_producer=w3, no_resident_weights=nores)
+                second_producer=w3, no_resident_weights=nores, cta_pair=pair)
 
 
 # every launch shape the tuner may pick, forced on layers it applies to
@@ -140,6 +151,21 @@ TUNED_CASES = [
     dict(cin=48, cout=96, k=3, stride=2, H=64, W=64, act="hard_swish", tune=_t(1, 96, ctas=2)),
     dict(cin=48, cout=96, k=3, stride=2, H=64, W=64, act="hard_swish", tune=_t(1, 96, eg=2)),
     dict(cin=96, cout=192, k=3, stride=2, H=64, W=64, act="hard_swish", tune=_t(1, 192, w3=0)),
+    # CTA-pair (cta_group::2) shapes
+    dict(cin=192, cout=192, k=3, stride=1, H=80, W=80, act="hard_swish", tune=_t(2, 192, pair=1)),
+    dict(cin=192, cout=192, k=3, stride=1, H=40, W=40, act="hard_swish", tune=_t(2, 192, pair=1, sb=1)),            # odd number of x tiles
+    dict(cin=192, cout=384, k=3, stride=1, H=48, W=40, act="silu", tune=_t(2, 192, pair=1)),                          # 2 N tiles
+    dict(cin=288, cout=288, k=3, stride=1, H=40, W=40, act="hard_swish", tune=_t(2, 192, pair=1)),                    # N tiles 192 + 96, K tail
+    dict(cin=96, cout=96, k=3, stride=1, H=48, W=40, act="hard_swish", res=True, tune=_t(2, 96, pair=1)),
+    dict(cin=192, cout=192, k=3, stride=1, H=80, W=80, act="hard_swish", tune=_t(1, 192, pair=1)),                    # generic pair
+    dict(cin=768, cout=768, k=1, stride=1, H=40, W=40, act="hard_swish", tune=_t(1, 256, pair=1)),
+    dict(cin=384, cout=384, k=1, stride=1, H=20, W=20, act="silu", tune=_t(1, 128, pair=1, sb=1)),
+    dict(cin=192, cout=384, k=3, stride=2, H=80, W=80, act="hard_swish", tune=_t(1, 192, pair=1)),
+    # nearest x2 upsample + concat folded into the loads (stride-0 tensor-map dimensions)
+    dict(cin=192, cout=384, k=1, stride=1, H=80, W=80, act="hard_swish", up_c=192, tune=_t(1, 192)),
+    dict(cin=96, cout=96, k=1, stride=1, H=40, W=24, act="silu", up_c=64, tune=_t(1, 96, ctas=2)),                  # resident weights, K tail
+    dict(cin=576, cout=1152, k=1, stride=1, H=40, W=40, act="hard_swish", up_c=576, tune=_t(1, 256, pair=1)),      # C3_p5.conv1+2
+    dict(cin=192, cout=384, k=1, stride=1, H=44, W=36, act="hard_swish", up_c=192, tune=_t(1, 192, pair=1, sb=1)), # ragged tiles
 ]
 
 

@@ -28,7 +28,7 @@ def ulp16(t):
     return torch.pow(2.0, e - 10)
 
 
-def eval_op(o, image, src, res, wblob, bblob, q, want_band=False):
+def eval_op(o, image, src, res, wblob, bblob, q, want_band=False, up=None):
     """Evaluate one planned op in fp32.  o: _capi.Op; image NCHW fp32 (S2D only); src/res NHWC fp32;
     wblob fp32 view of the fp16 weight blob, bblob fp32.  q: rounding applied where the engine rounds to
     fp16 (identity for an exact evaluation).  Returns NHWC [n,h,w,dst.c]."""
@@ -61,6 +61,8 @@ def eval_op(o, image, src, res, wblob, bblob, q, want_band=False):
     if o.kind == _capi.OP_CONV:
         k = o.ksize
         x = src.permute(0, 3, 1, 2)
+        if o.up.c > 0:  # fused torch.cat([nn.Upsample(2, "nearest")(up), src], 1)
+            x = torch.cat([F.interpolate(up.permute(0, 3, 1, 2), scale_factor=2, mode="nearest"), x], 1)
         x = F.pad(x, (0, 0, 0, 0, 0, o.cin_pad - x.shape[1]))
         w = wblob[o.w_offset // 2: o.w_offset // 2 + o.cout_pad * k * k * o.cin_pad]
         w = w.view(o.cout_pad, k, k, o.cin_pad).permute(0, 3, 1, 2)
@@ -125,9 +127,10 @@ def run_graph_cpu(g, image, quantize=False):
         o = ops[i]
         src = arena.read(o.src) if o.kind != _capi.OP_S2D else None
         res = arena.read(o.res) if (o.kind == _capi.OP_CONV and o.res.c > 0) else None
-        for t, what in ((src, "src"), (res, "residual")):
+        up = arena.read(o.up) if (o.kind == _capi.OP_CONV and o.up.c > 0) else None
+        for t, what in ((src, "src"), (res, "residual"), (up, "upsample source")):
             assert t is None or not torch.isnan(t).any(), f"op {i} {pop.name}: {what} reads uninitialised arena memory"
-        arena.write(o.dst, eval_op(o, image, src, res, wblob, bblob, q))
+        arena.write(o.dst, eval_op(o, image, src, res, wblob, bblob, q, up=up))
     outs = g.outputs
     A, B = outs["reg"].h, g.batch
 
@@ -155,8 +158,9 @@ def teacher_forced_errors(model, x):
             src = eng.view_tensor(o.src).float() if o.kind != _capi.OP_S2D else None
             res = eng.view_tensor(o.res).float().clone() if (o.kind == _capi.OP_CONV and o.res.c > 0) else None
             band = None
+            up = eng.view_tensor(o.up).float() if (o.kind == _capi.OP_CONV and o.up.c > 0) else None
             if o.kind == _capi.OP_CONV:                            # before the op runs (dst may alias res)
-                ref, band = eval_op(o, xf, src, res, wblob, bblob, q, want_band=True)
+                ref, band = eval_op(o, xf, src, res, wblob, bblob, q, want_band=True, up=up)
             else:
                 ref = eval_op(o, xf, src, res, wblob, bblob, q)
             eng.run_ops(x, i, 1)
