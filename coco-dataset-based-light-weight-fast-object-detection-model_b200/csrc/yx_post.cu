@@ -69,6 +69,19 @@ __device__ __forceinline__ uint64_t make_key(float score, int anchor) {
   return (static_cast<uint64_t>(f2sortable(score)) << 32) | static_cast<uint64_t>(0xFFFFFFFFu - (uint32_t)anchor);
 }
 
+// Warp-aggregated counter increment (callable under divergence): lanes that target the same counter elect a leader
+// that performs ONE atomicAdd for all of them.  Per-candidate atomics on one address per image serialise in L2
+// (~34 000 same-address atomics per image made the selection kernel 25x slower than its HBM time).
+__device__ __forceinline__ int warp_agg_inc(int* ctr) {
+  const unsigned active = __activemask();
+  const unsigned same = __match_any_sync(active, reinterpret_cast<unsigned long long>(ctr));
+  const int lane = threadIdx.x & 31, leader = __ffs(same) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(ctr, __popc(same));
+  base = __shfl_sync(same, base, leader);
+  return base + __popc(same & ((1u << lane) - 1u));
+}
+
 // ------------------------------------------------------------------------------------------------
 // workspace
 // ------------------------------------------------------------------------------------------------
@@ -191,7 +204,7 @@ __global__ void select_infer_kernel(const T* __restrict__ reg, int64_t reg_sb, i
       const T* r = reg + b * reg_sb + a * reg_sa;
       ws.box[i] = decode_box_xyxy(ldf(r), ldf(r + 1), ldf(r + 2), ldf(r + 3), gx, gy, s);
       ws.objc[i] = oc; ws.col5[i] = best; ws.score[i] = best; ws.label[i] = bi;
-      const int pos = atomicAdd(ws.count + b, 1);
+      const int pos = warp_agg_inc(ws.count + b);
       ws.keys[(int64_t)b * ws.Apad + pos] = make_key(best, a);
     }
   }
@@ -213,7 +226,7 @@ __global__ void select_decoded_kernel(const float* __restrict__ boxes, const flo
     if (best >= thr) {
       ws.box[i] = reinterpret_cast<const float4*>(boxes)[i];
       ws.objc[i] = obj_conf[i]; ws.col5[i] = best; ws.score[i] = best; ws.label[i] = bi;
-      const int pos = atomicAdd(ws.count + b, 1);
+      const int pos = warp_agg_inc(ws.count + b);
       ws.keys[(int64_t)b * ws.Apad + pos] = make_key(best, a);
     }
   }
@@ -252,7 +265,7 @@ __global__ void select_yolox_kernel(T* __restrict__ pred, int B, int A, int C, f
     if (sc >= rnd<T>(thr)) {
       ws.box[i] = make_float4(x1, y1, x2, y2);
       ws.objc[i] = oc; ws.col5[i] = best; ws.score[i] = sc; ws.label[i] = bi;
-      const int pos = atomicAdd(ws.count + b, 1);
+      const int pos = warp_agg_inc(ws.count + b);
       ws.keys[(int64_t)b * ws.Apad + pos] = make_key(sc, a);
     }
   }
