@@ -7,6 +7,7 @@ Mirrors (reference root relative):
   :225-246 (SPPBottleneck), :249-320 (CSPLayer[Custom]), :323-361 (Focus[Custom])
   choijhanyangackr/yolox_infer/models/blocks.py (BN-free twins; bn=False here)
 """
+import os
 from typing import Optional
 
 import torch
@@ -105,6 +106,13 @@ class Bottleneck(nn.Module):
 
     def emit(self, g, name, x, out=None):
         y = self.conv1.emit(g, name + ".conv1", x)
+        if self.use_add and os.environ.get("YX_INPLACE_RESIDUAL", "1") != "0":
+            # y = x + conv2(conv1(x)) computed IN PLACE on x's buffer: the engine stores conv2's tile with a TMA
+            # reduce-add (fp16 add in L2), so the residual is never loaded into shared memory.  x has no other reader
+            # (network_blocks.py:199-205; inside CSPLayer the chain m.0 -> m.1 -> ... owns its input slice).
+            assert out is None or (out.buf is x.buf and out.c_off == x.c_off and out.c == x.c), \
+                "in-place Bottleneck: the requested output must be the input slice"
+            return self.conv2.emit(g, name + ".conv2", y, x, res=x)
         return self.conv2.emit(g, name + ".conv2", y, out, res=x if self.use_add else None)
 
     def forward(self, x):

@@ -256,8 +256,12 @@ __device__ __forceinline__ void halo_chunk_mma(uint32_t d0, uint32_t d1, uint32_
 
 // MODE: 0 = generic (one A box per tap), 1 = halo with one 128-pixel half per CTA, 2 = halo with two stacked halves
 // PAIR: two CTAs of a cluster share every MMA (cta_group::2, M = 256): half of the weight tile per CTA
-template <int ACT, bool HAS_RES, int MODE, bool PAIR>
+// RES:  0 = no residual; 1 = residual tile TMA-loaded into the staging buffer and added in registers;
+//       2 = the residual IS the destination (Bottleneck y = x + f(x) computed in place): the tile is stored with a TMA
+//           reduce-add, so the residual never passes through shared memory and the epilogue never waits for it
+template <int ACT, int RES, int MODE, bool PAIR>
 __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant__ ConvParams p) {
+  constexpr bool HAS_RES = RES == 1;
   constexpr bool HALO = MODE > 0;
   constexpr int MH = MODE == 2 ? 2 : 1;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;  // position in the CTA pair; rank 0 = leader (issues the MMAs)
@@ -589,8 +593,10 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
         named_bar_sync(2, n_epi);
         if (lead_warp && !(p.diag & 1)) {
           if (elect_one()) {
-            for (int g = 0; g < groups_cur; ++g)
-              tma_store_4d(&p.tmOut, sStage + g * kTileBytes, tc.n0 + g * 64, tc.x0, yh, tc.img);
+            for (int g = 0; g < groups_cur; ++g) {
+              if (RES == 2) tma_reduce_add_4d(&p.tmOut, sStage + g * kTileBytes, tc.n0 + g * 64, tc.x0, yh, tc.img);
+              else tma_store_4d(&p.tmOut, sStage + g * kTileBytes, tc.n0 + g * 64, tc.x0, yh, tc.img);
+            }
             tma_store_commit();
             if (h == MH - 1) YX_TRACE(5, t);
           }
@@ -862,7 +868,9 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
   pl.tune = t;
   ConvParams& p = pl.p;
   const int pad = op.ksize / 2;
-  p.ksize = op.ksize; p.stride = op.stride; p.act = op.act; p.has_res = g.has_res;
+  p.ksize = op.ksize; p.stride = op.stride; p.act = op.act;
+  const bool inplace = g.has_res && op.res.offset == d.offset && op.res.nstride == d.nstride && op.res.pitch == d.pitch;
+  p.has_res = !g.has_res ? 0 : (inplace ? 2 : 1);
   p.ky = op.ksize; p.kx = g.rowpack ? 1 : op.ksize;
   p.pad_y = pad; p.pad_x = g.rowpack ? 0 : pad;
   p.cin = op.cin_pad;
@@ -1023,17 +1031,17 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
   }
   pl.flops = g.flops;
   pl.bytes = g.act_bytes + 2.0 * (double)d.c * g.cin_real * op.ksize * op.ksize;
-  snprintf(pl.desc, sizeof pl.desc, "%s%s BN%d%s mh%d ctas%d epi%d sbuf%d A%dx%dK B%d%s w3:%d grid%d smem%dK", pair ? "pair-" : "", halo ? "halo" : "generic",
+  snprintf(pl.desc, sizeof pl.desc, "%s%s%s BN%d%s mh%d ctas%d epi%d sbuf%d A%dx%dK B%d%s w3:%d grid%d smem%dK", p.has_res == 2 ? "inplace-" : "", pair ? "pair-" : "", halo ? "halo" : "generic",
            p.BN, p.n_tiles_n > 1 ? "*" : "", p.mh, t.ctas, p.epi_groups, p.stage_bufs, p.stages_a, p.a_stage_bytes >> 10, p.b_slots,
            p.b_resident ? "res" : "", p.w3_role, pl.grid, pl.smem_bytes >> 10);
   *out = pl;
   return YX_OK;
 }
 
-template <int ACT, bool HAS_RES, int MODE, bool PAIR>
+template <int ACT, int RES, int MODE, bool PAIR>
 static int launch_variant(const ConvPlan& plan, cudaStream_t stream) {
   static bool attr_set = false;
-  auto kernel = conv_gemm_kernel<ACT, HAS_RES, MODE, PAIR>;
+  auto kernel = conv_gemm_kernel<ACT, RES, MODE, PAIR>;
   if (!attr_set) {
     YX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     attr_set = true;
@@ -1060,18 +1068,21 @@ static int launch_variant(const ConvPlan& plan, cudaStream_t stream) {
   return YX_OK;
 }
 
-template <int ACT, bool HAS_RES>
+template <int ACT, int RES>
 static int launch_mode(const ConvPlan& plan, cudaStream_t stream) {
   if (plan.p.pair)
-    return plan.p.halo ? launch_variant<ACT, HAS_RES, 1, true>(plan, stream) : launch_variant<ACT, HAS_RES, 0, true>(plan, stream);
-  if (plan.p.halo && plan.p.mh == 2) return launch_variant<ACT, HAS_RES, 2, false>(plan, stream);
-  if (plan.p.halo) return launch_variant<ACT, HAS_RES, 1, false>(plan, stream);
-  return launch_variant<ACT, HAS_RES, 0, false>(plan, stream);
+    return plan.p.halo ? launch_variant<ACT, RES, 1, true>(plan, stream) : launch_variant<ACT, RES, 0, true>(plan, stream);
+  if (plan.p.halo && plan.p.mh == 2) return launch_variant<ACT, RES, 2, false>(plan, stream);
+  if (plan.p.halo) return launch_variant<ACT, RES, 1, false>(plan, stream);
+  return launch_variant<ACT, RES, 0, false>(plan, stream);
 }
 
 template <int ACT>
 static int launch_act(const ConvPlan& plan, cudaStream_t stream) {
-  return plan.p.has_res ? launch_mode<ACT, true>(plan, stream) : launch_mode<ACT, false>(plan, stream);
+  // plan.store_only (tuning / profiling of an in-place residual conv): plain stores, so repeated launches do not accumulate
+  const int res = (plan.p.has_res == 2 && plan.store_only) ? 0 : plan.p.has_res;
+  if (res == 2) return launch_mode<ACT, 2>(plan, stream);
+  return res == 1 ? launch_mode<ACT, 1>(plan, stream) : launch_mode<ACT, 0>(plan, stream);
 }
 
 int conv_launch(const ConvPlan& plan, cudaStream_t stream) {

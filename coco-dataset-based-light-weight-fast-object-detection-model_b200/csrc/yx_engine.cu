@@ -66,6 +66,29 @@ static int run_step(yx_engine* e, const Step& s, const void* image, int image_dt
   }
 }
 
+// In-place residual convs (dst == res, stored with a TMA reduce-add) are not idempotent.  Tuning and profiling launch
+// them repeatedly with plain stores instead (same tiles, same traffic up to the L2 read-modify-write) and restore the
+// destination from a snapshot before the one real launch.
+struct DstSnapshot {
+  void* copy = nullptr;
+  uint8_t* first = nullptr;
+  size_t bytes = 0;
+  int take(yx_engine* e, const yx_view& v, cudaStream_t st) {
+    first = static_cast<uint8_t*>(e->arena) + v.offset;
+    bytes = ((size_t)(v.n - 1) * v.nstride + ((size_t)v.h * v.w - 1) * v.pitch + v.c) * 2;
+    YX_CUDA(cudaMalloc(&copy, bytes));
+    YX_CUDA(cudaMemcpyAsync(copy, first, bytes, cudaMemcpyDeviceToDevice, st));
+    return YX_OK;
+  }
+  int restore(cudaStream_t st) {
+    YX_CUDA(cudaMemcpyAsync(first, copy, bytes, cudaMemcpyDeviceToDevice, st));
+    return YX_OK;
+  }
+  void release(cudaStream_t st) {
+    if (copy) { cudaStreamSynchronize(st); cudaFree(copy); copy = nullptr; }
+  }
+};
+
 extern "C" const char* yx_last_error(void) { return g_last_error.c_str(); }
 extern "C" int yx_abi_version(void) { return YX_ABI_VERSION; }
 
@@ -207,9 +230,13 @@ extern "C" int yx_engine_tune(yx_engine* e, const void* image, int image_dtype, 
     conv_candidates(s.op, &cands);
     float best_ms = 1e30f;
     ConvPlan best = s.conv;
+    const bool inplace = s.conv.p.has_res == 2;
+    DstSnapshot snap;
+    if (inplace && (rc = snap.take(e, s.op.dst, st)) != YX_OK) break;
     for (const ConvTune& t : cands) {
       ConvPlan pl;
       if (conv_plan(s.op, e->arena, e->weights, e->biases, e->num_sms, &t, &pl) != YX_OK) continue;  // shape does not fit
+      pl.store_only = inplace ? 1 : 0;
       if ((rc = conv_launch(pl, st)) != YX_OK) break;  // warm-up (also sets the smem attribute)
       float ms_min = 1e30f;
       for (int k = 0; k < iters && rc == YX_OK; ++k) {
@@ -225,10 +252,13 @@ extern "C" int yx_engine_tune(yx_engine* e, const void* image, int image_dtype, 
       if (verbose) fprintf(stderr, "  tune op %zu  %-90s %.4f ms\n", i, pl.desc, ms_min);
       if (ms_min < best_ms) { best_ms = ms_min; best = pl; }
     }
-    if (rc != YX_OK) break;
+    if (rc != YX_OK) { snap.release(st); break; }
+    best.store_only = 0;
     s.conv = best;
     if (verbose) fprintf(stderr, "tune op %zu -> %s  %.4f ms\n", i, best.desc, best_ms);
-    rc = conv_launch(s.conv, st);  // leave the chosen variant's output in the arena
+    if (inplace) rc = snap.restore(st);
+    if (rc == YX_OK) rc = conv_launch(s.conv, st);  // leave the chosen variant's output in the arena
+    snap.release(st);
   }
   cudaEventDestroy(ev0);
   cudaEventDestroy(ev1);
@@ -261,16 +291,28 @@ extern "C" int yx_engine_profile(yx_engine* e, const void* image, int image_dtyp
   int rc = YX_OK;
   for (int i = 0; i < n_ops && rc == YX_OK; ++i) {
     const Step& s = e->steps[i];
-    // every op is idempotent on the arena (each reads buffers that later ops do not overwrite
-    // before it re-runs in this loop only if the plan has no aliasing between its src and dst)
-    rc = run_step(e, s, image, image_dtype, 1.0f, 0.0f, st);  // warm
-    if (rc) break;
+    // every op is idempotent on the arena except the in-place residual convs, which are timed with plain stores and
+    // then re-run once for real on the restored destination
+    const bool inplace = s.op.kind == YX_OP_CONV && s.conv.p.has_res == 2;
+    DstSnapshot snap;
+    Step timed = s;
+    if (inplace) {
+      if ((rc = snap.take(e, s.op.dst, st)) != YX_OK) break;
+      timed.conv.store_only = 1;
+    }
+    rc = run_step(e, timed, image, image_dtype, 1.0f, 0.0f, st);  // warm
+    if (rc) { snap.release(st); break; }
     cudaEventRecord(ev0, st);
-    for (int k = 0; k < iters && rc == YX_OK; ++k) rc = run_step(e, s, image, image_dtype, 1.0f, 0.0f, st);
+    for (int k = 0; k < iters && rc == YX_OK; ++k) rc = run_step(e, timed, image, image_dtype, 1.0f, 0.0f, st);
     cudaEventRecord(ev1, st);
+    if (inplace) {
+      if (rc == YX_OK) rc = snap.restore(st);
+      if (rc == YX_OK) rc = run_step(e, s, image, image_dtype, 1.0f, 0.0f, st);
+    }
     if (cudaEventSynchronize(ev1) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "profile sync", __FILE__, __LINE__); break; }
     float ms = 0;
     cudaEventElapsedTime(&ms, ev0, ev1);
+    snap.release(st);
     ms_host[i] = ms / iters;
     if (flops_host) flops_host[i] = s.flops;
     if (bytes_host) bytes_host[i] = s.bytes;

@@ -77,6 +77,7 @@ struct ConvPlan {
   ConvParams p;
   ConvTune tune;
   int grid, threads;
+  int store_only;  // launch an in-place residual conv (p.has_res == 2) with plain stores (tuning / profiling only)
   int smem_bytes;
   double flops;  // algorithmic: 2*N*Hout*Wout*Cout*Cin*k*k (real channel counts)
   double bytes;  // algorithmic: fp16 in + out (+ residual) + weights

@@ -48,7 +48,10 @@ def run_conv_case(cin, cout, k, stride, H, W, B=2, act="silu", res=False, src_pi
     region(0, x.numel()).copy_(x.reshape(-1).to(device))
     dst_init = torch.full((B * Ho * Wo * dst_pitch,), 7.0, dtype=torch.float16, device=device)  # sentinel
     region(sb, dst_init.numel()).copy_(dst_init)
-    if res:
+    inplace = res == "inplace"   # Bottleneck computed in place: the residual IS the destination (TMA reduce-add store)
+    if inplace:
+        region(sb, r.numel()).copy_(r.reshape(-1).to(device))
+    elif res:
         region(sb + db, r.numel()).copy_(r.reshape(-1).to(device))
     if up_c:
         region(sb + 2 * db, xu.numel()).copy_(xu.reshape(-1).to(device))
@@ -66,7 +69,7 @@ def run_conv_case(cin, cout, k, stride, H, W, B=2, act="silu", res=False, src_pi
     op.dst.offset, op.dst.nstride = sb + dst_off * 2, Ho * Wo * dst_pitch
     op.dst.n, op.dst.h, op.dst.w, op.dst.c, op.dst.pitch = B, Ho, Wo, dst_c, dst_pitch
     if res:
-        op.res.offset, op.res.nstride = sb + db + dst_off * 2, Ho * Wo * dst_pitch
+        op.res.offset, op.res.nstride = (sb if inplace else sb + db) + dst_off * 2, Ho * Wo * dst_pitch
         op.res.n, op.res.h, op.res.w, op.res.c, op.res.pitch = B, Ho, Wo, dst_c, dst_pitch
     if up_c:
         op.up.offset, op.up.nstride = sb + 2 * db, (H // 2) * (W // 2) * up_c
@@ -95,7 +98,8 @@ def run_conv_case(cin, cout, k, stride, H, W, B=2, act="silu", res=False, src_pi
     # untouched channels of the wider dst buffer must still hold the sentinel
     mask = torch.ones(dst_pitch, dtype=torch.bool)
     mask[dst_off:dst_off + dst_c] = False
-    clobbered = bool((out_full[..., mask] != 7.0).any()) if mask.any() else False
+    untouched = r.float()[..., mask] if inplace else 7.0
+    clobbered = bool((out_full[..., mask] != untouched).any()) if mask.any() else False
     pad_bad = bool((out_full[..., dst_off + cout:dst_off + dst_c] != 0).any()) if dst_c > cout else False
     return dict(max_err=float(err.max()), mean_err=float(err.mean()), ref_scale=float(ref.abs().mean()),
                 clobbered=clobbered, pad_nonzero=pad_bad, out=out, ref=ref)
@@ -161,6 +165,12 @@ TUNED_CASES = [
     dict(cin=768, cout=768, k=1, stride=1, H=40, W=40, act="hard_swish", tune=_t(1, 256, pair=1)),
     dict(cin=384, cout=384, k=1, stride=1, H=20, W=20, act="silu", tune=_t(1, 128, pair=1, sb=1)),
     dict(cin=192, cout=384, k=3, stride=2, H=80, W=80, act="hard_swish", tune=_t(1, 192, pair=1)),
+    # in-place residual (dst == res): stored with a TMA reduce-add
+    dict(cin=96, cout=96, k=3, stride=1, H=48, W=40, act="hard_swish", res="inplace", tune=_t(2, 96, halves=2)),
+    dict(cin=48, cout=48, k=3, stride=1, H=64, W=64, act="hard_swish", res="inplace", tune=_t(2, 48, halves=1, eg=2)),
+    dict(cin=192, cout=192, k=3, stride=1, H=80, W=80, act="silu", res="inplace", tune=_t(2, 192, pair=1)),
+    dict(cin=192, cout=192, k=3, stride=1, H=40, W=40, act="hard_swish", res="inplace", tune=_t(1, 192, sb=1)),
+    dict(cin=96, cout=96, k=1, stride=1, H=32, W=32, act="silu", res="inplace", dst_pitch=192, dst_off=0, tune=_t(1, 96, ctas=2)),  # slice of a wider buffer
     # nearest x2 upsample + concat folded into the loads (stride-0 tensor-map dimensions)
     dict(cin=192, cout=384, k=1, stride=1, H=80, W=80, act="hard_swish", up_c=192, tune=_t(1, 192)),
     dict(cin=96, cout=96, k=1, stride=1, H=40, W=24, act="silu", up_c=64, tune=_t(1, 96, ctas=2)),                  # resident weights, K tail

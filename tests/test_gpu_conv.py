@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _id(c):
-    return f"{c['cin']}->{c['cout']}_k{c['k']}s{c['stride']}_{c['H']}x{c['W']}" + ("_res" if c.get("res") else "") + \
+    return f"{c['cin']}->{c['cout']}_k{c['k']}s{c['stride']}_{c['H']}x{c['W']}" + ("_res" + ("inplace" if c.get("res") == "inplace" else "") if c.get("res") else "") + \
         ("_slice" if c.get("src_pitch") else "")
 
 
