@@ -8,7 +8,7 @@ One process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE); rank 0 prints ON
   value     device-resident images/s (inputs already in HBM), max-over-ranks device time
   e2e       same metric through the public API with pinned HOST buffers: H2D of the batch and D2H of the
             detections inside the timed region (copies double-buffered against compute)
-  roofline  all launches of the dominant kernel (conv_igemm_kernel): algorithmic conv FLOPs / their
+  roofline  all launches of the dominant kernel (conv_gemm_kernel): algorithmic conv FLOPs / their
             summed CUDA-event time, against MEASURED_PEAKS.json
   cpu_baseline / --impl reference: the CPU restatement of the reference path (oracle/) on the host cores.
 """
@@ -298,8 +298,17 @@ def run_ours(args, rank, world, local_rank):
     achieved_tf = conv_flops / (conv_ms * 1e-3) / 1e12
     hbm_bound = [p for p in conv if p["flops"] / max(p["bytes"], 1) < peaks["tflops"] * 1e12 / (peaks["hbm_gbs"] * 1e9)]
     hbm_ms, hbm_bytes = sum(p["ms"] for p in hbm_bound), sum(p["bytes"] for p in hbm_bound)
-    roof = dict(bound="tensor", kernel="conv_igemm_kernel", achieved=achieved_tf, peak=peaks["tflops"], unit="TFLOP/s",
-                frac=achieved_tf / peaks["tflops"], traffic=None, peak_source=peaks["source"],
+    traffic, traffic_src = None, None   # measured DRAM bytes per conv launch, from the committed ncu launch list
+    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tp):
+        tj = json.load(open(tp))
+        fam = tj["families"].get("conv_gemm_kernel")
+        if fam:
+            traffic, traffic_src = fam["dram_bytes_per_launch"], f"profiles/r01_traffic.json ({tj['source']})"
+    roof = dict(bound="tensor", kernel="conv_gemm_kernel (all instantiations)", achieved=achieved_tf, peak=peaks["tflops"],
+                unit="TFLOP/s", frac=achieved_tf / peaks["tflops"], traffic=traffic, traffic_source=traffic_src,
+                algorithmic_bytes_per_launch=sum(p["bytes"] for p in conv) / max(len(conv), 1),
+                algorithmic_flops_per_launch=conv_flops / max(len(conv), 1), peak_source=peaks["source"],
                 launches_per_step=len(conv), share_of_step=conv_ms / all_ms,
                 hbm_bound_layers=dict(n=len(hbm_bound), achieved_gbs=hbm_bytes / max(hbm_ms, 1e-9) / 1e6,
                                       peak_gbs=peaks["hbm_gbs"]))

@@ -25,7 +25,7 @@ def per_op(src, dst, title):
              f"batch {d['batch']}, {d['size']}x{d['size']}.  Peaks: {HBM:.0f} GB/s HBM, {TF:.0f} TFLOP/s (measured, sustained).",
              f"Total {tot:.2f} ms over {len(ops)} launches.  `bound` = roofline side of the op (AI vs ridge {TF * 1e3 / HBM:.0f} FLOP/B); "
              "`frac` = achieved / peak on that side.", "",
-             "| # | op | ms | % | GFLOP | MB | AI | TFLOP/s | GB/s | bound | frac |", "|---|---|---|---|---|---|---|---|---|---|---|"]
+             "| # | op | ms | % | GFLOP | MB | AI | TFLOP/s | GB/s | bound | frac | launch shape |", "|---|---|---|---|---|---|---|---|---|---|---|---|"]
     ridge = TF * 1e3 / HBM
     agg = collections.defaultdict(float)
     for i, o in enumerate(ops):
@@ -36,7 +36,7 @@ def per_op(src, dst, title):
         frac = tf / TF if bound == "tensor" else gb / HBM
         agg[bound + "_ms"] += o["ms"]; agg[bound + "_w"] += (o["flops"] if bound == "tensor" else o["bytes"])
         lines.append(f"| {i} | {o['name']} | {o['ms']:.3f} | {100 * o['ms'] / tot:.1f} | {o['flops'] / 1e9:.1f} | {o['bytes'] / 1e6:.1f} | "
-                     f"{ai:.0f} | {tf:.0f} | {gb:.0f} | {bound} | {frac:.2f} |")
+                     f"{ai:.0f} | {tf:.0f} | {gb:.0f} | {bound} | {frac:.2f} | {o.get('shape', '')} |")
     lines += ["", f"Tensor-bound ops: {agg['tensor_ms']:.2f} ms, aggregate {agg['tensor_w'] / max(agg['tensor_ms'], 1e-9) / 1e9:.0f} TFLOP/s "
               f"({agg['tensor_w'] / max(agg['tensor_ms'], 1e-9) / 1e9 / TF:.2f} of peak).",
               f"HBM-bound ops: {agg['hbm_ms']:.2f} ms, aggregate {agg['hbm_w'] / max(agg['hbm_ms'], 1e-9) / 1e6:.0f} GB/s "
@@ -46,21 +46,48 @@ def per_op(src, dst, title):
 
 
 def launches(src, dst):
-    rows = [r for r in csv.reader(open(src)) if len(r) > 10 and r[0] != "ID"]
-    tot = collections.OrderedDict()
-    for r in rows:
-        v, u = float(r[-1].replace(",", "")), r[-2]
-        us = v / 1000 if u in ("nsecond", "ns") else v if u in ("usecond", "us") else v * 1000
+    """ncu launch list (one row per launch and metric).  Writes the share table and, when the list carries
+    dram__bytes_*, profiles/<tag>_traffic.json = measured DRAM bytes per launch of each kernel family (bench.py
+    reports the conv family's figure as roofline.traffic)."""
+    by_id = collections.OrderedDict()
+    for r in csv.reader(open(src)):
+        if len(r) < 11 or r[0] == "ID":
+            continue
+        v, u, metric = float(r[-1].replace(",", "")), r[-2], r[-3]
         k = r[4].split("(")[0].replace("void ", "")
-        tot.setdefault(k, [0, 0.0]); tot[k][0] += 1; tot[k][1] += us
+        e = by_id.setdefault(r[0], dict(kernel=k))
+        if metric.startswith("gpu__time_duration"):
+            e["us"] = v / 1000 if u in ("nsecond", "ns") else v if u in ("usecond", "us") else v * 1000
+        elif metric.startswith("dram__bytes"):
+            scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+            e["dram"] = e.get("dram", 0.0) + v * scale
+    tot = collections.OrderedDict()
+    for e in by_id.values():
+        t = tot.setdefault(e["kernel"], [0, 0.0, 0.0])
+        t[0] += 1; t[1] += e.get("us", 0.0); t[2] += e.get("dram", 0.0)
     s = sum(v[1] for v in tot.values())
-    lines = ["# ncu launch list of one bench step (gpu__time_duration.sum, --clock-control none)", "",
+    has_dram = any(v[2] > 0 for v in tot.values())
+    lines = ["# ncu launch list of bench steps (gpu__time_duration.sum" + (", dram__bytes_read/write.sum" if has_dram else "") +
+             ", --clock-control none)", "",
              "Per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes.", "",
-             f"{len(rows)} launches, {s / 1000:.2f} ms summed.", "", "| kernel | launches | sum us | share |", "|---|---|---|---|"]
+             f"{len(by_id)} launches, {s / 1000:.2f} ms summed.", "",
+             "| kernel | launches | sum us | share | DRAM MB / launch |", "|---|---|---|---|---|"]
     for k, v in sorted(tot.items(), key=lambda kv: -kv[1][1]):
-        lines.append(f"| `{k}` | {v[0]} | {v[1]:.1f} | {100 * v[1] / s:.1f} % |")
+        lines.append(f"| `{k}` | {v[0]} | {v[1]:.1f} | {100 * v[1] / s:.1f} % | {v[2] / v[0] / 1e6:.1f} |")
+    fam = collections.defaultdict(lambda: [0, 0.0, 0.0])
+    for k, v in tot.items():
+        f = "conv_gemm_kernel" if "conv_gemm_kernel" in k else k.split("<")[0]
+        fam[f][0] += v[0]; fam[f][1] += v[1]; fam[f][2] += v[2]
+    lines += ["", "| kernel family | launches | share | DRAM MB / launch |", "|---|---|---|---|"]
+    for f, v in sorted(fam.items(), key=lambda kv: -kv[1][1]):
+        lines.append(f"| `{f}` | {v[0]} | {100 * v[1] / s:.1f} % | {v[2] / v[0] / 1e6:.1f} |")
     open(dst, "w").write("\n".join(lines) + "\n")
     print("wrote", dst)
+    if has_dram:
+        j = {f: dict(launches=v[0], share=v[1] / s, dram_bytes_per_launch=v[2] / v[0]) for f, v in fam.items()}
+        jp = os.path.join(OUT, f"{TAG}_traffic.json")
+        json.dump(dict(source=os.path.basename(src), families=j), open(jp, "w"), indent=1)
+        print("wrote", jp)
 
 
 WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
@@ -72,10 +99,19 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__warp_issue_stalled_barrier_per_warp_active.pct", "smsp__warp_issue_stalled_membar_per_warp_active.pct"]
 
 
+WANT += ["sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg", "l1tex__data_pipe_tc_wavefronts_mem_shared.sum",
+         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__inst_executed.sum", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+         "lts__throughput.avg.pct_of_peak_sustained_elapsed", "launch__cluster_size", "sm__inst_executed_pipe_uniform.sum"]
+
+
 def ncu(rep, dst, note):
+    """rep: an .ncu-rep, or the `--page raw --csv` export of one (made on the GPU box: reports exceed its return limit)."""
     if not os.path.exists(rep):
         return
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):
+        out = open(rep).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     if len(rows) < 3:
         return
@@ -100,4 +136,6 @@ if __name__ == "__main__":
         elif name.startswith("launches") and name.endswith(".csv"):
             launches(p, os.path.join(OUT, f"{TAG}_ncu_{name[:-4]}.md"))
         elif name.endswith(".ncu-rep"):
+            ncu(p, os.path.join(OUT, f"{TAG}_ncu_{name[:-8]}.txt"), name)
+        elif name.endswith("_raw.csv"):
             ncu(p, os.path.join(OUT, f"{TAG}_ncu_{name[:-8]}.txt"), name)
