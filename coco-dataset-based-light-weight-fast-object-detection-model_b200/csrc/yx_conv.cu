@@ -254,7 +254,9 @@ __device__ __forceinline__ void halo_chunk_mma(uint32_t d0, uint32_t d1, uint32_
   }
 }
 
-// MODE: 0 = generic (one A box per tap), 1 = halo with one 128-pixel half per CTA, 2 = halo with two stacked halves
+// MODE: 0 = generic (one A box per tap), 1 = halo with one 128-pixel half per CTA, 2 = halo with two stacked halves,
+//       3 = generic with a 256-pixel tile (two 128-row halves per A box): halves every per-tile fixed cost of the
+//           HBM-bound small-channel layers (N <= 128)
 // PAIR: two CTAs of a cluster share every MMA (cta_group::2, M = 256): half of the weight tile per CTA
 // RES:  0 = no residual; 1 = residual tile TMA-loaded into the staging buffer and added in registers;
 //       2 = the residual IS the destination (Bottleneck y = x + f(x) computed in place): the tile is stored with a TMA
@@ -262,8 +264,8 @@ __device__ __forceinline__ void halo_chunk_mma(uint32_t d0, uint32_t d1, uint32_
 template <int ACT, int RES, int MODE, bool PAIR>
 __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant__ ConvParams p) {
   constexpr bool HAS_RES = RES == 1;
-  constexpr bool HALO = MODE > 0;
-  constexpr int MH = MODE == 2 ? 2 : 1;
+  constexpr bool HALO = MODE == 1 || MODE == 2;
+  constexpr int MH = (MODE == 2 || MODE == 3) ? 2 : 1;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;  // position in the CTA pair; rank 0 = leader (issues the MMAs)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -492,6 +494,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
         }
       } else {
         const int k_iters = taps * k_chunks;
+        const uint32_t half_units = (uint32_t)(p.TH / 2 * p.TW) * 8;  // MODE 3: second half starts (TH/2)*TW rows of 128 B later
         int kc = 0;
         for (int i = 0; i < k_iters; ++i) {
           mbar_wait_acc(bar_fa + 8 * sa, pha, tracing, w_acc0);   // shared ring: covers the weights of this k-iteration too
@@ -502,14 +505,18 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
           if (elect_one()) {
             if (p.diag & 4) {
             } else if (!last || ks_last == 4) {
-              umma_x<PAIR>(d0, a_lo, a_hi, b_lo, b_hi, idesc, accum);
-              umma_x<PAIR>(d0, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
-              umma_x<PAIR>(d0, a_lo + 4, a_hi, b_lo + 4, b_hi, idesc, 1u);
-              umma_x<PAIR>(d0, a_lo + 6, a_hi, b_lo + 6, b_hi, idesc, 1u);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                umma_x<PAIR>(d0, a_lo + 2 * ks, a_hi, b_lo + 2 * ks, b_hi, idesc, ks == 0 ? accum : 1u);
+                if (MH == 2) umma_x<PAIR>(d1, a_lo + half_units + 2 * ks, a_hi, b_lo + 2 * ks, b_hi, idesc, ks == 0 ? accum : 1u);
+              }
             } else {
-              umma_x<PAIR>(d0, a_lo, a_hi, b_lo, b_hi, idesc, accum);
-              if (ks_last > 1) umma_x<PAIR>(d0, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
-              if (ks_last > 2) umma_x<PAIR>(d0, a_lo + 4, a_hi, b_lo + 4, b_hi, idesc, 1u);
+#pragma unroll
+              for (int ks = 0; ks < 3; ++ks)
+                if (ks < ks_last) {
+                  umma_x<PAIR>(d0, a_lo + 2 * ks, a_hi, b_lo + 2 * ks, b_hi, idesc, ks == 0 ? accum : 1u);
+                  if (MH == 2) umma_x<PAIR>(d1, a_lo + half_units + 2 * ks, a_hi, b_lo + 2 * ks, b_hi, idesc, ks == 0 ? accum : 1u);
+                }
             }
             commit_x<PAIR>(bar_ea + 8 * sa);  // frees the stage (A, and B when the ring is shared) when these MMAs retire
           }
@@ -533,11 +540,11 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     const int group = (warp - 4) >> 2;
     const int row = q * 32 + lane;
-    const bool row_valid = HALO ? true : (row < p.TH * p.TW);
+    const bool row_valid = HALO ? true : (row < p.TH / MH * p.TW);
     const bool lead_warp = warp == 4;  // issues the residual loads and the stores (one elected lane)
     const int epi_groups = p.epi_groups, stage_bufs = p.stage_bufs;
     const uint32_t n_epi = 128u * epi_groups;
-    const int store_th = HALO ? 16 : p.TH;
+    const int store_th = HALO ? 16 : p.TH / MH;
     const int BN = p.BN, cout16 = p.cout16;
     const uint32_t acc_stride = p.acc_stride;
     uint32_t t = 0, u = 0;  // tile counter, staging-unit counter (MH units per tile)
@@ -681,12 +688,13 @@ static int encode_view(CUtensorMap* m, void* base, const yx_view& v, int tw, int
   return encode_map(m, static_cast<uint8_t*>(base) + v.offset, 4, dims, st, box, true, what);
 }
 
-static void choose_tile(int H, int W, int* th, int* tw, bool even = false) {
+static void choose_tile(int H, int W, int* th, int* tw, bool even = false, int px = 128) {
   // minimise padded MMA rows; ties -> squarer tile (fewer halo re-reads from L2)
   double best = 1e30;
   int bh = even ? 2 : 1, bw = even ? 2 : 1;
-  for (int w = 1; w <= std::min(W, 128); ++w) {
-    int h = std::min(H, 128 / w);
+  for (int w = 1; w <= std::min(W, px); ++w) {
+    int h = std::min(H, px / w);
+    if (h > 256 || w > 256) continue;
     if (even) h &= ~1;
     if (even && (w & 1)) continue;
     if (h < 1) continue;
@@ -820,6 +828,10 @@ void conv_candidates(const yx_op& op, std::vector<ConvTune>* out) {
           memset(&t, 0, sizeof t);
           t.variant = 1; t.bn = bn; t.ctas = ctas; t.epi_groups = eg; t.stage_bufs = sb; t.w3 = 1;
           push(t);
+          if (bn <= 128 && ctas == 1 && !g.has_up) {  // 256-pixel tiles
+            t.mh = 2;
+            push(t);
+          }
         }
     if (bn >= 64 && cout16 >= 96)  // CTA-pair shapes: half of the weight tile per CTA
       for (int v = 1; v <= (halo_ok(op, g) ? 2 : 1); ++v)
@@ -905,6 +917,20 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
     p.acc_stride = stride_cols;
     p.tmem_cols = 32;
     while (p.tmem_cols < 2 * mh * stride_cols) p.tmem_cols <<= 1;
+  } else if (t.mh == 2) {
+    // generic with a 256-pixel tile: two halves of (TH/2) x TW pixels stacked in one A box
+    YX_REQUIRE(!pair && !g.has_up && 4 * stride_cols <= 512 && t.ctas == 1,
+               "conv tune: the 256-pixel generic tile needs N <= 128, one CTA per SM, no CTA pair and no fused upsample");
+    p.mh = 2;
+    choose_tile(g.Hout, g.Wout, &p.TH, &p.TW, true, 256);
+    YX_REQUIRE(p.TH % 2 == 0 && p.TH / 2 * p.TW <= 128 && (p.TH / 2 * p.TW) % 8 == 0 && p.TH / 2 * p.TW >= 64,
+               "conv tune: the map does not tile into two aligned 128-row halves");
+    p.a_box_bytes = p.TH * p.TW * 128;
+    p.a_stage_bytes = 2 * kTileBytes;
+    p.out_box_bytes = p.a_box_bytes / 2;
+    p.acc_stride = stride_cols;
+    p.tmem_cols = 32;
+    while (p.tmem_cols < 4 * stride_cols) p.tmem_cols <<= 1;
   } else {
     p.mh = 1;
     choose_tile(g.Hout, g.Wout, &p.TH, &p.TW, g.has_up);
@@ -1022,7 +1048,7 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
     YX_REQUIRE(op.w_offset % 16 == 0, "weight offset must be 16-byte aligned");
     if ((rc = encode_map(&p.tmW, addr, 3, dims, st, box, true, "W")) != YX_OK) return rc;
   }
-  const int store_th = halo ? 16 : p.TH;  // the halo variant stores one 16x8 half at a time
+  const int store_th = halo ? 16 : p.TH / p.mh;  // stacked halves are stored one at a time
   if ((rc = encode_view(&p.tmOut, base, d, p.TW, store_th, "out")) != YX_OK) return rc;
   if (g.has_res) {
     if ((rc = encode_view(&p.tmRes, base, op.res, p.TW, store_th, "res")) != YX_OK) return rc;
@@ -1074,6 +1100,7 @@ static int launch_mode(const ConvPlan& plan, cudaStream_t stream) {
     return plan.p.halo ? launch_variant<ACT, RES, 1, true>(plan, stream) : launch_variant<ACT, RES, 0, true>(plan, stream);
   if (plan.p.halo && plan.p.mh == 2) return launch_variant<ACT, RES, 2, false>(plan, stream);
   if (plan.p.halo) return launch_variant<ACT, RES, 1, false>(plan, stream);
+  if (plan.p.mh == 2) return launch_variant<ACT, RES, 3, false>(plan, stream);
   return launch_variant<ACT, RES, 0, false>(plan, stream);
 }
 

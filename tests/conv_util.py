@@ -165,6 +165,12 @@ TUNED_CASES = [
     dict(cin=768, cout=768, k=1, stride=1, H=40, W=40, act="hard_swish", tune=_t(1, 256, pair=1)),
     dict(cin=384, cout=384, k=1, stride=1, H=20, W=20, act="silu", tune=_t(1, 128, pair=1, sb=1)),
     dict(cin=192, cout=384, k=3, stride=2, H=80, W=80, act="hard_swish", tune=_t(1, 192, pair=1)),
+    # generic with 256-pixel tiles (two stacked halves per A box)
+    dict(cin=96, cout=96, k=1, stride=1, H=64, W=64, act="hard_swish", tune=_t(1, 96, halves=2)),
+    dict(cin=48, cout=96, k=3, stride=2, H=128, W=96, act="hard_swish", tune=_t(1, 96, halves=2, eg=2)),
+    dict(cin=48, cout=48, k=3, stride=1, H=64, W=48, act="hard_swish", res=True, tune=_t(1, 48, halves=2)),
+    dict(cin=16, cout=48, k=3, stride=1, H=64, W=64, act="silu", tune=_t(1, 48, halves=2)),
+    dict(cin=384, cout=384, k=1, stride=1, H=40, W=40, act="silu", res="inplace", tune=_t(1, 128, halves=2, nores=1)),   # 3 N tiles, ragged map
     # in-place residual (dst == res): stored with a TMA reduce-add
     dict(cin=96, cout=96, k=3, stride=1, H=48, W=40, act="hard_swish", res="inplace", tune=_t(2, 96, halves=2)),
     dict(cin=48, cout=48, k=3, stride=1, H=64, W=64, act="hard_swish", res="inplace", tune=_t(2, 48, halves=1, eg=2)),
