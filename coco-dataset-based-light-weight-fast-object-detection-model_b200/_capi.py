@@ -58,7 +58,8 @@ def make_levels(level_hw, strides) -> Levels:
 SYMBOLS = ["yx_last_error", "yx_abi_version", "yx_engine_create", "yx_engine_destroy", "yx_engine_run",
            "yx_engine_profile", "yx_engine_run_ops", "yx_engine_num_launches", "yx_engine_tune", "yx_engine_op_desc",
            "yx_conv2d", "yx_conv2d_ex", "yx_decode_infer", "yx_detect_workspace_bytes",
-           "yx_nms_main", "yx_detect_main", "yx_head_assemble", "yx_decode_outputs", "yx_postprocess_yolox"]
+           "yx_nms_main", "yx_detect_main", "yx_head_assemble", "yx_decode_outputs", "yx_postprocess_yolox",
+           "yx_preprocess_batch", "yx_coco_records"]
 
 _lib = None
 
@@ -106,6 +107,8 @@ def load():
     lib.yx_decode_outputs.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, ctypes.POINTER(Levels), c_vp]
     lib.yx_postprocess_yolox.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_f32, c_i32, c_vp, c_sz, c_vp, c_vp,
                                          c_vp, c_vp]
+    lib.yx_preprocess_batch.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_vp]
+    lib.yx_coco_records.argtypes = [c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp]
     if lib.yx_abi_version() != 2:
         raise RuntimeError("libyolox_b200.so ABI version mismatch")
     _lib = lib

@@ -823,7 +823,7 @@ void conv_candidates(const yx_op& op, std::vector<ConvTune>* out) {
       for (int eg = 1; eg <= 2; ++eg)
         for (int sb = 2; sb >= 1; --sb) {
           if (ctas == 2 && (bn > 128 || sb == 1 || eg == 2)) continue;  // 2 x 384 threads x ~90 regs exceed the register file
-          if (sb == 1 && bn < 128) continue;  // small tiles: the second staging buffer is cheap, keep it
+          if (sb == 1 && bn < 96) continue;  // small tiles: the second staging buffer is cheap, keep it
           ConvTune t;
           memset(&t, 0, sizeof t);
           t.variant = 1; t.bn = bn; t.ctas = ctas; t.epi_groups = eg; t.stage_bufs = sb; t.w3 = 1;

@@ -211,6 +211,25 @@ int yx_postprocess_yolox(void* prediction, int dtype, int B, int A, int C, float
                          void* workspace, size_t workspace_bytes, float* det, int32_t* det_count,
                          int32_t* det_anchor, void* stream);
 
+/* ---- the rows either side of the hot path ----------------------------------- */
+
+/* Device-side pre-processing of decoded RGB uint8 images (packed HWC, image b at src + src_off[b]):
+ * aspect-preserving Pillow-BILINEAR resize (bit-identical to PIL.Image.resize, two passes with uint8 rounding),
+ * top-left paste into a 114-filled [B,3,Hp,Wp] batch, RGB -> BGR, NCHW, values 0..255 in fp16 / fp32.
+ * geom[B][4] = (h, w, new_h, new_w); bounds_* / kk_* are Pillow's per-axis coefficient tables (first input index and
+ * tap count per output index; 22-bit fixed-point weights, ks_* per output index), built by the Python shim exactly
+ * like Resample.c's precompute_coeffs.  All pointers are device pointers.
+ * replaces: yolox_load_one_image_pil + yolox_collate_batch, choijhanyangackr/yolox_infer/preprocess_utils.py:9-55. */
+int yx_preprocess_batch(const void* src, const int64_t* src_off, const int32_t* geom, const int32_t* bounds_h,
+                        const int32_t* kk_h, const int32_t* bounds_v, const int32_t* kk_v, int ks_h, int ks_v, int B,
+                        int Hp, int Wp, void* out, int out_dtype, void* stream);
+
+/* det[B,max_det,7] (+ det_count[B]) -> records[B,max_det,6] = [x, y, w, h, score, category_id]: corners divided by
+ * scale[b] (fp32 division), xyxy -> xywh, score = det[4]*det[5], category_id = class_ids[(int)det[6]]; rows beyond
+ * det_count are zero.  replaces: convert_to_coco_format, choijhanyangackr/common/utils.py:27-73. */
+int yx_coco_records(const float* det, const int32_t* det_count, int B, int max_det, const float* scale,
+                    const int32_t* class_ids, int n_classes, float* records, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
