@@ -715,7 +715,7 @@ struct ConvGeom {
 static int conv_geom(const yx_op& op, ConvGeom* g) {
   const yx_view& s = op.src;
   const yx_view& d = op.dst;
-  YX_REQUIRE(op.ksize == 1 || op.ksize == 3, "conv ksize must be 1 or 3");
+  YX_REQUIRE(op.ksize == 1 || op.ksize == 3 || (op.ksize == 4 && op.stride == 2), "conv ksize must be 1, 3, or 4 with stride 2");
   YX_REQUIRE(op.stride == 1 || op.stride == 2, "conv stride must be 1 or 2");
   YX_REQUIRE(op.cin_pad % 16 == 0 && op.cout_pad % 16 == 0, "cin_pad/cout_pad must be multiples of 16");
   YX_REQUIRE(s.c % 8 == 0, "src channels must be a multiple of 8");
@@ -732,7 +732,7 @@ static int conv_geom(const yx_op& op, ConvGeom* g) {
   if (g->rowpack)
     YX_REQUIRE(op.ksize == 3 && op.stride == 1 && s.c == 16 && s.pitch == 16 && op.cin_pad == 48 && s.w > 4 && op.res.c == 0,
                "row-packed conv needs k=3, s=1, a padded 16-channel source and cin_pad = 48");
-  const int pad = op.ksize / 2;
+  const int pad = (op.ksize - 1) / 2;  // BaseConv: pad = (ksize - 1) // 2 (network_blocks.py:54); 4x4/s2 (P6-v2) pads 1
   g->Hout = g->rowpack ? s.h : (s.h + 2 * pad - op.ksize) / op.stride + 1;
   g->Wout = g->rowpack ? s.w - 4 : (s.w + 2 * pad - op.ksize) / op.stride + 1;
   YX_REQUIRE(d.h == g->Hout && d.w == g->Wout && d.n == s.n, "dst spatial dims do not match the conv geometry");
@@ -879,7 +879,7 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
   memset(&pl, 0, sizeof pl);
   pl.tune = t;
   ConvParams& p = pl.p;
-  const int pad = op.ksize / 2;
+  const int pad = (op.ksize - 1) / 2;
   p.ksize = op.ksize; p.stride = op.stride; p.act = op.act;
   const bool inplace = g.has_res && op.res.offset == d.offset && op.res.nstride == d.nstride && op.res.pitch == d.pitch;
   p.has_res = !g.has_res ? 0 : (inplace ? 2 : 1);

@@ -66,20 +66,24 @@ class CSPDarknet(nn.Module):
 class CSPDarknetCustomP6(CSPDarknet):
     """yolox/models/darknet_p6.py:10-137 / yolox_infer/models/darknet_p6.py (P3-P6, CSPLayerCustom)."""
 
-    def __init__(self, dep_mul, wid_mul, out_features=("dark3", "dark4", "dark5", "dark6"), act="hard_swish", bn=True):
+    def __init__(self, dep_mul, wid_mul, out_features=("dark3", "dark4", "dark5", "dark6"), act="hard_swish", bn=True,
+                 v2=False):
+        """v2: CSPDarknetP6v2 (yolox_infer/models/darknet_p6_v2.py): 4x4 stride-2 convs, dark5 = 3x bottlenecks with
+        shortcuts."""
         nn.Module.__init__(self)
         assert out_features, "please provide output features of Darknet"
         self.out_features = out_features
         bc, bd = int(wid_mul * 64), max(round(dep_mul * 3), 1)
         kw = dict(act=act, bn=bn)
         ckw = dict(act=act, bn=bn, custom=True)
+        dk = 4 if v2 else 3
         self.stem = FocusCustom(3, bc, ksize=3, **kw)
-        self.dark2 = nn.Sequential(BaseConv(bc, bc * 2, 3, 2, **kw), CSPLayer(bc * 2, bc * 2, n=bd, **ckw))
-        self.dark3 = nn.Sequential(BaseConv(bc * 2, bc * 4, 3, 2, **kw), CSPLayer(bc * 4, bc * 4, n=bd * 3, **ckw))
-        self.dark4 = nn.Sequential(BaseConv(bc * 4, bc * 8, 3, 2, **kw), CSPLayer(bc * 8, bc * 8, n=bd * 3, **ckw))
-        self.dark5 = nn.Sequential(BaseConv(bc * 8, bc * 12, 3, 2, **kw),
-                                   CSPLayer(bc * 12, bc * 12, n=bd, shortcut=False, **ckw))
-        self.dark6 = nn.Sequential(BaseConv(bc * 12, bc * 16, 3, 2, **kw),
+        self.dark2 = nn.Sequential(BaseConv(bc, bc * 2, dk, 2, **kw), CSPLayer(bc * 2, bc * 2, n=bd, **ckw))
+        self.dark3 = nn.Sequential(BaseConv(bc * 2, bc * 4, dk, 2, **kw), CSPLayer(bc * 4, bc * 4, n=bd * 3, **ckw))
+        self.dark4 = nn.Sequential(BaseConv(bc * 4, bc * 8, dk, 2, **kw), CSPLayer(bc * 8, bc * 8, n=bd * 3, **ckw))
+        self.dark5 = nn.Sequential(BaseConv(bc * 8, bc * 12, dk, 2, **kw),
+                                   CSPLayer(bc * 12, bc * 12, n=bd * 3 if v2 else bd, shortcut=bool(v2), **ckw))
+        self.dark6 = nn.Sequential(BaseConv(bc * 12, bc * 16, dk, 2, **kw),
                                    SPPBottleneck(bc * 16, bc * 16, activation=act, bn=bn),
                                    CSPLayer(bc * 16, bc * 16, n=bd, shortcut=False, **ckw))
         self.stages = ("dark2", "dark3", "dark4", "dark5", "dark6")
@@ -151,9 +155,11 @@ class YOLOPAFPNCustomP6(nn.Module):
     """yolox/models/yolo_pafpn_p6.py:14-178 / yolox_infer/models/yolo_pafpn_p6.py."""
 
     def __init__(self, depth=1.0, width=1.0, in_features=("dark3", "dark4", "dark5", "dark6"),
-                 in_channels=(256, 512, 768, 1024), act="hard_swish", bn=True):
+                 in_channels=(256, 512, 768, 1024), act="hard_swish", bn=True, v2=False):
+        """v2: YOLOPAFPNP6v2 (yolox_infer/models/yolo_pafpn_p6_v2.py): 4x4 stride-2 bottom-up convs, v2 backbone."""
         super().__init__()
-        self.backbone = CSPDarknetCustomP6(depth, width, act=act, bn=bn)
+        self.backbone = CSPDarknetCustomP6(depth, width, act=act, bn=bn, v2=v2)
+        dk = 4 if v2 else 3
         self.in_features, self.in_channels = in_features, in_channels
         assert len(in_channels) == 4
         c = [int(ch * width) for ch in in_channels]
@@ -167,11 +173,11 @@ class YOLOPAFPNCustomP6(nn.Module):
         self.C3_p4 = CSPLayer(2 * c[1], c[1], n, **ckw)
         self.reduce_conv1 = BaseConv(c[1], c[0], 1, 1, **kw)
         self.C3_p3 = CSPLayer(2 * c[0], c[0], n, **ckw)
-        self.bu_conv2 = BaseConv(c[0], c[0], 3, 2, **kw)
+        self.bu_conv2 = BaseConv(c[0], c[0], dk, 2, **kw)
         self.C3_n3 = CSPLayer(2 * c[0], c[1], n, **ckw)
-        self.bu_conv1 = BaseConv(c[1], c[1], 3, 2, **kw)
+        self.bu_conv1 = BaseConv(c[1], c[1], dk, 2, **kw)
         self.C3_n4 = CSPLayer(2 * c[1], c[2], n, **ckw)
-        self.bu_conv0 = BaseConv(c[2], c[2], 3, 2, **kw)
+        self.bu_conv0 = BaseConv(c[2], c[2], dk, 2, **kw)
         self.C3_n5 = CSPLayer(2 * c[2], c[3], n, **ckw)
         self.c = c
 
@@ -364,6 +370,18 @@ class _InferYOLOXP6(_EngineModel):
     def __init__(self, depth=1.0, width=1.0, act="hard_swish", num_classes: int = 80):
         super().__init__()
         self.backbone = YOLOPAFPNCustomP6(depth, width, in_channels=(256, 512, 768, 1024), act=act, bn=False)
+        self.head = YOLOXHead(num_classes, width, strides=(8, 16, 32, 64), in_channels=(256, 512, 768, 1024), act=act,
+                              bn=False)
+        self.eval()
+
+
+class _InferYOLOXP6v2(_EngineModel):
+    """choijhanyangackr/yolox_infer/models/yolox_p6_v2.py (main.py:39-41 builds it with act="silu")."""
+    flavour = "infer"
+
+    def __init__(self, depth=1.0, width=1.0, act="hard_swish", num_classes: int = 80):
+        super().__init__()
+        self.backbone = YOLOPAFPNCustomP6(depth, width, in_channels=(256, 512, 768, 1024), act=act, bn=False, v2=True)
         self.head = YOLOXHead(num_classes, width, strides=(8, 16, 32, 64), in_channels=(256, 512, 768, 1024), act=act,
                               bn=False)
         self.eval()

@@ -156,7 +156,7 @@ class Graph:
              res: Optional[V] = None, up: Optional[V] = None) -> V:
         """up: conv over torch.cat([upsample2x(up), src], channel) without materialising either (1x1 only)."""
         cout, cin, k, k2 = weight.shape
-        assert k == k2 and k in (1, 3), f"{name}: unsupported kernel size {k}"
+        assert k == k2 and (k in (1, 3) or (k == 4 and stride == 2)), f"{name}: unsupported kernel size {k}"
         if up is not None:
             assert k == 1 and stride == 1 and self.can_fuse_upsample(up), f"{name}: cannot fuse this upsample"
             assert (2 * up.H, 2 * up.W) == (src.H, src.W) and cin == up.c + src.c, f"{name}: upsample/concat shape mismatch"
@@ -166,7 +166,7 @@ class Graph:
                                        cin_pad=up.c + _rup(src.c, 16), cout_pad=_rup(cout, 16)))
         assert cin <= src.c <= _rup(cin, 16), f"{name}: src has {src.c} channels, weight expects {cin}"
         assert cout <= dst.c <= _rup(cout, 16), f"{name}: dst has {dst.c} channels, weight gives {cout}"
-        pad = k // 2
+        pad = (k - 1) // 2
         ho, wo = (src.H + 2 * pad - k) // stride + 1, (src.W + 2 * pad - k) // stride + 1
         assert (dst.H, dst.W) == (ho, wo), f"{name}: dst is {dst.H}x{dst.W}, conv gives {ho}x{wo}"
         if res is not None:
@@ -343,8 +343,10 @@ class Engine:
         """Strided fp16 torch view [n,h,w,c] of a C view (no copy)."""
         import torch
         a16 = self.arena[self._arena_pad:self._arena_pad + (self.graph.arena_bytes // 2) * 2].view(torch.float16)
+        # as_strided's storage_offset is absolute in the storage: add the slice's own offset (the alignment pad)
         return torch.as_strided(a16, (cview.n, cview.h, cview.w, cview.c),
-                                (cview.nstride, cview.w * cview.pitch, cview.pitch, 1), cview.offset // 2)
+                                (cview.nstride, cview.w * cview.pitch, cview.pitch, 1),
+                                a16.storage_offset() + cview.offset // 2)
 
     def profile(self, image, iters: int = 5):
         import ctypes

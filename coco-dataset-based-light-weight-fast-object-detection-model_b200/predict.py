@@ -13,10 +13,12 @@ def build_yolox(cfg: dict, device="cuda"):
     """main.py:31-59: model selected by substring of cfg["model"]["type"]; sparse checkpoints densified."""
     d, w = cfg["model"]["depth"], cfg["model"]["width"]
     model_type = cfg["model"]["type"].lower()
-    if "dw" in model_type or "p6-v2" in model_type:
-        raise NotImplementedError(f"model type {model_type!r}: depthwise-5x5 / P6-v2 variants are a later row "
-                                  "(SURVEY §8f N4)")
-    model = infer.YOLOXP6(d, w) if "p6" in model_type else infer.YOLOX(d, w)
+    if "dw" in model_type:
+        raise NotImplementedError(f"model type {model_type!r}: the depthwise-5x5 variant is a later row (SURVEY §8f N4)")
+    if "p6-v2" in model_type:
+        model = infer.YOLOXP6v2(d, w, act="silu")       # main.py:39-41 (SiLU!)
+    else:
+        model = infer.YOLOXP6(d, w) if "p6" in model_type else infer.YOLOX(d, w)
     model.eval()
     if cfg.get("ckpt") is not None:
         weights.load_checkpoint(model, cfg["ckpt"], sparse=bool(cfg.get("sparse")))

@@ -45,7 +45,7 @@ typedef enum yx_act {  /* replaces: get_activation, yolox/models/network_blocks.
 typedef enum yx_dtype { YX_F16 = 0, YX_F32 = 1 } yx_dtype;
 
 typedef enum yx_op_kind {
-  YX_OP_CONV = 0,      /* BaseConv.fused_forward: conv(k in {1,3}, stride in {1,2}, same pad)+bias+act(+residual)
+  YX_OP_CONV = 0,      /* BaseConv.fused_forward: conv(k in {1,3}, stride in {1,2}; k = 4 with stride 2; pad (k-1)/2)+bias+act(+residual)
                           replaces: network_blocks.py:73-84,199-205 ; yolox_infer/models/blocks.py:21-49 */
   YX_OP_S2D = 1,       /* Focus / FocusCustom space-to-depth of the NCHW input image into NHWC[.,.,.,16]
                           replaces: network_blocks.py:330-361 ; blocks.py:286-304 */
@@ -68,7 +68,7 @@ typedef struct yx_view {
 
 typedef struct yx_op {
   int32_t kind;       /* yx_op_kind */
-  int32_t ksize;      /* CONV/DWCONV: 1,3 (DWCONV also 5) */
+  int32_t ksize;      /* CONV: 1, 3, or 4 (stride 2 only); DWCONV: 3, 5 */
   int32_t stride;     /* CONV: 1 or 2 */
   int32_t act;        /* yx_act */
   yx_view src;        /* S2D: ignored (reads the external image) */

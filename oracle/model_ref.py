@@ -41,6 +41,8 @@ class ModelCfg:
     act: str = "hard_swish"
     num_classes: int = 80
     depthwise_neck: bool = False  # YOLOPAFPN(depthwise=True): DWConv in the neck bottlenecks
+    v2: bool = False              # P6-v2 (yolox_infer/models/*_p6_v2.py): every stride-2 conv is 4x4, dark5's CSP has
+                                  # 3x the bottlenecks WITH shortcuts (darknet_p6_v2.py:65-75), activation SiLU (main.py:40)
 
     @property
     def strides(self) -> Tuple[int, ...]:
@@ -60,6 +62,8 @@ CONFIGS = {
     # tiny variants used for fast CPU parity tests / committed golden vectors
     "tiny": ModelCfg("yolox", 0.33, 0.25, "silu", 80, False),
     "tiny_p6": ModelCfg("p6", 0.33, 0.25, "hard_swish", 80, False),
+    "yolox_m_p6_v2": ModelCfg("p6", 0.67, 0.75, "silu", 80, False, True),
+    "tiny_p6_v2": ModelCfg("p6", 0.33, 0.25, "silu", 80, False, True),
 }
 
 
@@ -104,22 +108,23 @@ def conv_specs(cfg: ModelCfg) -> List[Tuple[str, int, int, int, int, int]]:
     bd = max(round(cfg.depth * 3), 1)
     n_neck = round(3 * cfg.depth)
     custom = cfg.kind == "p6"
+    dk = 4 if cfg.v2 else 3  # stride-2 ("down") conv kernel size
     bb = "backbone.backbone."
     s: List[Tuple[str, int, int, int, int, int]] = []
     s.append((bb + "stem.conv", 12, base, 3, 1, 1))
-    s.append((bb + "dark2.0", base, base * 2, 3, 2, 1))
+    s.append((bb + "dark2.0", base, base * 2, dk, 2, 1))
     s += _csp_specs(bb + "dark2.1", base * 2, base * 2, bd, custom, False)
-    s.append((bb + "dark3.0", base * 2, base * 4, 3, 2, 1))
+    s.append((bb + "dark3.0", base * 2, base * 4, dk, 2, 1))
     s += _csp_specs(bb + "dark3.1", base * 4, base * 4, bd * 3, custom, False)
-    s.append((bb + "dark4.0", base * 4, base * 8, 3, 2, 1))
+    s.append((bb + "dark4.0", base * 4, base * 8, dk, 2, 1))
     s += _csp_specs(bb + "dark4.1", base * 8, base * 8, bd * 3, custom, False)
     if custom:
-        s.append((bb + "dark5.0", base * 8, base * 12, 3, 2, 1))
-        s += _csp_specs(bb + "dark5.1", base * 12, base * 12, bd, True, False)
+        s.append((bb + "dark5.0", base * 8, base * 12, dk, 2, 1))
+        s += _csp_specs(bb + "dark5.1", base * 12, base * 12, bd * 3 if cfg.v2 else bd, True, False)
         last, lc = "dark6", base * 12
     else:
         last, lc = "dark5", base * 8
-    s.append((bb + last + ".0", lc, base * 16, 3, 2, 1))
+    s.append((bb + last + ".0", lc, base * 16, dk, 2, 1))
     s.append((bb + last + ".1.conv1", base * 16, base * 8, 1, 1, 1))
     s.append((bb + last + ".1.conv2", base * 32, base * 16, 1, 1, 1))
     s += _csp_specs(bb + last + ".2", base * 16, base * 16, bd, custom, False)
@@ -134,20 +139,20 @@ def conv_specs(cfg: ModelCfg) -> List[Tuple[str, int, int, int, int, int]]:
         s += _csp_specs(nb + "C3_p4", 2 * ic[1], ic[1], n_neck, True, dw)
         s.append((nb + "reduce_conv1", ic[1], ic[0], 1, 1, 1))
         s += _csp_specs(nb + "C3_p3", 2 * ic[0], ic[0], n_neck, True, dw)
-        s.append((nb + "bu_conv2", ic[0], ic[0], 3, 2, 1))
+        s.append((nb + "bu_conv2", ic[0], ic[0], dk, 2, 1))
         s += _csp_specs(nb + "C3_n3", 2 * ic[0], ic[1], n_neck, True, dw)
-        s.append((nb + "bu_conv1", ic[1], ic[1], 3, 2, 1))
+        s.append((nb + "bu_conv1", ic[1], ic[1], dk, 2, 1))
         s += _csp_specs(nb + "C3_n4", 2 * ic[1], ic[2], n_neck, True, dw)
-        s.append((nb + "bu_conv0", ic[2], ic[2], 3, 2, 1))
+        s.append((nb + "bu_conv0", ic[2], ic[2], dk, 2, 1))
         s += _csp_specs(nb + "C3_n5", 2 * ic[2], ic[3], n_neck, True, dw)
     else:
         s.append((nb + "lateral_conv0", ic[2], ic[1], 1, 1, 1))
         s += _csp_specs(nb + "C3_p4", 2 * ic[1], ic[1], n_neck, False, dw)
         s.append((nb + "reduce_conv1", ic[1], ic[0], 1, 1, 1))
         s += _csp_specs(nb + "C3_p3", 2 * ic[0], ic[0], n_neck, False, dw)
-        s.append((nb + "bu_conv2", ic[0], ic[0], 3, 2, 1))
+        s.append((nb + "bu_conv2", ic[0], ic[0], dk, 2, 1))
         s += _csp_specs(nb + "C3_n3", 2 * ic[0], ic[1], n_neck, False, dw)
-        s.append((nb + "bu_conv1", ic[1], ic[1], 3, 2, 1))
+        s.append((nb + "bu_conv1", ic[1], ic[1], dk, 2, 1))
         s += _csp_specs(nb + "C3_n4", 2 * ic[1], ic[2], n_neck, False, dw)
 
     hc = int(256 * cfg.width)
@@ -371,7 +376,7 @@ def backbone_features(sd, cfg: ModelCfg, x):
     feats = [d3, d4]
     if custom:
         x = _bconv(sd, bb + "dark5.0", x, 2, act)
-        x = _csp(sd, bb + "dark5.1", x, bd, act, False)
+        x = _csp(sd, bb + "dark5.1", x, bd * 3 if cfg.v2 else bd, act, cfg.v2)
         feats.append(x)
         last = "dark6"
     else:

@@ -26,7 +26,7 @@ def run_conv_case(cin, cout, k, stride, H, W, B=2, act="silu", res=False, src_pi
     the source (fused into the conv's loads); the weight then has up_c + cin input channels."""
     lib = _capi.load()
     g = torch.Generator().manual_seed(seed)
-    pad = k // 2
+    pad = (k - 1) // 2
     Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
     src_pitch = src_pitch or cin
     dst_c = dst_c or cout
@@ -127,6 +127,8 @@ CASES = [
     dict(cin=1152, cout=864, k=1, stride=1, H=40, W=40, act="hard_swish", B=1),  # deep K, 4 N tiles
     dict(cin=576, cout=768, k=3, stride=2, H=40, W=40, act="hard_swish", B=1),
     dict(cin=192, cout=192, k=3, stride=1, H=160, W=160, act="hard_swish", B=2),  # many tiles per CTA
+    dict(cin=48, cout=96, k=4, stride=2, H=64, W=48, act="silu"),              # P6-v2 down conv (4x4, stride 2, pad 1)
+    dict(cin=192, cout=384, k=4, stride=2, H=40, W=40, act="silu"),
 ]
 
 

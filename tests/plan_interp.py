@@ -67,7 +67,7 @@ def eval_op(o, image, src, res, wblob, bblob, q, want_band=False, up=None):
         w = wblob[o.w_offset // 2: o.w_offset // 2 + o.cout_pad * k * k * o.cin_pad]
         w = w.view(o.cout_pad, k, k, o.cin_pad).permute(0, 3, 1, 2)
         b = bblob[o.b_offset // 4: o.b_offset // 4 + o.cout_pad]
-        y0 = q(F.conv2d(x, w, b, stride=o.stride, padding=k // 2))
+        y0 = q(F.conv2d(x, w, b, stride=o.stride, padding=(k - 1) // 2))
         y = _act(y0, o.act)
         band = None
         if want_band:  # output change when the fp32 sum rounds to a NEIGHBOURING fp16 value (order of accumulation)

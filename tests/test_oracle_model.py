@@ -53,6 +53,21 @@ def test_forward_matches_reference(path):
     _close(mr.forward_yolox(train_sd, cfg, x, decode=True).numpy(), g["yolox_decoded_unfused"], 5e-4, 5e-4)
 
 
+def test_p6_v2_forward_matches_reference():
+    """P6-v2 (4x4 stride-2 convs, 3x dark5 bottlenecks with shortcuts, SiLU): raw logits of the reference's inference twin
+    loaded strictly with these weights (tests/golden/make_golden.py::golden_infer_v2)."""
+    path = os.path.join(os.path.dirname(__file__), "golden", "infer_tiny_p6_v2_128x128_b1_s4.npz")
+    g = np.load(path)
+    cfg = mr.CONFIGS["tiny_p6_v2"]
+    fused = mr.fold_bn(mr.synth_train_state(cfg, 4, calib_hw=(128, 128)))
+    x = mr.synth_images(1004, 1, 128, 128)
+    np.testing.assert_array_equal(x.numpy(), g["x"])
+    assert fused["backbone.backbone.dark2.0.conv.weight"].shape[-2:] == (4, 4)
+    assert fused["backbone.bu_conv0.conv.weight"].shape[-2:] == (4, 4)
+    reg, obj, cls = mr.forward_raw(fused, cfg, x)
+    _close(reg.numpy(), g["reg"]); _close(obj.numpy(), g["obj"]); _close(cls.numpy(), g["cls"])
+
+
 def test_state_dict_key_count_m_p6():
     """the M-P6 inference twin has 278 tensors."""
     cfg = mr.CONFIGS["yolox_m_p6"]
