@@ -10,6 +10,7 @@ import bench
 import yolox_b200 as yb
 
 torch.set_grad_enabled(False)
+os.environ["YX_TUNE"] = "0"   # bit-equality across DIFFERENT per-rank batch sizes needs the shape-only heuristic launch shapes
 rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
