@@ -96,13 +96,35 @@ class DWConv(nn.Module):
         _no_eager(self)
 
 
+class DWConvNoP(nn.Module):
+    """Depthwise conv only (yolox_infer/models/blocks.py:66-78)."""
+
+    def __init__(self, in_channels, out_channels, ksize, stride=1, act="silu", bn=True):
+        super().__init__()
+        assert out_channels == in_channels
+        self.dconv = BaseConv(in_channels, in_channels, ksize, stride, groups=in_channels, act=act, bn=bn)
+
+    def emit(self, g, name, x, out=None, res=None):
+        assert res is None
+        return self.dconv.emit(g, name + ".dconv", x, out)
+
+    def forward(self, x):
+        _no_eager(self)
+
+
 class Bottleneck(nn.Module):
-    def __init__(self, in_channels, out_channels, shortcut=True, expansion=0.5, depthwise=False, act="silu", bn=True):
+    def __init__(self, in_channels, out_channels, shortcut=True, expansion=0.5, depthwise=False, act="silu", bn=True,
+                 kernel_size=3, custom=False, is_last=False):
+        """custom=True: BottleneckCustom (yolox_infer/models/blocks.py:113-147): a depthwise bottleneck that is neither
+        the last of its CSP nor a residual one has no pointwise conv (DWConvNoP)."""
         super().__init__()
         hidden = int(out_channels * expansion)
         self.conv1 = BaseConv(in_channels, hidden, 1, 1, act=act, bn=bn)
-        self.conv2 = (DWConv if depthwise else BaseConv)(hidden, out_channels, 3, 1, act=act, bn=bn)
         self.use_add = shortcut and in_channels == out_channels
+        if depthwise and custom and not is_last and not self.use_add:
+            self.conv2 = DWConvNoP(hidden, out_channels, kernel_size, 1, act=act, bn=bn)
+        else:
+            self.conv2 = (DWConv if depthwise else BaseConv)(hidden, out_channels, kernel_size, 1, act=act, bn=bn)
 
     def emit(self, g, name, x, out=None):
         y = self.conv1.emit(g, name + ".conv1", x)
@@ -146,13 +168,14 @@ class CSPLayer(nn.Module):
     """stock CSP (custom=False, network_blocks.py:249-283) or CSPLayerCustom (custom=True, :286-320)."""
 
     def __init__(self, in_channels, out_channels, n=1, shortcut=True, expansion=0.5, depthwise=False, act="silu",
-                 bn=True, custom=False):
+                 bn=True, custom=False, kernel_size=3):
         super().__init__()
         hidden = int(out_channels * expansion)
         c2 = (in_channels - hidden) if custom else hidden
         self.conv1 = BaseConv(in_channels, hidden, 1, 1, act=act, bn=bn)
         self.conv2 = BaseConv(in_channels, c2, 1, 1, act=act, bn=bn)
-        self.m = nn.Sequential(*[Bottleneck(hidden, hidden, shortcut, 1.0, depthwise, act=act, bn=bn) for _ in range(n)])
+        self.m = nn.Sequential(*[Bottleneck(hidden, hidden, shortcut, 1.0, depthwise, act=act, bn=bn, kernel_size=kernel_size,
+                                            custom=custom, is_last=(i == n - 1)) for i in range(n)])
         self.conv3 = BaseConv(hidden + c2, out_channels, 1, 1, act=act, bn=bn)
         self.hidden, self.c2 = hidden, c2
 

@@ -89,6 +89,27 @@ class CSPDarknetCustomP6(CSPDarknet):
         self.stages = ("dark2", "dark3", "dark4", "dark5", "dark6")
 
 
+class CSPDarknetDepthwise(CSPDarknet):
+    """choijhanyangackr/yolox_infer/models/darknet_dw.py:6-101: P3-P5 with (4b, 8b, 12b) channels, 4x4 stride-2 convs,
+    CSPLayerCustom whose dark3..dark5 bottlenecks are depthwise 5x5."""
+
+    def __init__(self, dep_mul, wid_mul, out_features=("dark3", "dark4", "dark5"), act="hard_swish", bn=True):
+        nn.Module.__init__(self)
+        self.out_features = out_features
+        bc, bd = int(wid_mul * 64), max(round(dep_mul * 3), 1)
+        kw = dict(act=act, bn=bn)
+        ckw = dict(act=act, bn=bn, custom=True)
+        dkw = dict(depthwise=True, kernel_size=5, **ckw)
+        self.stem = FocusCustom(3, bc, ksize=3, **kw)
+        self.dark2 = nn.Sequential(BaseConv(bc, bc * 2, 4, 2, **kw), CSPLayer(bc * 2, bc * 2, n=bd, **ckw))
+        self.dark3 = nn.Sequential(BaseConv(bc * 2, bc * 4, 4, 2, **kw), CSPLayer(bc * 4, bc * 4, n=bd * 3, **dkw))
+        self.dark4 = nn.Sequential(BaseConv(bc * 4, bc * 8, 4, 2, **kw), CSPLayer(bc * 8, bc * 8, n=bd * 3, **dkw))
+        self.dark5 = nn.Sequential(BaseConv(bc * 8, bc * 12, 4, 2, **kw),
+                                   SPPBottleneck(bc * 12, bc * 12, activation=act, bn=bn),
+                                   CSPLayer(bc * 12, bc * 12, n=bd, shortcut=False, **dkw))
+        self.stages = ("dark2", "dark3", "dark4", "dark5")
+
+
 # ==========================================================================================
 # necks
 # ==========================================================================================
@@ -149,6 +170,31 @@ class YOLOPAFPN(nn.Module):
 
     def forward(self, x):
         _no_eager(self)
+
+
+class YOLOPAFPNDepthwise(YOLOPAFPN):
+    """choijhanyangackr/yolox_infer/models/yolo_pafpn_dw.py:8-140: the 3-level PAFPN over CSPDarknetDepthwise, depthwise
+    5x5 CSPLayerCustom blocks, 4x4 stride-2 bottom-up convs (same dataflow as YOLOPAFPN, so emit() is inherited)."""
+
+    def __init__(self, depth=1.0, width=1.0, in_features=("dark3", "dark4", "dark5"), in_channels=(256, 512, 768),
+                 act="hard_swish", bn=True):
+        nn.Module.__init__(self)
+        self.backbone = CSPDarknetDepthwise(depth, width, act=act, bn=bn)
+        self.in_features, self.in_channels = in_features, in_channels
+        c = [int(ch * width) for ch in in_channels]
+        n = round(3 * depth)
+        kw = dict(act=act, bn=bn)
+        ckw = dict(shortcut=False, depthwise=True, kernel_size=5, custom=True, act=act, bn=bn)
+        self.upsample = nn.Upsample(scale_factor=2, mode="nearest")
+        self.lateral_conv0 = BaseConv(c[2], c[1], 1, 1, **kw)
+        self.C3_p4 = CSPLayer(2 * c[1], c[1], n, **ckw)
+        self.reduce_conv1 = BaseConv(c[1], c[0], 1, 1, **kw)
+        self.C3_p3 = CSPLayer(2 * c[0], c[0], n, **ckw)
+        self.bu_conv2 = BaseConv(c[0], c[0], 4, 2, **kw)
+        self.C3_n3 = CSPLayer(2 * c[0], c[1], n, **ckw)
+        self.bu_conv1 = BaseConv(c[1], c[1], 4, 2, **kw)
+        self.C3_n4 = CSPLayer(2 * c[1], c[2], n, **ckw)
+        self.c = c
 
 
 class YOLOPAFPNCustomP6(nn.Module):
@@ -384,6 +430,17 @@ class _InferYOLOXP6v2(_EngineModel):
         self.backbone = YOLOPAFPNCustomP6(depth, width, in_channels=(256, 512, 768, 1024), act=act, bn=False, v2=True)
         self.head = YOLOXHead(num_classes, width, strides=(8, 16, 32, 64), in_channels=(256, 512, 768, 1024), act=act,
                               bn=False)
+        self.eval()
+
+
+class _InferYOLOXDepthwise(_EngineModel):
+    """choijhanyangackr/yolox_infer/models/yolox_dw.py (main.py:36-38)."""
+    flavour = "infer"
+
+    def __init__(self, depth=1.0, width=1.0, act="hard_swish", num_classes: int = 80):
+        super().__init__()
+        self.backbone = YOLOPAFPNDepthwise(depth, width, in_channels=(256, 512, 768), act=act, bn=False)
+        self.head = YOLOXHead(num_classes, width, strides=(8, 16, 32), in_channels=(256, 512, 768), act=act, bn=False)
         self.eval()
 
 

@@ -14,8 +14,8 @@ def build_yolox(cfg: dict, device="cuda"):
     d, w = cfg["model"]["depth"], cfg["model"]["width"]
     model_type = cfg["model"]["type"].lower()
     if "dw" in model_type:
-        raise NotImplementedError(f"model type {model_type!r}: the depthwise-5x5 variant is a later row (SURVEY §8f N4)")
-    if "p6-v2" in model_type:
+        model = infer.YOLOXDepthwise(d, w)              # main.py:36-38
+    elif "p6-v2" in model_type:
         model = infer.YOLOXP6v2(d, w, act="silu")       # main.py:39-41 (SiLU!)
     else:
         model = infer.YOLOXP6(d, w) if "p6" in model_type else infer.YOLOX(d, w)

@@ -34,7 +34,10 @@ import torch.nn.functional as F
 class ModelCfg:
     """kind: "yolox" = stock CSPDarknet/YOLOPAFPN (3 levels, Focus patch-major order, CSPLayer)
              "p6"    = CSPDarknetCustomP6/YOLOPAFPNCustomP6 (4 levels, pixel_unshuffle order,
-                       CSPLayerCustom)."""
+                       CSPLayerCustom)
+             "dw"    = YOLOXDepthwise (yolox_infer/models/{darknet,yolo_pafpn,yolox}_dw.py): 3 levels with channels
+                       (256, 512, 768), pixel_unshuffle stem, 4x4 stride-2 convs, CSPLayerCustom whose bottlenecks use
+                       depthwise 5x5 convs (BottleneckCustom, blocks.py:113-147)."""
     kind: str = "p6"
     depth: float = 0.67
     width: float = 0.75
@@ -50,6 +53,8 @@ class ModelCfg:
 
     @property
     def head_in_channels(self) -> Tuple[int, ...]:
+        if self.kind == "dw":
+            return (256, 512, 768)
         return (256, 512, 768, 1024) if self.kind == "p6" else (256, 512, 1024)
 
 
@@ -64,6 +69,8 @@ CONFIGS = {
     "tiny_p6": ModelCfg("p6", 0.33, 0.25, "hard_swish", 80, False),
     "yolox_m_p6_v2": ModelCfg("p6", 0.67, 0.75, "silu", 80, False, True),
     "tiny_p6_v2": ModelCfg("p6", 0.33, 0.25, "silu", 80, False, True),
+    "yolox_l_dw": ModelCfg("dw", 1.0, 1.0, "hard_swish", 80, False),     # choijhanyangackr/config/yolox_l_dw.json
+    "tiny_dw": ModelCfg("dw", 0.33, 0.25, "hard_swish", 80, False),
 }
 
 
@@ -87,7 +94,9 @@ def activation(x: torch.Tensor, name: str) -> torch.Tensor:
 # layer enumeration: (key prefix, cin, cout, k, stride, groups) for every conv of a model,
 # in state-dict order.  Used to synthesise weights and to fold BN.
 # --------------------------------------------------------------------------------------
-def _csp_specs(p, cin, cout, n, custom, depthwise):
+def _csp_specs(p, cin, cout, n, custom, depthwise, dw_k=3, nop_rule=False, shortcut=True):
+    """nop_rule: BottleneckCustom (blocks.py:129-137): a depthwise bottleneck that is neither the last of its CSP nor a
+    residual one has NO pointwise conv (DWConvNoP)."""
     h = int(cout * 0.5)
     out = [(p + ".conv1", cin, h, 1, 1, 1),
            (p + ".conv2", cin, (cin - h) if custom else h, 1, 1, 1)]
@@ -95,15 +104,54 @@ def _csp_specs(p, cin, cout, n, custom, depthwise):
     for i in range(n):
         out.append((f"{p}.m.{i}.conv1", h, h, 1, 1, 1))
         if depthwise:
-            out.append((f"{p}.m.{i}.conv2.dconv", h, h, 3, 1, h))
-            out.append((f"{p}.m.{i}.conv2.pconv", h, h, 1, 1, 1))
+            out.append((f"{p}.m.{i}.conv2.dconv", h, h, dw_k, 1, h))
+            if not (nop_rule and i != n - 1 and not shortcut):
+                out.append((f"{p}.m.{i}.conv2.pconv", h, h, 1, 1, 1))
         else:
             out.append((f"{p}.m.{i}.conv2", h, h, 3, 1, 1))
     out.append((p + ".conv3", cin if custom else 2 * h, cout, 1, 1, 1))
     return out
 
 
+def _dw_conv_specs(cfg: ModelCfg):
+    """YOLOXDepthwise: darknet_dw.py:21-85, yolo_pafpn_dw.py:24-98."""
+    base = int(cfg.width * 64)
+    bd = max(round(cfg.depth * 3), 1)
+    n = round(3 * cfg.depth)
+    bb, nb = "backbone.backbone.", "backbone."
+    kw = dict(dw_k=5, nop_rule=True)
+    s = [(bb + "stem.conv", 12, base, 3, 1, 1), (bb + "dark2.0", base, base * 2, 4, 2, 1)]
+    s += _csp_specs(bb + "dark2.1", base * 2, base * 2, bd, True, False)
+    s.append((bb + "dark3.0", base * 2, base * 4, 4, 2, 1))
+    s += _csp_specs(bb + "dark3.1", base * 4, base * 4, bd * 3, True, True, shortcut=True, **kw)
+    s.append((bb + "dark4.0", base * 4, base * 8, 4, 2, 1))
+    s += _csp_specs(bb + "dark4.1", base * 8, base * 8, bd * 3, True, True, shortcut=True, **kw)
+    s.append((bb + "dark5.0", base * 8, base * 12, 4, 2, 1))
+    s.append((bb + "dark5.1.conv1", base * 12, base * 6, 1, 1, 1))
+    s.append((bb + "dark5.1.conv2", base * 24, base * 12, 1, 1, 1))
+    s += _csp_specs(bb + "dark5.2", base * 12, base * 12, bd, True, True, shortcut=False, **kw)
+    ic = [int(c * cfg.width) for c in cfg.head_in_channels]
+    s.append((nb + "lateral_conv0", ic[2], ic[1], 1, 1, 1))
+    s += _csp_specs(nb + "C3_p4", 2 * ic[1], ic[1], n, True, True, shortcut=False, **kw)
+    s.append((nb + "reduce_conv1", ic[1], ic[0], 1, 1, 1))
+    s += _csp_specs(nb + "C3_p3", 2 * ic[0], ic[0], n, True, True, shortcut=False, **kw)
+    s.append((nb + "bu_conv2", ic[0], ic[0], 4, 2, 1))
+    s += _csp_specs(nb + "C3_n3", 2 * ic[0], ic[1], n, True, True, shortcut=False, **kw)
+    s.append((nb + "bu_conv1", ic[1], ic[1], 4, 2, 1))
+    s += _csp_specs(nb + "C3_n4", 2 * ic[1], ic[2], n, True, True, shortcut=False, **kw)
+    hc = int(256 * cfg.width)
+    for k, c in enumerate(ic):
+        s.append((f"head.stems.{k}", c, hc, 1, 1, 1))
+        for j in range(2):
+            s.append((f"head.cls_convs.{k}.{j}", hc, hc, 3, 1, 1))
+        for j in range(2):
+            s.append((f"head.reg_convs.{k}.{j}", hc, hc, 3, 1, 1))
+    return s
+
+
 def conv_specs(cfg: ModelCfg) -> List[Tuple[str, int, int, int, int, int]]:
+    if cfg.kind == "dw":
+        return _dw_conv_specs(cfg)
     base = int(cfg.width * 64)
     bd = max(round(cfg.depth * 3), 1)
     n_neck = round(3 * cfg.depth)
@@ -328,7 +376,8 @@ def _bottleneck(sd, p, x, act, use_add, depthwise):
     y = _bconv(sd, p + ".conv1", x, 1, act)
     if depthwise:
         y = _bconv(sd, p + ".conv2.dconv", y, 1, act, groups=y.shape[1])
-        y = _bconv(sd, p + ".conv2.pconv", y, 1, act)
+        if p + ".conv2.pconv.conv.weight" in sd:      # absent for DWConvNoP (BottleneckCustom, blocks.py:129-131)
+            y = _bconv(sd, p + ".conv2.pconv", y, 1, act)
     else:
         y = _bconv(sd, p + ".conv2", y, 1, act)
     return y + x if use_add else y
@@ -364,6 +413,13 @@ def backbone_features(sd, cfg: ModelCfg, x):
     act = cfg.act
     bd = max(round(cfg.depth * 3), 1)
     bb = "backbone.backbone."
+    if cfg.kind == "dw":                              # CSPDarknetDepthwise.forward, darknet_dw.py:87-101
+        x = _bconv(sd, bb + "stem.conv", space_to_depth(x, "unshuffle"), 1, act)
+        x = _csp(sd, bb + "dark2.1", _bconv(sd, bb + "dark2.0", x, 2, act), bd, act, True)
+        d3 = x = _csp(sd, bb + "dark3.1", _bconv(sd, bb + "dark3.0", x, 2, act), bd * 3, act, True, True)
+        d4 = x = _csp(sd, bb + "dark4.1", _bconv(sd, bb + "dark4.0", x, 2, act), bd * 3, act, True, True)
+        x = _spp(sd, bb + "dark5.1", _bconv(sd, bb + "dark5.0", x, 2, act), act)
+        return [d3, d4, _csp(sd, bb + "dark5.2", x, bd, act, False, True)]
     custom = cfg.kind == "p6"
     x = space_to_depth(x, "unshuffle" if custom else "focus")
     x = _bconv(sd, bb + "stem.conv", x, 1, act)
@@ -393,7 +449,7 @@ def _up(x):
 
 
 def neck(sd, cfg: ModelCfg, feats):
-    act, n, dw = cfg.act, round(3 * cfg.depth), cfg.depthwise_neck
+    act, n, dw = cfg.act, round(3 * cfg.depth), cfg.depthwise_neck or cfg.kind == "dw"
     nb = "backbone."
     if cfg.kind == "p6":
         x3, x2, x1, x0 = feats

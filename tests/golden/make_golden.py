@@ -105,11 +105,15 @@ def golden_infer_v2(name, H, W, batch, seed):
     """P6-v2 inference twin (choijhanyangackr/yolox_infer/models/yolox_p6_v2.py, built like main.py:39-41 with
     act="silu"): the oracle's folded synthetic weights must load STRICTLY (same keys / shapes: 4x4 stride-2 convs, three
     times the dark5 bottlenecks), and its raw logits are the golden output."""
-    from yolox_infer.models.yolox_p6_v2 import YOLOXP6v2
     cfg = mr.CONFIGS[name]
     fused = mr.fold_bn(mr.synth_train_state(cfg, seed, calib_hw=(H, W)))
     x = mr.synth_images(seed + 1000, batch, H, W)
-    im = YOLOXP6v2(cfg.depth, cfg.width, act=cfg.act).eval()
+    if cfg.kind == "dw":      # YOLOXDepthwise (yolox_infer/models/yolox_dw.py), main.py:36-38
+        from yolox_infer.models.yolox_dw import YOLOXDepthwise
+        im = YOLOXDepthwise(cfg.depth, cfg.width, act=cfg.act).eval()
+    else:
+        from yolox_infer.models.yolox_p6_v2 import YOLOXP6v2
+        im = YOLOXP6v2(cfg.depth, cfg.width, act=cfg.act).eval()
     im.load_state_dict(fused, strict=True)
     reg, obj, cls = im(x.clone())
     np.savez_compressed(os.path.join(OUT, f"infer_{name}_{H}x{W}_b{batch}_s{seed}.npz"), x=x.numpy(),
@@ -210,10 +214,12 @@ def golden_post(tag, seed, B, img, strides, C, dist, conf, nms_thr, half_yolox=F
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "v2":       # only the P6-v2 vectors
+    if len(sys.argv) > 1 and sys.argv[1] == "v2":       # only the P6-v2 / depthwise variant vectors
         golden_infer_v2("tiny_p6_v2", 128, 128, 1, 4)
+        golden_infer_v2("tiny_dw", 96, 128, 1, 5)
         sys.exit(0)
     golden_infer_v2("tiny_p6_v2", 128, 128, 1, 4)
+    golden_infer_v2("tiny_dw", 96, 128, 1, 5)
     golden_model("tiny_p6", 128, 128, 2, 0)
     golden_model("tiny", 96, 160, 1, 1)
     golden_model("nano", 64, 64, 1, 2)

@@ -24,7 +24,7 @@ def _build(name, H, W, seed, flavour="infer"):
     cfg = mr.CONFIGS[name]
     train = mr.synth_train_state(cfg, seed, calib_hw=(H, W))
     fused = mr.fold_bn(train)
-    cls_ = (yb.infer.YOLOXP6v2 if cfg.v2 else yb.infer.YOLOXP6) if cfg.kind == "p6" else yb.infer.YOLOX
+    cls_ = {"p6": yb.infer.YOLOXP6v2 if cfg.v2 else yb.infer.YOLOXP6, "dw": yb.infer.YOLOXDepthwise}.get(cfg.kind, yb.infer.YOLOX)
     model = cls_(cfg.depth, cfg.width, act=cfg.act, num_classes=cfg.num_classes)
     model.load_state_dict(fused, strict=True)
     return cfg, fused, model.cuda().half()
@@ -44,7 +44,7 @@ def _q16(sd):
 
 
 @pytest.mark.parametrize("name,H,W,B", [("tiny_p6", 128, 192, 2), ("tiny", 96, 160, 3), ("yolox_m_p6", 320, 320, 2),
-                                        ("yolox_m", 384, 384, 1), ("tiny_p6_v2", 128, 192, 2)])
+                                        ("yolox_m", 384, 384, 1), ("tiny_p6_v2", 128, 192, 2), ("tiny_dw", 96, 160, 2)])
 def test_infer_logits_match_oracle(name, H, W, B):
     cfg, fused, model = _build(name, H, W, 3)
     x = mr.synth_images(11, B, H, W)
@@ -56,10 +56,11 @@ def test_infer_logits_match_oracle(name, H, W, B):
     assert torch.equal(reg8[..., :4], reg) and torch.equal(cls2[..., :cfg.num_classes], cls)
 
 
-def test_p6_v2_reference_golden():
-    """P6-v2 inference twin: the engine vs the reference's raw logits (tests/golden/infer_tiny_p6_v2_*.npz)."""
-    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "infer_tiny_p6_v2_128x128_b1_s4.npz"))
-    cfg, fused, model = _build("tiny_p6_v2", 128, 128, 4)
+@pytest.mark.parametrize("name,H,W,seed", [("tiny_p6_v2", 128, 128, 4), ("tiny_dw", 96, 128, 5)])
+def test_variant_reference_golden(name, H, W, seed):
+    """P6-v2 / depthwise inference twins: the engine vs the reference's raw logits (tests/golden/infer_*.npz)."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"infer_{name}_{H}x{W}_b1_s{seed}.npz"))
+    cfg, fused, model = _build(name, H, W, seed)
     reg, obj, cls = model(torch.from_numpy(g["x"]).cuda().half())
     _check(reg, torch.from_numpy(g["reg"]), "reg"); _check(obj, torch.from_numpy(g["obj"]), "obj")
     _check(cls, torch.from_numpy(g["cls"]), "cls")
@@ -155,7 +156,8 @@ def test_predict_loop_end_to_end():
 
 
 @pytest.mark.parametrize("name,H,W,B", [("yolox_m_p6", 640, 640, 2), ("yolox_m", 320, 320, 1), ("tiny", 160, 96, 2),
-                                        ("tiny_p6_v2", 128, 128, 1), ("yolox_m_p6_v2", 256, 256, 1)])
+                                        ("tiny_p6_v2", 128, 128, 1), ("yolox_m_p6_v2", 256, 256, 1), ("tiny_dw", 128, 96, 1),
+                                        ("yolox_l_dw", 256, 256, 1)])
 def test_every_op_teacher_forced(name, H, W, B):
     """Each of the ~125 launches of a real network, run one at a time, equals a torch fp32 evaluation of the
     SAME device inputs to within one fp16 rounding step of the pre-activation sum (x1.5 slack)."""

@@ -68,6 +68,20 @@ def test_p6_v2_forward_matches_reference():
     _close(reg.numpy(), g["reg"]); _close(obj.numpy(), g["obj"]); _close(cls.numpy(), g["cls"])
 
 
+def test_depthwise_variant_forward_matches_reference():
+    """YOLOXDepthwise (depthwise 5x5 BottleneckCustom with the DWConvNoP rule, 4x4 stride-2 convs): raw logits of the
+    reference's inference twin loaded strictly with these weights."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "infer_tiny_dw_96x128_b1_s5.npz"))
+    cfg = mr.CONFIGS["tiny_dw"]
+    fused = mr.fold_bn(mr.synth_train_state(cfg, 5, calib_hw=(96, 128)))
+    x = mr.synth_images(1005, 1, 96, 128)
+    np.testing.assert_array_equal(x.numpy(), g["x"])
+    assert fused["backbone.backbone.dark3.1.m.0.conv2.dconv.conv.weight"].shape[1:] == (1, 5, 5)
+    assert "backbone.C3_p4.m.0.conv2.pconv.conv.weight" in fused       # n = 1: the only bottleneck is the last one
+    reg, obj, cls = mr.forward_raw(fused, cfg, x)
+    _close(reg.numpy(), g["reg"]); _close(obj.numpy(), g["obj"]); _close(cls.numpy(), g["cls"])
+
+
 def test_state_dict_key_count_m_p6():
     """the M-P6 inference twin has 278 tensors."""
     cfg = mr.CONFIGS["yolox_m_p6"]

@@ -18,11 +18,12 @@ def _q16(sd):
 
 def _infer_model(name):
     cfg = mr.CONFIGS[name]
-    cls = (yb.infer.YOLOXP6v2 if cfg.v2 else yb.infer.YOLOXP6) if cfg.kind == "p6" else yb.infer.YOLOX
+    cls = {"p6": yb.infer.YOLOXP6v2 if cfg.v2 else yb.infer.YOLOXP6, "dw": yb.infer.YOLOXDepthwise}.get(cfg.kind, yb.infer.YOLOX)
     return cfg, cls(cfg.depth, cfg.width, act=cfg.act, num_classes=cfg.num_classes)
 
 
-@pytest.mark.parametrize("name,H,W,B", [("tiny_p6", 128, 192, 2), ("tiny", 96, 160, 1), ("tiny_p6_v2", 128, 128, 1)])
+@pytest.mark.parametrize("name,H,W,B", [("tiny_p6", 128, 192, 2), ("tiny", 96, 160, 1), ("tiny_p6_v2", 128, 128, 1),
+                                        ("tiny_dw", 96, 128, 2)])
 def test_infer_graph_matches_oracle(name, H, W, B):
     cfg, model = _infer_model(name)
     fused = mr.fold_bn(mr.synth_train_state(cfg, 3, calib_hw=(H, W)))
