@@ -56,7 +56,7 @@ def make_levels(level_hw, strides) -> Levels:
 
 
 SYMBOLS = ["yx_last_error", "yx_abi_version", "yx_engine_create", "yx_engine_destroy", "yx_engine_run",
-           "yx_engine_profile", "yx_engine_run_ops", "yx_engine_num_launches", "yx_engine_tune", "yx_engine_op_desc",
+           "yx_engine_profile", "yx_engine_run_ops", "yx_engine_num_launches", "yx_engine_tune", "yx_engine_op_desc", "yx_engine_tune_mismatches",
            "yx_conv2d", "yx_conv2d_ex", "yx_decode_infer", "yx_detect_workspace_bytes",
            "yx_nms_main", "yx_detect_main", "yx_head_assemble", "yx_decode_outputs", "yx_postprocess_yolox",
            "yx_preprocess_batch", "yx_coco_records"]
@@ -97,6 +97,7 @@ def load():
     lib.yx_conv2d_ex.argtypes = [ctypes.POINTER(Op), c_vp, c_vp, c_vp, ctypes.POINTER(ConvTune), c_vp]
     lib.yx_engine_tune.argtypes = [c_vp, c_vp, c_i32, c_f32, c_f32, c_i32, c_vp]
     lib.yx_engine_op_desc.argtypes = [c_vp, c_i32, ctypes.c_char_p, c_i32]
+    lib.yx_engine_tune_mismatches.argtypes = [c_vp, ctypes.c_char_p, c_i32]
     logits = [c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64]
     lib.yx_decode_infer.argtypes = logits + [c_i32, c_i32, c_i32, c_i32, ctypes.POINTER(Levels), c_vp, c_vp, c_vp, c_vp]
     lib.yx_nms_main.argtypes = [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_f32, c_f32, c_i32, c_i32, c_i32, c_vp, c_sz,

@@ -263,4 +263,46 @@ int dwconv_launch(void* base, const yx_op& op, const void* weights, const void* 
   return YX_OK;
 }
 
+// ------------------------------------------------------------------------------------ tuner self-check helpers
+// copy a strided NHWC view into a contiguous buffer / max |view - contiguous| (as the bits of a non-negative float)
+__global__ void view_gather_kernel(const __half* __restrict__ src, __half* __restrict__ out, int H, int W, int C, int pitch,
+                                   int64_t nstride, int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = i % C;
+    const int64_t pix = i / C;
+    const int64_t b = pix / ((int64_t)H * W), r = pix % ((int64_t)H * W);
+    out[i] = src[b * nstride + r * pitch + c];
+  }
+}
+__global__ void view_diff_kernel(const __half* __restrict__ src, const __half* __restrict__ ref, int H, int W, int C, int pitch,
+                                 int64_t nstride, int64_t total, unsigned int* __restrict__ out_bits) {
+  float m = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = i % C;
+    const int64_t pix = i / C;
+    const int64_t b = pix / ((int64_t)H * W), r = pix % ((int64_t)H * W);
+    const float d = fabsf(__half2float(src[b * nstride + r * pitch + c]) - __half2float(ref[i]));
+    m = fmaxf(m, d == d ? d : 65504.f);  // NaN counts as a maximal difference
+  }
+  atomicMax(out_bits, __float_as_uint(m));
+}
+
+int view_gather(void* base, const yx_view& v, void* out, cudaStream_t st) {
+  const int64_t total = (int64_t)v.n * v.h * v.w * v.c;
+  view_gather_kernel<<<(int)std::min<int64_t>((total + 255) / 256, 148 * 8), 256, 0, st>>>(
+      reinterpret_cast<const __half*>(static_cast<uint8_t*>(base) + v.offset), static_cast<__half*>(out), v.h, v.w, v.c, v.pitch,
+      v.nstride, total);
+  YX_CUDA(cudaGetLastError());
+  return YX_OK;
+}
+int view_max_diff(void* base, const yx_view& v, const void* ref, unsigned int* out_bits, cudaStream_t st) {
+  const int64_t total = (int64_t)v.n * v.h * v.w * v.c;
+  YX_CUDA(cudaMemsetAsync(out_bits, 0, 4, st));
+  view_diff_kernel<<<(int)std::min<int64_t>((total + 255) / 256, 148 * 8), 256, 0, st>>>(
+      reinterpret_cast<const __half*>(static_cast<uint8_t*>(base) + v.offset), static_cast<const __half*>(ref), v.h, v.w, v.c,
+      v.pitch, v.nstride, total, out_bits);
+  YX_CUDA(cudaGetLastError());
+  return YX_OK;
+}
+
 }  // namespace yx

@@ -189,43 +189,47 @@ __device__ __forceinline__ void commit_x(uint32_t bar) {
   else umma_commit(bar);
 }
 
-template <int MH, bool RING, bool PAIR>
+// RP: the row-packed stem (3 vertical taps over rows of TW = 8 pixels whose 128-byte smem row already holds the three
+// horizontal neighbours): the halo box is (TH+2) x 8 rows, tap dy starts dy*8 rows (= one swizzle atom) later, SBO = 1024.
+template <int MH, bool RING, bool PAIR, bool RP>
 __device__ __forceinline__ void halo_chunk_mma(uint32_t d0, uint32_t d1, uint32_t a0, uint32_t a_hi, uint32_t& b_lo, uint32_t b_hi,
                                                uint32_t idesc, uint32_t& accum, int ksteps, uint32_t bar_fb, uint32_t bar_eb,
                                                uint32_t& sb, uint32_t& phb, uint32_t b_slots, uint32_t b_lo0, uint32_t b_step,
                                                bool wait_b, bool tracing, long long& w_acc, bool skip_mma) {
+  constexpr int TAPS = RP ? 3 : 9;
+  constexpr int HW = RP ? 8 : kHaloW;  // halo row width in pixels
   if (!RING && !wait_b) {
     // resident weights already in shared memory: nothing to wait for inside the chunk, so the whole 9-tap sequence
     // is ONE elected straight-line block (no per-tap elect / branch / reconvergence)
     if (elect_one() && !skip_mma) {
 #pragma unroll
-      for (int tap = 0; tap < 9; ++tap) {
-        const uint32_t a_tap = a0 + ((tap / 3) * kHaloW + (tap % 3)) * 8;
+      for (int tap = 0; tap < TAPS; ++tap) {
+        const uint32_t a_tap = a0 + (RP ? tap * HW : (tap / 3) * HW + (tap % 3)) * 8;
         const uint32_t b_tap = b_lo + tap * b_step;
         if (ksteps == 4) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             umma_x<PAIR>(d0, a_tap + 2 * ks, a_hi, b_tap + 2 * ks, b_hi, idesc, (tap | ks) == 0 ? accum : 1u);
-            if (MH == 2) umma_x<PAIR>(d1, a_tap + 16 * kHaloW * 8 + 2 * ks, a_hi, b_tap + 2 * ks, b_hi, idesc, (tap | ks) == 0 ? accum : 1u);
+            if (MH == 2) umma_x<PAIR>(d1, a_tap + 16 * HW * 8 + 2 * ks, a_hi, b_tap + 2 * ks, b_hi, idesc, (tap | ks) == 0 ? accum : 1u);
           }
         } else {
 #pragma unroll
           for (int ks = 0; ks < 3; ++ks)
             if (ks < ksteps) {
               umma_x<PAIR>(d0, a_tap + 2 * ks, a_hi, b_tap + 2 * ks, b_hi, idesc, (tap | ks) == 0 ? accum : 1u);
-              if (MH == 2) umma_x<PAIR>(d1, a_tap + 16 * kHaloW * 8 + 2 * ks, a_hi, b_tap + 2 * ks, b_hi, idesc, (tap | ks) == 0 ? accum : 1u);
+              if (MH == 2) umma_x<PAIR>(d1, a_tap + 16 * HW * 8 + 2 * ks, a_hi, b_tap + 2 * ks, b_hi, idesc, (tap | ks) == 0 ? accum : 1u);
             }
         }
       }
     }
     accum = 1;
-    b_lo += 9 * b_step;
+    b_lo += TAPS * b_step;
     return;
   }
 #pragma unroll
-  for (int tap = 0; tap < 9; ++tap) {
+  for (int tap = 0; tap < TAPS; ++tap) {
     // tap (dy,dx) of half h starts (16h + dy) halo rows down and dx pixels right: rows are 128 B = 8 descriptor units
-    const uint32_t a_tap = a0 + ((tap / 3) * kHaloW + (tap % 3)) * 8;
+    const uint32_t a_tap = a0 + (RP ? tap * HW : (tap / 3) * HW + (tap % 3)) * 8;
     if (wait_b) {
       mbar_wait_acc(bar_fb + 8 * sb, phb, tracing, w_acc);
       tc_fence_after();
@@ -236,12 +240,12 @@ __device__ __forceinline__ void halo_chunk_mma(uint32_t d0, uint32_t d1, uint32_
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
           umma_x<PAIR>(d0, a_tap + 2 * ks, a_hi, b_lo + 2 * ks, b_hi, idesc, ks == 0 ? accum : 1u);
-          if (MH == 2) umma_x<PAIR>(d1, a_tap + 16 * kHaloW * 8 + 2 * ks, a_hi, b_lo + 2 * ks, b_hi, idesc, ks == 0 ? accum : 1u);
+          if (MH == 2) umma_x<PAIR>(d1, a_tap + 16 * HW * 8 + 2 * ks, a_hi, b_lo + 2 * ks, b_hi, idesc, ks == 0 ? accum : 1u);
         }
       } else {
         for (int ks = 0; ks < ksteps; ++ks) {
           umma_x<PAIR>(d0, a_tap + 2 * ks, a_hi, b_lo + 2 * ks, b_hi, idesc, ks == 0 ? accum : 1u);
-          if (MH == 2) umma_x<PAIR>(d1, a_tap + 16 * kHaloW * 8 + 2 * ks, a_hi, b_lo + 2 * ks, b_hi, idesc, ks == 0 ? accum : 1u);
+          if (MH == 2) umma_x<PAIR>(d1, a_tap + 16 * HW * 8 + 2 * ks, a_hi, b_lo + 2 * ks, b_hi, idesc, ks == 0 ? accum : 1u);
         }
       }
       if (RING) commit_x<PAIR>(bar_eb + 8 * sb);
@@ -250,6 +254,8 @@ __device__ __forceinline__ void halo_chunk_mma(uint32_t d0, uint32_t d1, uint32_
     b_lo += b_step;
     if (RING) {
       if (++sb == b_slots) { sb = 0; phb ^= 1; b_lo = b_lo0; }
+    } else {
+      ++sb;  // resident weights, first tile: every tap waits on ITS OWN slot's barrier (the loads arrive one by one)
     }
   }
 }
@@ -257,6 +263,8 @@ __device__ __forceinline__ void halo_chunk_mma(uint32_t d0, uint32_t d1, uint32_
 // MODE: 0 = generic (one A box per tap), 1 = halo with one 128-pixel half per CTA, 2 = halo with two stacked halves,
 //       3 = generic with a 256-pixel tile (two 128-row halves per A box): halves every per-tile fixed cost of the
 //           HBM-bound small-channel layers (N <= 128)
+//       4/5 = row-packed stem as a VERTICAL halo (one / two halves): one (TH+2)-row box per tile instead of three
+//           shifted boxes -> 2.7x fewer bytes through L2->smem for the layer that was bound by exactly that
 // PAIR: two CTAs of a cluster share every MMA (cta_group::2, M = 256): half of the weight tile per CTA
 // RES:  0 = no residual; 1 = residual tile TMA-loaded into the staging buffer and added in registers;
 //       2 = the residual IS the destination (Bottleneck y = x + f(x) computed in place): the tile is stored with a TMA
@@ -264,8 +272,9 @@ __device__ __forceinline__ void halo_chunk_mma(uint32_t d0, uint32_t d1, uint32_
 template <int ACT, int RES, int MODE, bool PAIR>
 __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant__ ConvParams p) {
   constexpr bool HAS_RES = RES == 1;
-  constexpr bool HALO = MODE == 1 || MODE == 2;
-  constexpr int MH = (MODE == 2 || MODE == 3) ? 2 : 1;
+  constexpr bool HALO = MODE == 1 || MODE == 2 || MODE == 4 || MODE == 5;
+  constexpr bool RP = MODE >= 4;
+  constexpr int MH = (MODE == 2 || MODE == 3 || MODE == 5) ? 2 : 1;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;  // position in the CTA pair; rank 0 = leader (issues the MMAs)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -355,10 +364,10 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
                 mbar_arrive(bar_fa + 8 * s);
               } else if (PAIR) {  // the leader's barrier collects the bytes of both CTAs' tiles
                 if (rank == 0) mbar_expect_tx(bar_fa + 8 * s, 2 * a_box_bytes);
-                tma_load_4d_2sm(sA + s * a_stage_bytes, &p.tmA[0], bar_fa + 8 * s, kc * 64, x0 - 1, y0 - 1, img);
+                tma_load_4d_2sm(sA + s * a_stage_bytes, &p.tmA[0], bar_fa + 8 * s, kc * 64, x0 - (RP ? 0 : 1), y0 - 1, img);
               } else {
                 mbar_expect_tx(bar_fa + 8 * s, a_box_bytes);
-                tma_load_4d(sA + s * a_stage_bytes, &p.tmA[0], bar_fa + 8 * s, kc * 64, x0 - 1, y0 - 1, img);
+                tma_load_4d(sA + s * a_stage_bytes, &p.tmA[0], bar_fa + 8 * s, kc * 64, x0 - (RP ? 0 : 1), y0 - 1, img);
               }
             }
           }
@@ -454,7 +463,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
   } else if (warp == 1 && rank == 0) {
     // ================================ MMA issuer (leader CTA only in PAIR mode) ================================
     uint32_t t = 0, sa = 0, pha = 0, sb = 0, phb = 0;
-    const uint32_t a_hi = sdesc_hi(HALO ? kHaloW * 128 : 1024), b_hi = sdesc_hi(1024);
+    const uint32_t a_hi = sdesc_hi(HALO && !RP ? kHaloW * 128 : 1024), b_hi = sdesc_hi(1024);
     const uint32_t a_lo0 = sdesc_lo(sA), a_step = p.a_stage_bytes >> 4;
     const uint32_t b_lo0 = sdesc_lo(sB), b_step = p.b_stage_bytes >> 4;
     uint32_t a_lo = a_lo0, b_lo = b_lo0;
@@ -483,10 +492,10 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
           tc_fence_after();
           const int ksteps = (kc == k_chunks - 1) ? ks_last : 4;
           if (resident)
-            halo_chunk_mma<MH, false, PAIR>(d0, d1, a_lo, a_hi, b_lo, b_hi, idesc, accum, ksteps, bar_fb, bar_eb, sb, phb, b_slots, b_lo0,
+            halo_chunk_mma<MH, false, PAIR, RP>(d0, d1, a_lo, a_hi, b_lo, b_hi, idesc, accum, ksteps, bar_fb, bar_eb, sb, phb, b_slots, b_lo0,
                                       b_step, !b_ready, tracing, w_acc1, (p.diag & 4) != 0);
           else
-            halo_chunk_mma<MH, true, PAIR>(d0, d1, a_lo, a_hi, b_lo, b_hi, idesc, accum, ksteps, bar_fb, bar_eb, sb, phb, b_slots, b_lo0,
+            halo_chunk_mma<MH, true, PAIR, RP>(d0, d1, a_lo, a_hi, b_lo, b_hi, idesc, accum, ksteps, bar_fb, bar_eb, sb, phb, b_slots, b_lo0,
                                      b_step, true, tracing, w_acc1, (p.diag & 4) != 0);
           if (elect_one()) commit_x<PAIR>(bar_ea + 8 * sa);
           a_lo += a_step;
@@ -762,7 +771,7 @@ static int conv_geom(const yx_op& op, ConvGeom* g) {
 }
 
 static bool halo_ok(const yx_op& op, const ConvGeom& g) {
-  if (!(op.ksize == 3 && op.stride == 1 && !g.rowpack && g.Hout >= 16 && g.Wout >= 8)) return false;
+  if (!(op.ksize == 3 && op.stride == 1 && g.Hout >= 16 && g.Wout >= 8)) return false;  // (row-packed stem: vertical halo)
   const double eff16 = (double)(ceil_div(g.Hout, 16) * 16) * (ceil_div(g.Wout, 8) * 8) / ((double)g.Hout * g.Wout);
   return eff16 <= 1.25;
 }
@@ -833,7 +842,7 @@ void conv_candidates(const yx_op& op, std::vector<ConvTune>* out) {
             push(t);
           }
         }
-    if (bn >= 64 && cout16 >= 96)  // CTA-pair shapes: half of the weight tile per CTA
+    if (bn >= 64 && cout16 >= 96 && !g.rowpack)  // CTA-pair shapes: half of the weight tile per CTA
       for (int v = 1; v <= (halo_ok(op, g) ? 2 : 1); ++v)
         for (int sb = 2; sb >= 1; --sb) {
           ConvTune t;
@@ -866,7 +875,8 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
   const bool halo = t.variant == 2;
   const bool pair = t.pair != 0;
   YX_REQUIRE(t.variant == 1 || t.variant == 2, "conv tune: variant must be 1 (generic) or 2 (halo)");
-  YX_REQUIRE(!pair || (t.ctas == 1 && (!halo || t.mh != 2)), "conv tune: CTA-pair mode runs one CTA per SM and one 128-pixel half per CTA");
+  YX_REQUIRE(!pair || (t.ctas == 1 && (!halo || t.mh != 2) && !g.rowpack),
+             "conv tune: CTA-pair mode runs one CTA per SM and one 128-pixel half per CTA (not for the row-packed stem)");
   YX_REQUIRE(!halo || halo_ok(op, g), "conv tune: halo variant needs a 3x3 stride-1 conv on a map of at least 16x8");
   YX_REQUIRE(!g.has_up || !halo, "fused upsample is a 1x1 conv: generic variant only");
   YX_REQUIRE(t.bn >= 16 && t.bn <= 256 && t.bn % 16 == 0 && (t.bn % 64 == 0 || t.bn >= op.cout_pad),
@@ -893,6 +903,7 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
   p.BN = std::min(t.bn, p.cout16);
   p.n_tiles_n = ceil_div(p.cout16, p.BN);
   p.halo = halo ? 1 : 0;
+  p.rowpack = g.rowpack ? 1 : 0;
   p.pair = pair ? 1 : 0;
   p.epi_groups = t.epi_groups;
   p.bias_bytes = round_up(p.cout16 * 4, 128);
@@ -911,7 +922,7 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
     if (2 * mh * stride_cols > 512) mh = 1;
     p.mh = mh;
     p.TH = 16 * mh; p.TW = 8;
-    p.a_box_bytes = (p.TH + 2) * kHaloW * 128;
+    p.a_box_bytes = (p.TH + 2) * (g.rowpack ? 8 : kHaloW) * 128;
     p.a_stage_bytes = round_up(p.a_box_bytes, 1024);
     p.out_box_bytes = kTileBytes;
     p.acc_stride = stride_cols;
@@ -1001,7 +1012,14 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
   if (p.w3_role == 1 && p.stages_a < 2) p.w3_role = 0;
   if (p.w3_role == 2 && p.b_slots < 2) p.w3_role = 0;
 
-  if (halo) {
+  if (halo && g.rowpack) {
+    uint64_t dims[4] = {64, (uint64_t)g.Wout, (uint64_t)s.h, (uint64_t)s.n};
+    uint64_t st[4] = {2, 32, (uint64_t)s.w * 32, (uint64_t)s.nstride * 2};
+    uint32_t box[4] = {64, 8, (uint32_t)(p.TH + 2), 1};
+    if ((rc = encode_map(&p.tmA[0], static_cast<uint8_t*>(base) + s.offset, 4, dims, st, box, true, "A-rowpack-halo")) != YX_OK)
+      return rc;
+    for (int i = 1; i < 4; ++i) p.tmA[i] = p.tmA[0];
+  } else if (halo) {
     uint64_t dims[4] = {(uint64_t)s.c, (uint64_t)s.w, (uint64_t)s.h, (uint64_t)s.n};
     uint64_t st[4] = {2, (uint64_t)s.pitch * 2, (uint64_t)s.pitch * 2 * s.w, (uint64_t)s.nstride * 2};
     uint32_t box[4] = {64, (uint32_t)kHaloW, (uint32_t)(p.TH + 2), 1};
@@ -1098,6 +1116,8 @@ template <int ACT, int RES>
 static int launch_mode(const ConvPlan& plan, cudaStream_t stream) {
   if (plan.p.pair)
     return plan.p.halo ? launch_variant<ACT, RES, 1, true>(plan, stream) : launch_variant<ACT, RES, 0, true>(plan, stream);
+  if (plan.p.halo && plan.p.rowpack)  // the stem has no residual: only RES = 0 is instantiated
+    return plan.p.mh == 2 ? launch_variant<ACT, 0, 5, false>(plan, stream) : launch_variant<ACT, 0, 4, false>(plan, stream);
   if (plan.p.halo && plan.p.mh == 2) return launch_variant<ACT, RES, 2, false>(plan, stream);
   if (plan.p.halo) return launch_variant<ACT, RES, 1, false>(plan, stream);
   if (plan.p.mh == 2) return launch_variant<ACT, RES, 3, false>(plan, stream);

@@ -42,6 +42,7 @@ struct yx_engine {
   cudaGraphExec_t graph_exec = nullptr;
   cudaStream_t graph_stream = nullptr;  // private stream used only to capture the graph
   bool tuned = false;
+  std::vector<std::string> tune_mismatches;  // YX_TUNE_CHECK: candidates whose output differed from the default shape
 };
 
 using namespace yx;
@@ -220,6 +221,8 @@ extern "C" int yx_engine_tune(yx_engine* e, const void* image, int image_dtype, 
   YX_CUDA(cudaEventCreate(&ev1));
   int rc = YX_OK;
   const bool verbose = getenv("YX_TUNE_VERBOSE") != nullptr;
+  const bool check = getenv("YX_TUNE_CHECK") != nullptr;
+  e->tune_mismatches.clear();
   std::vector<ConvTune> cands;
   for (size_t i = 0; i < e->steps.size() && rc == YX_OK; ++i) {
     Step& s = e->steps[i];
@@ -233,11 +236,42 @@ extern "C" int yx_engine_tune(yx_engine* e, const void* image, int image_dtype, 
     const bool inplace = s.conv.p.has_res == 2;
     DstSnapshot snap;
     if (inplace && (rc = snap.take(e, s.op.dst, st)) != YX_OK) break;
+    // YX_TUNE_CHECK=1 (tests): every candidate must reproduce the default shape's output (same function, different
+    // fp32 accumulation order => at most a few fp16 steps apart); a candidate that does not is reported and rejected.
+    void* check_ref = nullptr;
+    unsigned int* check_bits = nullptr;
+    float check_scale = 0.f;
+    if (check) {
+      const size_t n_el = (size_t)s.op.dst.n * s.op.dst.h * s.op.dst.w * s.op.dst.c;
+      ConvPlan ref_plan = s.conv;
+      ref_plan.store_only = inplace ? 1 : 0;
+      if (cudaMalloc(&check_ref, n_el * 2) != cudaSuccess || cudaMalloc(&check_bits, 8) != cudaSuccess) {
+        rc = cuda_fail(cudaGetLastError(), "tune check alloc", __FILE__, __LINE__);
+        break;
+      }
+      if ((rc = conv_launch(ref_plan, st)) != YX_OK || (rc = view_gather(e->arena, s.op.dst, check_ref, st)) != YX_OK) break;
+    }
     for (const ConvTune& t : cands) {
       ConvPlan pl;
       if (conv_plan(s.op, e->arena, e->weights, e->biases, e->num_sms, &t, &pl) != YX_OK) continue;  // shape does not fit
       pl.store_only = inplace ? 1 : 0;
       if ((rc = conv_launch(pl, st)) != YX_OK) break;  // warm-up (also sets the smem attribute)
+      if (check) {
+        unsigned int bits = 0;
+        if ((rc = view_max_diff(e->arena, s.op.dst, check_ref, check_bits, st)) != YX_OK) break;
+        cudaMemcpyAsync(&bits, check_bits, 4, cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+        float d;
+        memcpy(&d, &bits, 4);
+        (void)check_scale;
+        if (d > 0.26f) {   // activations are O(1): a wrong tile / tap / barrier shows as O(1)+ differences or NaN
+          char msg[400];
+          snprintf(msg, sizeof msg, "tune check: op %zu candidate '%s' differs from the default shape by %g", i, pl.desc, d);
+          fprintf(stderr, "%s\n", msg);
+          e->tune_mismatches.push_back(msg);
+          continue;
+        }
+      }
       float ms_min = 1e30f;
       for (int k = 0; k < iters && rc == YX_OK; ++k) {
         cudaEventRecord(ev0, st);
@@ -252,6 +286,8 @@ extern "C" int yx_engine_tune(yx_engine* e, const void* image, int image_dtype, 
       if (verbose) fprintf(stderr, "  tune op %zu  %-90s %.4f ms\n", i, pl.desc, ms_min);
       if (ms_min < best_ms) { best_ms = ms_min; best = pl; }
     }
+    if (check_ref) cudaFree(check_ref);
+    if (check_bits) cudaFree(check_bits);
     if (rc != YX_OK) { snap.release(st); break; }
     best.store_only = 0;
     s.conv = best;
@@ -269,6 +305,14 @@ extern "C" int yx_engine_tune(yx_engine* e, const void* image, int image_dtype, 
   if (rc == YX_OK) YX_CUDA(cudaStreamSynchronize(st));
   e->tuned = rc == YX_OK;
   return rc;
+}
+
+extern "C" int yx_engine_tune_mismatches(const yx_engine* e, char* buf_host, int buf_len) {
+  YX_REQUIRE(e && buf_host && buf_len > 0, "bad argument");
+  std::string all;
+  for (const std::string& m : e->tune_mismatches) all += m + "\n";
+  snprintf(buf_host, buf_len, "%s", all.c_str());
+  return (int)e->tune_mismatches.size();
 }
 
 extern "C" int yx_engine_op_desc(const yx_engine* e, int i, char* buf_host, int buf_len) {

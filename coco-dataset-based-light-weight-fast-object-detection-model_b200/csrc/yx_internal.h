@@ -49,6 +49,7 @@ struct ConvParams {
   int k_chunks;
   int halo, mh;                  // halo variant: mh stacked 128-pixel halves per CTA
   int pair;                      // CTA-pair mode (cluster of 2, cta_group::2 MMAs of M = 256)
+  int rowpack;                   // row-packed stem (aux == 1); with halo: vertical halo of 8-pixel rows, 3 taps
   int stages_a, a_stage_bytes, a_box_bytes;  // A ring
   int b_slots, b_stage_bytes, b_resident;    // B ring (or the whole weight tile, loaded once)
   int shared_ring;               // generic + streamed weights: A and B share one full/empty barrier pair per stage
@@ -95,5 +96,7 @@ int s2d_launch(const void* image, int image_dtype, int aux, int B, int H, int W,
 int spp_launch(void* base, const yx_view& src, const yx_view& dst, cudaStream_t stream);
 int upsample_launch(void* base, const yx_view& src, const yx_view& dst, cudaStream_t stream);
 int dwconv_launch(void* base, const yx_op& op, const void* weights, const void* biases, cudaStream_t stream);
+int view_gather(void* base, const yx_view& v, void* out_contiguous, cudaStream_t stream);
+int view_max_diff(void* base, const yx_view& v, const void* ref_contiguous, unsigned int* out_bits, cudaStream_t stream);
 
 }  // namespace yx

@@ -359,6 +359,13 @@ class Engine:
         return [dict(name=op.name, kind=op.kind, ms=ms[i], flops=fl[i], bytes=by[i], shape=self.op_desc(i))
                 for i, op in enumerate(self.graph.ops)]
 
+    def tune_mismatches(self):
+        """(YX_TUNE_CHECK=1) descriptions of tuning candidates whose output differed from the default launch shape."""
+        import ctypes
+        buf = ctypes.create_string_buffer(1 << 16)
+        n = self.lib.yx_engine_tune_mismatches(self.handle, buf, 1 << 16)
+        return [m for m in buf.value.decode().split("\n") if m] if n > 0 else []
+
     def op_desc(self, i: int) -> str:
         import ctypes
         buf = ctypes.create_string_buffer(320)

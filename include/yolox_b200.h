@@ -127,6 +127,9 @@ int yx_engine_num_launches(const yx_engine* e); /* kernels launched by one yx_en
  * result afterwards.  Host-synchronising setup call. */
 int yx_engine_tune(yx_engine* e, const void* image, int image_dtype, float in_scale, float in_shift, int iters,
                    void* stream);
+/* With YX_TUNE_CHECK=1 in the environment yx_engine_tune also verifies that every candidate shape reproduces the default
+ * shape's output; returns the number of candidates that did not (and were rejected) and their descriptions. */
+int yx_engine_tune_mismatches(const yx_engine* e, char* buf_host, int buf_len);
 /* Human-readable description of op i and of the launch shape chosen for it (diagnostics / profiles). */
 int yx_engine_op_desc(const yx_engine* e, int i, char* buf_host, int buf_len);
 

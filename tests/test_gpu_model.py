@@ -66,6 +66,19 @@ def test_variant_reference_golden(name, H, W, seed):
     _check(cls, torch.from_numpy(g["cls"]), "cls")
 
 
+@pytest.mark.parametrize("name,H,W,B", [("yolox_m_p6", 320, 320, 2), ("yolox_m_p6", 640, 384, 3), ("yolox_m", 416, 416, 2),
+                                        ("yolox_m_p6_v2", 256, 256, 2), ("tiny_dw", 160, 128, 5), ("yolox_m_p6", 1280, 1280, 4)])
+def test_every_tuning_candidate_agrees(name, H, W, B, monkeypatch):
+    """yx_engine_tune self-check: on every conv of a real network, EVERY candidate launch shape (generic / halo / pair /
+    256-pixel tiles / resident or streamed weights / ...) reproduces the default shape's output."""
+    monkeypatch.setenv("YX_TUNE_CHECK", "1")
+    cfg, fused, model = _build(name, H, W, 3)
+    x = mr.synth_images(11, B, H, W).cuda().half()
+    model(x)
+    bad = model.engine_for(x).tune_mismatches()
+    assert not bad, bad[:8]
+
+
 GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "model_*.npz")))
 
 
