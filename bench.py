@@ -188,15 +188,21 @@ def run_ours(args, rank, world, local_rank):
     dev_img = host_imgs[0].to(dev, non_blocking=True)
     strides = MODEL["strides"]
 
-    gathered = None
+    # N > 1: every rank ends the step holding the detections of the whole global batch.  Default: the NMS kernel stores
+    # its rows straight into every rank's window over NVLink (yx_detect_main_gather); YX_PEER_GATHER=0 selects the
+    # separate NCCL all-gather it replaces.
+    gathered, peer = None, None
     if world > 1:
-        gathered = torch.empty(world, B, MAX_DET * 7 + 1, dtype=torch.float32, device=dev)
+        if os.environ.get("YX_PEER_GATHER", "1") != "0":
+            peer = yb.dist.PeerGather(B, MAX_DET, dev)
+        else:
+            gathered = torch.empty(world, B, MAX_DET * 7 + 1, dtype=torch.float32, device=dev)
 
     def step(img):
         eng, reg8, cls = model.run_engine(img, in_scale=0.9, in_shift=11.4)
         det, cnt, _ = pp.detect_main(reg8[..., :4], reg8[..., 4:5], cls[..., :MODEL["num_classes"]], model.head.hw, strides,
-                                     CONF_THR, NMS_THR, MAX_NMS, MAX_DET)
-        if world > 1:  # one all-gather of fixed-shape detections (+count packed as a trailing column)
+                                     CONF_THR, NMS_THR, MAX_NMS, MAX_DET, gather=peer)
+        if gathered is not None:  # one all-gather of fixed-shape detections (+count packed as a trailing column)
             packed = torch.cat([det.view(B, -1), cnt.view(B, 1).float()], dim=1)
             dist.all_gather_into_tensor(gathered.view(world * B, -1), packed)
         return det, cnt
@@ -209,7 +215,7 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(max(args.warmup, 3)):
         det, cnt = step(dev_img)
     barrier()
-    n_launch_step = model.engine_for(dev_img).n_launches + 3  # + select, sort, nms kernels
+    n_launch_step = model.engine_for(dev_img).n_launches + 3 + (1 if peer is not None else 0)  # + select, sort, nms (+ gather wait)
 
     # ---- device-resident timing -------------------------------------------------------------
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -331,7 +337,9 @@ def run_ours(args, rank, world, local_rank):
                 config=dict(workload=f"pruned {MODEL['name']} {S}x{S}, {B} images/GPU/step (global {B * world}), 49% synthetic "
                                      f"magnitude masks dense-with-zeros, conf {CONF_THR} nms {NMS_THR} top-{MAX_NMS}/{MAX_DET}, "
                                      f"random-init preds => ~all {sum((S // s) ** 2 for s in strides)} anchors/img are candidates",
-                            model=MODEL["name"], global_batch=B * world, parallelism=f"dp{world} batch shard, all-gather of detections",
+                            model=MODEL["name"], global_batch=B * world, parallelism=(f"dp{world} batch shard, detections gathered " +
+                                         ("by the NMS kernel into peer windows (NVLink stores)" if peer is not None
+                                          else "with one NCCL all-gather")) if world > 1 else "single GPU",
                             l2="inputs larger than L2 (activations per layer >> 126 MB at bs64)"),
                 e2e=dict(value=imgs / (ms_e2e * 1e-3), unit="images/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                          note="pinned host fp16 NCHW batch -> H2D (double-buffered) -> forward+decode+NMS -> D2H detections"),

@@ -98,8 +98,17 @@ struct Workspace {
   int* klabel;     // [B][A]
   int* kidx;       // [B][A]  kept candidate rank
   int* count;      // [B]
-  int Apad;
+  int Apad;        // keys per image (power of two >= A*K)
+  int K;           // candidates per anchor: 1, or C in multi_class mode (candidate id = anchor*K + class)
+  int R;           // rows per image of sbox/slabel/kbox/klabel/kidx
 };
+
+// inverse of f2sortable on the high word of a key
+__device__ __forceinline__ float key_score(uint64_t key) {
+  const uint32_t u = (uint32_t)(key >> 32);
+  return __uint_as_float((u & 0x80000000u) ? (u ^ 0x80000000u) : ~u);
+}
+__device__ __forceinline__ int key_id(uint64_t key) { return (int)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull)); }
 
 static int next_pow2(int v) {
   int p = 1;
@@ -107,23 +116,24 @@ static int next_pow2(int v) {
   return p;
 }
 
-static size_t ws_layout(int B, int A, uint8_t* base, Workspace* ws) {
+// K = candidates per anchor, R = rows per image that can reach the NMS (A for K == 1; min(max_nms, A*K) otherwise)
+static size_t ws_layout(int B, int A, int K, int64_t R, uint8_t* base, Workspace* ws) {
   size_t off = 0;
   auto take = [&](size_t bytes) {
     uint8_t* p = base ? base + off : nullptr;
     off += (bytes + 255) & ~size_t(255);
     return p;
   };
-  const size_t n = (size_t)B * A;
-  const int Apad = next_pow2(std::max(A, 2));
+  const size_t n = (size_t)B * A, r = (size_t)B * (size_t)R;
+  const int Apad = next_pow2(std::max(A * K, 2));
   Workspace w;
   w.box = (float4*)take(n * 16); w.objc = (float*)take(n * 4); w.col5 = (float*)take(n * 4);
   w.score = (float*)take(n * 4); w.label = (int*)take(n * 4);
   w.keys = (uint64_t*)take((size_t)B * Apad * 8);
-  w.sbox = (float4*)take(n * 16); w.slabel = (int*)take(n * 4);
-  w.kbox = (float4*)take(n * 16); w.klabel = (int*)take(n * 4); w.kidx = (int*)take(n * 4);
+  w.sbox = (float4*)take(r * 16); w.slabel = (int*)take(r * 4);
+  w.kbox = (float4*)take(r * 16); w.klabel = (int*)take(r * 4); w.kidx = (int*)take(r * 4);
   w.count = (int*)take((size_t)B * 4);
-  w.Apad = Apad;
+  w.Apad = Apad; w.K = K; w.R = (int)R;
   if (ws) *ws = w;
   return off;
 }
@@ -226,6 +236,53 @@ __global__ void select_decoded_kernel(const float* __restrict__ boxes, const flo
     if (best >= thr) {
       ws.box[i] = reinterpret_cast<const float4*>(boxes)[i];
       ws.objc[i] = obj_conf[i]; ws.col5[i] = best; ws.score[i] = best; ws.label[i] = bi;
+      const int pos = warp_agg_inc(ws.count + b);
+      ws.keys[(int64_t)b * ws.Apad + pos] = make_key(best, a);
+    }
+  }
+}
+
+// multi_class (postprocess_utils.py:90-95): one candidate per (anchor, class) with cls_conf >= thr; the candidate id
+// a*C + c in the key's low word reproduces nonzero()'s row-major order for ties.  One thread per score.
+__global__ void select_multiclass_kernel(const float* __restrict__ boxes, const float* __restrict__ obj_conf,
+                                         const float* __restrict__ cls_conf, int B, int A, int C, float thr, Workspace ws) {
+  const int64_t per = (int64_t)A * C, total = (int64_t)B * per;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / per);
+    const int id = (int)(i - (int64_t)b * per);
+    const float v = cls_conf[i];
+    if (id % C == 0) {  // the anchor's box / objectness travel once
+      const int64_t ia = (int64_t)b * A + id / C;
+      ws.box[ia] = reinterpret_cast<const float4*>(boxes)[ia];
+      ws.objc[ia] = obj_conf[ia];
+    }
+    if (v >= thr) {
+      const int pos = warp_agg_inc(ws.count + b);
+      ws.keys[(int64_t)b * ws.Apad + pos] = make_key(v, id);
+    }
+  }
+}
+
+// rmmop (postprocess_utils.py:74-84): top-1 class per anchor, kept when top1 >= top2 * r1 and obj^2 >= top1 * r2
+// (fp32 products as torch evaluates them; no confidence threshold in this mode).
+__global__ void select_rmmop_kernel(const float* __restrict__ boxes, const float* __restrict__ obj_conf,
+                                    const float* __restrict__ cls_conf, int B, int A, int C, float r1, float r2,
+                                    Workspace ws) {
+  const int64_t total = (int64_t)B * A;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int a = i % A, b = i / A;
+    const float* c = cls_conf + i * C;
+    float best = c[0], second = -INFINITY;
+    int bi = 0;
+    for (int k = 1; k < C; ++k) {
+      const float v = c[k];
+      if (v > best) { second = best; best = v; bi = k; }
+      else if (v > second) second = v;
+    }
+    const float o = obj_conf[i];
+    if (best >= __fmul_rn(second, r1) && __fmul_rn(o, o) >= __fmul_rn(best, r2)) {
+      ws.box[i] = reinterpret_cast<const float4*>(boxes)[i];
+      ws.objc[i] = o; ws.col5[i] = best; ws.score[i] = best; ws.label[i] = bi;
       const int pos = warp_agg_inc(ws.count + b);
       ws.keys[(int64_t)b * ws.Apad + pos] = make_key(best, a);
     }
@@ -447,9 +504,18 @@ __device__ __forceinline__ bool iou_gt(const float4 a, const float4 b, float thr
   return ovr > thr;
 }
 
+// Where the NMS tail also stores an image's rows when the detections are gathered across GPUs: rank w's receive window,
+// mapped into this process through CUDA IPC (stores travel over NVLink / NVSwitch as posted writes).
+struct PeerDev {
+  float* det[YX_MAX_PEERS];  // this rank's [B, det_rows, 7] block inside rank w's window
+  int* cnt[YX_MAX_PEERS];    // this rank's [B] block inside rank w's window
+  int* arrive[YX_MAX_PEERS]; // rank w's arrival counter for this rank
+  int world;                 // 0: no gather
+};
+
 __global__ void __launch_bounds__(kNmsThreads, 1)
 nms_kernel(Workspace ws, int A, float nms_thr, int max_nms, int max_det, int mode, int det_rows, float* __restrict__ det,
-           int* __restrict__ det_count, int* __restrict__ det_anchor) {
+           int* __restrict__ det_count, int* __restrict__ det_anchor, const PeerDev po) {
   __shared__ float4 s_kbox[kKeptSmem];
   __shared__ int s_klab[kKeptSmem];
   __shared__ float4 s_cbox[64];
@@ -464,22 +530,24 @@ nms_kernel(Workspace ws, int A, float nms_thr, int max_nms, int max_det, int mod
   if (max_nms > 0 && n > max_nms) n = max_nms;
   if (mode == YX_NMS_AUTO) mode = (4 * (int64_t)n > 100000) ? YX_NMS_VANILLA : YX_NMS_TRICK;
   const uint64_t* keys = ws.keys + (int64_t)b * ws.Apad;
-  const int64_t ib = (int64_t)b * A;
-  float4* sbox = ws.sbox + ib;
-  int* slab = ws.slabel + ib;
-  int* kidx = ws.kidx + ib;
+  const int64_t ib = (int64_t)b * A, ic = (int64_t)b * ws.R;
+  const int K = ws.K;
+  float4* sbox = ws.sbox + ic;
+  int* slab = ws.slabel + ic;
+  int* kidx = ws.kidx + ic;
   const bool kept_in_smem = (max_det > 0 && max_det <= kKeptSmem);
-  float4* kbox = kept_in_smem ? s_kbox : (ws.kbox + ib);
-  int* klab = kept_in_smem ? s_klab : (ws.klabel + ib);
+  float4* kbox = kept_in_smem ? s_kbox : (ws.kbox + ic);
+  int* klab = kept_in_smem ? s_klab : (ws.klabel + ic);
   const int cap = max_det > 0 ? max_det : 0x7fffffff;
 
   // ---- gather the selected candidates in score order; coordinate-trick offsets -----------------
   float mx = -INFINITY;
   for (int i = tid; i < n; i += kNmsThreads) {
-    const int a = (int)(0xFFFFFFFFu - (uint32_t)(keys[i] & 0xFFFFFFFFull));
+    const int id = key_id(keys[i]);
+    const int a = K > 1 ? id / K : id;
     const float4 bx = ws.box[ib + a];
     sbox[i] = bx;
-    slab[i] = ws.label[ib + a];
+    slab[i] = K > 1 ? id % K : ws.label[ib + a];
     mx = fmaxf(fmaxf(mx, fmaxf(bx.x, bx.y)), fmaxf(bx.z, bx.w));
   }
   if (mode == YX_NMS_TRICK) {
@@ -554,17 +622,48 @@ nms_kernel(Workspace ws, int A, float nms_thr, int max_nms, int max_det, int mod
     float* d = drow + (int64_t)k * 7;
     if (k < kept) {
       const int r = kidx[k];
-      const int a = (int)(0xFFFFFFFFu - (uint32_t)(keys[r] & 0xFFFFFFFFull));
+      const uint64_t key = keys[r];
+      const int id = key_id(key);
+      const int a = K > 1 ? id / K : id;
       const float4 bx = ws.box[ib + a];
       d[0] = bx.x; d[1] = bx.y; d[2] = bx.z; d[3] = bx.w;
-      d[4] = ws.objc[ib + a]; d[5] = ws.col5[ib + a]; d[6] = (float)ws.label[ib + a];
+      d[4] = ws.objc[ib + a];
+      if (K > 1) { d[5] = key_score(key); d[6] = (float)(id % K); }
+      else { d[5] = ws.col5[ib + a]; d[6] = (float)ws.label[ib + a]; }
       if (det_anchor) det_anchor[(int64_t)b * det_rows + k] = a;
     } else {
 #pragma unroll
       for (int j = 0; j < 7; ++j) d[j] = 0.0f;
       if (det_anchor) det_anchor[(int64_t)b * det_rows + k] = -1;
     }
+    // fused all-gather: the same row goes into every rank's window while it is still in registers / L1
+    for (int w = 0; w < po.world; ++w) {
+      float* r = po.det[w] + ((int64_t)b * det_rows + k) * 7;
+#pragma unroll
+      for (int j = 0; j < 7; ++j) r[j] = d[j];
+    }
   }
+  if (po.world > 0) {
+    if (tid < po.world) po.cnt[tid][b] = kept;
+    __threadfence_system();  // rows and count are visible system-wide before the arrival is counted
+    __syncthreads();
+    if (tid < po.world) atomicAdd_system(po.arrive[tid], 1);
+  }
+}
+
+// Completes the gather on the receiving side: returns (stream-ordered) once every rank's images of this step have
+// arrived in this GPU's window.  A bounded wait: on timeout *status is set and the kernel returns.
+__global__ void peer_wait_kernel(const int* arrive, int world, int target, int* status, long long timeout_cycles) {
+  const int lane = threadIdx.x;
+  if (lane < world) {
+    const long long t0 = clock64();
+    const volatile int* f = arrive + lane;
+    while (*f - target < 0) {  // counters only grow; difference form tolerates wrap-around
+      __nanosleep(200);
+      if (clock64() - t0 > timeout_cycles) { atomicExch(status, 1 + lane); break; }
+    }
+  }
+  __threadfence_system();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -575,7 +674,8 @@ static int grid_for(int64_t total, int threads) {
 }
 
 static int sort_and_nms(const Workspace& ws, int B, int A, float nms_thr, int max_nms, int max_det, int mode,
-                        int det_rows, float* det, int32_t* det_count, int32_t* det_anchor, cudaStream_t st) {
+                        int det_rows, float* det, int32_t* det_count, int32_t* det_anchor, cudaStream_t st,
+                        const PeerDev* peer = nullptr) {
   static bool attr = false;
   if (!attr) {
     YX_CUDA(cudaFuncSetAttribute(sort_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortChunk * 8));
@@ -583,15 +683,23 @@ static int sort_and_nms(const Workspace& ws, int B, int A, float nms_thr, int ma
   }
   sort_keys_kernel<<<B, kSortThreads, kSortChunk * 8, st>>>(ws, max_nms);
   YX_CUDA(cudaGetLastError());
-  nms_kernel<<<B, kNmsThreads, 0, st>>>(ws, A, nms_thr, max_nms, max_det, mode, det_rows, det, det_count, det_anchor);
+  PeerDev po;
+  if (peer) po = *peer; else po.world = 0;
+  nms_kernel<<<B, kNmsThreads, 0, st>>>(ws, A, nms_thr, max_nms, max_det, mode, det_rows, det, det_count, det_anchor, po);
   YX_CUDA(cudaGetLastError());
   return YX_OK;
 }
 
-static int check_ws(int B, int A, void* workspace, size_t bytes, Workspace* ws) {
+static int64_t cand_rows(int A, int K, int max_nms) {
+  const int64_t all = (int64_t)A * K;
+  return (K > 1 && max_nms > 0) ? std::min<int64_t>(all, max_nms) : all;
+}
+
+static int check_ws(int B, int A, void* workspace, size_t bytes, Workspace* ws, int K = 1, int max_nms = 0) {
   YX_REQUIRE(B >= 1 && A >= 1, "B, A must be positive");
+  YX_REQUIRE((int64_t)A * K < (int64_t(1) << 30), "too many candidates per image");
   YX_REQUIRE(workspace != nullptr && ((uintptr_t)workspace % 256) == 0, "workspace must be 256-byte aligned");
-  const size_t need = ws_layout(B, A, static_cast<uint8_t*>(workspace), ws);
+  const size_t need = ws_layout(B, A, K, cand_rows(A, K, max_nms), static_cast<uint8_t*>(workspace), ws);
   YX_REQUIRE(bytes >= need, "workspace too small (see yx_detect_workspace_bytes)");
   return YX_OK;
 }
@@ -602,7 +710,14 @@ using namespace yx;
 
 extern "C" size_t yx_detect_workspace_bytes(int B, int A) {
   if (B < 1 || A < 1) return 0;
-  return ws_layout(B, A, nullptr, nullptr);
+  return ws_layout(B, A, 1, A, nullptr, nullptr);
+}
+
+extern "C" size_t yx_nms_workspace_bytes(int B, int A, int C, int cand_mode, int max_nms) {
+  if (B < 1 || A < 1 || C < 1) return 0;
+  const int K = cand_mode == YX_CAND_MULTI_CLASS ? C : 1;
+  if ((int64_t)A * K >= (int64_t(1) << 30)) return 0;
+  return ws_layout(B, A, K, cand_rows(A, K, max_nms), nullptr, nullptr);
 }
 
 extern "C" int yx_decode_infer(const void* reg, int64_t reg_sb, int64_t reg_sa, const void* obj, int64_t obj_sb,
@@ -627,26 +742,43 @@ extern "C" int yx_decode_infer(const void* reg, int64_t reg_sb, int64_t reg_sa, 
   return YX_OK;
 }
 
-extern "C" int yx_nms_main(const float* boxes, const float* obj_conf, const float* cls_conf, int B, int A, int C,
-                           float conf_thr, float nms_thr, int max_nms, int max_det, int mode, void* workspace,
-                           size_t workspace_bytes, float* det, int32_t* det_count, int32_t* det_anchor, void* stream) {
-  Workspace ws;
-  int rc = check_ws(B, A, workspace, workspace_bytes, &ws);
-  if (rc) return rc;
+extern "C" int yx_nms_main_ex(const float* boxes, const float* obj_conf, const float* cls_conf, int B, int A, int C,
+                              float conf_thr, float nms_thr, int max_nms, int max_det, int mode, int cand_mode,
+                              float rmmop_r1, float rmmop_r2, void* workspace, size_t workspace_bytes, float* det,
+                              int32_t* det_count, int32_t* det_anchor, void* stream) {
   YX_REQUIRE(mode >= 0 && mode <= 3 && C >= 1, "bad nms mode / C");
+  YX_REQUIRE(cand_mode >= YX_CAND_MAX && cand_mode <= YX_CAND_RMMOP, "bad candidate mode");
+  YX_REQUIRE(cand_mode != YX_CAND_RMMOP || C >= 2, "rmmop needs at least two classes");  // cls_conf_sorted[:, 1]
+  const int K = cand_mode == YX_CAND_MULTI_CLASS ? C : 1;
+  Workspace ws;
+  int rc = check_ws(B, A, workspace, workspace_bytes, &ws, K, max_nms);
+  if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int det_rows = max_det > 0 ? max_det : A;
+  const int64_t all = (int64_t)A * K;
+  const int det_rows = max_det > 0 ? max_det : (int)all;
   YX_CUDA(cudaMemsetAsync(ws.count, 0, (size_t)B * 4, st));
-  select_decoded_kernel<<<grid_for((int64_t)B * A, 256), 256, 0, st>>>(boxes, obj_conf, cls_conf, B, A, C, conf_thr, ws);
+  if (cand_mode == YX_CAND_MULTI_CLASS)
+    select_multiclass_kernel<<<grid_for((int64_t)B * all, 256), 256, 0, st>>>(boxes, obj_conf, cls_conf, B, A, C, conf_thr, ws);
+  else if (cand_mode == YX_CAND_RMMOP)
+    select_rmmop_kernel<<<grid_for((int64_t)B * A, 256), 256, 0, st>>>(boxes, obj_conf, cls_conf, B, A, C, rmmop_r1, rmmop_r2, ws);
+  else
+    select_decoded_kernel<<<grid_for((int64_t)B * A, 256), 256, 0, st>>>(boxes, obj_conf, cls_conf, B, A, C, conf_thr, ws);
   YX_CUDA(cudaGetLastError());
   return sort_and_nms(ws, B, A, nms_thr, max_nms, max_det, mode, det_rows, det, det_count, det_anchor, st);
 }
 
-extern "C" int yx_detect_main(const void* reg, int64_t reg_sb, int64_t reg_sa, const void* obj, int64_t obj_sb,
-                              int64_t obj_sa, const void* cls, int64_t cls_sb, int64_t cls_sa, int logits_dtype, int B,
-                              int A, int C, const yx_levels* lv_host, float conf_thr, float nms_thr, int max_nms,
-                              int max_det, int mode, void* workspace, size_t workspace_bytes, float* det,
-                              int32_t* det_count, int32_t* det_anchor, void* stream) {
+extern "C" int yx_nms_main(const float* boxes, const float* obj_conf, const float* cls_conf, int B, int A, int C,
+                           float conf_thr, float nms_thr, int max_nms, int max_det, int mode, void* workspace,
+                           size_t workspace_bytes, float* det, int32_t* det_count, int32_t* det_anchor, void* stream) {
+  return yx_nms_main_ex(boxes, obj_conf, cls_conf, B, A, C, conf_thr, nms_thr, max_nms, max_det, mode, YX_CAND_MAX, 0.0f,
+                        0.0f, workspace, workspace_bytes, det, det_count, det_anchor, stream);
+}
+
+static int detect_main_impl(const void* reg, int64_t reg_sb, int64_t reg_sa, const void* obj, int64_t obj_sb,
+                            int64_t obj_sa, const void* cls, int64_t cls_sb, int64_t cls_sa, int logits_dtype, int B,
+                            int A, int C, const yx_levels* lv_host, float conf_thr, float nms_thr, int max_nms,
+                            int max_det, int mode, void* workspace, size_t workspace_bytes, float* det,
+                            int32_t* det_count, int32_t* det_anchor, void* stream, const yx::PeerDev* peer) {
   LevelsDev lv;
   int rc = make_levels(lv_host, A, &lv);
   if (rc) return rc;
@@ -673,7 +805,45 @@ extern "C" int yx_detect_main(const void* reg, int64_t reg_sb, int64_t reg_sa, c
     YX_REQUIRE(false, "logits dtype must be YX_F16 or YX_F32");
   }
   YX_CUDA(cudaGetLastError());
-  return sort_and_nms(ws, B, A, nms_thr, max_nms, max_det, mode, det_rows, det, det_count, det_anchor, st);
+  return sort_and_nms(ws, B, A, nms_thr, max_nms, max_det, mode, det_rows, det, det_count, det_anchor, st, peer);
+}
+
+extern "C" int yx_detect_main(const void* reg, int64_t reg_sb, int64_t reg_sa, const void* obj, int64_t obj_sb,
+                              int64_t obj_sa, const void* cls, int64_t cls_sb, int64_t cls_sa, int logits_dtype, int B,
+                              int A, int C, const yx_levels* lv_host, float conf_thr, float nms_thr, int max_nms,
+                              int max_det, int mode, void* workspace, size_t workspace_bytes, float* det,
+                              int32_t* det_count, int32_t* det_anchor, void* stream) {
+  return detect_main_impl(reg, reg_sb, reg_sa, obj, obj_sb, obj_sa, cls, cls_sb, cls_sa, logits_dtype, B, A, C, lv_host,
+                          conf_thr, nms_thr, max_nms, max_det, mode, workspace, workspace_bytes, det, det_count, det_anchor,
+                          stream, nullptr);
+}
+
+extern "C" int yx_detect_main_gather(const void* reg, int64_t reg_sb, int64_t reg_sa, const void* obj, int64_t obj_sb,
+                                     int64_t obj_sa, const void* cls, int64_t cls_sb, int64_t cls_sa, int logits_dtype,
+                                     int B, int A, int C, const yx_levels* lv_host, float conf_thr, float nms_thr,
+                                     int max_nms, int max_det, int mode, void* workspace, size_t workspace_bytes,
+                                     float* det, int32_t* det_count, int32_t* det_anchor, const yx_peer_out* peer,
+                                     void* stream) {
+  YX_REQUIRE(peer != nullptr && peer->world >= 1 && peer->world <= YX_MAX_PEERS, "peer: world must be 1..YX_MAX_PEERS");
+  YX_REQUIRE(max_det > 0, "gathered detections need a fixed row count (max_det > 0)");
+  YX_REQUIRE(peer->local_arrive != nullptr && peer->status != nullptr, "peer: local_arrive / status missing");
+  PeerDev po;
+  po.world = peer->world;
+  for (int w = 0; w < peer->world; ++w) {
+    YX_REQUIRE(peer->det[w] && peer->cnt[w] && peer->arrive[w], "peer: missing window pointer");
+    po.det[w] = static_cast<float*>(peer->det[w]);
+    po.cnt[w] = static_cast<int*>(peer->cnt[w]);
+    po.arrive[w] = static_cast<int*>(peer->arrive[w]);
+  }
+  int rc = detect_main_impl(reg, reg_sb, reg_sa, obj, obj_sb, obj_sa, cls, cls_sb, cls_sa, logits_dtype, B, A, C, lv_host,
+                            conf_thr, nms_thr, max_nms, max_det, mode, workspace, workspace_bytes, det, det_count,
+                            det_anchor, stream, &po);
+  if (rc) return rc;
+  const long long timeout = peer->timeout_ms > 0 ? (long long)peer->timeout_ms * 2000000ll : 20000000000ll;  // ~2 GHz
+  peer_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const int*>(peer->local_arrive), peer->world,
+                                                                   peer->wait_target, static_cast<int*>(peer->status), timeout);
+  YX_CUDA(cudaGetLastError());
+  return YX_OK;
 }
 
 extern "C" int yx_head_assemble(const void* reg, int64_t reg_sb, int64_t reg_sa, const void* obj, int64_t obj_sb,

@@ -39,6 +39,95 @@ def all_gather_detections(det: torch.Tensor, cnt: torch.Tensor, group=None) -> T
     return unpack_detections(torch.cat(out, 0), det.shape[1])
 
 
+class PeerGather:
+    """Receive windows for the all-gather fused into the NMS kernel (include/yolox_b200.h, yx_detect_main_gather).
+
+    Every rank owns ONE device buffer holding two windows (consecutive steps alternate) of
+    det [world,B,rows,7] fp32 + cnt [world,B] int32, the arrival counters int32[world] and a status word.  The buffers
+    are exported with CUDA IPC and the 64-byte handles exchanged once over the process group; from then on a step moves
+    no data through torch.distributed: each rank's NMS kernel stores its rows into all windows over NVLink.
+    Consumers of result() must run on the stream the step was issued on (or be ordered after it)."""
+
+    def __init__(self, batch: int, rows: int, device, group=None, timeout_ms: int = 10000):
+        from . import _capi
+        self._capi, self.lib = _capi, _capi.load()
+        self.group, self.B, self.rows, self.timeout_ms = group, int(batch), int(rows), int(timeout_ms)
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if self.world > _capi.MAX_PEERS:
+            raise ValueError(f"PeerGather supports up to {_capi.MAX_PEERS} ranks on one node")
+        self.device = torch.device(device)
+        W, B = self.world, self.B
+        self.det_bytes = W * B * self.rows * 7 * 4
+        self.cnt_bytes = (W * B * 4 + 255) // 256 * 256
+        self.win_bytes = self.det_bytes + self.cnt_bytes
+        self.arrive_off = 2 * self.win_bytes
+        self.status_off = self.arrive_off + 256
+        self.buf = torch.zeros(self.status_off + 256, dtype=torch.uint8, device=self.device)
+        self.step = 0
+        # ---- exchange IPC handles, map the peers' buffers ---------------------------------------------------
+        import ctypes
+        handle = (ctypes.c_ubyte * _capi.IPC_HANDLE_BYTES)()
+        off = ctypes.c_int64(0)
+        self.ptrs = [0] * W
+        self.ptrs[self.rank] = self.buf.data_ptr()
+        self._opened = []
+        if W > 1:
+            with torch.cuda.device(self.device):
+                _capi.check(self.lib.yx_ipc_export(self.buf.data_ptr(), handle, ctypes.byref(off)), "yx_ipc_export")
+                mine = (bytes(handle), int(off.value))
+                everyone = [None] * W
+                dist.all_gather_object(everyone, mine, group=group)
+                for r, (h, o) in enumerate(everyone):
+                    if r == self.rank:
+                        continue
+                    base = ctypes.c_void_p()
+                    hb = (ctypes.c_ubyte * _capi.IPC_HANDLE_BYTES).from_buffer_copy(h)
+                    _capi.check(self.lib.yx_ipc_open(hb, ctypes.byref(base)), "yx_ipc_open")
+                    self._opened.append(base.value)
+                    self.ptrs[r] = base.value + o
+            torch.cuda.synchronize(self.device)     # zero fill done before any peer may store into this buffer
+            dist.barrier(group=group)
+
+    def _window(self, parity: int):
+        w = self.buf[parity * self.win_bytes:(parity + 1) * self.win_bytes]
+        det = w[:self.det_bytes].view(torch.float32).view(self.world * self.B, self.rows, 7)
+        cnt = w[self.det_bytes:self.det_bytes + self.world * self.B * 4].view(torch.int32)
+        return det, cnt
+
+    def next_step(self, batch: int, rows: int):
+        """yx_peer_out for the next step (pointers of this rank's block inside every rank's window)."""
+        if batch != self.B or rows != self.rows:
+            raise ValueError("PeerGather was sized for a different batch / row count")
+        parity = self.step & 1
+        self.step += 1
+        po = self._capi.PeerOut()
+        po.world, po.wait_target, po.timeout_ms = self.world, (self.step * self.B) & 0x7FFFFFFF, self.timeout_ms
+        blk_det, blk_cnt = self.B * self.rows * 7 * 4, self.B * 4
+        for w in range(self.world):
+            win = self.ptrs[w] + parity * self.win_bytes
+            po.det[w] = win + self.rank * blk_det
+            po.cnt[w] = win + self.det_bytes + self.rank * blk_cnt
+            po.arrive[w] = self.ptrs[w] + self.arrive_off + 4 * self.rank
+        po.local_arrive = self.buf.data_ptr() + self.arrive_off
+        po.status = self.buf.data_ptr() + self.status_off
+        return po
+
+    def result(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(det [world*B, rows, 7], cnt [world*B]) of the most recent step, rank-major; views of the window, valid
+        until the step after next is issued."""
+        return self._window((self.step - 1) & 1)
+
+    def status(self) -> int:
+        """0 while healthy; 1 + rank of a peer whose rows did not arrive within the timeout (host sync)."""
+        return int(self.buf[self.status_off:self.status_off + 4].view(torch.int32).item())
+
+    def close(self):
+        for base in self._opened:
+            self.lib.yx_ipc_close(base)
+        self._opened = []
+
+
 def gathered_for_images(det_all, cnt_all, n_images: int, world: int, per_rank: int):
     """Drop the padding rows added so every rank ran the same batch size."""
     keep = []

@@ -8,6 +8,7 @@
 
 All tensors must live on a CUDA device; there is no CPU path (the oracle under oracle/ is the checker).
 """
+import ctypes
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -33,8 +34,8 @@ def _rows(t: torch.Tensor) -> torch.Tensor:
     return t if t.stride(2) == 1 or t.shape[2] == 1 else t.contiguous()
 
 
-def _workspace(B: int, A: int, device) -> torch.Tensor:
-    n = _capi.load().yx_detect_workspace_bytes(B, A)
+def _workspace(B: int, A: int, device, nbytes: Optional[int] = None) -> torch.Tensor:
+    n = _capi.load().yx_detect_workspace_bytes(B, A) if nbytes is None else nbytes
     ws = torch.empty(n + 256, dtype=torch.uint8, device=device)
     off = (-ws.data_ptr()) % 256
     return ws[off:off + n]
@@ -112,7 +113,11 @@ def _split(det: torch.Tensor, count: torch.Tensor, dtype=None) -> List[Optional[
     return out
 
 
-def nms_main_raw(reg_boxes, obj_conf, cls_conf, nms_threshold, conf_threshold, max_num_nms, max_num_det, mode="auto"):
+CAND_MAX, CAND_MULTI_CLASS, CAND_RMMOP = 0, 1, 2  # yx_cand_mode
+
+
+def nms_main_raw(reg_boxes, obj_conf, cls_conf, nms_threshold, conf_threshold, max_num_nms, max_num_det, mode="auto",
+                 multi_class=False, rmmop=None):
     """Device-side result of yolox_nms_torch_batch: det [B,R,7], count [B], anchor [B,R] (no sync)."""
     lib = _capi.load()
     for t in (reg_boxes, obj_conf, cls_conf):
@@ -121,38 +126,52 @@ def nms_main_raw(reg_boxes, obj_conf, cls_conf, nms_threshold, conf_threshold, m
     objc = obj_conf.float().contiguous()
     clsc = cls_conf.float().contiguous()
     B, A, C = clsc.shape
-    rows = max_num_det if max_num_det > 0 else A
+    cand = CAND_RMMOP if rmmop is not None else (CAND_MULTI_CLASS if multi_class else CAND_MAX)  # rmmop wins, :74
+    r1, r2 = (float(rmmop[0]), float(rmmop[1])) if rmmop is not None else (0.0, 0.0)
+    per_image = A * C if cand == CAND_MULTI_CLASS else A
+    if max_num_det >= per_image:
+        max_num_det = 0                                   # no cap can bind: size det by the candidate count
+    rows = max_num_det if max_num_det > 0 else per_image
     det = torch.empty(B, rows, 7, dtype=torch.float32, device=clsc.device)
     cnt = torch.empty(B, dtype=torch.int32, device=clsc.device)
     anc = torch.empty(B, rows, dtype=torch.int32, device=clsc.device)
-    ws = _workspace(B, A, clsc.device)
+    if cand == CAND_MULTI_CLASS:
+        nbytes = lib.yx_nms_workspace_bytes(B, A, C, cand, int(max_num_nms))
+        if nbytes == 0:
+            raise RuntimeError("multi_class candidate set too large")
+        ws = _workspace(B, A, clsc.device, nbytes)
+    else:
+        ws = _workspace(B, A, clsc.device)
     with torch.cuda.device(clsc.device):
-        _capi.check(lib.yx_nms_main(boxes.data_ptr(), objc.data_ptr(), clsc.data_ptr(), B, A, C, float(conf_threshold),
-                                    float(nms_threshold), int(max_num_nms), int(max_num_det), _NMS_MODES[mode],
-                                    ws.data_ptr(), ws.numel(), det.data_ptr(), cnt.data_ptr(), anc.data_ptr(),
-                                    _capi.current_stream_ptr()), "yx_nms_main")
+        _capi.check(lib.yx_nms_main_ex(boxes.data_ptr(), objc.data_ptr(), clsc.data_ptr(), B, A, C, float(conf_threshold),
+                                       float(nms_threshold), int(max_num_nms), int(max_num_det), _NMS_MODES[mode], cand,
+                                       r1, r2, ws.data_ptr(), ws.numel(), det.data_ptr(), cnt.data_ptr(),
+                                       anc.data_ptr(), _capi.current_stream_ptr()), "yx_nms_main_ex")
     return det, cnt, anc
 
 
 def yolox_nms_torch_batch(reg_boxes, obj_conf, cls_conf, nms_threshold: float = 0.65, conf_threshold: float = 0.001,
                           soft: bool = False, max_num_nms: int = 5000, max_num_det: int = 300,
                           multi_class: bool = False, rmmop=None, class_agnostic: bool = False):
-    """postprocess_utils.py:55-129 (default mode + class_agnostic).  Returns list[B] of [n,7] or None."""
+    """postprocess_utils.py:55-129, every candidate rule (default, multi_class, rmmop) and class_agnostic.
+    Returns list[B] of [n,7] or None."""
     if soft:
         raise ValueError("Soft-NMS is not installed, but using soft_nms.")  # nms.py:21,36
-    if multi_class or rmmop is not None:
-        raise NotImplementedError("multi_class / rmmop candidate modes are not built yet (SURVEY §8f N4)")
-    big = 2 ** 31 - 1
     det, cnt, _ = nms_main_raw(reg_boxes, obj_conf, cls_conf, nms_threshold, conf_threshold, max_num_nms,
-                               0 if max_num_det >= big or max_num_det >= cls_conf.shape[1] else max_num_det,
-                               "agnostic" if class_agnostic else "auto")
-    return _split(det, cnt)
+                               max(1, min(int(max_num_det), 2 ** 31 - 1)), "agnostic" if class_agnostic else "auto",
+                               multi_class=multi_class, rmmop=rmmop)
+    out = _split(det, cnt)
+    if max_num_det <= 0:  # :123-124 slices to zero rows; images without candidates stay None
+        out = [None if d is None else d[:0] for d in out]
+    return out
 
 
 def detect_main(reg, obj, cls, level_hw, strides, conf_threshold=0.001, nms_threshold=0.65, max_num_nms=5000,
-                max_num_det=300, mode="auto"):
+                max_num_det=300, mode="auto", gather=None):
     """Fused decode + threshold + top-k + NMS from raw logits [B,A,*] (fp16/fp32).  No host sync.
-    Returns det [B,max_num_det,7] fp32 (rows beyond count are zero), count [B] int32, anchor [B,max_num_det]."""
+    Returns det [B,max_num_det,7] fp32 (rows beyond count are zero), count [B] int32, anchor [B,max_num_det].
+    gather: a dist.PeerGather — the NMS kernel also stores the rows into every rank's window (fused all-gather);
+    read the global result from gather.result() afterwards."""
     lib = _capi.load()
     reg, obj, cls = _rows(reg), _rows(obj), _rows(cls)
     B, A, C = cls.shape
@@ -162,6 +181,15 @@ def detect_main(reg, obj, cls, level_hw, strides, conf_threshold=0.001, nms_thre
     cnt = torch.empty(B, dtype=torch.int32, device=cls.device)
     anc = torch.empty(B, rows, dtype=torch.int32, device=cls.device)
     ws = _workspace(B, A, cls.device)
+    if gather is not None:
+        po = gather.next_step(B, rows)
+        with torch.cuda.device(cls.device):
+            _capi.check(lib.yx_detect_main_gather(
+                reg.data_ptr(), reg.stride(0), reg.stride(1), obj.data_ptr(), obj.stride(0), obj.stride(1), cls.data_ptr(),
+                cls.stride(0), cls.stride(1), _dt(cls), B, A, C, lv, float(conf_threshold), float(nms_threshold),
+                int(max_num_nms), int(max_num_det), _NMS_MODES[mode], ws.data_ptr(), ws.numel(), det.data_ptr(),
+                cnt.data_ptr(), anc.data_ptr(), ctypes.byref(po), _capi.current_stream_ptr()), "yx_detect_main_gather")
+        return det, cnt, anc
     with torch.cuda.device(cls.device):
         _capi.check(lib.yx_detect_main(reg.data_ptr(), reg.stride(0), reg.stride(1), obj.data_ptr(), obj.stride(0),
                                        obj.stride(1), cls.data_ptr(), cls.stride(0), cls.stride(1), _dt(cls), B, A, C, lv,

@@ -1,6 +1,7 @@
 """Predict entry point: the device side of choijhanyangackr/main.py (build_yolox :31-59 and the body of
 the run loop :153-203).  Host I/O around it (image folder dataset, COCO json) is the caller's, as in the
 reference."""
+import os
 from typing import Iterable, List, Optional, Tuple
 
 import torch
@@ -38,9 +39,10 @@ class Predictor:
         self.kw = dict(conf_threshold=conf_threshold, nms_threshold=nms_threshold, max_num_nms=max_num_nms,
                        max_num_det=max_num_det)
         self.in_scale, self.in_shift, self.use_graph = in_scale, in_shift, use_graph
+        self._gathers = {}
 
     @torch.no_grad()
-    def __call__(self, img: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    def __call__(self, img: torch.Tensor, gather=None) -> Tuple[torch.Tensor, torch.Tensor]:
         """img: [B,3,H,W] fp16/fp32, BGR 0-255 (host pinned or device).  -> det [B,max_det,7], count [B]."""
         dev = next(self.model.parameters()).device
         if img.device != dev:
@@ -48,8 +50,15 @@ class Predictor:
         eng, reg8, cls = self.model.run_engine(img, self.in_scale, self.in_shift, self.use_graph)  # :164-167
         C = self.model.head.num_classes
         det, cnt, _ = postprocess.detect_main(reg8[..., :4], reg8[..., 4:5], cls[..., :C], self.model.head.hw,
-                                              self.model.head.strides, **self.kw)       # :180-188
+                                              self.model.head.strides, gather=gather, **self.kw)       # :180-188
         return det, cnt
+
+    def _peer_gather(self, per_rank: int, device):
+        """Windows of the fused gather, created once per batch shape (collective: every rank calls it together)."""
+        key = (per_rank, self.kw["max_num_det"])
+        if key not in self._gathers:
+            self._gathers[key] = ydist.PeerGather(per_rank, self.kw["max_num_det"], device)
+        return self._gathers[key]
 
     def predict_sharded(self, img_global: torch.Tensor):
         """Batch-sharded multi-GPU step: this rank runs its contiguous slice, then ONE all-gather."""
@@ -62,6 +71,16 @@ class Predictor:
         mine = img_global[s:e]
         if e - s < per:                                                # pad so every rank runs the same batch
             mine = torch.cat([mine, mine[-1:].expand(per - (e - s), -1, -1, -1)], 0)
-        det, cnt = self(mine)
-        det_all, cnt_all = ydist.all_gather_detections(det, cnt)
-        return ydist.gathered_for_images(det_all, cnt_all, n, world, per) if world > 1 else (det, cnt)
+        if world == 1:
+            return self(mine)
+        dev = next(self.model.parameters()).device
+        fused = (tdist.get_backend() == "nccl" and self.kw["max_num_det"] > 0
+                 and os.environ.get("YX_PEER_GATHER", "1") != "0")
+        if fused:      # the NMS kernel stores its rows into every rank's window; no collective call on the data path
+            g = self._peer_gather(per, dev)
+            self(mine, gather=g)
+            det_all, cnt_all = g.result()
+        else:
+            det, cnt = self(mine)
+            det_all, cnt_all = ydist.all_gather_detections(det, cnt)
+        return ydist.gathered_for_images(det_all, cnt_all, n, world, per)

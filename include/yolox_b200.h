@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define YX_ABI_VERSION 2
+#define YX_ABI_VERSION 3
 
 typedef enum yx_status {
   YX_OK = 0,
@@ -189,6 +189,25 @@ int yx_nms_main(const float* boxes, const float* obj_conf, const float* cls_conf
                 float conf_thr, float nms_thr, int max_nms, int max_det, int mode, void* workspace,
                 size_t workspace_bytes, float* det, int32_t* det_count, int32_t* det_anchor, void* stream);
 
+/* How yx_nms_main_ex forms candidates (yolox_infer/postprocess_utils.py:74-95). */
+typedef enum yx_cand_mode {
+  YX_CAND_MAX = 0,          /* :86-89 one per anchor: first-max class, kept when max >= conf_thr (every shipped config) */
+  YX_CAND_MULTI_CLASS = 1,  /* :90-95 multi_class=True: one per (anchor, class) with cls_conf >= conf_thr */
+  YX_CAND_RMMOP = 2         /* :74-84 rmmop=(r1, r2): top-1 class per anchor, kept when top1 >= top2*r1 and
+                               obj^2 >= top1*r2; conf_thr is not applied; needs C >= 2 */
+} yx_cand_mode;
+
+/* Workspace (bytes) for yx_nms_main_ex: multi_class ranks up to A*C candidates per image. */
+size_t yx_nms_workspace_bytes(int B, int A, int C, int cand_mode, int max_nms);
+
+/* yx_nms_main with the candidate rule selectable.  In multi_class mode a detection's label is the candidate's class
+ * and det rows default to A*C when max_det <= 0.
+ * replaces: yolox_nms_torch_batch(..., multi_class=..., rmmop=...), yolox_infer/postprocess_utils.py:55-129. */
+int yx_nms_main_ex(const float* boxes, const float* obj_conf, const float* cls_conf, int B, int A, int C,
+                   float conf_thr, float nms_thr, int max_nms, int max_det, int mode, int cand_mode, float rmmop_r1,
+                   float rmmop_r2, void* workspace, size_t workspace_bytes, float* det, int32_t* det_count,
+                   int32_t* det_anchor, void* stream);
+
 /* Fused decode + threshold + compaction + NMS straight from the raw head logits (no [B,A,C]
  * fp32 tensor is ever materialised).  Same results as yx_decode_infer followed by yx_nms_main.
  * replaces: main.py:180-188 (decode + NMS of the predict loop). */
@@ -197,6 +216,45 @@ int yx_detect_main(const void* reg, int64_t reg_sb, int64_t reg_sa, const void* 
                    const yx_levels* lv_host, float conf_thr, float nms_thr, int max_nms, int max_det, int mode,
                    void* workspace, size_t workspace_bytes, float* det, int32_t* det_count, int32_t* det_anchor,
                    void* stream);
+
+/* ---- multi-GPU: detections gathered by the NMS kernel itself ------------------------------------ *
+ * Images shard over ranks (one process per GPU); every rank needs all detections.  Instead of a separate
+ * collective, the NMS kernel's tail stores each image's [max_det,7] rows and count straight into every rank's receive
+ * window (peer memory mapped with CUDA IPC, NVLink / NVSwitch posted writes) and counts the image in that rank's arrival
+ * counter; a one-warp kernel on the receiving stream then waits until all ranks' images of the step have arrived.
+ * replaces: the pickled gloo gather of yolox/evaluators/coco_evaluator.py:127 + yolox/utils/dist.py:224-265.
+ *
+ * The window is ordinary device memory owned by the caller (a torch tensor); yx_ipc_export / yx_ipc_open turn it into
+ * pointers valid in the other ranks' processes (the 64-byte handles travel through any host-side exchange). */
+#define YX_MAX_PEERS 8
+#define YX_IPC_HANDLE_BYTES 64
+
+/* handle of the allocation that contains dev_ptr + dev_ptr's byte offset inside it */
+int yx_ipc_export(const void* dev_ptr, void* handle_out, int64_t* offset_out);
+/* maps a peer's allocation into this process (peer access enabled lazily); *base_out + offset = the peer's pointer */
+int yx_ipc_open(const void* handle, void** base_out);
+int yx_ipc_close(void* base);
+
+typedef struct yx_peer_out {
+  int32_t world;                /* number of ranks (1..YX_MAX_PEERS), own rank included */
+  int32_t wait_target;          /* value every local arrival counter reaches when the step's images are all here:
+                                   step_index * B (counters are never reset) */
+  int32_t timeout_ms;           /* bound of the device-side wait (<= 0: 10 s); on expiry *status = 1 + late rank */
+  int32_t reserved;
+  void* det[YX_MAX_PEERS];      /* this rank's [B,max_det,7] fp32 block inside rank w's window */
+  void* cnt[YX_MAX_PEERS];      /* this rank's [B] int32 block inside rank w's window */
+  void* arrive[YX_MAX_PEERS];   /* rank w's int32 arrival counter for this rank */
+  void* local_arrive;           /* this rank's own int32[world] counters */
+  void* status;                 /* int32 in this rank's memory, 0 while healthy */
+} yx_peer_out;
+
+/* yx_detect_main + the gather described above.  Requires max_det > 0 and the same B on every rank.  The caller
+ * alternates between two windows on consecutive steps (a rank can run at most one step ahead of its peers). */
+int yx_detect_main_gather(const void* reg, int64_t reg_sb, int64_t reg_sa, const void* obj, int64_t obj_sb, int64_t obj_sa,
+                          const void* cls, int64_t cls_sb, int64_t cls_sa, int logits_dtype, int B, int A, int C,
+                          const yx_levels* lv_host, float conf_thr, float nms_thr, int max_nms, int max_det, int mode,
+                          void* workspace, size_t workspace_bytes, float* det, int32_t* det_count, int32_t* det_anchor,
+                          const yx_peer_out* peer, void* stream);
 
 /* yolox-package head output: out[B,A,5+C] = [reg, sigmoid(obj), sigmoid(cls)] in `out_dtype`, then
  * (decode != 0) decoded in place like decode_outputs.

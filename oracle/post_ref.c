@@ -175,25 +175,47 @@ int yxref_batched_nms_vanilla(const float* boxes, const float* scores, const flo
   return m;
 }
 
-/* ---- yolox_nms_torch_batch, one image (postprocess_utils.py:86-124, default mode) ------------
+/* ---- yolox_nms_torch_batch, one image (postprocess_utils.py:73-127) -----------------------------
  * boxes [A,4], obj_conf [A], cls_conf [A,C].  mode: 0 = coordinate trick, 1 = vanilla, 2 = class-agnostic.
- * det_out [max_det,7] = [x1,y1,x2,y2,obj,cls_conf_max,label]; anchor_out = source anchor per row.
+ * cand: how candidates are formed --
+ *   0  default      (:86-89)  one per anchor: first-max class, kept when max >= conf_thr
+ *   1  multi_class  (:90-95)  one per (anchor, class) with cls_conf >= conf_thr, in nonzero() (row-major) order
+ *   2  rmmop        (:74-84)  one per anchor: top-1 class, kept when top1 >= top2 * r1 and obj^2 >= top1 * r2
+ *                             (no conf threshold; descending sort ties resolved to the lower class index)
+ * det_out [max_det,7] = [x1,y1,x2,y2,obj,score,label]; anchor_out = source anchor per row.
  * max_nms <= 0 disables the top-k cap.  Returns number of detections. */
-int yxref_nms_image_main(const float* boxes, const float* obj_conf, const float* cls_conf, int A, int C,
-                         float conf_thr, float nms_thr, int max_nms, int max_det, int mode,
-                         float* det_out, int* anchor_out) {
-  float* cb = (float*)malloc(sizeof(float) * 4 * (size_t)A);
-  float* cs = (float*)malloc(sizeof(float) * (size_t)A);
-  float* cl = (float*)malloc(sizeof(float) * (size_t)A);
-  float* co = (float*)malloc(sizeof(float) * (size_t)A);
-  int* ca = (int*)malloc(sizeof(int) * (size_t)A);
+int yxref_nms_image_main_ex(const float* boxes, const float* obj_conf, const float* cls_conf, int A, int C,
+                            float conf_thr, float nms_thr, int max_nms, int max_det, int mode, int cand,
+                            float r1, float r2, float* det_out, int* anchor_out) {
+  const size_t cap = cand == 1 ? (size_t)A * (size_t)C : (size_t)A;
+  float* cb = (float*)malloc(sizeof(float) * 4 * (cap ? cap : 1));
+  float* cs = (float*)malloc(sizeof(float) * (cap ? cap : 1));
+  float* cl = (float*)malloc(sizeof(float) * (cap ? cap : 1));
+  float* co = (float*)malloc(sizeof(float) * (cap ? cap : 1));
+  int* ca = (int*)malloc(sizeof(int) * (cap ? cap : 1));
   int n = 0;
   for (int a = 0; a < A; ++a) {
     const float* c = cls_conf + (size_t)a * C;
+    if (cand == 1) {
+      for (int k = 0; k < C; ++k)
+        if (c[k] >= conf_thr) {
+          memcpy(cb + (size_t)n * 4, boxes + a * 4, 16); cs[n] = c[k]; cl[n] = (float)k; co[n] = obj_conf[a]; ca[n] = a; ++n;
+        }
+      continue;
+    }
     float best = c[0]; int bi = 0;
     for (int k = 1; k < C; ++k) if (c[k] > best) { best = c[k]; bi = k; }  /* first max wins */
-    if (best >= conf_thr) {
-      memcpy(cb + n * 4, boxes + a * 4, 16); cs[n] = best; cl[n] = (float)bi; co[n] = obj_conf[a]; ca[n] = a; ++n;
+    int pass;
+    if (cand == 2) {
+      float second = -INFINITY;
+      for (int k = 0; k < C; ++k) if (k != bi && c[k] > second) second = c[k];
+      const float o = obj_conf[a];
+      pass = (best >= second * r1) && (o * o >= best * r2);
+    } else {
+      pass = best >= conf_thr;
+    }
+    if (pass) {
+      memcpy(cb + (size_t)n * 4, boxes + a * 4, 16); cs[n] = best; cl[n] = (float)bi; co[n] = obj_conf[a]; ca[n] = a; ++n;
     }
   }
   if (max_nms > 0 && n > max_nms) { /* argsort(desc)[:max_nms], detections reordered by score */
@@ -206,7 +228,7 @@ int yxref_nms_image_main(const float* boxes, const float* obj_conf, const float*
     int* a2 = (int*)malloc(sizeof(int) * (size_t)max_nms);
     for (int t = 0; t < max_nms; ++t) {
       int j = ord[t];
-      memcpy(b2 + t * 4, cb + j * 4, 16); s2[t] = cs[j]; l2[t] = cl[j]; o2[t] = co[j]; a2[t] = ca[j];
+      memcpy(b2 + t * 4, cb + (size_t)j * 4, 16); s2[t] = cs[j]; l2[t] = cl[j]; o2[t] = co[j]; a2[t] = ca[j];
     }
     free(cb); free(cs); free(cl); free(co); free(ca); free(ord);
     cb = b2; cs = s2; cl = l2; co = o2; ca = a2; n = max_nms;
@@ -218,12 +240,19 @@ int yxref_nms_image_main(const float* boxes, const float* obj_conf, const float*
   if (nk > max_det) nk = max_det;
   for (int t = 0; t < nk; ++t) {
     int j = keep[t];
-    memcpy(det_out + t * 7, cb + j * 4, 16);
+    memcpy(det_out + t * 7, cb + (size_t)j * 4, 16);
     det_out[t * 7 + 4] = co[j]; det_out[t * 7 + 5] = cs[j]; det_out[t * 7 + 6] = cl[j];
     anchor_out[t] = ca[j];
   }
   free(cb); free(cs); free(cl); free(co); free(ca); free(keep);
   return nk;
+}
+
+int yxref_nms_image_main(const float* boxes, const float* obj_conf, const float* cls_conf, int A, int C,
+                         float conf_thr, float nms_thr, int max_nms, int max_det, int mode,
+                         float* det_out, int* anchor_out) {
+  return yxref_nms_image_main_ex(boxes, obj_conf, cls_conf, A, C, conf_thr, nms_thr, max_nms, max_det, mode, 0, 0.0f,
+                                 0.0f, det_out, anchor_out);
 }
 
 /* ---- yolox.utils.postprocess, one image (boxes.py:38-75), fp32 ----------------------------

@@ -82,14 +82,19 @@ def batched_nms(boxes, scores, labels, thr, mode="trick"):
 _MODES = {"trick": 0, "vanilla": 1, "agnostic": 2}
 
 
-def nms_image_main(boxes, obj_conf, cls_conf, conf_thr, nms_thr, max_nms=5000, max_det=300, mode="trick"):
+def nms_image_main(boxes, obj_conf, cls_conf, conf_thr, nms_thr, max_nms=5000, max_det=300, mode="trick",
+                   multi_class=False, rmmop=None):
+    """postprocess_utils.py:73-127 for one image; multi_class / rmmop select the candidate rule (:74-95)."""
     boxes = np.ascontiguousarray(boxes, np.float32); obj_conf = np.ascontiguousarray(obj_conf, np.float32).reshape(-1)
     cls_conf = np.ascontiguousarray(cls_conf, np.float32)
     A, C = cls_conf.shape
-    md = min(max_det, A)
+    cand = 2 if rmmop is not None else (1 if multi_class else 0)
+    r1, r2 = (np.float32(rmmop[0]), np.float32(rmmop[1])) if rmmop is not None else (0.0, 0.0)
+    md = min(max_det, A * C if cand == 1 else A)
     det = np.empty((max(md, 1), 7), np.float32); anc = np.empty(max(md, 1), np.int32)
-    k = lib().yxref_nms_image_main(_p(boxes), _p(obj_conf), _p(cls_conf), A, C, ctypes.c_float(conf_thr),
-                                   ctypes.c_float(nms_thr), int(max_nms), int(md), _MODES[mode], _p(det), _p(anc))
+    k = lib().yxref_nms_image_main_ex(_p(boxes), _p(obj_conf), _p(cls_conf), A, C, ctypes.c_float(conf_thr),
+                                      ctypes.c_float(nms_thr), int(max_nms), int(md), _MODES[mode], cand,
+                                      ctypes.c_float(r1), ctypes.c_float(r2), _p(det), _p(anc))
     return det[:k].copy(), anc[:k].copy()
 
 

@@ -56,6 +56,47 @@ def test_golden_main_flavour(path):
 
 
 @pytest.mark.parametrize("path", FILES, ids=[os.path.basename(p) for p in FILES])
+def test_golden_candidate_modes(path):
+    """multi_class / rmmop candidate rules (postprocess_utils.py:74-95) against the reference function's own output
+    (tests/golden/make_golden_modes.py, tie-free scores) and against the oracle in the GPU's NMS dispatch mode."""
+    from tests.test_oracle_post import MODE_CASES, mode_candidates
+    mpath = os.path.join(os.path.dirname(path), "postmodes_" + os.path.basename(path)[len("post_"):])
+    if not os.path.exists(mpath):
+        pytest.skip("no mode vectors for this case")
+    g, gm = np.load(path), np.load(mpath)
+    conf, thr = float(g["conf"]), float(g["nms_thr"])
+    rb, ro, rc = (torch.from_numpy(a).to(DEV) for a in (g["boxes"], g["obj_conf"], gm["cls_conf"]))
+    for key, okw in MODE_CASES.items():
+        if f"{key}_det_0" not in gm:
+            continue
+        kw = dict(multi_class=okw.get("multi_class", False), rmmop=okw.get("rmmop"),
+                  class_agnostic=okw.get("mode") == "agnostic")
+        if "max_nms" in okw:
+            kw.update(max_num_nms=okw["max_nms"], max_num_det=okw["max_det"])
+        dets = yb.postprocess.yolox_nms_torch_batch(rb, ro, rc, nms_threshold=thr, conf_threshold=conf, **kw)
+        for i, d in enumerate(dets):
+            want = gm[f"{key}_det_{i}"]
+            n = mode_candidates(gm["cls_conf"][i], g["obj_conf"][i].reshape(-1), conf, okw)
+            if okw.get("max_nms", 5000) > 0:
+                n = min(n, okw.get("max_nms", 5000))
+            o = dict(okw)
+            o.setdefault("mode", pr.torchvision_mode(n, "cuda"))
+            ref, _ = pr.nms_image_main(g["boxes"][i], g["obj_conf"][i], gm["cls_conf"][i], conf, thr, **o)
+            np.testing.assert_array_equal(_np(d), ref, err_msg=f"{key} img {i}")
+            assert {tuple(r) for r in _np(d)} == {tuple(r) for r in want}, f"{key} img {i}: kept set differs from the reference"
+
+
+def test_candidate_mode_errors():
+    z = torch.zeros(1, 8, 4, device=DEV), torch.zeros(1, 8, 1, device=DEV), torch.zeros(1, 8, 1, device=DEV)
+    with pytest.raises(RuntimeError):          # rmmop reads the second-best class (cls_conf_sorted[:, 1])
+        yb.postprocess.yolox_nms_torch_batch(*z, rmmop=(1.0, 1.0))
+    with pytest.raises(ValueError):            # nms.py:21,36
+        yb.postprocess.yolox_nms_torch_batch(*z, soft=True)
+    out = yb.postprocess.yolox_nms_torch_batch(*z, conf_threshold=0.0, max_num_det=0)
+    assert out[0] is not None and out[0].shape == (0, 7)
+
+
+@pytest.mark.parametrize("path", FILES, ids=[os.path.basename(p) for p in FILES])
 def test_golden_yolox_postprocess(path):
     g = np.load(path)
     conf, thr = float(g["conf"]), float(g["nms_thr"])
@@ -164,3 +205,23 @@ def test_score_monotonic_in_logit():
         _, oc, cc = yb.postprocess.yolox_postprocess_output_torch_batch(reg, obj, cls, grids.to(DEV), scales.to(DEV))
         s = cc.view(-1)
         assert bool((s[1:] >= s[:-1]).all()), f"score not monotone for obj logit {o}"
+
+
+def test_nms_fused_gather_single_rank():
+    """yx_detect_main_gather with world = 1: the NMS tail stores into this GPU's own window, the wait kernel sees the
+    arrivals; both window parities and growing arrival targets are exercised.  (N = 2 over NVLink: tools/dist_check.py.)"""
+    g = np.load(FILES[0])
+    img, strides = int(g["img"]), [int(s) for s in g["strides"]]
+    hw = [(img // s, img // s) for s in strides]
+    reg, obj, cls = (torch.from_numpy(g[k]).to(DEV) for k in ("reg", "obj", "cls"))
+    B = reg.shape[0]
+    want = yb.postprocess.detect_main(reg, obj, cls, hw, strides, float(g["conf"]), float(g["nms_thr"]))
+    pg = yb.dist.PeerGather(B, 300, DEV, timeout_ms=2000)
+    for it in range(3):
+        det, cnt, _ = yb.postprocess.detect_main(reg, obj, cls, hw, strides, float(g["conf"]), float(g["nms_thr"]), gather=pg)
+        da, ca = pg.result()
+        assert torch.equal(det, want[0]) and torch.equal(cnt, want[1])
+        assert torch.equal(da, want[0]) and torch.equal(ca, want[1]), f"window differs at step {it}"
+    assert pg.status() == 0
+    with pytest.raises(ValueError):
+        pg.next_step(B + 1, 300)

@@ -102,3 +102,46 @@ def test_golden_yolox_postprocess(path):
         np.testing.assert_array_equal(det, g[f"yolox_det_{i}"])
         det, anc, _ = pr.postprocess_image(pred[i], conf, thr, "agnostic")
         np.testing.assert_array_equal(det, g[f"yoloxa_det_{i}"])
+
+
+# ---- alternate candidate rules (multi_class / rmmop), goldens from the reference function itself -------------
+MODE_CASES = {  # key -> oracle kwargs (mirrors tests/golden/make_golden_modes.py CASES)
+    "mc": dict(multi_class=True),
+    "mcu": dict(multi_class=True, max_nms=0, max_det=10 ** 9),
+    "mca": dict(multi_class=True, mode="agnostic"),
+    "rm": dict(rmmop=(2.0, 0.5)),
+    "rmu": dict(rmmop=(1.0, 1.5), max_nms=0, max_det=10 ** 9),
+    "rml": dict(rmmop=(1.05, 0.3)),
+}
+
+
+def mode_candidates(rc, ro, conf, kw):
+    """Candidate count per image for the torchvision trick/vanilla dispatch."""
+    if kw.get("multi_class"):
+        return int((rc >= conf).sum())
+    if kw.get("rmmop") is not None:
+        r1, r2 = (np.float32(v) for v in kw["rmmop"])
+        srt = np.sort(rc, -1)[:, ::-1]
+        return int(((srt[:, 0] >= srt[:, 1] * r1) & (ro * ro >= srt[:, 0] * r2)).sum())
+    return int((rc.max(-1) >= conf).sum())
+
+
+@pytest.mark.parametrize("path", FILES, ids=[os.path.basename(p) for p in FILES])
+def test_golden_candidate_modes(path):
+    mpath = os.path.join(os.path.dirname(path), "postmodes_" + os.path.basename(path)[len("post_"):])
+    if not os.path.exists(mpath):
+        pytest.skip("no mode vectors for this case")
+    g, gm = np.load(path), np.load(mpath)
+    conf, thr = float(g["conf"]), float(g["nms_thr"])
+    for i in range(g["reg"].shape[0]):
+        rb, ro, rc = g["boxes"][i], g["obj_conf"][i].reshape(-1), gm["cls_conf"][i]  # tie-free scores
+        for key, kw in MODE_CASES.items():
+            if f"{key}_det_{i}" not in gm:
+                continue
+            kw = dict(kw)
+            n = mode_candidates(rc, ro, conf, kw)
+            if kw.get("max_nms", 5000) > 0:
+                n = min(n, kw.get("max_nms", 5000))
+            kw.setdefault("mode", pr.torchvision_mode(n, "cpu"))
+            det, anc = pr.nms_image_main(rb, ro, rc, conf, thr, **kw)
+            np.testing.assert_array_equal(det, gm[f"{key}_det_{i}"], err_msg=key)

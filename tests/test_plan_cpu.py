@@ -106,3 +106,15 @@ def test_errors():
         model(torch.zeros(1, 3, 64, 64))                        # CPU tensor: no CPU path
     with pytest.raises(ValueError):
         yb.postprocess.yolox_nms_torch_batch(None, None, None, soft=True)
+
+
+def test_peer_out_struct_matches_header():
+    """ctypes mirror of yx_peer_out: 4 int32 + 3 pointer tables of YX_MAX_PEERS + 2 pointers."""
+    import ctypes
+    import os
+    import re
+    from yolox_b200 import _capi
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "yolox_b200.h")).read()
+    assert int(re.search(r"#define YX_MAX_PEERS (\d+)", hdr).group(1)) == _capi.MAX_PEERS
+    assert int(re.search(r"#define YX_IPC_HANDLE_BYTES (\d+)", hdr).group(1)) == _capi.IPC_HANDLE_BYTES
+    assert ctypes.sizeof(_capi.PeerOut) == 16 + 3 * 8 * _capi.MAX_PEERS + 16
