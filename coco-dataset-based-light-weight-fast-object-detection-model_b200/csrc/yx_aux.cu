@@ -148,16 +148,81 @@ __global__ void spp_kernel(const __half* __restrict__ src, __half* __restrict__ 
   }
 }
 
+// Tiled version for maps that fit in shared memory (every P5 / P6 configuration: 20x20 .. 40x40): one CTA per
+// (image, group of CV 8-channel vectors).  Uses the exact identities pool9 = pool5 o pool5, pool13 = pool5 o pool5 o pool5
+// (max is associative and the -inf padding is its neutral element) and the separability of the 5x5 window: 30 shared
+// memory reads per output vector instead of 169 global ones.
+__global__ void __launch_bounds__(256) spp_tiled_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int H, int W,
+                                                        int C, int CV, int spitch, int dpitch, int64_t sn, int64_t dn) {
+  extern __shared__ uint4 spp_smem[];
+  const int cv = C >> 3, groups = (cv + CV - 1) / CV;
+  const int b = blockIdx.x / groups, g = blockIdx.x % groups;
+  const int c0 = g * CV, ncv = min(CV, cv - c0);
+  const int n = H * W * ncv;
+  uint4* bufA = spp_smem;
+  uint4* bufB = spp_smem + H * W * CV;
+  const uint4 ninf = make_uint4(0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int v = i % ncv, pix = i / ncv;
+    bufA[i] = __ldg(reinterpret_cast<const uint4*>(src + b * sn + (int64_t)pix * spitch) + c0 + v);
+  }
+  __syncthreads();
+  for (int level = 0; level < 3; ++level) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {  // horizontal 5-max: A -> B
+      const int v = i % ncv, pix = i / ncv, x = pix % W;
+      uint4 m = bufA[i];
+#pragma unroll
+      for (int d = 1; d <= 2; ++d) {
+        if (x - d >= 0) m = hmax8(m, bufA[i - d * ncv]);
+        if (x + d < W) m = hmax8(m, bufA[i + d * ncv]);
+      }
+      (void)v;
+      bufB[i] = m;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {  // vertical 5-max: B -> A, and out to slice `level`
+      const int v = i % ncv, pix = i / ncv, y = pix / W;
+      uint4 m = bufB[i];
+#pragma unroll
+      for (int d = 1; d <= 2; ++d) {
+        if (y - d >= 0) m = hmax8(m, bufB[i - d * W * ncv]);
+        if (y + d < H) m = hmax8(m, bufB[i + d * W * ncv]);
+      }
+      bufA[i] = m;
+      reinterpret_cast<uint4*>(dst + b * dn + (int64_t)pix * dpitch)[level * cv + c0 + v] = m;
+    }
+    __syncthreads();
+  }
+  (void)ninf;
+}
+
 int spp_launch(void* base, const yx_view& src, const yx_view& dst, cudaStream_t stream) {
   YX_REQUIRE(src.c % 8 == 0 && dst.c == 3 * src.c && dst.n == src.n && dst.h == src.h && dst.w == src.w,
              "spp dst must be [B,h,w,3C]");
   YX_REQUIRE(src.offset % 16 == 0 && dst.offset % 16 == 0 && src.pitch % 8 == 0 && dst.pitch % 8 == 0, "spp alignment");
+  const __half* sp = reinterpret_cast<const __half*>(static_cast<uint8_t*>(base) + src.offset);
+  __half* dp = reinterpret_cast<__half*>(static_cast<uint8_t*>(base) + dst.offset);
+  static const bool direct_only = getenv("YX_SPP_DIRECT") != nullptr;
+  const int cv = src.c / 8;
+  const int64_t pix_bytes = (int64_t)src.h * src.w * 16 * 2;  // two buffers, per 8-channel vector
+  int CV = (int)std::min<int64_t>(4, (96 * 1024) / std::max<int64_t>(pix_bytes, 1));
+  CV = std::min(CV, cv);
+  if (CV >= 1 && !direct_only) {
+    static bool attr = false;
+    if (!attr) {
+      YX_CUDA(cudaFuncSetAttribute(spp_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      attr = true;
+    }
+    const int groups = (cv + CV - 1) / CV;
+    spp_tiled_kernel<<<src.n * groups, 256, (size_t)(pix_bytes * CV), stream>>>(sp, dp, src.h, src.w, src.c, CV, src.pitch,
+                                                                             dst.pitch, src.nstride, dst.nstride);
+    YX_CUDA(cudaGetLastError());
+    return YX_OK;
+  }
   const int64_t total = (int64_t)src.n * src.h * src.w * (src.c / 8);
   const int threads = 256;
   const int blocks = (int)std::min<int64_t>((total + threads - 1) / threads, 148 * 16);
-  spp_kernel<<<blocks, threads, 0, stream>>>(reinterpret_cast<const __half*>(static_cast<uint8_t*>(base) + src.offset),
-                                             reinterpret_cast<__half*>(static_cast<uint8_t*>(base) + dst.offset), src.n,
-                                             src.h, src.w, src.c, src.pitch, dst.pitch, src.nstride, dst.nstride);
+  spp_kernel<<<blocks, threads, 0, stream>>>(sp, dp, src.n, src.h, src.w, src.c, src.pitch, dst.pitch, src.nstride, dst.nstride);
   YX_CUDA(cudaGetLastError());
   return YX_OK;
 }

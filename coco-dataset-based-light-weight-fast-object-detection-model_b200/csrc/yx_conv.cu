@@ -600,7 +600,12 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
-            if (PAIR) mbar_arrive_cluster(mapa_shared(bar_tempty + 8 * acc, 0)); else mbar_arrive(bar_tempty + 8 * acc);
+            if (PAIR) {
+              if (p.diag & 8) mbar_arrive_cluster(mapa_shared(bar_tempty + 8 * acc, 0));
+              else mbar_arrive_cluster_relaxed(mapa_shared(bar_tempty + 8 * acc, 0));
+            } else {
+              mbar_arrive(bar_tempty + 8 * acc);
+            }
           }
         }
         // publish the staged tile to the async proxy and store it
@@ -844,12 +849,13 @@ void conv_candidates(const yx_op& op, std::vector<ConvTune>* out) {
         }
     if (bn >= 64 && cout16 >= 96 && !g.rowpack)  // CTA-pair shapes: half of the weight tile per CTA
       for (int v = 1; v <= (halo_ok(op, g) ? 2 : 1); ++v)
-        for (int sb = 2; sb >= 1; --sb) {
-          ConvTune t;
-          memset(&t, 0, sizeof t);
-          t.variant = v; t.bn = bn; t.ctas = 1; t.mh = 1; t.epi_groups = 1; t.stage_bufs = sb; t.w3 = v == 2 ? 2 : 1; t.pair = 1;
-          push(t);
-        }
+        for (int eg = 1; eg <= (bn <= 128 ? 2 : 1); ++eg)  // short MMA phases (N <= 128) can be epilogue-bound
+          for (int sb = 2; sb >= 1; --sb) {
+            ConvTune t;
+            memset(&t, 0, sizeof t);
+            t.variant = v; t.bn = bn; t.ctas = 1; t.mh = 1; t.epi_groups = eg; t.stage_bufs = sb; t.w3 = v == 2 ? 2 : 1; t.pair = 1;
+            push(t);
+          }
     if (halo_ok(op, g))
       for (int mh = 1; mh <= 2; ++mh)
         for (int eg = 1; eg <= 2; ++eg)
@@ -965,7 +971,9 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
     const int fixed = 1024 + kBarBytes + p.bias_bytes + p.stage_bufs * groups64 * kTileBytes;
     const int avail = budget - fixed;
     const int min_a = (halo ? 2 : 2) * p.a_stage_bytes;
-    const bool can_res = !pair && p.n_tiles_n == 1 && k_loads_b <= kMaxBRing && t.no_resident == 0 &&
+    // (pair: each CTA keeps ITS half of the weight rows resident -> the 96-channel 3x3 layers, whose 166 KB of weights
+    // never fit one CTA, run with resident weights at the full N/2 MMA rate)
+    const bool can_res = p.n_tiles_n == 1 && k_loads_b <= kMaxBRing && t.no_resident == 0 &&
                          k_loads_b * p.b_stage_bytes + min_a <= avail;
     if (can_res) {
       p.b_resident = 1;

@@ -162,7 +162,12 @@ TUNED_CASES = [
     dict(cin=192, cout=192, k=3, stride=1, H=40, W=40, act="hard_swish", tune=_t(2, 192, pair=1, sb=1)),            # odd number of x tiles
     dict(cin=192, cout=384, k=3, stride=1, H=48, W=40, act="silu", tune=_t(2, 192, pair=1)),                          # 2 N tiles
     dict(cin=288, cout=288, k=3, stride=1, H=40, W=40, act="hard_swish", tune=_t(2, 192, pair=1)),                    # N tiles 192 + 96, K tail
-    dict(cin=96, cout=96, k=3, stride=1, H=48, W=40, act="hard_swish", res=True, tune=_t(2, 96, pair=1)),
+    dict(cin=96, cout=96, k=3, stride=1, H=48, W=40, act="hard_swish", res=True, tune=_t(2, 96, pair=1)),             # weights resident, half per CTA
+    dict(cin=96, cout=96, k=3, stride=1, H=48, W=40, act="hard_swish", res=True, tune=_t(2, 96, pair=1, nores=1)),    # streamed
+    dict(cin=96, cout=96, k=3, stride=1, H=160, W=160, act="hard_swish", res="inplace", tune=_t(2, 96, pair=1, eg=2)),
+    dict(cin=96, cout=96, k=3, stride=1, H=40, W=24, act="silu", tune=_t(2, 96, pair=1, sb=1)),                        # odd number of x tiles
+    dict(cin=192, cout=192, k=1, stride=1, H=40, W=40, act="hard_swish", tune=_t(1, 192, pair=1)),                     # generic pair, resident
+    dict(cin=96, cout=128, k=3, stride=2, H=80, W=80, act="hard_swish", tune=_t(1, 128, pair=1, eg=2)),
     dict(cin=192, cout=192, k=3, stride=1, H=80, W=80, act="hard_swish", tune=_t(1, 192, pair=1)),                    # generic pair
     dict(cin=768, cout=768, k=1, stride=1, H=40, W=40, act="hard_swish", tune=_t(1, 256, pair=1)),
     dict(cin=384, cout=384, k=1, stride=1, H=20, W=20, act="silu", tune=_t(1, 128, pair=1, sb=1)),

@@ -180,3 +180,31 @@ def test_every_op_teacher_forced(name, H, W, B):
     errs = teacher_forced_errors(model, x)
     bad = [e for e in errs if e[2] > 1.5]
     assert not bad, bad[:5]
+
+
+@pytest.mark.parametrize("H,W,C", [(20, 20, 384), (5, 3, 8), (40, 40, 72), (64, 48, 16)])
+def test_spp_pools_exact(H, W, C):
+    """SPP (network_blocks.py:239-246): slices 1..3 of the concat buffer = max_pool2d 5/9/13 of slice 0, exactly (max is
+    exact in fp16).  Covers the tiled kernel with 4 and 1 channel vectors per CTA and the direct kernel for large maps."""
+    import torch.nn.functional as F
+    from yolox_b200 import plan
+    B = 2
+    g = plan.Graph(B, 2 * H, 2 * W)
+    img = g.new_buf("img16", H, W, 16)
+    cat = g.new_buf("cat", H, W, 4 * C)
+    g.s2d(img.view(), "unshuffle")
+    g.spp(cat.view(0, C), cat.view(C, 3 * C))
+    g.place_buffers()
+    g.weight_blob = torch.zeros(128, dtype=torch.float16)
+    g.bias_blob = torch.zeros(64, dtype=torch.float32)
+    eng = plan.Engine(g, "cuda")
+    x = torch.randn(B, H, W, C, generator=torch.Generator().manual_seed(H * W + C)).half().cuda()
+    t = eng.tensor_of(cat)
+    t.zero_()
+    t[..., :C] = x
+    eng.run_ops(torch.zeros(B, 3, 2 * H, 2 * W, dtype=torch.float16, device="cuda"), 1, 1)
+    xn = x.permute(0, 3, 1, 2).float()
+    for i, k in enumerate((5, 9, 13)):
+        want = F.max_pool2d(xn, k, 1, k // 2).permute(0, 2, 3, 1).half()
+        assert torch.equal(t[..., (i + 1) * C:(i + 2) * C], want), f"pool {k}"
+    assert torch.equal(t[..., :C], x)

@@ -9,6 +9,4 @@ YX_TUNE_VERBOSE=1 timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-base
 cat gpurun_out/bench_ci.json >> $LOG
 timeout 1200 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest all exit=$?" >> $LOG
 tail -5 gpurun_out/pytest_gpu.log >> $LOG
-bash tools/gpu_trace.sh > /dev/null 2>&1
 cat $LOG | cut -c1-600
-grep -E "CASE|blocked|^ +(4|5) " gpurun_out/trace19.log | cut -c1-250
