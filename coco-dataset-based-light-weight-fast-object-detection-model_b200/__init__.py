@@ -15,6 +15,7 @@ _capi.load()  # fail loudly if the native library cannot be built / loaded
 
 from . import blocks, dist, models, plan, postprocess, weights  # noqa: E402
 from . import infer, predict  # noqa: E402
+from . import cocoeval, evaluator  # noqa: E402  (the evaluation loop around the hot path)
 from . import io  # noqa: E402  (rows next to the hot path: device-side pre-processing, COCO records)
 from .models import YOLOX, YOLOXCustomP6, YOLOPAFPN, YOLOPAFPNCustomP6, YOLOXHead, YOLOXHeadCustom, fuse_model  # noqa: E402,F401
 from .postprocess import (decode_outputs, detect_main, postprocess as postprocess_fn, yolox_generate_grid,  # noqa: E402,F401

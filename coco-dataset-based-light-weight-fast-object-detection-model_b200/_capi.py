@@ -70,7 +70,7 @@ SYMBOLS = ["yx_last_error", "yx_abi_version", "yx_engine_create", "yx_engine_des
            "yx_conv2d", "yx_conv2d_ex", "yx_decode_infer", "yx_detect_workspace_bytes",
            "yx_nms_main", "yx_nms_main_ex", "yx_nms_workspace_bytes", "yx_detect_main",
            "yx_detect_main_gather", "yx_ipc_export", "yx_ipc_open", "yx_ipc_close", "yx_head_assemble", "yx_decode_outputs", "yx_postprocess_yolox",
-           "yx_preprocess_batch", "yx_coco_records"]
+           "yx_preprocess_batch", "yx_coco_records", "yx_cocoeval_bbox"]
 
 _lib = None
 
@@ -130,6 +130,8 @@ def load():
                                          c_vp, c_vp]
     lib.yx_preprocess_batch.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_vp]
     lib.yx_coco_records.argtypes = [c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp]
+    lib.yx_cocoeval_bbox.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp,
+                                     c_i32, c_vp, c_vp, c_vp]
     if lib.yx_abi_version() != 3:
         raise RuntimeError("libyolox_b200.so ABI version mismatch")
     _lib = lib

@@ -111,7 +111,7 @@ def preprocess_batch(images: Sequence, img_size: int, device="cuda", dtype=torch
     return out, [(int(g[0]), int(g[1])) for g in geom]
 
 
-def coco_records(det: torch.Tensor, count: torch.Tensor, img_hw: Sequence[Tuple[int, int]], img_size: int,
+def coco_records(det: torch.Tensor, count: torch.Tensor, img_hw: Sequence[Tuple[int, int]], img_size,
                  class_ids: Optional[Sequence[int]] = None) -> torch.Tensor:
     """det [B,max_det,7] fp32 (detect_main / Predictor output), count [B] -> records [B,max_det,6] fp32 on the device:
     [x, y, w, h, score, category_id], rows beyond count zero."""
@@ -121,7 +121,8 @@ def coco_records(det: torch.Tensor, count: torch.Tensor, img_hw: Sequence[Tuple[
     if seven != 7 or det.dtype != torch.float32:
         raise RuntimeError("det must be float32 [B, max_det, 7]")
     ids = torch.tensor(COCO_CLASS_ID if class_ids is None else list(class_ids), dtype=torch.int32, device=det.device)
-    scale = torch.tensor([min(img_size / float(h), img_size / float(w)) for h, w in img_hw], dtype=torch.float32,
+    sh, sw = (img_size, img_size) if isinstance(img_size, (int, float)) else img_size   # evaluator: (h, w)
+    scale = torch.tensor([min(sh / float(h), sw / float(w)) for h, w in img_hw], dtype=torch.float32,
                          device=det.device)   # Python double -> float32, like `boxes /= scale` on a float32 tensor
     rec = torch.empty(B, M, 6, dtype=torch.float32, device=det.device)
     det = det.contiguous()

@@ -291,6 +291,20 @@ int yx_preprocess_batch(const void* src, const int64_t* src_off, const int32_t* 
 int yx_coco_records(const float* det, const int32_t* det_count, int B, int max_det, const float* scale,
                     const int32_t* class_ids, int n_classes, float* records, void* stream);
 
+/* ---- COCO bounding-box evaluation (host code) ---------------------------------------- *
+ * The computation behind COCOEvaluator.evaluate_prediction: pycocotools COCOeval(gt, dt, "bbox") evaluate() +
+ * accumulate() + summarize() (ten IoU thresholds .50:.05:.95, 101 recall points, area ranges all/small/medium/large,
+ * 1/10/100 detections per image).  Arrays are host memory; bboxes are [x, y, w, h] doubles; image_ids / category_ids
+ * list what is evaluated (duplicates are ignored).  stats12 = the twelve numbers summarize() prints (AP, AP50, AP75,
+ * APs, APm, APl, AR1, AR10, AR100, ARs, ARm, ARl; -1 where undefined).  precision_out [10][101][K][4][3] and
+ * recall_out [10][K][4][3] are optional (NULL), K = number of distinct category ids, ascending.
+ * replaces: yolox/evaluators/coco_evaluator.py:198-215 (pycocotools / yolox.layers.COCOeval_opt, csrc/cocoeval). */
+int yx_cocoeval_bbox(const int64_t* gt_image, const int32_t* gt_category, const double* gt_bbox, const double* gt_area,
+                     const int32_t* gt_iscrowd, int64_t n_gt, const int64_t* dt_image, const int32_t* dt_category,
+                     const double* dt_bbox, const double* dt_score, int64_t n_dt, const int64_t* image_ids,
+                     int64_t n_images, const int32_t* category_ids, int32_t n_categories, double* stats12,
+                     double* precision_out, double* recall_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -61,3 +61,33 @@ def test_all_gather_detections_world2():
         assert all(p.exitcode == 0 for p in procs)
         assert out[0] and out[1]
         port += 1
+
+
+def _records_worker(rank, world, port, out):
+    from yolox_b200.evaluator import gather_records
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = [dict(image_id=100 * rank + i, category_id=3 + i, bbox=[1.5 * i, 2.0, 3.25, 4.0 + rank], score=0.125 * (i + 1),
+                 segmentation=[]) for i in range(3 if rank == 0 else 0)]      # rank 1 has nothing to report
+    got = gather_records(mine, dst=0)
+    if rank == 0:
+        ok = len(got) == world and got[0] == mine and got[1] == []
+    else:
+        ok = got == []
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_evaluator_gather_records_world2():
+    """COCOEvaluator's distributed collect (coco_evaluator.py:127): ragged per-rank record lists arrive on rank 0."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    out = ctx.Manager().dict()
+    procs = [ctx.Process(target=_records_worker, args=(r, 2, port, out)) for r in range(2)]
+    [p.start() for p in procs]
+    [p.join(120) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    assert out[0] and out[1]
