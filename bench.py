@@ -194,8 +194,12 @@ def run_ours(args, rank, world, local_rank):
     gathered, peer = None, None
     if world > 1:
         if os.environ.get("YX_PEER_GATHER", "1") != "0":
-            peer = yb.dist.PeerGather(B, MAX_DET, dev)
-        else:
+            try:
+                peer = yb.dist.PeerGather(B, MAX_DET, dev)
+            except RuntimeError as e:     # raised on every rank together (CUDA IPC not permitted on this box)
+                if rank == 0:
+                    print(f"bench: {e}; using the NCCL all-gather", file=sys.stderr, flush=True)
+        if peer is None:
             gathered = torch.empty(world, B, MAX_DET * 7 + 1, dtype=torch.float32, device=dev)
 
     def step(img):
@@ -345,6 +349,9 @@ def run_ours(args, rank, world, local_rank):
                          note="pinned host fp16 NCHW batch -> H2D (double-buffered) -> forward+decode+NMS -> D2H detections"),
                 gpu_launches=n_launch_step * args.steps, clocks=clocks, roofline=roof, cpu_baseline=cpu,
                 latency_bs1_ms_p50=lat_p50, detections_last_step=int(cnt.sum().item()))
+    if world > 1:
+        line["gather"] = dict(kind="nms_fused_peer_store" if peer is not None else "nccl_all_gather",
+                              status=peer.status() if peer is not None else 0)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -48,7 +48,7 @@ class PeerGather:
     no data through torch.distributed: each rank's NMS kernel stores its rows into all windows over NVLink.
     Consumers of result() must run on the stream the step was issued on (or be ordered after it)."""
 
-    def __init__(self, batch: int, rows: int, device, group=None, timeout_ms: int = 10000):
+    def __init__(self, batch: int, rows: int, device, group=None, timeout_ms: int = 60000):
         from . import _capi
         self._capi, self.lib = _capi, _capi.load()
         self.group, self.B, self.rows, self.timeout_ms = group, int(batch), int(rows), int(timeout_ms)
@@ -73,19 +73,36 @@ class PeerGather:
         self.ptrs[self.rank] = self.buf.data_ptr()
         self._opened = []
         if W > 1:
+            # Every rank takes the same decision: a failure anywhere (export or open) is exchanged before anyone raises,
+            # so a caller may fall back to the NCCL gather on all ranks together.
+            mine, err = None, None
             with torch.cuda.device(self.device):
-                _capi.check(self.lib.yx_ipc_export(self.buf.data_ptr(), handle, ctypes.byref(off)), "yx_ipc_export")
-                mine = (bytes(handle), int(off.value))
+                try:
+                    _capi.check(self.lib.yx_ipc_export(self.buf.data_ptr(), handle, ctypes.byref(off)), "yx_ipc_export")
+                    mine = (bytes(handle), int(off.value))
+                except RuntimeError as e:
+                    err = f"rank {self.rank}: {e}"
                 everyone = [None] * W
                 dist.all_gather_object(everyone, mine, group=group)
-                for r, (h, o) in enumerate(everyone):
-                    if r == self.rank:
-                        continue
-                    base = ctypes.c_void_p()
-                    hb = (ctypes.c_ubyte * _capi.IPC_HANDLE_BYTES).from_buffer_copy(h)
-                    _capi.check(self.lib.yx_ipc_open(hb, ctypes.byref(base)), "yx_ipc_open")
-                    self._opened.append(base.value)
-                    self.ptrs[r] = base.value + o
+                if err is None and all(x is not None for x in everyone):
+                    try:
+                        for r, (h, o) in enumerate(everyone):
+                            if r == self.rank:
+                                continue
+                            base = ctypes.c_void_p()
+                            hb = (ctypes.c_ubyte * _capi.IPC_HANDLE_BYTES).from_buffer_copy(h)
+                            _capi.check(self.lib.yx_ipc_open(hb, ctypes.byref(base)), "yx_ipc_open")
+                            self._opened.append(base.value)
+                            self.ptrs[r] = base.value + o
+                    except RuntimeError as e:
+                        err = f"rank {self.rank}: {e}"
+                elif err is None:
+                    err = f"rank {self.rank}: a peer could not export its window"
+                errors = [None] * W
+                dist.all_gather_object(errors, err, group=group)
+            if any(errors):
+                self.close()
+                raise RuntimeError("peer gather unavailable: " + "; ".join(e for e in errors if e))
             torch.cuda.synchronize(self.device)     # zero fill done before any peer may store into this buffer
             dist.barrier(group=group)
 

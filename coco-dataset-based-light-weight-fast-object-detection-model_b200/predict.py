@@ -40,6 +40,7 @@ class Predictor:
                        max_num_det=max_num_det)
         self.in_scale, self.in_shift, self.use_graph = in_scale, in_shift, use_graph
         self._gathers = {}
+        self._peer_unavailable = False
 
     @torch.no_grad()
     def __call__(self, img: torch.Tensor, gather=None) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -70,14 +71,20 @@ class Predictor:
         s, e = ydist.shard_range(n, rank, world)
         mine = img_global[s:e]
         if e - s < per:                                                # pad so every rank runs the same batch
-            mine = torch.cat([mine, mine[-1:].expand(per - (e - s), -1, -1, -1)], 0)
+            filler = mine[-1:] if e > s else img_global[:1]            # (a rank may own no image at all when n < world)
+            mine = torch.cat([mine, filler.expand(per - (e - s), -1, -1, -1)], 0)
         if world == 1:
             return self(mine)
         dev = next(self.model.parameters()).device
-        fused = (tdist.get_backend() == "nccl" and self.kw["max_num_det"] > 0
+        fused = (tdist.get_backend() == "nccl" and self.kw["max_num_det"] > 0 and not self._peer_unavailable
                  and os.environ.get("YX_PEER_GATHER", "1") != "0")
-        if fused:      # the NMS kernel stores its rows into every rank's window; no collective call on the data path
-            g = self._peer_gather(per, dev)
+        g = None
+        if fused:
+            try:
+                g = self._peer_gather(per, dev)
+            except RuntimeError:          # CUDA IPC not permitted here; raised on every rank together
+                self._peer_unavailable = True
+        if g is not None:   # the NMS kernel stores its rows into every rank's window; no collective call on the data path
             self(mine, gather=g)
             det_all, cnt_all = g.result()
         else:

@@ -17,16 +17,18 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 model = bench.build_model(torch.device("cuda", local))
 pred = yb.predict.Predictor(model)
 g = torch.Generator().manual_seed(7)
-img = (torch.rand(7, 3, 256, 320, generator=g) * 255).half().cuda()      # 7 images over 2 ranks: 4 + 3(+1 pad)
-det_one, cnt_one = pred(img)
+world = dist.get_world_size()
 ok = True
-for fused in ("1", "0"):                      # NMS-fused peer gather, then the NCCL all-gather it replaces
-    os.environ["YX_PEER_GATHER"] = fused
-    for it in range(5):                       # several steps: window parity, arrival-counter targets
-        det_all, cnt_all = pred.predict_sharded(img)
-        same = torch.equal(det_all, det_one) and torch.equal(cnt_all, cnt_one)
-        ok = ok and same
-    print(f"dist_check rank {rank}: peer_gather={fused} sharded==single {same} counts {cnt_all.tolist()}", flush=True)
+for n_img in (3 * world + 1, world - 1):      # ragged shards (last ranks padded); fewer images than ranks (empty shards)
+    img = (torch.rand(n_img, 3, 256, 320, generator=g) * 255).half().cuda()
+    det_one, cnt_one = pred(img)
+    for fused in ("1", "0"):                  # NMS-fused peer gather, then the NCCL all-gather it replaces
+        os.environ["YX_PEER_GATHER"] = fused
+        for it in range(5):                   # several steps: window parity, arrival-counter targets
+            det_all, cnt_all = pred.predict_sharded(img)
+            same = torch.equal(det_all, det_one) and torch.equal(cnt_all, cnt_one)
+            ok = ok and same
+        print(f"dist_check rank {rank}: {n_img} images peer_gather={fused} sharded==single {same} counts {cnt_all.tolist()}", flush=True)
 for g in pred._gathers.values():
     st = g.status()
     ok = ok and st == 0
