@@ -341,6 +341,13 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
   const bool is_a_prod = (warp == 0) || (warp == 3 && p.w3_role == 1);
   const bool is_b_prod = (warp == 2) || (warp == 3 && p.w3_role == 2);
 
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, bias copy: none of it touches an
+  // activation) overlapped the previous layer's tail.  The weight producers go on without waiting -- weights are constants,
+  // so resident weights are already streaming in while the previous layer finishes; every other role reads or writes
+  // activations and waits for the previous grid to complete first.
+  griddep_launch_dependents();
+  if (!is_b_prod) griddep_wait();
+
   // Producer and MMA warps run their loops WARP-UNIFORMLY (all 32 lanes, uniform values) and elect one lane only
   // around the issue itself: under `if (lane == 0)` ptxas cannot prove uniformity and wraps every UTMALDG / UTCHMMA
   // in an ELECT + 8x R2UR.BROADCAST loop (~200 cycles per TMA instruction, profiles/r01_tma_issue_probe.txt).
@@ -1098,24 +1105,29 @@ static int launch_variant(const ConvPlan& plan, cudaStream_t stream) {
     YX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     attr_set = true;
   }
-  if (!PAIR) {
-    kernel<<<plan.grid, plan.threads, plan.smem_bytes, stream>>>(plan.p);
-    YX_CUDA(cudaGetLastError());
-    return YX_OK;
-  }
+  static const bool pdl = !(getenv("YX_PDL") && atoi(getenv("YX_PDL")) == 0);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = dim3(plan.grid, 1, 1);
   cfg.blockDim = dim3(plan.threads, 1, 1);
   cfg.dynamicSmemBytes = plan.smem_bytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;  // the CTA pair
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (PAIR) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;  // the CTA pair
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl) {  // may start while the previous kernel of the stream drains; the kernel orders itself with griddepcontrol.wait
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = na;
   YX_CUDA(cudaLaunchKernelEx(&cfg, kernel, plan.p));
   return YX_OK;
 }

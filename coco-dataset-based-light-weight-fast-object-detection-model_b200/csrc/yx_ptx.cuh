@@ -211,6 +211,12 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Programmatic dependent launch: a grid launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while
+// its predecessor in the stream is still draining; griddepcontrol.wait blocks until the predecessor has completed and its
+// memory is visible (a no-op for a normal launch); launch_dependents lets the successor start early in turn.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // No memory ordering: for signals whose payload is not generic-proxy memory (e.g. "this warp's tcgen05.ld have completed").
 __device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");

@@ -9,5 +9,6 @@ cap() {  # name, demangled kernel regex, skip, count
 cap pairhalo "conv_gemm_kernel<.int.2, .int.0, .int.1, .bool.1>" 5 1
 cap pairgeneric "conv_gemm_kernel<.int.2, .int.0, .int.0, .bool.1>" 0 1
 cap generic "conv_gemm_kernel<.int.2, .int.0, .int.0, .bool.0>" 0 1
-cap inplace "conv_gemm_kernel<.int.2, .int.2, " 0 1
-cap post "select_infer|sort_keys|nms_kernel|s2d_kernel|spp_kernel" 0 5
+cap inplace "conv_gemm_kernel<.int.2, .int.2, .int.2, .bool.0>" 0 1
+cap pairinplace "conv_gemm_kernel<.int.2, .int.2, .int.1, .bool.1>" 0 1
+cap post "select_infer|sort_keys|nms_kernel|s2d_kernel|spp_" 0 5
