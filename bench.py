@@ -283,15 +283,14 @@ def run_ours(args, rank, world, local_rank):
             dist.destroy_process_group()
         return
 
-    # ---- bs1 latency (CUDA graph replay), p50 --------------------------------------------------
+    # ---- bs1 latency, p50: the whole step (network + decode + NMS) replayed as ONE CUDA graph -------
     x1 = dev_img[:1].contiguous()
+    lat_pred = yb.predict.Predictor(model, CONF_THR, NMS_THR, MAX_NMS, MAX_DET, in_scale=0.9, in_shift=11.4, whole_graph=True)
     lat = []
     for i in range(60):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        eng, reg8, cls = model.run_engine(x1, 0.9, 11.4, use_graph=True)
-        pp.detect_main(reg8[..., :4], reg8[..., 4:5], cls[..., :MODEL["num_classes"]], model.head.hw, strides, CONF_THR,
-                       NMS_THR, MAX_NMS, MAX_DET)
+        lat_pred(x1)
         b.record()
         torch.cuda.synchronize()
         if i >= 10:

@@ -208,3 +208,17 @@ def test_spp_pools_exact(H, W, C):
         want = F.max_pool2d(xn, k, 1, k // 2).permute(0, 2, 3, 1).half()
         assert torch.equal(t[..., (i + 1) * C:(i + 2) * C], want), f"pool {k}"
     assert torch.equal(t[..., :C], x)
+
+
+def test_predictor_whole_step_graph_equals_eager():
+    """Predictor(whole_graph=True): network + decode + NMS replayed as one CUDA graph gives the eager result, for
+    successive different inputs and two shapes."""
+    cfg, fused, model = _build("tiny_p6", 128, 128, 9)
+    eager = yb.predict.Predictor(model, conf_threshold=0.05, nms_threshold=0.55)
+    graphed = yb.predict.Predictor(model, conf_threshold=0.05, nms_threshold=0.55, whole_graph=True)
+    for seed, (B, H, W) in enumerate([(1, 128, 128), (1, 128, 128), (2, 128, 192), (1, 128, 128)]):
+        x = mr.synth_images(30 + seed, B, H, W).cuda().half()
+        d0, c0 = eager(x)
+        d1, c1 = graphed(x)
+        assert torch.equal(c0, c1) and torch.equal(d0, d1), (seed, c0.tolist(), c1.tolist())
+    assert len(graphed._step_graphs) == 2
