@@ -834,6 +834,10 @@ void conv_candidates(const yx_op& op, std::vector<ConvTune>* out) {
   if (cout16 > 128) add_bn(128);
   if (cout16 > 192) add_bn(192);
   if (cout16 > 64 && cout16 % 64 == 0 && cout16 <= 128) add_bn(64);
+  {  // latency regime (bs1, deep 20x20 / 40x40 maps): too few tiles to fill the SMs -> narrower N tiles spread the layer
+    const int64_t m_tiles = (int64_t)op.dst.n * ceil_div(op.dst.h * op.dst.w, 128);
+    if (cout16 > 64 && m_tiles * ceil_div(cout16, 128) < 148) add_bn(64);
+  }
   auto push = [&](ConvTune t) {
     for (const ConvTune& o : *out)
       if (memcmp(&o, &t, sizeof t) == 0) return;
