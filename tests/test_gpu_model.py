@@ -169,6 +169,8 @@ def test_predict_loop_end_to_end():
 
 
 @pytest.mark.parametrize("name,H,W,B", [("yolox_m_p6", 640, 640, 2), ("yolox_m", 320, 320, 1), ("tiny", 160, 96, 2),
+                                        ("yolox_m", 640, 640, 2),      # BASELINE config 2 geometry (YOLOX-M 640x640)
+                                        ("yolox_l", 640, 640, 1),      # BASELINE config 5 geometry (YOLOX-L 640x640)
                                         ("tiny_p6_v2", 128, 128, 1), ("yolox_m_p6_v2", 256, 256, 1), ("tiny_dw", 128, 96, 1),
                                         ("yolox_l_dw", 256, 256, 1)])
 def test_every_op_teacher_forced(name, H, W, B):
