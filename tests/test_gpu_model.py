@@ -224,3 +224,32 @@ def test_predictor_whole_step_graph_equals_eager():
         d1, c1 = graphed(x)
         assert torch.equal(c0, c1) and torch.equal(d0, d1), (seed, c0.tolist(), c1.tolist())
     assert len(graphed._step_graphs) == 2
+
+
+def test_full_size_batch_independence(monkeypatch):
+    """BASELINE.json's full configuration (YOLOX-M-P6, 1280x1280, 64 images per step): a size-independent property in place
+    of an oracle run that would take minutes -- no operator on the path mixes images, so every image's logits and
+    detections in the bs64 step are BIT-identical to the same image run alone (shape-only launch shapes: YX_TUNE=0;
+    tuned shapes may order the K loop differently between batch sizes)."""
+    monkeypatch.setenv("YX_TUNE", "0")
+    cfg = mr.CONFIGS["yolox_m_p6"]
+    model = yb.infer.YOLOXP6(cfg.depth, cfg.width, act=cfg.act, num_classes=cfg.num_classes)
+    g = torch.Generator().manual_seed(5)
+    for p in model.parameters():          # random weights, default-initialised prediction biases (SURVEY C4)
+        with torch.no_grad():
+            p.copy_(torch.randn(p.shape, generator=g) * (0.5 / max(p[0].numel(), 1) ** 0.5) if p.dim() == 4
+                    else torch.randn(p.shape, generator=g) * 0.1)
+    model = model.cuda().half().eval()
+    B, S = 64, 1280
+    x = (torch.rand(B, 3, S, S, device="cuda", generator=torch.Generator("cuda").manual_seed(6)) * 255).half()
+    pred = yb.predict.Predictor(model, conf_threshold=0.001, nms_threshold=0.65)
+    eng, reg8, cls = model.run_engine(x, 0.9, 11.4)
+    reg8, cls = reg8.clone(), cls.clone()
+    assert torch.isfinite(reg8.float()).all() and torch.isfinite(cls.float()).all()
+    det, cnt = pred(x)
+    assert int(cnt.min()) > 0, "random-init predictions should produce candidates (sigmoid ~ 0.5)"
+    for i in (0, 17, 63):
+        e1, r1, c1 = model.run_engine(x[i:i + 1].contiguous(), 0.9, 11.4)
+        assert torch.equal(r1[0], reg8[i]) and torch.equal(c1[0], cls[i]), f"image {i}: logits differ from the bs1 run"
+        d1, n1 = pred(x[i:i + 1].contiguous())
+        assert int(n1[0]) == int(cnt[i]) and torch.equal(d1[0], det[i]), f"image {i}: detections differ from the bs1 run"
