@@ -34,11 +34,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = []
     build_dir = os.path.join(_HERE, "lib", "obj")
     os.makedirs(build_dir, exist_ok=True)
-    for src in sources():
+    def compile_one(src):
         obj = os.path.join(build_dir, os.path.basename(src)[:-3] + ".o")
         cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         subprocess.check_call(cmd)
-        objs.append(obj)
+        return obj
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:   # translation units are independent
+        objs = list(pool.map(compile_one, sources()))
     subprocess.check_call([nvcc, "-shared", "--cudart", "static", "-o", LIB] + objs)
     return LIB
 
