@@ -253,3 +253,27 @@ def test_full_size_batch_independence(monkeypatch):
         assert torch.equal(r1[0], reg8[i]) and torch.equal(c1[0], cls[i]), f"image {i}: logits differ from the bs1 run"
         d1, n1 = pred(x[i:i + 1].contiguous())
         assert int(n1[0]) == int(cnt[i]) and torch.equal(d1[0], det[i]), f"image {i}: detections differ from the bs1 run"
+
+
+@pytest.mark.parametrize("masks", ["magnitude49", "two_four"])
+def test_pruned_checkpoint_through_build_yolox(masks, tmp_path):
+    """BASELINE config 3 (pruned model): main.py:31-59's path -- a {"model": sparse COO} checkpoint written to disk, ingested
+    by build_yolox(sparse=True), run dense-with-zeros -- against the oracle evaluated on the same masked weights; both the
+    49 % global-magnitude masks of the shipped recipe (01_mask_generator.py) and the synthetic 2:4-compliant set."""
+    cfg = mr.CONFIGS["tiny_p6"]
+    H, W, B = 128, 192, 2
+    train = mr.synth_train_state(cfg, 8, calib_hw=(H, W))
+    m = mr.magnitude_masks(train, 49.0) if masks == "magnitude49" else mr.two_four_masks(train)
+    fused = mr.apply_masks(mr.fold_bn(train), m)
+    path = str(tmp_path / "pruned.pth")
+    torch.save(mr.to_sparse_ckpt(fused), path)
+    model = yb.predict.build_yolox(dict(model=dict(type="yolox-p6", depth=cfg.depth, width=cfg.width), ckpt=path, sparse=True,
+                                        half=True))
+    for k, v in model.state_dict().items():               # the ingest reproduced the dense-with-zeros weights
+        assert torch.equal(v.float().cpu(), fused[k].half().float()), k
+    dens = yb.weights.density({k: v for k, v in model.state_dict().items() if "head" not in k})
+    assert 0.4 < dens < 0.6
+    x = mr.synth_images(12, B, H, W)
+    reg, obj, cls = model(x.cuda().half())
+    rr, ro, rc = mr.forward_raw(_q16(fused), cfg, x.half().float())
+    _check(reg, rr, "reg"); _check(obj, ro, "obj"); _check(cls, rc, "cls")
