@@ -34,16 +34,27 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = []
     build_dir = os.path.join(_HERE, "lib", "obj")
     os.makedirs(build_dir, exist_ok=True)
-    def compile_one(src):
-        obj = os.path.join(build_dir, os.path.basename(src)[:-3] + ".o")
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+    # (source, extra defines, object name): yx_conv.cu is compiled once for planning / dispatch and once per activation
+    # (-DYX_CONV_ACT_SLICE=<yx_act>), so its ~100 kernel instantiations build in parallel
+    units = []
+    for src in sources():
+        base = os.path.basename(src)[:-3]
+        units.append((src, [], base))
+        if base == "yx_conv":
+            units += [(src, [f"-DYX_CONV_ACT_SLICE={a}", "-diag-suppress", "177"], f"{base}_act{a}") for a in range(5)]
+
+    def compile_one(unit):
+        src, defs, name = unit
+        obj = os.path.join(build_dir, name + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + defs + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         subprocess.check_call(cmd)
         return obj
 
     from concurrent.futures import ThreadPoolExecutor
-    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:   # translation units are independent
-        objs = list(pool.map(compile_one, sources()))
+    with ThreadPoolExecutor(max_workers=min(12, os.cpu_count() or 1)) as pool:   # translation units are independent
+        objs = list(pool.map(compile_one, units))
     subprocess.check_call([nvcc, "-shared", "--cudart", "static", "-o", LIB] + objs)
+    shutil.rmtree(build_dir, ignore_errors=True)   # only the .so needs to travel with the tree
     return LIB
 
 

@@ -649,6 +649,10 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
 // --------------------------------------------------------------------------------------------
 // host side
 // --------------------------------------------------------------------------------------------
+// Build layout: this file is compiled once as it is (planning + dispatch) and once per activation with
+// -DYX_CONV_ACT_SLICE=<yx_act value> (the ~20 kernel instantiations of that activation and their launcher), so the
+// instantiations compile in parallel (_build.py).
+#ifndef YX_CONV_ACT_SLICE
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1101,6 +1105,9 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
   return YX_OK;
 }
 
+#endif  // !YX_CONV_ACT_SLICE
+
+#ifdef YX_CONV_ACT_SLICE
 template <int ACT, int RES, int MODE, bool PAIR>
 static int launch_variant(const ConvPlan& plan, cudaStream_t stream) {
   static bool attr_set = false;
@@ -1156,15 +1163,28 @@ static int launch_act(const ConvPlan& plan, cudaStream_t stream) {
   return res == 1 ? launch_mode<ACT, 1>(plan, stream) : launch_mode<ACT, 0>(plan, stream);
 }
 
+#define YX_CAT2(a, b) a##b
+#define YX_CAT(a, b) YX_CAT2(a, b)
+int YX_CAT(conv_launch_act_, YX_CONV_ACT_SLICE)(const ConvPlan& plan, cudaStream_t stream) {
+  return launch_act<YX_CONV_ACT_SLICE>(plan, stream);
+}
+#else   // planning TU: dispatch to the per-activation launchers
+int conv_launch_act_0(const ConvPlan& plan, cudaStream_t stream);
+int conv_launch_act_1(const ConvPlan& plan, cudaStream_t stream);
+int conv_launch_act_2(const ConvPlan& plan, cudaStream_t stream);
+int conv_launch_act_3(const ConvPlan& plan, cudaStream_t stream);
+int conv_launch_act_4(const ConvPlan& plan, cudaStream_t stream);
+
 int conv_launch(const ConvPlan& plan, cudaStream_t stream) {
   switch (plan.p.act) {
-    case YX_ACT_NONE: return launch_act<YX_ACT_NONE>(plan, stream);
-    case YX_ACT_SILU: return launch_act<YX_ACT_SILU>(plan, stream);
-    case YX_ACT_HSWISH: return launch_act<YX_ACT_HSWISH>(plan, stream);
-    case YX_ACT_RELU: return launch_act<YX_ACT_RELU>(plan, stream);
-    case YX_ACT_LRELU: return launch_act<YX_ACT_LRELU>(plan, stream);
+    case YX_ACT_NONE: return conv_launch_act_0(plan, stream);
+    case YX_ACT_SILU: return conv_launch_act_1(plan, stream);
+    case YX_ACT_HSWISH: return conv_launch_act_2(plan, stream);
+    case YX_ACT_RELU: return conv_launch_act_3(plan, stream);
+    case YX_ACT_LRELU: return conv_launch_act_4(plan, stream);
     default: set_error("unknown activation code"); return YX_ERR_INVALID;
   }
 }
+#endif  // YX_CONV_ACT_SLICE
 
 }  // namespace yx
