@@ -7,6 +7,7 @@
 
 Pixel / box arithmetic runs in csrc/yx_io.cu; the host side only builds Pillow's per-axis coefficient tables (O(W + H) per
 image, double precision like Resample.c) and Python dicts.  No CPU fallback."""
+import functools
 import math
 from typing import List, Optional, Sequence, Tuple
 
@@ -35,8 +36,10 @@ def resized_shape(h: int, w: int, img_size: int) -> Tuple[int, int]:
     return new_h, new_w
 
 
+@functools.lru_cache(maxsize=512)
 def _coeffs(in_size: int, out_size: int):
-    """Pillow's precompute_coeffs + normalize_coeffs_8bpc for the triangle (BILINEAR) filter, vectorised over the output
+    """(cached per (in, out) pair: datasets repeat a handful of image sizes; the arrays are treated as read-only)
+    Pillow's precompute_coeffs + normalize_coeffs_8bpc for the triangle (BILINEAR) filter, vectorised over the output
     index in float64 (same operation order as the C code).  -> bounds int32 [out, 2], kk int32 [out, ksize]."""
     scale = in_size / out_size
     filterscale = max(scale, 1.0)
@@ -55,6 +58,18 @@ def _coeffs(in_size: int, out_size: int):
     k = np.where(ww[:, None] != 0.0, k / np.where(ww[:, None] != 0.0, ww[:, None], 1.0), k)
     kk = (0.5 + k * (1 << PRECISION_BITS)).astype(np.int64).astype(np.int32)   # weights are >= 0 for this filter
     return np.stack([xmin, xmax], 1).astype(np.int32), kk
+
+
+_STAGING = {"buf": None, "event": None}
+
+
+def _staging(nbytes: int) -> torch.Tensor:
+    """Grow-only pinned host buffer for the raw pixels of a batch (pinning fresh memory per call costs milliseconds)."""
+    if _STAGING["event"] is not None:
+        _STAGING["event"].synchronize()
+    if _STAGING["buf"] is None or _STAGING["buf"].numel() < nbytes:
+        _STAGING["buf"] = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8).pin_memory()
+    return _STAGING["buf"]
 
 
 def preprocess_batch(images: Sequence, img_size: int, device="cuda", dtype=torch.float32):
@@ -92,12 +107,15 @@ def preprocess_batch(images: Sequence, img_size: int, device="cuda", dtype=torch
     for i, a in enumerate(arrs):
         offs[i] = total
         total += a.size
-    packed = torch.empty(total, dtype=torch.uint8).pin_memory()
+    packed = _staging(total)
+    pk = packed.numpy()
     for i, a in enumerate(arrs):
-        packed[offs[i]:offs[i] + a.size] = torch.from_numpy(a.reshape(-1))
+        np.copyto(pk[offs[i]:offs[i] + a.size], a.reshape(-1))
     with torch.cuda.device(dev):
         d = lambda x: torch.from_numpy(x).to(dev, non_blocking=True)
-        src, d_off, d_geom = packed.to(dev, non_blocking=True), d(offs), d(geom)
+        src, d_off, d_geom = packed[:total].to(dev, non_blocking=True), d(offs), d(geom)
+        _STAGING["event"] = torch.cuda.Event()
+        _STAGING["event"].record()                      # the staging buffer may be rewritten once this copy has run
         d_bh, d_kh, d_bv, d_kv = d(bh), d(kh), d(bv), d(kv)
         out = torch.empty(B, 3, Hp, Wp, dtype=dtype, device=dev)
         dt = _capi.YX_F16 if dtype == torch.float16 else _capi.YX_F32
