@@ -857,7 +857,7 @@ void conv_candidates(const yx_op& op, std::vector<ConvTune>* out) {
           memset(&t, 0, sizeof t);
           t.variant = 1; t.bn = bn; t.ctas = ctas; t.epi_groups = eg; t.stage_bufs = sb; t.w3 = 1;
           push(t);
-          if (bn <= 128 && ctas == 1 && !g.has_up) {  // 256-pixel tiles
+          if (bn <= 128 && ctas == 1) {  // 256-pixel tiles (also with a fused upsample: the 5-D box simply covers TH x TW)
             t.mh = 2;
             push(t);
           }
@@ -951,8 +951,8 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
     while (p.tmem_cols < 2 * mh * stride_cols) p.tmem_cols <<= 1;
   } else if (t.mh == 2) {
     // generic with a 256-pixel tile: two halves of (TH/2) x TW pixels stacked in one A box
-    YX_REQUIRE(!pair && !g.has_up && 4 * stride_cols <= 512 && t.ctas == 1,
-               "conv tune: the 256-pixel generic tile needs N <= 128, one CTA per SM, no CTA pair and no fused upsample");
+    YX_REQUIRE(!pair && 4 * stride_cols <= 512 && t.ctas == 1,
+               "conv tune: the 256-pixel generic tile needs N <= 128, one CTA per SM and no CTA pair");
     p.mh = 2;
     choose_tile(g.Hout, g.Wout, &p.TH, &p.TW, true, 256);
     YX_REQUIRE(p.TH % 2 == 0 && p.TH / 2 * p.TW <= 128 && (p.TH / 2 * p.TW) % 8 == 0 && p.TH / 2 * p.TW >= 64,

@@ -189,6 +189,8 @@ TUNED_CASES = [
     dict(cin=96, cout=96, k=1, stride=1, H=40, W=24, act="silu", up_c=64, tune=_t(1, 96, ctas=2)),                  # resident weights, K tail
     dict(cin=576, cout=1152, k=1, stride=1, H=40, W=40, act="hard_swish", up_c=576, tune=_t(1, 256, pair=1)),      # C3_p5.conv1+2
     dict(cin=192, cout=384, k=1, stride=1, H=44, W=36, act="hard_swish", up_c=192, tune=_t(1, 192, pair=1, sb=1)), # ragged tiles
+    dict(cin=192, cout=384, k=1, stride=1, H=160, W=160, act="hard_swish", up_c=192, tune=_t(1, 128, halves=2)),       # C3_p3.conv1+2, 256-pixel tiles
+    dict(cin=192, cout=128, k=1, stride=1, H=48, W=40, act="silu", up_c=64, tune=_t(1, 128, halves=2, eg=2, sb=1)),     # 12 x 20 tiles: halves of 6 rows
 ]
 
 
