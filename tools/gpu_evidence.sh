@@ -6,11 +6,11 @@ mkdir -p gpurun_out
 LOG=gpurun_out/evidence.log
 : > $LOG
 timeout 900 python bench.py --profile-out gpurun_out/profile_bs64.json > gpurun_out/bench_evidence.json 2> gpurun_out/bench_evidence.err; echo "bench exit=$?" >> $LOG
-timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_evidence_ref.json 2>> gpurun_out/bench_evidence.err; echo "ref exit=$?" >> $LOG
+if [ -z "$YX_SKIP_CAPTURES" ]; then timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_evidence_ref.json 2>> gpurun_out/bench_evidence.err; echo "ref exit=$?" >> $LOG; fi
 python tools/profile_ops.py 1 1280 gpurun_out/profile_bs1.json 5 >> $LOG 2>&1
 YX_STEPS=2 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
   -c 400 --csv --log-file gpurun_out/launches_step.csv python tools/ncu_target.py >> $LOG 2>&1
 echo "ncu list exit=$?" >> $LOG
-bash tools/gpu_ncu.sh >> $LOG 2>&1
+if [ -z "$YX_SKIP_CAPTURES" ]; then bash tools/gpu_ncu.sh >> $LOG 2>&1; fi   # --set full captures: ~5 GPU-minutes
 grep -E "exit=|sum ops" $LOG
 cut -c1-400 gpurun_out/bench_evidence.json
