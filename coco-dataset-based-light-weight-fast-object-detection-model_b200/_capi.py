@@ -10,7 +10,16 @@ from . import _build
 
 c_i32, c_i64, c_f32, c_vp, c_sz = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
 
-YX_F16, YX_F32 = 0, 1
+YX_F16, YX_F32, YX_U8 = 0, 1, 2
+
+
+def image_dtype(t) -> int:
+    """yx_dtype of an image batch (fp16 / fp32 / uint8 pixel values)."""
+    import torch
+    try:
+        return {torch.float16: YX_F16, torch.float32: YX_F32, torch.uint8: YX_U8}[t.dtype]
+    except KeyError:
+        raise RuntimeError(f"unsupported image dtype {t.dtype}") from None
 ACT = {"none": 0, "identity": 0, "silu": 1, "swish": 1, "hsilu": 2, "hswish": 2, "hard_silu": 2, "hard_swish": 2,
        "relu": 3, "lrelu": 4, "leaky_relu": 4}
 OP_CONV, OP_S2D, OP_SPP, OP_UPSAMPLE, OP_DWCONV = 0, 1, 2, 3, 4

@@ -37,6 +37,10 @@ __device__ __forceinline__ float affine_in<__half>(__half v, float scale, float 
   return x;
 }
 template <>
+__device__ __forceinline__ float affine_in<uint8_t>(uint8_t v, float scale, float shift, bool on) {
+  return affine_in<__half>(__ushort2half_rn(v), scale, shift, on);   // 0..255 is exact in fp16: same bits as a half image
+}
+template <>
 __device__ __forceinline__ float affine_in<float>(float v, float scale, float shift, bool on) {
   return on ? (v * scale) + shift : v;
 }
@@ -98,8 +102,11 @@ int s2d_launch(const void* image, int image_dtype, int aux, int B, int H, int W,
   else if (image_dtype == YX_F32)
     s2d_kernel<float><<<blocks, threads, 0, stream>>>(static_cast<const float*>(image), out, B, H, W, dst.pitch,
                                                       dst.nstride, order, padded, scale, shift, affine);
+  else if (image_dtype == YX_U8)
+    s2d_kernel<uint8_t><<<blocks, threads, 0, stream>>>(static_cast<const uint8_t*>(image), out, B, H, W, dst.pitch,
+                                                        dst.nstride, order, padded, scale, shift, affine);
   else
-    YX_REQUIRE(false, "image dtype must be YX_F16 or YX_F32");
+    YX_REQUIRE(false, "image dtype must be YX_F16, YX_F32 or YX_U8");
   YX_CUDA(cudaGetLastError());
   return YX_OK;
 }

@@ -15,6 +15,9 @@ namespace yx {
 
 constexpr int kPrecisionBits = 22;
 
+template <typename T> __device__ __forceinline__ T from_pixel(int v) { return static_cast<T>(static_cast<float>(v)); }
+template <> __device__ __forceinline__ uint8_t from_pixel<uint8_t>(int v) { return static_cast<uint8_t>(v); }
+
 template <typename T>
 __global__ void preprocess_kernel(const uint8_t* __restrict__ src, const int64_t* __restrict__ src_off,
                                   const int32_t* __restrict__ geom,      // [B][4] = h, w, new_h, new_w
@@ -58,9 +61,9 @@ __global__ void preprocess_kernel(const uint8_t* __restrict__ src, const int64_t
   }
   const int64_t plane = (int64_t)Hp * Wp;
   T* o = out + (int64_t)b * 3 * plane + (int64_t)y * Wp + x;
-  o[0] = static_cast<T>(static_cast<float>(bl));  // BGR
-  o[plane] = static_cast<T>(static_cast<float>(g));
-  o[2 * plane] = static_cast<T>(static_cast<float>(r));
+  o[0] = from_pixel<T>(bl);  // BGR
+  o[plane] = from_pixel<T>(g);
+  o[2 * plane] = from_pixel<T>(r);
 }
 
 __global__ void coco_records_kernel(const float* __restrict__ det, const int32_t* __restrict__ count, int B, int max_det,
@@ -93,12 +96,15 @@ extern "C" int yx_preprocess_batch(const void* src, const int64_t* src_off, cons
                                    int Hp, int Wp, void* out, int out_dtype, void* stream) {
   YX_REQUIRE(src && src_off && geom && bounds_h && kk_h && bounds_v && kk_v && out, "null argument");
   YX_REQUIRE(B > 0 && Hp > 0 && Wp > 0 && ks_h > 0 && ks_v > 0 && Hp <= 65535 && B <= 65535, "bad batch geometry");
-  YX_REQUIRE(out_dtype == YX_F16 || out_dtype == YX_F32, "output dtype must be fp16 or fp32");
+  YX_REQUIRE(out_dtype == YX_F16 || out_dtype == YX_F32 || out_dtype == YX_U8, "output dtype must be fp16, fp32 or uint8");
   const dim3 block(128), grid(ceil_div(Wp, 128), Hp, B);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (out_dtype == YX_F16)
     preprocess_kernel<__half><<<grid, block, 0, st>>>(static_cast<const uint8_t*>(src), src_off, geom, bounds_h, kk_h, bounds_v,
                                                        kk_v, ks_h, ks_v, B, Hp, Wp, static_cast<__half*>(out));
+  else if (out_dtype == YX_U8)
+    preprocess_kernel<uint8_t><<<grid, block, 0, st>>>(static_cast<const uint8_t*>(src), src_off, geom, bounds_h, kk_h, bounds_v,
+                                                        kk_v, ks_h, ks_v, B, Hp, Wp, static_cast<uint8_t*>(out));
   else
     preprocess_kernel<float><<<grid, block, 0, st>>>(static_cast<const uint8_t*>(src), src_off, geom, bounds_h, kk_h, bounds_v,
                                                      kk_v, ks_h, ks_v, B, Hp, Wp, static_cast<float*>(out));

@@ -118,9 +118,9 @@ def preprocess_batch(images: Sequence, img_size: int, device="cuda", dtype=torch
         _STAGING["event"].record()                      # the staging buffer may be rewritten once this copy has run
         d_bh, d_kh, d_bv, d_kv = d(bh), d(kh), d(bv), d(kv)
         out = torch.empty(B, 3, Hp, Wp, dtype=dtype, device=dev)
-        dt = _capi.YX_F16 if dtype == torch.float16 else _capi.YX_F32
-        if dtype not in (torch.float16, torch.float32):
-            raise RuntimeError("dtype must be float16 or float32")
+        if dtype not in (torch.float16, torch.float32, torch.uint8):
+            raise RuntimeError("dtype must be float16, float32 or uint8")
+        dt = {torch.float16: _capi.YX_F16, torch.float32: _capi.YX_F32, torch.uint8: _capi.YX_U8}[dtype]
         _capi.check(lib.yx_preprocess_batch(src.data_ptr(), d_off.data_ptr(), d_geom.data_ptr(), d_bh.data_ptr(),
                                             d_kh.data_ptr(), d_bv.data_ptr(), d_kv.data_ptr(), ks_h, ks_v, B, Hp, Wp,
                                             out.data_ptr(), dt, _capi.current_stream_ptr()), "yx_preprocess_batch")

@@ -389,14 +389,15 @@ class _EngineModel(nn.Module):
     def forward(self, x, targets=None):
         eng, reg8, cls = self.run_engine(x)
         C = self.head.num_classes
+        out_dtype = torch.float16 if x.dtype == torch.uint8 else x.dtype   # uint8 pixels are evaluated as the same values in fp16
         if self.flavour == "infer":
             # fresh tensors like the reference (yolo_head.py:130-133 returns permuted views of new tensors)
             reg8 = reg8.clone()
-            cls = cls.clone().to(x.dtype) if x.dtype != torch.float16 else cls.clone()
-            reg8 = reg8.to(x.dtype)
+            cls = cls.clone().to(out_dtype) if out_dtype != torch.float16 else cls.clone()
+            reg8 = reg8.to(out_dtype)
             return reg8[..., :4], reg8[..., 4:5], cls[..., :C]
         from .postprocess import head_assemble
-        return head_assemble(reg8, cls, C, self.head.hw, self.head.strides, self.head.decode_in_inference, x.dtype)
+        return head_assemble(reg8, cls, C, self.head.hw, self.head.strides, self.head.decode_in_inference, out_dtype)
 
 
 class _InferYOLOX(_EngineModel):

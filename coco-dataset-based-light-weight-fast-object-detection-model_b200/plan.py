@@ -316,12 +316,7 @@ class Engine:
         _capi.require_cuda(image, "image")
         if tuple(image.shape) != (g.batch, 3, g.in_h, g.in_w):
             raise RuntimeError(f"engine built for {(g.batch, 3, g.in_h, g.in_w)}, got {tuple(image.shape)}")
-        if image.dtype == torch.float16:
-            dt = _capi.YX_F16
-        elif image.dtype == torch.float32:
-            dt = _capi.YX_F32
-        else:
-            raise RuntimeError(f"unsupported image dtype {image.dtype}")
+        dt = _capi.image_dtype(image)
         image = image.contiguous()
         if not self.tuned:
             self.tuned = True
@@ -334,7 +329,7 @@ class Engine:
     def run_ops(self, image, first: int, count: int, in_scale: float = 1.0, in_shift: float = 0.0):
         """Diagnostic: run ops [first, first+count) only."""
         import torch
-        dt = _capi.YX_F16 if image.dtype == torch.float16 else _capi.YX_F32
+        dt = _capi.image_dtype(image)
         _capi.check(self.lib.yx_engine_run_ops(self.handle, image.contiguous().data_ptr(), dt, float(in_scale),
                                                float(in_shift), first, count, _capi.current_stream_ptr()),
                     "yx_engine_run_ops")
@@ -353,7 +348,7 @@ class Engine:
         import torch
         n = len(self.graph.ops)
         ms = (ctypes.c_float * n)(); fl = (ctypes.c_double * n)(); by = (ctypes.c_double * n)()
-        dt = _capi.YX_F16 if image.dtype == torch.float16 else _capi.YX_F32
+        dt = _capi.image_dtype(image)
         _capi.check(self.lib.yx_engine_profile(self.handle, image.contiguous().data_ptr(), dt, iters,
                                                _capi.current_stream_ptr(), ms, fl, by, n), "yx_engine_profile")
         return [dict(name=op.name, kind=op.kind, ms=ms[i], flops=fl[i], bytes=by[i], shape=self.op_desc(i))

@@ -42,7 +42,12 @@ typedef enum yx_act {  /* replaces: get_activation, yolox/models/network_blocks.
   YX_ACT_LRELU = 4     /* LeakyReLU(0.1) */
 } yx_act;
 
-typedef enum yx_dtype { YX_F16 = 0, YX_F32 = 1 } yx_dtype;
+typedef enum yx_dtype {
+  YX_F16 = 0,
+  YX_F32 = 1,
+  YX_U8 = 2   /* images only (engine input, yx_preprocess_batch output): pixel values 0..255, which is what the reference's
+                 float batches hold (PIL uint8 pixels); the engine evaluates them exactly as the same values in fp16 */
+} yx_dtype;
 
 typedef enum yx_op_kind {
   YX_OP_CONV = 0,      /* BaseConv.fused_forward: conv(k in {1,3}, stride in {1,2}; k = 4 with stride 2; pad (k-1)/2)+bias+act(+residual)

@@ -77,3 +77,26 @@ def test_predict_loop_with_device_io():
     recs = yb.io.convert_to_coco_format((det, cnt), [(h, w, f"x_{i}.jpg") for i, (h, w) in enumerate(info)], 128)
     assert len(recs) == sum(max(int(c), 1) for c in cnt.tolist())
     assert all(set(r) == {"image_id", "category_id", "bbox", "score"} for r in recs)
+
+
+def test_uint8_images_end_to_end():
+    """uint8 image batches (yx_dtype YX_U8): preprocess_batch can emit them and the engine consumes them, bit-identical to the
+    same pixel values passed as fp16 -- 4x fewer bytes than the reference's float32 batch on the host->device link."""
+    import yolox_b200 as yb
+    from oracle import model_ref as mr
+    rs = np.random.RandomState(3)
+    images = [rs.randint(0, 256, (h, w, 3), dtype=np.uint8) for h, w in ((120, 160), (97, 131))]
+    b8, info8 = yb.io.preprocess_batch(images, 128, "cuda", torch.uint8)
+    b16, info16 = yb.io.preprocess_batch(images, 128, "cuda", torch.float16)
+    assert b8.dtype == torch.uint8 and info8 == info16 and torch.equal(b8.half(), b16)
+    cfg = mr.CONFIGS["tiny_p6"]
+    model = yb.infer.YOLOXP6(cfg.depth, cfg.width, act=cfg.act, num_classes=cfg.num_classes)
+    model.load_state_dict(mr.fold_bn(mr.synth_train_state(cfg, 5, calib_hw=(128, 128))), strict=True)
+    model = model.cuda().half().eval()
+    pred = yb.predict.Predictor(model, conf_threshold=0.05)
+    d8, c8 = pred(b8)
+    d16, c16 = pred(b16)
+    assert torch.equal(c8, c16) and torch.equal(d8, d16)
+    r8, o8, k8 = model(b8)
+    r16, o16, k16 = model(b16)
+    assert r8.dtype == torch.float16 and torch.equal(r8, r16) and torch.equal(o8, o16) and torch.equal(k8, k16)
