@@ -25,15 +25,30 @@ def _stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compiles csrc/*.cu and links lib/libyolox_b200.so.  Safe under `torchrun --nproc-per-node N` on a fresh checkout:
+    an inter-process file lock serialises the build, staleness is re-checked once the lock is held (the other ranks find
+    the finished library), objects go to a per-process directory and the library is moved into place atomically, so no
+    process can ever dlopen a half-written file."""
     if not force and not _stale():
         return LIB
+    import fcntl
+    import tempfile
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    with open(os.path.join(os.path.dirname(LIB), ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():       # another process built it while this one waited for the lock
+                return LIB
+            return _build_locked(verbose, tempfile.mkdtemp(prefix=f"obj.{os.getpid()}.", dir=os.path.dirname(LIB)))
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool, build_dir: str) -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
+        shutil.rmtree(build_dir, ignore_errors=True)
         raise RuntimeError("nvcc not found: cannot build libyolox_b200.so (there is no fallback path)")
-    os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    objs = []
-    build_dir = os.path.join(_HERE, "lib", "obj")
-    os.makedirs(build_dir, exist_ok=True)
     # (source, extra defines, object name): yx_conv.cu is compiled once for planning / dispatch and once per activation
     # (-DYX_CONV_ACT_SLICE=<yx_act>), so its ~100 kernel instantiations build in parallel
     units = []
@@ -51,10 +66,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return obj
 
     from concurrent.futures import ThreadPoolExecutor
-    with ThreadPoolExecutor(max_workers=min(12, os.cpu_count() or 1)) as pool:   # translation units are independent
-        objs = list(pool.map(compile_one, units))
-    subprocess.check_call([nvcc, "-shared", "--cudart", "static", "-o", LIB] + objs)
-    shutil.rmtree(build_dir, ignore_errors=True)   # only the .so needs to travel with the tree
+    try:
+        with ThreadPoolExecutor(max_workers=min(12, os.cpu_count() or 1)) as pool:   # translation units are independent
+            objs = list(pool.map(compile_one, units))
+        tmp_lib = os.path.join(build_dir, "libyolox_b200.so.tmp")
+        subprocess.check_call([nvcc, "-shared", "--cudart", "static", "-o", tmp_lib] + objs)
+        os.replace(tmp_lib, LIB)                 # atomic: readers see the old library or the complete new one
+    finally:
+        shutil.rmtree(build_dir, ignore_errors=True)   # only the .so needs to travel with the tree
     return LIB
 
 

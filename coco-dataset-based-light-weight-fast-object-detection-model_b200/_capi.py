@@ -67,18 +67,22 @@ def make_levels(level_hw, strides) -> Levels:
 MAX_PEERS, IPC_HANDLE_BYTES = 8, 64
 
 
+PEER_WAIT_NONE, PEER_WAIT_AFTER, PEER_WAIT_BEFORE = 0, 1, 2
+
+
 class PeerOut(ctypes.Structure):
     """yx_peer_out (include/yolox_b200.h)."""
     _fields_ = [("world", ctypes.c_int32), ("wait_target", ctypes.c_int32), ("timeout_ms", ctypes.c_int32),
-                ("reserved", ctypes.c_int32), ("det", ctypes.c_void_p * MAX_PEERS), ("cnt", ctypes.c_void_p * MAX_PEERS),
-                ("arrive", ctypes.c_void_p * MAX_PEERS), ("local_arrive", ctypes.c_void_p), ("status", ctypes.c_void_p)]
+                ("wait_mode", ctypes.c_int32), ("det", ctypes.c_void_p * MAX_PEERS), ("cnt", ctypes.c_void_p * MAX_PEERS),
+                ("arrive", ctypes.c_void_p * MAX_PEERS), ("local_arrive", ctypes.c_void_p), ("status", ctypes.c_void_p),
+                ("wait_cnt", ctypes.c_void_p)]
 
 
 SYMBOLS = ["yx_last_error", "yx_abi_version", "yx_engine_create", "yx_engine_destroy", "yx_engine_run",
            "yx_engine_profile", "yx_engine_run_ops", "yx_engine_num_launches", "yx_engine_tune", "yx_engine_op_desc", "yx_engine_tune_mismatches",
-           "yx_conv2d", "yx_conv2d_ex", "yx_decode_infer", "yx_detect_workspace_bytes",
+           "yx_conv2d", "yx_conv2d_ex", "yx_decode_infer", "yx_decode_infer_grids", "yx_detect_workspace_bytes",
            "yx_nms_main", "yx_nms_main_ex", "yx_nms_workspace_bytes", "yx_detect_main",
-           "yx_detect_main_gather", "yx_ipc_export", "yx_ipc_open", "yx_ipc_close", "yx_head_assemble", "yx_decode_outputs", "yx_postprocess_yolox",
+           "yx_detect_main_gather", "yx_peer_wait", "yx_ipc_export", "yx_ipc_open", "yx_ipc_close", "yx_head_assemble", "yx_decode_outputs", "yx_postprocess_yolox",
            "yx_preprocess_batch", "yx_coco_records", "yx_cocoeval_bbox"]
 
 _lib = None
@@ -120,6 +124,7 @@ def load():
     lib.yx_engine_tune_mismatches.argtypes = [c_vp, ctypes.c_char_p, c_i32]
     logits = [c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64]
     lib.yx_decode_infer.argtypes = logits + [c_i32, c_i32, c_i32, c_i32, ctypes.POINTER(Levels), c_vp, c_vp, c_vp, c_vp]
+    lib.yx_decode_infer_grids.argtypes = logits + [c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]
     lib.yx_nms_main.argtypes = [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_f32, c_f32, c_i32, c_i32, c_i32, c_vp, c_sz,
                                 c_vp, c_vp, c_vp, c_vp]
     lib.yx_nms_main_ex.argtypes = [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_f32, c_f32, c_i32, c_i32, c_i32, c_i32, c_f32,
@@ -130,6 +135,7 @@ def load():
                                             c_i32, c_i32, c_vp, c_sz, c_vp, c_vp, c_vp, c_vp]
     lib.yx_detect_main_gather.argtypes = logits + [c_i32, c_i32, c_i32, c_i32, ctypes.POINTER(Levels), c_f32, c_f32, c_i32,
                                                    c_i32, c_i32, c_vp, c_sz, c_vp, c_vp, c_vp, ctypes.POINTER(PeerOut), c_vp]
+    lib.yx_peer_wait.argtypes = [c_vp, c_i32, c_i32, c_vp, c_i32, c_vp, c_i32, c_vp]
     lib.yx_ipc_export.argtypes = [c_vp, c_vp, ctypes.POINTER(c_i64)]
     lib.yx_ipc_open.argtypes = [c_vp, ctypes.POINTER(c_vp)]
     lib.yx_ipc_close.argtypes = [c_vp]
@@ -141,7 +147,7 @@ def load():
     lib.yx_coco_records.argtypes = [c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp]
     lib.yx_cocoeval_bbox.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp,
                                      c_i32, c_vp, c_vp, c_vp]
-    if lib.yx_abi_version() != 3:
+    if lib.yx_abi_version() != 4:
         raise RuntimeError("libyolox_b200.so ABI version mismatch")
     _lib = lib
     return lib

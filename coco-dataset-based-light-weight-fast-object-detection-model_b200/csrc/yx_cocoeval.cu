@@ -164,7 +164,10 @@ extern "C" int yx_cocoeval_bbox(const int64_t* gt_image, const int32_t* gt_categ
               if (all_match[t][o]) tp += 1; else fp += 1;
             }
             rc[j] = tp / (double)npig;
-            pr[j] = tp / (fp + tp + 2.220446049250313e-16);  // np.spacing(1)
+            // the reference's first choice is its C++ accelerator (coco_evaluator.py:204-205, cocoeval.cpp:332-335):
+            // precision = tp / (tp + fp) exactly, 0 while nothing counts; pycocotools' Python fallback divides by
+            // fp + tp + np.spacing(1) instead, one ulp away on some entries (oracle/cocoeval_ref.py keeps both forms)
+            pr[j] = (tp + fp) > 0 ? tp / (tp + fp) : 0.0;
           }
           Rc(t, k, a, m) = n ? rc[n - 1] : 0.0;
           for (int64_t j = n - 1; j > 0; --j)

@@ -13,6 +13,7 @@
 // the CPU restatement in oracle/post_ref.c.
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <string.h>
 
 #include <algorithm>
 
@@ -144,13 +145,24 @@ static size_t ws_layout(int B, int A, int K, int64_t R, uint8_t* base, Workspace
 template <typename T>
 __global__ void decode_infer_kernel(const T* __restrict__ reg, int64_t reg_sb, int64_t reg_sa, const T* __restrict__ obj,
                                     int64_t obj_sb, int64_t obj_sa, const T* __restrict__ cls, int64_t cls_sb,
-                                    int64_t cls_sa, int B, int A, int C, LevelsDev lv, float* __restrict__ boxes,
+                                    int64_t cls_sa, int B, int A, int C, LevelsDev lv, const void* __restrict__ grids,
+                                    const void* __restrict__ scales, int geom_dtype, float* __restrict__ boxes,
                                     float* __restrict__ obj_conf, float* __restrict__ cls_conf) {
   const int64_t total = (int64_t)B * A;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int a = i % A, b = i / A;
     float gx, gy, s;
-    anchor_geom(lv, a, &gx, &gy, &s);
+    if (grids != nullptr) {  // the caller's own grids (1,A,2) / scales (1,A,1) tensors, promoted to fp32 like torch does
+      if (geom_dtype == YX_F16) {
+        const __half* g = static_cast<const __half*>(grids) + 2 * a;
+        gx = __half2float(g[0]); gy = __half2float(g[1]); s = __half2float(static_cast<const __half*>(scales)[a]);
+      } else {
+        const float* g = static_cast<const float*>(grids) + 2 * a;
+        gx = g[0]; gy = g[1]; s = static_cast<const float*>(scales)[a];
+      }
+    } else {
+      anchor_geom(lv, a, &gx, &gy, &s);
+    }
     const T* r = reg + b * reg_sb + a * reg_sa;
     const float4 bx = decode_box_xyxy(ldf(r), ldf(r + 1), ldf(r + 2), ldf(r + 3), gx, gy, s);
     reinterpret_cast<float4*>(boxes)[i] = bx;
@@ -645,25 +657,44 @@ nms_kernel(Workspace ws, int A, float nms_thr, int max_nms, int max_det, int mod
   }
   if (po.world > 0) {
     if (tid < po.world) po.cnt[tid][b] = kept;
-    __threadfence_system();  // rows and count are visible system-wide before the arrival is counted
+    __threadfence_system();  // every thread: its own rows / count are ordered before what follows, system-wide
     __syncthreads();
-    if (tid < po.world) atomicAdd_system(po.arrive[tid], 1);
+    if (tid < po.world) {
+      __threadfence_system();  // release by the signalling thread AFTER the barrier (cumulative over the CTA's stores)
+      atomicAdd_system(po.arrive[tid], 1);
+    }
   }
 }
 
-// Completes the gather on the receiving side: returns (stream-ordered) once every rank's images of this step have
-// arrived in this GPU's window.  A bounded wait: on timeout *status is set and the kernel returns.
-__global__ void peer_wait_kernel(const int* arrive, int world, int target, int* status, long long timeout_cycles) {
+// Completes the gather on the receiving side: returns (stream-ordered) once every rank's images of the awaited step have
+// arrived in this GPU's window.  A bounded wait: on timeout *status = 1 + late rank, the late rank's counts in the
+// awaited window are zeroed (so no stale row can be read as a detection) and the kernel returns.
+__global__ void peer_wait_kernel(const int* arrive, int world, int target, int* status, long long timeout_cycles,
+                                 int* wait_cnt, int B) {
   const int lane = threadIdx.x;
   if (lane < world) {
     const long long t0 = clock64();
     const volatile int* f = arrive + lane;
     while (*f - target < 0) {  // counters only grow; difference form tolerates wrap-around
       __nanosleep(200);
-      if (clock64() - t0 > timeout_cycles) { atomicExch(status, 1 + lane); break; }
+      if (clock64() - t0 > timeout_cycles) {
+        atomicExch(status, 1 + lane);
+        if (wait_cnt != nullptr)
+          for (int i = 0; i < B; ++i) wait_cnt[lane * B + i] = 0;
+        break;
+      }
     }
   }
   __threadfence_system();
+}
+
+static int launch_peer_wait(const void* local_arrive, int world, int target, void* status, int timeout_ms, void* wait_cnt,
+                            int B, cudaStream_t st) {
+  const long long timeout = timeout_ms > 0 ? (long long)timeout_ms * 2000000ll : 20000000000ll;  // ~2 GHz
+  peer_wait_kernel<<<1, 32, 0, st>>>(static_cast<const int*>(local_arrive), world, target, static_cast<int*>(status), timeout,
+                                     static_cast<int*>(wait_cnt), B);
+  YX_CUDA(cudaGetLastError());
+  return YX_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -720,6 +751,27 @@ extern "C" size_t yx_nms_workspace_bytes(int B, int A, int C, int cand_mode, int
   return ws_layout(B, A, K, cand_rows(A, K, max_nms), nullptr, nullptr);
 }
 
+static int decode_infer_impl(const void* reg, int64_t reg_sb, int64_t reg_sa, const void* obj, int64_t obj_sb, int64_t obj_sa,
+                             const void* cls, int64_t cls_sb, int64_t cls_sa, int logits_dtype, int B, int A, int C,
+                             const LevelsDev& lv, const void* grids, const void* scales, int geom_dtype, float* boxes,
+                             float* obj_conf, float* cls_conf, void* stream) {
+  YX_REQUIRE(B >= 1 && C >= 1, "B, C must be positive");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int g = grid_for((int64_t)B * A, 256);
+  if (logits_dtype == YX_F16)
+    decode_infer_kernel<__half><<<g, 256, 0, st>>>((const __half*)reg, reg_sb, reg_sa, (const __half*)obj, obj_sb, obj_sa,
+                                                   (const __half*)cls, cls_sb, cls_sa, B, A, C, lv, grids, scales, geom_dtype,
+                                                   boxes, obj_conf, cls_conf);
+  else if (logits_dtype == YX_F32)
+    decode_infer_kernel<float><<<g, 256, 0, st>>>((const float*)reg, reg_sb, reg_sa, (const float*)obj, obj_sb, obj_sa,
+                                                  (const float*)cls, cls_sb, cls_sa, B, A, C, lv, grids, scales, geom_dtype,
+                                                  boxes, obj_conf, cls_conf);
+  else
+    YX_REQUIRE(false, "logits dtype must be YX_F16 or YX_F32");
+  YX_CUDA(cudaGetLastError());
+  return YX_OK;
+}
+
 extern "C" int yx_decode_infer(const void* reg, int64_t reg_sb, int64_t reg_sa, const void* obj, int64_t obj_sb,
                                int64_t obj_sa, const void* cls, int64_t cls_sb, int64_t cls_sa, int logits_dtype, int B,
                                int A, int C, const yx_levels* lv_host, float* boxes, float* obj_conf, float* cls_conf,
@@ -727,19 +779,22 @@ extern "C" int yx_decode_infer(const void* reg, int64_t reg_sb, int64_t reg_sa, 
   LevelsDev lv;
   int rc = make_levels(lv_host, A, &lv);
   if (rc) return rc;
-  YX_REQUIRE(B >= 1 && C >= 1, "B, C must be positive");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int g = grid_for((int64_t)B * A, 256);
-  if (logits_dtype == YX_F16)
-    decode_infer_kernel<__half><<<g, 256, 0, st>>>((const __half*)reg, reg_sb, reg_sa, (const __half*)obj, obj_sb, obj_sa,
-                                                   (const __half*)cls, cls_sb, cls_sa, B, A, C, lv, boxes, obj_conf, cls_conf);
-  else if (logits_dtype == YX_F32)
-    decode_infer_kernel<float><<<g, 256, 0, st>>>((const float*)reg, reg_sb, reg_sa, (const float*)obj, obj_sb, obj_sa,
-                                                  (const float*)cls, cls_sb, cls_sa, B, A, C, lv, boxes, obj_conf, cls_conf);
-  else
-    YX_REQUIRE(false, "logits dtype must be YX_F16 or YX_F32");
-  YX_CUDA(cudaGetLastError());
-  return YX_OK;
+  return decode_infer_impl(reg, reg_sb, reg_sa, obj, obj_sb, obj_sa, cls, cls_sb, cls_sa, logits_dtype, B, A, C, lv, nullptr,
+                           nullptr, YX_F32, boxes, obj_conf, cls_conf, stream);
+}
+
+// Same decode with the anchor geometry READ from the caller's grids (1,A,2) / scales (1,A,1) device tensors, exactly as
+// postprocess_utils.py:37-38 uses them (any values, e.g. a custom grid offset); no pyramid description is needed.
+extern "C" int yx_decode_infer_grids(const void* reg, int64_t reg_sb, int64_t reg_sa, const void* obj, int64_t obj_sb,
+                                     int64_t obj_sa, const void* cls, int64_t cls_sb, int64_t cls_sa, int logits_dtype, int B,
+                                     int A, int C, const void* grids, const void* scales, int geom_dtype, float* boxes,
+                                     float* obj_conf, float* cls_conf, void* stream) {
+  YX_REQUIRE(grids != nullptr && scales != nullptr, "grids / scales must be device pointers");
+  YX_REQUIRE(geom_dtype == YX_F16 || geom_dtype == YX_F32, "grids / scales dtype must be YX_F16 or YX_F32");
+  LevelsDev lv;
+  memset(&lv, 0, sizeof lv);
+  return decode_infer_impl(reg, reg_sb, reg_sa, obj, obj_sb, obj_sa, cls, cls_sb, cls_sa, logits_dtype, B, A, C, lv, grids,
+                           scales, geom_dtype, boxes, obj_conf, cls_conf, stream);
 }
 
 extern "C" int yx_nms_main_ex(const float* boxes, const float* obj_conf, const float* cls_conf, int B, int A, int C,
@@ -835,15 +890,29 @@ extern "C" int yx_detect_main_gather(const void* reg, int64_t reg_sb, int64_t re
     po.cnt[w] = static_cast<int*>(peer->cnt[w]);
     po.arrive[w] = static_cast<int*>(peer->arrive[w]);
   }
-  int rc = detect_main_impl(reg, reg_sb, reg_sa, obj, obj_sb, obj_sa, cls, cls_sb, cls_sa, logits_dtype, B, A, C, lv_host,
-                            conf_thr, nms_thr, max_nms, max_det, mode, workspace, workspace_bytes, det, det_count,
-                            det_anchor, stream, &po);
+  YX_REQUIRE(peer->wait_mode >= YX_PEER_WAIT_NONE && peer->wait_mode <= YX_PEER_WAIT_BEFORE, "peer: bad wait_mode");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc;
+  // BEFORE: the awaited step is an EARLIER one (its rows arrived while this step's network ran), so the wait costs nothing
+  // and no rank is lock-stepped to the slowest one; the consumer reads that earlier step's window after this call.
+  if (peer->wait_mode == YX_PEER_WAIT_BEFORE &&
+      (rc = launch_peer_wait(peer->local_arrive, peer->world, peer->wait_target, peer->status, peer->timeout_ms,
+                             peer->wait_cnt, B, st)) != YX_OK)
+    return rc;
+  rc = detect_main_impl(reg, reg_sb, reg_sa, obj, obj_sb, obj_sa, cls, cls_sb, cls_sa, logits_dtype, B, A, C, lv_host,
+                        conf_thr, nms_thr, max_nms, max_det, mode, workspace, workspace_bytes, det, det_count,
+                        det_anchor, stream, &po);
   if (rc) return rc;
-  const long long timeout = peer->timeout_ms > 0 ? (long long)peer->timeout_ms * 2000000ll : 20000000000ll;  // ~2 GHz
-  peer_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const int*>(peer->local_arrive), peer->world,
-                                                                   peer->wait_target, static_cast<int*>(peer->status), timeout);
-  YX_CUDA(cudaGetLastError());
+  if (peer->wait_mode == YX_PEER_WAIT_AFTER)
+    return launch_peer_wait(peer->local_arrive, peer->world, peer->wait_target, peer->status, peer->timeout_ms,
+                            peer->wait_cnt, B, st);
   return YX_OK;
+}
+
+extern "C" int yx_peer_wait(const void* local_arrive, int world, int wait_target, void* status, int timeout_ms,
+                            void* wait_cnt, int B, void* stream) {
+  YX_REQUIRE(local_arrive != nullptr && status != nullptr && world >= 1 && world <= YX_MAX_PEERS && B >= 0, "bad peer wait arguments");
+  return launch_peer_wait(local_arrive, world, wait_target, status, timeout_ms, wait_cnt, B, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int yx_head_assemble(const void* reg, int64_t reg_sb, int64_t reg_sa, const void* obj, int64_t obj_sb,

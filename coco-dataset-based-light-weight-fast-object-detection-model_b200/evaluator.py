@@ -65,7 +65,14 @@ class COCOEvaluator:
 
     # ---- coco_evaluator.py:51-133 ------------------------------------------------------------------------------
     def evaluate(self, model, distributed=False, half=False, trt_file=None, decoder=None, test_size=None):
-        """Returns (ap50_95, ap50, summary) on the main process, (0, 0, None) elsewhere."""
+        """Returns (ap50_95, ap50, summary) on the main process, (0, 0, None) elsewhere.
+
+        half=True deviation (deliberate): the reference keeps the whole post-processing in fp16 --
+        torchvision.batched_nms adds fp16 class offsets to fp16 boxes, and `bboxes /= scale`, `obj * cls` run in fp16 on
+        the CPU copy (coco_evaluator.py:147-157).  Here the scores / threshold of the selection are evaluated in fp16 like
+        the reference, but the IoU tests run in fp32 on the fp16 box values and the record arithmetic (unscale, xywh,
+        score product) runs in fp32: records and AP under half=True are therefore closer to the fp32 evaluation than the
+        reference's, not bit-identical to it.  With half=False everything is fp32 on both sides and the records agree."""
         if trt_file is not None:
             raise NotImplementedError("TensorRT engines (torch2trt) are outside this package; pass the model itself")
         model = model.eval()

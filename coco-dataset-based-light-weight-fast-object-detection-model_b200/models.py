@@ -286,8 +286,9 @@ class YOLOXHead(nn.Module):
     def initialize_biases(self, prior_prob):
         """yolo_head.py:120-129."""
         import math
-        for conv in list(self.cls_preds) + list(self.obj_preds):
-            conv.bias.data.fill_(-math.log((1 - prior_prob) / prior_prob))
+        with torch.no_grad():   # in-place on the parameter itself: bumps its version, so cached engines are rebuilt
+            for conv in list(self.cls_preds) + list(self.obj_preds):
+                conv.bias.fill_(-math.log((1 - prior_prob) / prior_prob))
 
     def emit(self, g: Graph, feats: List[V]) -> Tuple["Buf", "Buf", List[Tuple[int, int]]]:
         assert len(feats) == len(self.strides) == len(self.stems), \
@@ -344,7 +345,16 @@ class _EngineModel(nn.Module):
     max_engines = 4
 
     def _weights_version(self):
+        """Identity of the weights an engine was packed from.  In-place edits of a parameter bump `_version`; writes
+        through `p.data` do NOT (`.data` carries its own version counter) -- after such an edit call
+        invalidate_engines()."""
         return tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
+
+    def invalidate_engines(self):
+        """Drop every cached engine: the next forward repacks the current parameter values.  Needed only after weight
+        edits the version counters cannot see (`p.data.copy_(...)`, `p.data.fill_(...)`)."""
+        self.__dict__.pop("_engines", None)
+        return self
 
     def build_graph(self, batch: int, in_h: int, in_w: int) -> Graph:
         stride_max = max(self.head.strides)

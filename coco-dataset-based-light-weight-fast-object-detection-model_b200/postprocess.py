@@ -60,36 +60,44 @@ def yolox_generate_grid(img_size, strides=(8, 16, 32), dtype=torch.float32):
     return grids, scales
 
 
-_GEOM = {}
-
-
-def _geometry(grids: torch.Tensor, scales: torch.Tensor):
-    """Pyramid (level_hw, strides) recovered from a grids/scales pair (one small read-back, cached per
-    tensor: main.py:171-178 builds them once per image size and reuses them for every batch)."""
-    key = (grids.data_ptr(), scales.data_ptr(), grids.shape[1], str(grids.device))
-    if key not in _GEOM:
-        if len(_GEOM) > 64:
-            _GEOM.clear()
-        sc = scales.reshape(-1).float().cpu()
-        gr = grids.reshape(-1, 2).float().cpu()
-        vals, counts = torch.unique_consecutive(sc, return_counts=True)
-        hw, off = [], 0
-        for v, c in zip(vals.tolist(), counts.tolist()):
-            w = int(gr[off:off + c, 0].max().item()) + 1
-            hw.append((c // w, w)); off += c
-        _GEOM[key] = (hw, tuple(int(v) for v in vals.tolist()))
-    return _GEOM[key]
-
-
 def yolox_postprocess_output_torch_batch(reg_output, obj_output, cls_output, grids, scales):
-    """postprocess_utils.py:27-52: fp32 xyxy boxes [B,A,4], obj_conf [B,A,1], cls_conf [B,A,C]=sig(cls)*sig(obj)."""
+    """postprocess_utils.py:27-52: fp32 xyxy boxes [B,A,4], obj_conf [B,A,1], cls_conf [B,A,C]=sig(cls)*sig(obj).
+
+    The kernel READS `grids` (1,A,2) and `scales` (1,A,1) per anchor, as the reference's add_/mul_ do: nothing about
+    them is cached or inferred (main.py:171-178 rebinds both whenever the batch's (h, w) changes, and equal-sized
+    replacements tend to land on the same device addresses)."""
     lib = _capi.load()
     reg, obj, cls = _rows(reg_output), _rows(obj_output), _rows(cls_output)
     if not (reg.dtype == obj.dtype == cls.dtype):
         raise RuntimeError("reg/obj/cls must share a dtype")
     B, A, C = cls.shape
-    hw, strides = _geometry(grids, scales)
-    lv = _capi.make_levels(hw, strides)
+    _capi.require_cuda(grids, "grids")
+    _capi.require_cuda(scales, "scales")
+    if grids.numel() != 2 * A or scales.numel() != A:
+        raise RuntimeError(f"grids / scales must hold (1,{A},2) / (1,{A},1) values, got {tuple(grids.shape)} / {tuple(scales.shape)}")
+    if grids.dtype != scales.dtype:
+        scales = scales.to(grids.dtype)
+    if grids.dtype not in (torch.float16, torch.float32):
+        grids, scales = grids.float(), scales.float()
+    grids, scales = grids.contiguous(), scales.contiguous()
+    boxes = torch.empty(B, A, 4, dtype=torch.float32, device=cls.device)
+    obj_conf = torch.empty(B, A, 1, dtype=torch.float32, device=cls.device)
+    cls_conf = torch.empty(B, A, C, dtype=torch.float32, device=cls.device)
+    with torch.cuda.device(cls.device):
+        _capi.check(lib.yx_decode_infer_grids(reg.data_ptr(), reg.stride(0), reg.stride(1), obj.data_ptr(), obj.stride(0),
+                                              obj.stride(1), cls.data_ptr(), cls.stride(0), cls.stride(1), _dt(cls), B, A, C,
+                                              grids.data_ptr(), scales.data_ptr(), _dt(grids), boxes.data_ptr(),
+                                              obj_conf.data_ptr(), cls_conf.data_ptr(), _capi.current_stream_ptr()),
+                    "yx_decode_infer_grids")
+    return boxes, obj_conf, cls_conf
+
+
+def decode_infer(reg_output, obj_output, cls_output, level_hw, strides):
+    """The same decode from a pyramid description (level_hw, strides) instead of grids / scales tensors."""
+    lib = _capi.load()
+    reg, obj, cls = _rows(reg_output), _rows(obj_output), _rows(cls_output)
+    B, A, C = cls.shape
+    lv = _capi.make_levels(level_hw, strides)
     boxes = torch.empty(B, A, 4, dtype=torch.float32, device=cls.device)
     obj_conf = torch.empty(B, A, 1, dtype=torch.float32, device=cls.device)
     cls_conf = torch.empty(B, A, C, dtype=torch.float32, device=cls.device)

@@ -47,6 +47,7 @@ class Predictor:
         self.in_scale, self.in_shift, self.use_graph = in_scale, in_shift, use_graph
         self._gathers = {}
         self._peer_unavailable = False
+        self.peer_check_every = 32      # fused gather: host check of the peers' status word every N sharded steps
 
     @torch.no_grad()
     def __call__(self, img: torch.Tensor, gather=None) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -114,7 +115,11 @@ class Predictor:
                 self._peer_unavailable = True
         if g is not None:   # the NMS kernel stores its rows into every rank's window; no collective call on the data path
             self(mine, gather=g)
-            det_all, cnt_all = g.result()
+            det_all, cnt_all = g.result()      # completes THIS step (views valid until the next step is issued)
+            self._steps_since_check = getattr(self, "_steps_since_check", 0) + 1
+            if g.step == 1 or self._steps_since_check >= self.peer_check_every:
+                self._steps_since_check = 0
+                g.check()                      # host sync every N steps: a late / dead peer raises instead of going unnoticed
         else:
             det, cnt = self(mine)
             det_all, cnt_all = ydist.all_gather_detections(det, cnt)

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define YX_ABI_VERSION 3
+#define YX_ABI_VERSION 4
 
 typedef enum yx_status {
   YX_OK = 0,
@@ -182,6 +182,15 @@ int yx_decode_infer(const void* reg, int64_t reg_sb, int64_t reg_sa, const void*
                     const void* cls, int64_t cls_sb, int64_t cls_sa, int logits_dtype, int B, int A, int C,
                     const yx_levels* lv_host, float* boxes, float* obj_conf, float* cls_conf, void* stream);
 
+/* The same decode with the anchor geometry READ from the caller's device tensors grids (1,A,2) = (x, y) and
+ * scales (1,A,1), of dtype geom_dtype (YX_F16 / YX_F32, promoted to fp32 as torch promotes them): the values the
+ * caller built are the values used (a custom grid offset included), and no pyramid description has to be recovered.
+ * replaces: yolox_postprocess_output_torch_batch(reg, obj, cls, grids, scales), postprocess_utils.py:27-52. */
+int yx_decode_infer_grids(const void* reg, int64_t reg_sb, int64_t reg_sa, const void* obj, int64_t obj_sb,
+                          int64_t obj_sa, const void* cls, int64_t cls_sb, int64_t cls_sa, int logits_dtype, int B, int A,
+                          int C, const void* grids, const void* scales, int geom_dtype, float* boxes, float* obj_conf,
+                          float* cls_conf, void* stream);
+
 /* Workspace (bytes) for the detection entry points below. */
 size_t yx_detect_workspace_bytes(int B, int A);
 
@@ -240,26 +249,39 @@ int yx_ipc_export(const void* dev_ptr, void* handle_out, int64_t* offset_out);
 int yx_ipc_open(const void* handle, void** base_out);
 int yx_ipc_close(void* base);
 
+enum { YX_PEER_WAIT_NONE = 0, YX_PEER_WAIT_AFTER = 1, YX_PEER_WAIT_BEFORE = 2 };
+
 typedef struct yx_peer_out {
   int32_t world;                /* number of ranks (1..YX_MAX_PEERS), own rank included */
-  int32_t wait_target;          /* value every local arrival counter reaches when the step's images are all here:
-                                   step_index * B (counters are never reset) */
+  int32_t wait_target;          /* value every local arrival counter reaches when the awaited step's images are all here:
+                                   step_index * B as a wrapping 32-bit counter (counters are never reset) */
   int32_t timeout_ms;           /* bound of the device-side wait (<= 0: 10 s); on expiry *status = 1 + late rank */
-  int32_t reserved;
+  int32_t wait_mode;            /* YX_PEER_WAIT_AFTER: wait for THIS step's rows right after the NMS (lock-step);
+                                   YX_PEER_WAIT_BEFORE: wait for an EARLIER step (wait_target) before this step's selection
+                                   kernels: its rows arrived while this step's network ran, nobody waits for the slowest rank;
+                                   YX_PEER_WAIT_NONE: no wait in this call (yx_peer_wait completes the step on demand) */
   void* det[YX_MAX_PEERS];      /* this rank's [B,max_det,7] fp32 block inside rank w's window */
   void* cnt[YX_MAX_PEERS];      /* this rank's [B] int32 block inside rank w's window */
   void* arrive[YX_MAX_PEERS];   /* rank w's int32 arrival counter for this rank */
   void* local_arrive;           /* this rank's own int32[world] counters */
   void* status;                 /* int32 in this rank's memory, 0 while healthy */
+  void* wait_cnt;               /* [world,B] int32 counts of the AWAITED window in this rank's memory (a late rank's counts
+                                   are zeroed on timeout), or NULL */
 } yx_peer_out;
 
-/* yx_detect_main + the gather described above.  Requires max_det > 0 and the same B on every rank.  The caller
- * alternates between two windows on consecutive steps (a rank can run at most one step ahead of its peers). */
+/* yx_detect_main + the gather described above.  Requires max_det > 0 and the same B on every rank.  The caller rotates
+ * over THREE windows on consecutive steps: with YX_PEER_WAIT_BEFORE a rank may run one whole step ahead of a peer, and a
+ * window is overwritten three steps later, after every reader of it has issued its next step. */
 int yx_detect_main_gather(const void* reg, int64_t reg_sb, int64_t reg_sa, const void* obj, int64_t obj_sb, int64_t obj_sa,
                           const void* cls, int64_t cls_sb, int64_t cls_sa, int logits_dtype, int B, int A, int C,
                           const yx_levels* lv_host, float conf_thr, float nms_thr, int max_nms, int max_det, int mode,
                           void* workspace, size_t workspace_bytes, float* det, int32_t* det_count, int32_t* det_anchor,
                           const yx_peer_out* peer, void* stream);
+
+/* Stream-ordered completion of one gathered step on the receiving side (the wait yx_detect_main_gather performs in its
+ * AFTER / BEFORE modes, on demand): returns once every rank's B images counted by wait_target have arrived. */
+int yx_peer_wait(const void* local_arrive, int world, int wait_target, void* status, int timeout_ms, void* wait_cnt, int B,
+                 void* stream);
 
 /* yolox-package head output: out[B,A,5+C] = [reg, sigmoid(obj), sigmoid(cls)] in `out_dtype`, then
  * (decode != 0) decoded in place like decode_outputs.

@@ -4,9 +4,11 @@
 
 pycocotools is a third-party dependency (requirements.txt: "pycocotools>=2.0.2", unpinned) and is NOT installed in this
 image, so this file restates its published algorithm function by function (COCOeval._prepare, computeIoU, evaluateImg,
-accumulate, summarize; maskApi bbIou for the box IoU) -- PARITY UNPINNED: there is no pycocotools here to run against.
-It is cross-checked against hand-computed cases in tests/test_cocoeval.py and serves as the independent checker of the
-product's native implementation (csrc/yx_cocoeval.cu), which is structured differently on purpose.
+accumulate, summarize; maskApi bbIou for the box IoU).  PIN: evaluateImg + accumulate are checked bit for bit against the
+reference's OWN C++ COCO evaluation compiled into oracle/_ref (oracle/cocoeval_cpp.py, tests/test_cocoeval.py);
+_prepare / computeIoU / summarize remain restated third-party code (grouping, the box IoU formula, twelve means).
+It also carries hand-computed cases (tests/test_cocoeval.py) and is the independent checker of the product's native
+implementation (csrc/yx_cocoeval.cu), which is structured differently on purpose.
 """
 from collections import defaultdict
 
@@ -31,9 +33,14 @@ def bb_iou(d, g, crowd):
     return i / u
 
 
-def evaluate(gts, dts, img_ids, cat_ids):
+def evaluate(gts, dts, img_ids, cat_ids, cpp_precision=True):
     """gts: list of dict(image_id, category_id, bbox [x,y,w,h], area, iscrowd); dts: list of dict(image_id, category_id,
-    bbox, score).  Returns dict(stats [12], precision [T,R,K,A,M], recall [T,K,A,M])."""
+    bbox, score).  Returns dict(stats [12], precision [T,R,K,A,M], recall [T,K,A,M]).
+
+    cpp_precision: the reference evaluator first tries its C++ accelerator (yolox/evaluators/coco_evaluator.py:204-205),
+    whose precision is tp / (tp + fp) exactly (yolox/layers/csrc/cocoeval/cocoeval.cpp:332-335); False gives pycocotools'
+    Python form tp / (fp + tp + np.spacing(1)), the fallback when the extension is not built.  The two differ by one ulp
+    on some table entries (found by pinning this file against the compiled reference, oracle/cocoeval_cpp.py)."""
     img_ids = list(np.unique(img_ids))
     cat_ids = list(np.unique(cat_ids))
     _gts, _dts = defaultdict(list), defaultdict(list)
@@ -126,7 +133,11 @@ def evaluate(gts, dts, img_ids, cat_ids):
                     tp, fp = np.array(tp), np.array(fp)
                     nd = len(tp)
                     rc = tp / npig
-                    pr = tp / (fp + tp + np.spacing(1))
+                    if cpp_precision:
+                        with np.errstate(invalid="ignore", divide="ignore"):
+                            pr = np.where(tp + fp > 0, tp / (tp + fp), 0.0)
+                    else:
+                        pr = tp / (fp + tp + np.spacing(1))
                     q = np.zeros((R,))
                     recall[t, k, a, m] = rc[-1] if nd else 0
                     pr = pr.tolist()

@@ -1,6 +1,8 @@
 """COCO bbox evaluation: hand-computed known answers for the oracle (pycocotools is not installed: parity unpinned,
 see oracle/cocoeval_ref.py), then the native implementation (csrc/yx_cocoeval.cu through the C ABI, host code — runs
 without a GPU) against the oracle on randomised datasets with crowds, all area ranges, ties and > 100 detections."""
+import os
+
 import numpy as np
 import pytest
 
@@ -104,3 +106,42 @@ def test_accepts_coco_json_and_objects():
     c = cr.evaluate(gts, dts, [1, 2, 3, 4], [1, 2])["stats"]
     np.testing.assert_array_equal(a, b)
     np.testing.assert_allclose(a, c, rtol=0, atol=1e-12)
+
+
+def _cpp():
+    """The reference's compiled COCOeval (oracle/_ref): built on demand where /root/reference exists."""
+    from oracle import cocoeval_cpp as cc
+    if not cc.available():
+        if not os.path.isdir(cc.REF_SRC):
+            pytest.skip("oracle/_ref is not built and the reference tree is not here")
+        cc.build()
+    return cc
+
+
+@pytest.mark.parametrize("seed,n_img,n_cat,max_gt,max_dt,ties", [(0, 12, 3, 6, 10, False), (1, 5, 2, 3, 160, False),
+                                                                 (2, 20, 5, 8, 12, True), (3, 3, 1, 0, 4, False),
+                                                                 (7, 40, 6, 10, 30, True), (8, 6, 2, 12, 220, False)])
+def test_reference_cpp_pins_matching_and_accumulation(seed, n_img, n_cat, max_gt, max_dt, ties):
+    """Pins row N3: the reference's own cocoeval.cpp (EvaluateImages :140, Accumulate :370), compiled into oracle/_ref,
+    gives the same precision / recall tables -- bit for bit -- as the restatement and as the native yx_cocoeval_bbox."""
+    cc = _cpp()
+    gts, dts = _random_dataset(seed, n_img, n_cat, max_gt, max_dt, ties)
+    imgs, cats = list(range(1, n_img + 1)), list(range(1, n_cat + 1))
+    want = cc.evaluate(gts, dts, imgs, cats)
+    ref = cr.evaluate(gts, dts, imgs, cats)
+    np.testing.assert_array_equal(ref["precision"], want["precision"])
+    np.testing.assert_array_equal(ref["recall"], want["recall"])
+    ev = yb.cocoeval.COCOevalBBox(gts, dts, imgs, cats).evaluate()
+    np.testing.assert_array_equal(ev.precision, want["precision"])
+    np.testing.assert_array_equal(ev.recall, want["recall"])
+
+
+def test_reference_cpp_known_answers():
+    cc = _cpp()
+    gts = [_gt(1, 1, (0, 0, 100, 100)), _gt(1, 1, (200, 200, 100, 100), crowd=1)]
+    dts = [_dt(1, 1, (0, 0, 100, 100), 0.9), _dt(1, 1, (210, 210, 50, 50), 0.8), _dt(1, 1, (25, 0, 100, 100), 0.7)]
+    want = cc.evaluate(gts, dts, [1], [1])
+    ev = yb.cocoeval.COCOevalBBox(gts, dts, [1], [1]).evaluate()
+    np.testing.assert_array_equal(ev.precision, want["precision"])
+    np.testing.assert_array_equal(ev.recall, want["recall"])
+    assert want["recall"][0, 0, 0, 2] == 1.0

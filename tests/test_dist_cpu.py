@@ -28,6 +28,12 @@ def test_pack_roundtrip():
     assert torch.equal(d2, det) and torch.equal(c2, cnt)
 
 
+def test_wrap_i32_matches_device_counter():
+    wrap_i32 = ydist.wrap_i32
+    assert wrap_i32(5) == 5 and wrap_i32(2 ** 31 - 1) == 2 ** 31 - 1
+    assert wrap_i32(2 ** 31) == -2 ** 31 and wrap_i32(2 ** 32 + 7) == 7
+
+
 def _worker(rank, world, port, n_images, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)

@@ -207,21 +207,70 @@ def test_score_monotonic_in_logit():
         assert bool((s[1:] >= s[:-1]).all()), f"score not monotone for obj logit {o}"
 
 
-def test_nms_fused_gather_single_rank():
+@pytest.mark.parametrize("pipelined", [True, False], ids=["pipelined", "lockstep"])
+def test_nms_fused_gather_single_rank(pipelined):
     """yx_detect_main_gather with world = 1: the NMS tail stores into this GPU's own window, the wait kernel sees the
-    arrivals; both window parities and growing arrival targets are exercised.  (N = 2 over NVLink: tools/dist_check.py.)"""
+    arrivals; all three windows, growing arrival targets, the deferred (BEFORE) and the in-step (AFTER) wait and the
+    on-demand yx_peer_wait are exercised.  (N = 2 over NVLink: tools/dist_check.py.)"""
     g = np.load(FILES[0])
     img, strides = int(g["img"]), [int(s) for s in g["strides"]]
     hw = [(img // s, img // s) for s in strides]
     reg, obj, cls = (torch.from_numpy(g[k]).to(DEV) for k in ("reg", "obj", "cls"))
     B = reg.shape[0]
-    want = yb.postprocess.detect_main(reg, obj, cls, hw, strides, float(g["conf"]), float(g["nms_thr"]))
-    pg = yb.dist.PeerGather(B, 300, DEV, timeout_ms=2000)
-    for it in range(3):
-        det, cnt, _ = yb.postprocess.detect_main(reg, obj, cls, hw, strides, float(g["conf"]), float(g["nms_thr"]), gather=pg)
+    conf, thr = float(g["conf"]), float(g["nms_thr"])
+    want = yb.postprocess.detect_main(reg, obj, cls, hw, strides, conf, thr)
+    # a second, different input: consecutive steps must land in different windows
+    reg2 = reg.flip(0).contiguous()
+    obj2, cls2 = obj.flip(0).contiguous(), cls.flip(0).contiguous()
+    want2 = yb.postprocess.detect_main(reg2, obj2, cls2, hw, strides, conf, thr)
+    pg = yb.dist.PeerGather(B, 300, DEV, timeout_ms=2000, pipelined=pipelined)
+    for it in range(7):
+        a = (reg, obj, cls, want) if it % 2 == 0 else (reg2, obj2, cls2, want2)
+        det, cnt, _ = yb.postprocess.detect_main(a[0], a[1], a[2], hw, strides, conf, thr, gather=pg)
+        assert torch.equal(det, a[3][0]) and torch.equal(cnt, a[3][1])
+        if it >= 1:     # the previous step's window is complete without any further wait (and was not overwritten)
+            prev = want2 if it % 2 == 0 else want
+            dp, cp = pg.result(lag=1)
+            assert torch.equal(dp, prev[0]) and torch.equal(cp, prev[1]), f"previous window differs at step {it}"
         da, ca = pg.result()
-        assert torch.equal(det, want[0]) and torch.equal(cnt, want[1])
-        assert torch.equal(da, want[0]) and torch.equal(ca, want[1]), f"window differs at step {it}"
+        assert torch.equal(da, a[3][0]) and torch.equal(ca, a[3][1]), f"window differs at step {it}"
     assert pg.status() == 0
+    pg.check()
+    with pytest.raises(RuntimeError):
+        pg.result(lag=2)
     with pytest.raises(ValueError):
         pg.next_step(B + 1, 300)
+
+
+def test_decode_alternating_grid_shapes():
+    """main.py:171-178 rebinds grids / scales whenever the batch's (h, w) changes; a 512x640 batch and a 640x512 batch have
+    the same anchor count and their freed tensors are typically re-issued at the same device addresses (a cache
+    keyed on data_ptr decoded the second shape with the first shape's level widths).  The decode must follow the VALUES of
+    the tensors it is given, also when they are edited in place or carry a custom offset."""
+    strides = (8, 16, 32)
+    rng = np.random.default_rng(3)
+    for it in range(6):
+        h, w = (512, 640) if it % 2 == 0 else (640, 512)
+        hw = [(h // s, w // s) for s in strides]
+        A = sum(a * b for a, b in hw)
+        reg = rng.normal(0, 1, (2, A, 4)).astype(np.float32)
+        obj = rng.normal(0, 2, (2, A, 1)).astype(np.float32)
+        cls = rng.normal(0, 2, (2, A, 5)).astype(np.float32)
+        grids, scales = yb.postprocess.yolox_generate_grid((h, w), strides, torch.float32)
+        grids, scales = grids.to(DEV), scales.to(DEV)           # new tensors every iteration, old ones freed
+        got = yb.postprocess.yolox_postprocess_output_torch_batch(*(torch.from_numpy(a).to(DEV) for a in (reg, obj, cls)), grids, scales)
+        for b in range(2):
+            rb, ro, rc = pr.decode_infer(reg[b], obj[b], cls[b], hw, strides)
+            np.testing.assert_allclose(got[0][b].cpu().numpy(), rb, rtol=3e-6, atol=2e-4, err_msg=f"iteration {it} ({h}x{w})")
+            np.testing.assert_allclose(got[2][b].cpu().numpy(), rc, rtol=6e-6, atol=1e-7)
+        del grids, scales, got
+    # in-place edit / custom offset: boxes move by exactly offset * stride
+    grids, scales = (t.to(DEV) for t in yb.postprocess.yolox_generate_grid((64, 96), strides, torch.float32))
+    A = grids.shape[1]
+    r, o, c = torch.zeros(1, A, 4, device=DEV), torch.zeros(1, A, 1, device=DEV), torch.zeros(1, A, 3, device=DEV)
+    b0 = yb.postprocess.yolox_postprocess_output_torch_batch(r, o, c, grids, scales)[0]
+    grids.add_(0.5)
+    b1 = yb.postprocess.yolox_postprocess_output_torch_batch(r, o, c, grids, scales)[0]
+    assert torch.equal(b1 - b0, (0.5 * scales).expand(1, A, 4).contiguous())
+    with pytest.raises(RuntimeError):
+        yb.postprocess.yolox_postprocess_output_torch_batch(r, o, c, grids[:, :-1], scales)
