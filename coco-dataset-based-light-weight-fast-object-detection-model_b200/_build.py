@@ -11,6 +11,17 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-Xcompiler", "-fPIC", "--cudart", "static"]
 
 
+def kernel_rev() -> str:
+    """Revision of the conv kernels and their planner: launch shapes persisted by the tuner (plan.TuneCache) are valid
+    for exactly this revision."""
+    import hashlib
+    h = hashlib.sha1()
+    for name in ("yx_conv.cu", "yx_internal.h", "yx_ptx.cuh"):
+        with open(os.path.join(CSRC, name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:12]
+
+
 def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 

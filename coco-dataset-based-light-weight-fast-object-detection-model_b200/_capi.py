@@ -49,7 +49,20 @@ class ConvTune(ctypes.Structure):
     """Mirror of yx_conv_tune (include/yolox_b200.h)."""
     _fields_ = [("variant", c_i32), ("n_tile", c_i32), ("ctas_per_sm", c_i32), ("halves", c_i32),
                 ("epilogue_groups", c_i32), ("staging_buffers", c_i32), ("second_producer", c_i32),
-                ("no_resident_weights", c_i32), ("cta_pair", c_i32)]
+                ("no_resident_weights", c_i32), ("cta_pair", c_i32), ("sparse", c_i32), ("reserved", c_i32 * 2)]
+
+    FIELDS = ("variant", "n_tile", "ctas_per_sm", "halves", "epilogue_groups", "staging_buffers", "second_producer",
+              "no_resident_weights", "cta_pair", "sparse")
+
+    def as_list(self):
+        return [int(getattr(self, f)) for f in self.FIELDS]
+
+    @classmethod
+    def from_list(cls, vals):
+        t = cls()
+        for f, v in zip(cls.FIELDS, vals):
+            setattr(t, f, int(v))
+        return t
 
 
 class Levels(ctypes.Structure):
@@ -79,7 +92,7 @@ class PeerOut(ctypes.Structure):
 
 
 SYMBOLS = ["yx_last_error", "yx_abi_version", "yx_engine_create", "yx_engine_destroy", "yx_engine_run",
-           "yx_engine_profile", "yx_engine_run_ops", "yx_engine_num_launches", "yx_engine_tune", "yx_engine_op_desc", "yx_engine_tune_mismatches",
+           "yx_engine_profile", "yx_engine_run_ops", "yx_engine_num_launches", "yx_engine_tune", "yx_engine_get_tune", "yx_engine_set_tune", "yx_engine_op_desc", "yx_engine_tune_mismatches",
            "yx_conv2d", "yx_conv2d_ex", "yx_decode_infer", "yx_decode_infer_grids", "yx_detect_workspace_bytes",
            "yx_nms_main", "yx_nms_main_ex", "yx_nms_workspace_bytes", "yx_detect_main",
            "yx_detect_main_gather", "yx_peer_wait", "yx_ipc_export", "yx_ipc_open", "yx_ipc_close", "yx_head_assemble", "yx_decode_outputs", "yx_postprocess_yolox",
@@ -120,6 +133,8 @@ def load():
     lib.yx_conv2d.argtypes = [ctypes.POINTER(Op), c_vp, c_vp, c_vp, c_vp]
     lib.yx_conv2d_ex.argtypes = [ctypes.POINTER(Op), c_vp, c_vp, c_vp, ctypes.POINTER(ConvTune), c_vp]
     lib.yx_engine_tune.argtypes = [c_vp, c_vp, c_i32, c_f32, c_f32, c_i32, c_vp]
+    lib.yx_engine_get_tune.argtypes = [c_vp, c_i32, ctypes.POINTER(ConvTune)]
+    lib.yx_engine_set_tune.argtypes = [c_vp, c_i32, ctypes.POINTER(ConvTune)]
     lib.yx_engine_op_desc.argtypes = [c_vp, c_i32, ctypes.c_char_p, c_i32]
     lib.yx_engine_tune_mismatches.argtypes = [c_vp, ctypes.c_char_p, c_i32]
     logits = [c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64]

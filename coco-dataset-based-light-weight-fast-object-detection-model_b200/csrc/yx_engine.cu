@@ -240,7 +240,6 @@ extern "C" int yx_engine_tune(yx_engine* e, const void* image, int image_dtype, 
     // fp32 accumulation order => at most a few fp16 steps apart); a candidate that does not is reported and rejected.
     void* check_ref = nullptr;
     unsigned int* check_bits = nullptr;
-    float check_scale = 0.f;
     if (check) {
       const size_t n_el = (size_t)s.op.dst.n * s.op.dst.h * s.op.dst.w * s.op.dst.c;
       ConvPlan ref_plan = s.conv;
@@ -258,15 +257,17 @@ extern "C" int yx_engine_tune(yx_engine* e, const void* image, int image_dtype, 
       if ((rc = conv_launch(pl, st)) != YX_OK) break;  // warm-up (also sets the smem attribute)
       if (check) {
         unsigned int bits = 0;
-        if ((rc = view_max_diff(e->arena, s.op.dst, check_ref, check_bits, st)) != YX_OK) break;
+        // a conv that adds a separately loaded residual rounds f(x) to fp16 before the add: a one-step difference of f(x)
+        // can be many steps of a small x + f(x), so the step is measured at the activations' O(1) magnitude there
+        const float floor_mag = (s.conv.p.has_res == 1) ? 4.0f : 0.0625f;
+        if ((rc = view_max_diff(e->arena, s.op.dst, check_ref, floor_mag, check_bits, st)) != YX_OK) break;
         cudaMemcpyAsync(&bits, check_bits, 4, cudaMemcpyDeviceToHost, st);
         cudaStreamSynchronize(st);
         float d;
         memcpy(&d, &bits, 4);
-        (void)check_scale;
-        if (d > 0.26f) {   // activations are O(1): a wrong tile / tap / barrier shows as O(1)+ differences or NaN
+        if (d > 2.0f) {   // same products, other fp32 summation order: at most two fp16 rounding steps apart
           char msg[400];
-          snprintf(msg, sizeof msg, "tune check: op %zu candidate '%s' differs from the default shape by %g", i, pl.desc, d);
+          snprintf(msg, sizeof msg, "tune check: op %zu candidate '%s' differs from the default shape by %g fp16 steps", i, pl.desc, d);
           fprintf(stderr, "%s\n", msg);
           e->tune_mismatches.push_back(msg);
           continue;
@@ -305,6 +306,46 @@ extern "C" int yx_engine_tune(yx_engine* e, const void* image, int image_dtype, 
   if (rc == YX_OK) YX_CUDA(cudaStreamSynchronize(st));
   e->tuned = rc == YX_OK;
   return rc;
+}
+
+static ConvTune tune_from_abi(const yx_conv_tune& a) {
+  ConvTune t;
+  memset(&t, 0, sizeof t);
+  t.variant = a.variant; t.bn = a.n_tile; t.ctas = a.ctas_per_sm; t.mh = a.halves;
+  t.epi_groups = a.epilogue_groups; t.stage_bufs = a.staging_buffers; t.w3 = a.second_producer;
+  t.no_resident = a.no_resident_weights; t.pair = a.cta_pair; t.sparse = a.sparse;
+  return t;
+}
+static yx_conv_tune tune_to_abi(const ConvTune& t) {
+  yx_conv_tune a;
+  memset(&a, 0, sizeof a);
+  a.variant = t.variant; a.n_tile = t.bn; a.ctas_per_sm = t.ctas; a.halves = t.mh;
+  a.epilogue_groups = t.epi_groups; a.staging_buffers = t.stage_bufs; a.second_producer = t.w3;
+  a.no_resident_weights = t.no_resident; a.cta_pair = t.pair; a.sparse = t.sparse;
+  return a;
+}
+
+extern "C" int yx_engine_get_tune(const yx_engine* e, int i, yx_conv_tune* out_host) {
+  YX_REQUIRE(e && out_host && i >= 0 && i < (int)e->steps.size(), "bad op index");
+  YX_REQUIRE(e->steps[i].op.kind == YX_OP_CONV, "not a conv op");
+  *out_host = tune_to_abi(e->steps[i].conv.tune);
+  return YX_OK;
+}
+
+extern "C" int yx_engine_set_tune(yx_engine* e, int i, const yx_conv_tune* tune_host) {
+  YX_REQUIRE(e && tune_host && i >= 0 && i < (int)e->steps.size(), "bad op index");
+  Step& s = e->steps[i];
+  YX_REQUIRE(s.op.kind == YX_OP_CONV, "not a conv op");
+  const ConvTune t = tune_from_abi(*tune_host);
+  ConvPlan pl;
+  int rc = conv_plan(s.op, e->arena, e->weights, e->biases, e->num_sms, &t, &pl);
+  if (rc != YX_OK) return rc;
+  s.conv = pl;
+  if (e->graph_exec) {  // a graph captured with the old shape is stale
+    cudaGraphExecDestroy(e->graph_exec);
+    e->graph_exec = nullptr;
+  }
+  return YX_OK;
 }
 
 extern "C" int yx_engine_tune_mismatches(const yx_engine* e, char* buf_host, int buf_len) {
@@ -375,12 +416,7 @@ extern "C" int yx_conv2d_ex(const yx_op* op, void* base, const void* weights, co
   YX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   ConvPlan plan;
   ConvTune t;
-  if (tune) {
-    memset(&t, 0, sizeof t);
-    t.variant = tune->variant; t.bn = tune->n_tile; t.ctas = tune->ctas_per_sm; t.mh = tune->halves;
-    t.epi_groups = tune->epilogue_groups; t.stage_bufs = tune->staging_buffers; t.w3 = tune->second_producer;
-    t.no_resident = tune->no_resident_weights; t.pair = tune->cta_pair;
-  }
+  if (tune) t = tune_from_abi(*tune);
   int rc = conv_plan(*op, base, weights, biases, sms, tune ? &t : nullptr, &plan);
   if (rc) return rc;
   if (getenv("YX_CONV_TRACE")) {  // diagnostics: print the per-tile timeline of CTA 0 (cycles)

@@ -72,6 +72,7 @@ struct ConvTune {
   int w3;           // 0: no second producer warp, otherwise pick automatically
   int no_resident;  // 1: never keep the weights resident (experiments)
   int pair;         // 1: CTA-pair mode (cta_group::2)
+  int sparse;       // 1: 2:4 sparse tensor-core variant (weights = sparse A operand of tcgen05.mma.sp)
 };
 
 struct ConvPlan {
@@ -97,6 +98,8 @@ int spp_launch(void* base, const yx_view& src, const yx_view& dst, cudaStream_t 
 int upsample_launch(void* base, const yx_view& src, const yx_view& dst, cudaStream_t stream);
 int dwconv_launch(void* base, const yx_op& op, const void* weights, const void* biases, cudaStream_t stream);
 int view_gather(void* base, const yx_view& v, void* out_contiguous, cudaStream_t stream);
-int view_max_diff(void* base, const yx_view& v, const void* ref_contiguous, unsigned int* out_bits, cudaStream_t stream);
+// max |view - ref| in fp16 rounding steps at the larger operand's magnitude (>= floor_mag), as the bits of a float
+int view_max_diff(void* base, const yx_view& v, const void* ref_contiguous, float floor_mag, unsigned int* out_bits,
+                  cudaStream_t stream);
 
 }  // namespace yx

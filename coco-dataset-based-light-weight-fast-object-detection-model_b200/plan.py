@@ -274,6 +274,71 @@ class Graph:
         return t
 
 
+class TuneCache:
+    """Persists the launch shapes yx_engine_tune picked, so that they -- and with them the fp32 summation order and the
+    low bits of every result -- are the same from run to run (the counterpart of cuDNN's benchmark cache, which the
+    reference re-fills on every start, tools/eval.py:122).
+
+    One JSON file: {"<device name>|<kernel revision>": {"<layer geometry incl. batch>": [yx_conv_tune fields]}}.
+    Location: $YX_TUNE_CACHE, else tune_cache.json next to this file (shipped with the shapes measured on this pool's
+    B200s); YX_TUNE_CACHE=0 disables it, YX_TUNE=force re-tunes and overwrites, YX_TUNE=0 keeps the heuristic shapes.
+    An engine uses the cache only when EVERY conv of it has an entry that still plans; otherwise it tunes and the file
+    is rewritten atomically."""
+
+    def __init__(self):
+        env = os.environ.get("YX_TUNE_CACHE", "")
+        self.enabled = env != "0"
+        self.path = env if env not in ("", "0", "1") else os.path.join(os.path.dirname(os.path.abspath(__file__)), "tune_cache.json")
+
+    @staticmethod
+    def op_key(op: "PlannedOp", batch: int) -> str:
+        def v(x):
+            return "-" if x is None else f"{x.H}x{x.W}x{x.c}p{x.buf.c}" + (f"@{x.lvl_off}" if x.lvl_off or x.nstride else "")
+        inplace = op.res is not None and op.res.buf is op.dst.buf and op.res.c_off == op.dst.c_off
+        return (f"b{batch} k{op.ksize} s{op.stride} act{op.act} aux{op.aux} cin{op.cin_pad} cout{op.cout_pad} "
+                f"src{v(op.src)} dst{v(op.dst)} res{'inplace' if inplace else v(op.res)} up{v(op.up)}")
+
+    def section(self, device) -> str:
+        import torch
+        from . import _build
+        return f"{torch.cuda.get_device_name(device)}|{_build.kernel_rev()}"
+
+    def load(self, device) -> Dict[str, list]:
+        import json
+        if not self.enabled or not os.path.exists(self.path):
+            return {}
+        try:
+            with open(self.path) as f:
+                return json.load(f).get(self.section(device), {})
+        except (OSError, ValueError):
+            return {}
+
+    def store(self, device, entries: Dict[str, list]):
+        import fcntl
+        import json
+        if not self.enabled or os.environ.get("YX_TUNE_CACHE_WRITE", "1") == "0":
+            return
+        try:
+            with open(self.path + ".lock", "w") as lock:
+                fcntl.flock(lock, fcntl.LOCK_EX)
+                data = {}
+                if os.path.exists(self.path):
+                    try:
+                        with open(self.path) as f:
+                            data = json.load(f)
+                    except ValueError:
+                        data = {}
+                sec = self.section(device)
+                data = {sec: data.get(sec, {})}          # shapes of other kernel revisions are dead weight
+                data[sec].update(entries)
+                tmp = f"{self.path}.{os.getpid()}.tmp"
+                with open(tmp, "w") as f:
+                    json.dump(data, f, indent=0, sort_keys=True)
+                os.replace(tmp, self.path)
+        except OSError:
+            pass                                          # a read-only tree: the shapes simply are not persisted
+
+
 class Engine:
     """Owns the device arena / weight blobs and the native engine handle for one (B, H, W)."""
 
@@ -302,6 +367,7 @@ class Engine:
         # per-layer launch shapes are picked by measurement on the first real input (like cudnn.benchmark);
         # YX_TUNE=0 keeps the heuristic shapes
         self.tuned = os.environ.get("YX_TUNE", "1") == "0"
+        self.shape_source = "heuristic"     # -> "cache" (persisted shapes loaded) or "tuned" (measured in this process)
 
     def tensor_of(self, buf: Buf):
         """fp16 torch view [n, h, w, c] of an arena buffer (no copy)."""
@@ -320,11 +386,50 @@ class Engine:
         image = image.contiguous()
         if not self.tuned:
             self.tuned = True
-            _capi.check(self.lib.yx_engine_tune(self.handle, image.data_ptr(), dt, float(in_scale), float(in_shift),
-                                                int(os.environ.get("YX_TUNE_ITERS", "3")), _capi.current_stream_ptr()),
-                        "yx_engine_tune")
+            if not self._shapes_from_cache():
+                _capi.check(self.lib.yx_engine_tune(self.handle, image.data_ptr(), dt, float(in_scale), float(in_shift),
+                                                    int(os.environ.get("YX_TUNE_ITERS", "3")), _capi.current_stream_ptr()),
+                            "yx_engine_tune")
+                self.shape_source = "tuned"
+                self._shapes_to_cache()
         _capi.check(self.lib.yx_engine_run(self.handle, image.data_ptr(), dt, float(in_scale), float(in_shift),
                                            int(use_graph), _capi.current_stream_ptr()), "yx_engine_run")
+
+    # ---- persisted launch shapes (TuneCache) -----------------------------------------------------------------
+    def _conv_ops(self):
+        return [(i, op) for i, op in enumerate(self.graph.ops) if op.kind == _capi.OP_CONV]
+
+    def _shapes_from_cache(self) -> bool:
+        import ctypes
+        if os.environ.get("YX_TUNE", "1") == "force" or os.environ.get("YX_TUNE_CHECK"):
+            return False
+        cache = TuneCache()
+        entries = cache.load(self.device)
+        convs = self._conv_ops()
+        keys = [TuneCache.op_key(op, self.graph.batch) for _, op in convs]
+        if not entries or any(k not in entries for k in keys):
+            return False
+        previous = []
+        for (i, _), k in zip(convs, keys):
+            t = _capi.ConvTune()
+            self.lib.yx_engine_get_tune(self.handle, i, ctypes.byref(t))
+            previous.append(t)
+            new = _capi.ConvTune.from_list(entries[k])
+            if self.lib.yx_engine_set_tune(self.handle, i, ctypes.byref(new)) != 0:
+                for (j, _), old in zip(convs, previous):      # a stale entry: back to the heuristic shapes, then tune
+                    self.lib.yx_engine_set_tune(self.handle, j, ctypes.byref(old))
+                return False
+        self.shape_source = "cache"
+        return True
+
+    def _shapes_to_cache(self):
+        import ctypes
+        entries = {}
+        for i, op in self._conv_ops():
+            t = _capi.ConvTune()
+            _capi.check(self.lib.yx_engine_get_tune(self.handle, i, ctypes.byref(t)), "yx_engine_get_tune")
+            entries[TuneCache.op_key(op, self.graph.batch)] = t.as_list()
+        TuneCache().store(self.device, entries)
 
     def run_ops(self, image, first: int, count: int, in_scale: float = 1.0, in_shift: float = 0.0):
         """Diagnostic: run ops [first, first+count) only."""

@@ -126,23 +126,6 @@ int yx_engine_profile(yx_engine* e, const void* image, int image_dtype, int iter
                       float* ms_host, double* flops_host, double* bytes_host, int n_ops);
 int yx_engine_num_launches(const yx_engine* e); /* kernels launched by one yx_engine_run */
 
-/* Per-layer launch-shape selection by measurement (the counterpart of torch.backends.cudnn.benchmark = True, which
- * the reference sets in tools/eval.py:122).  Runs the network once on `image`, timing every candidate shape of every
- * conv on its real inputs (min of `iters` CUDA-event timings) and keeping the fastest; the arena holds a valid forward
- * result afterwards.  Host-synchronising setup call. */
-int yx_engine_tune(yx_engine* e, const void* image, int image_dtype, float in_scale, float in_shift, int iters,
-                   void* stream);
-/* With YX_TUNE_CHECK=1 in the environment yx_engine_tune also verifies that every candidate shape reproduces the default
- * shape's output; returns the number of candidates that did not (and were rejected) and their descriptions. */
-int yx_engine_tune_mismatches(const yx_engine* e, char* buf_host, int buf_len);
-/* Human-readable description of op i and of the launch shape chosen for it (diagnostics / profiles). */
-int yx_engine_op_desc(const yx_engine* e, int i, char* buf_host, int buf_len);
-
-/* ---- stand-alone operators (used by tests and by the reference-style Python functions) ---------- */
-
-/* One conv op outside an engine (same kernel the engine launches). Views are relative to `base`. */
-int yx_conv2d(const yx_op* op_host, void* base, const void* weights, const void* biases, void* stream);
-
 /* Launch-shape knobs of the conv kernel (see csrc/yx_conv.cu).  yx_engine_tune picks them per layer by timing;
  * yx_conv2d_ex lets the parity tests force every shape.  A shape that does not fit the layer is YX_ERR_INVALID. */
 typedef struct yx_conv_tune {
@@ -155,7 +138,35 @@ typedef struct yx_conv_tune {
   int32_t second_producer;     /* 0 = one TMA producer warp per operand, 1 = add a second one */
   int32_t no_resident_weights; /* 1 = always stream the weights through the ring */
   int32_t cta_pair;            /* 1 = two-CTA clusters issuing cta_group::2 MMAs (M = 256), half of the weights per CTA */
+  int32_t sparse;              /* 1 = the 2:4 sparse tensor-core variant (tcgen05.mma.sp, weights as the sparse A operand);
+                                  only valid for a layer whose weights are 2:4-compliant along Cin */
+  int32_t reserved[2];         /* 0 */
 } yx_conv_tune;
+
+/* Per-layer launch-shape selection by measurement (the counterpart of torch.backends.cudnn.benchmark = True, which
+ * the reference sets in tools/eval.py:122).  Runs the network once on `image`, timing every candidate shape of every
+ * conv on its real inputs (min of `iters` CUDA-event timings) and keeping the fastest; the arena holds a valid forward
+ * result afterwards.  Host-synchronising setup call. */
+int yx_engine_tune(yx_engine* e, const void* image, int image_dtype, float in_scale, float in_shift, int iters,
+                   void* stream);
+/* With YX_TUNE_CHECK=1 in the environment yx_engine_tune also verifies that every candidate shape reproduces the default
+ * shape's output; returns the number of candidates that did not (and were rejected) and their descriptions. */
+int yx_engine_tune_mismatches(const yx_engine* e, char* buf_host, int buf_len);
+/* Launch shape currently selected for conv op i (YX_ERR_INVALID for a non-conv op) / force one.  Together they let the
+ * caller PERSIST the tuner's choices (yolox_b200/plan.py keeps them in a cache file keyed by device, kernel revision and
+ * layer geometry) so that launch shapes -- and with them the fp32 summation order, i.e. the low bits of the result -- are
+ * reproducible from run to run.  yx_engine_set_tune re-plans the op; a shape that does not fit is YX_ERR_INVALID and
+ * leaves the op unchanged.  yx_engine_mark_tuned tells the engine not to tune again. */
+int yx_engine_get_tune(const yx_engine* e, int i, yx_conv_tune* out_host);
+int yx_engine_set_tune(yx_engine* e, int i, const yx_conv_tune* tune_host);
+/* Human-readable description of op i and of the launch shape chosen for it (diagnostics / profiles). */
+int yx_engine_op_desc(const yx_engine* e, int i, char* buf_host, int buf_len);
+
+/* ---- stand-alone operators (used by tests and by the reference-style Python functions) ---------- */
+
+/* One conv op outside an engine (same kernel the engine launches). Views are relative to `base`. */
+int yx_conv2d(const yx_op* op_host, void* base, const void* weights, const void* biases, void* stream);
+
 int yx_conv2d_ex(const yx_op* op_host, void* base, const void* weights, const void* biases, const yx_conv_tune* tune_host,
                  void* stream);
 

@@ -109,7 +109,7 @@ def test_errors():
 
 
 def test_peer_out_struct_matches_header():
-    """ctypes mirror of yx_peer_out: 4 int32 + 3 pointer tables of YX_MAX_PEERS + 2 pointers."""
+    """ctypes mirror of yx_peer_out: 4 int32 + 3 pointer tables of YX_MAX_PEERS + 3 pointers; yx_conv_tune: 12 int32."""
     import ctypes
     import os
     import re
@@ -117,4 +117,42 @@ def test_peer_out_struct_matches_header():
     hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "yolox_b200.h")).read()
     assert int(re.search(r"#define YX_MAX_PEERS (\d+)", hdr).group(1)) == _capi.MAX_PEERS
     assert int(re.search(r"#define YX_IPC_HANDLE_BYTES (\d+)", hdr).group(1)) == _capi.IPC_HANDLE_BYTES
-    assert ctypes.sizeof(_capi.PeerOut) == 16 + 3 * 8 * _capi.MAX_PEERS + 16
+    assert ctypes.sizeof(_capi.PeerOut) == 16 + 3 * 8 * _capi.MAX_PEERS + 24
+    body = re.search(r"typedef struct yx_peer_out \{(.*?)\} yx_peer_out;", hdr, re.S).group(1)
+    names = re.findall(r"(?:int32_t|void\*)\s+(\w+)(?:\[YX_MAX_PEERS\])?;", body)
+    assert names == [f[0] for f in _capi.PeerOut._fields_], names
+    body = re.search(r"typedef struct yx_conv_tune \{(.*?)\} yx_conv_tune;", hdr, re.S).group(1)
+    names = re.findall(r"int32_t\s+(\w+)(?:\[\d+\])?;", body)
+    assert names == [f[0] for f in _capi.ConvTune._fields_], names
+    assert ctypes.sizeof(_capi.ConvTune) == 48
+
+
+def test_tune_cache_roundtrip(tmp_path, monkeypatch):
+    """plan.TuneCache: keys are per layer geometry and batch, files are rewritten atomically, other kernel revisions are
+    dropped; the device name is only needed for the section, so a fake one is injected (no GPU here)."""
+    from yolox_b200 import plan
+    monkeypatch.setenv("YX_TUNE_CACHE", str(tmp_path / "tc.json"))
+    monkeypatch.setattr(plan.TuneCache, "section", lambda self, device: "fake B200|rev1")
+    cfg, model = _infer_model("tiny_p6")
+    g1, g2 = model.build_graph(1, 64, 64), model.build_graph(2, 64, 64)
+    convs = [op for op in g1.ops if op.kind == 0]
+    k1 = [plan.TuneCache.op_key(op, 1) for op in convs]
+    k2 = [plan.TuneCache.op_key(op, 2) for op in g2.ops if op.kind == 0]
+    assert len(set(k1)) <= len(k1) and not set(k1) & set(k2)          # batch is part of the key
+    assert any("inplace" in k for k in k1) and any("up" in k and "up-" not in k for k in k1)
+    c = plan.TuneCache()
+    assert c.load(None) == {}
+    c.store(None, {k1[0]: [1, 64, 1, 1, 1, 2, 1, 0, 0, 0]})
+    c.store(None, {k1[1]: [2, 96, 1, 2, 1, 2, 1, 0, 0, 0]})
+    got = plan.TuneCache().load(None)
+    assert got == {k1[0]: [1, 64, 1, 1, 1, 2, 1, 0, 0, 0], k1[1]: [2, 96, 1, 2, 1, 2, 1, 0, 0, 0]}
+    monkeypatch.setattr(plan.TuneCache, "section", lambda self, device: "fake B200|rev2")
+    assert plan.TuneCache().load(None) == {}
+    plan.TuneCache().store(None, {k1[0]: [1, 128, 1, 1, 1, 2, 1, 0, 0, 0]})
+    import json
+    assert list(json.load(open(tmp_path / "tc.json"))) == ["fake B200|rev2"]
+    monkeypatch.setenv("YX_TUNE_CACHE", "0")
+    assert plan.TuneCache().load(None) == {}
+    from yolox_b200 import _capi
+    t = _capi.ConvTune.from_list([2, 96, 1, 2, 1, 2, 1, 0, 1, 0])
+    assert t.as_list() == [2, 96, 1, 2, 1, 2, 1, 0, 1, 0] and t.cta_pair == 1
