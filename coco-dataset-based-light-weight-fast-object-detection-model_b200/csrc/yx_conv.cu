@@ -126,6 +126,45 @@ __device__ __forceinline__ void epilogue_convert(uint32_t taddr, int bn_cur, int
   }
 }
 
+// ---- sparse (transposed) epilogue: the accumulator holds output CHANNELS on the TMEM lanes and the tile's PIXELS on the
+// columns, so a thread owns one channel: bias is one register, and 16 loaded columns are 16 pixels of that channel.  The
+// staging tile keeps the dense layout (one 128-byte swizzled row per pixel and 64-channel group), written with 2-byte
+// stores: the 32 lanes of a warp are 32 consecutive channels of one pixel = 64 contiguous bytes, conflict-free.
+template <int ACT, bool HAS_RES>
+__device__ __forceinline__ void convert16_sp(const uint32_t (&v)[16], int p0, float bias, uint32_t cbase, uint32_t cchunk) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const uint32_t addr = cbase + (p0 + i) * 128 + ((cchunk ^ (uint32_t)(i & 7)) << 4);   // p0 is a multiple of 16
+    float f = apply_act<ACT>(__uint_as_float(v[i]) + bias);
+    if (HAS_RES) {  // half + half as torch computes it (see convert16)
+      unsigned short r;
+      asm volatile("ld.shared.u16 %0, [%1];" : "=h"(r) : "r"(addr));
+      f = __half2float(__float2half_rn(f)) + __half2float(__ushort_as_half(r));
+    }
+    const unsigned short o = __half_as_ushort(__float2half_rn(f));
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(o) : "memory");
+  }
+}
+template <int ACT, bool HAS_RES>
+__device__ __forceinline__ void epilogue_convert_sp(uint32_t taddr, int npix, int ch, bool ch_valid, float bias, uint32_t sStage,
+                                                    int group, int groups) {
+  const uint32_t cbase = sStage + (ch >> 6) * kTileBytes + (ch & 7) * 2;
+  const uint32_t cchunk = (uint32_t)(ch & 63) >> 3;
+  const int nch = (npix + 15) >> 4;
+  for (int j = group; j < nch; j += 2 * groups) {
+    const int j2 = j + groups;
+    const bool two = j2 < nch;  // warp-uniform
+    uint32_t v0[16], v1[16];
+    tmem_ld_32x32b_x16(taddr + j * 16, v0);
+    if (two) tmem_ld_32x32b_x16(taddr + j2 * 16, v1);
+    tmem_ld_wait();
+    if (ch_valid) {
+      convert16_sp<ACT, HAS_RES>(v0, j * 16, bias, cbase, cchunk);
+      if (two) convert16_sp<ACT, HAS_RES>(v1, j2 * 16, bias, cbase, cchunk);
+    }
+  }
+}
+
 // optional per-tile timeline (diagnostics): trace[tile_local * 8 + event] = clock64(), CTA 0 only
 #define YX_TRACE(ev, tl)                                                                          \
   do {                                                                                            \
@@ -194,13 +233,47 @@ __device__ __forceinline__ void commit_x(uint32_t bar) {
 
 // RP: the row-packed stem (3 vertical taps over rows of TW = 8 pixels whose 128-byte smem row already holds the three
 // horizontal neighbours): the halo box is (TH+2) x 8 rows, tap dy starts dy*8 rows (= one swizzle atom) later, SBO = 1024.
-template <int MH, bool RING, bool PAIR, bool RP>
+// SP (2:4 sparse variant): the weights are the sparse A operand and the pixels the B operand of tcgen05.mma.sp; ksteps counts
+// K = 32 steps (at most two per 64-channel chunk), the weight rows advance 32 bytes and the pixel rows 64 bytes per step,
+// e_addr is the TMEM address of the metadata column of (tap 0, this chunk, step 0), consecutive taps are e_step columns apart.
+template <int MH, bool RING, bool PAIR, bool RP, bool SP>
 __device__ __forceinline__ void halo_chunk_mma(uint32_t d0, uint32_t d1, uint32_t a0, uint32_t a_hi, uint32_t& b_lo, uint32_t b_hi,
                                                uint32_t idesc, uint32_t& accum, int ksteps, uint32_t bar_fb, uint32_t bar_eb,
                                                uint32_t& sb, uint32_t& phb, uint32_t b_slots, uint32_t b_lo0, uint32_t b_step,
-                                               bool wait_b, bool tracing, long long& w_acc, bool skip_mma) {
+                                               bool wait_b, bool tracing, long long& w_acc, bool skip_mma, uint32_t e_addr,
+                                               uint32_t e_step) {
   constexpr int TAPS = RP ? 3 : 9;
   constexpr int HW = RP ? 8 : kHaloW;  // halo row width in pixels
+  if (SP) {
+#pragma unroll
+    for (int tap = 0; tap < TAPS; ++tap) {
+      const uint32_t a_tap = a0 + ((tap / 3) * HW + (tap % 3)) * 8;
+      if (RING || wait_b) {
+        mbar_wait_acc(bar_fb + 8 * sb, phb, tracing, w_acc);
+        tc_fence_after();
+      }
+      if (elect_one()) {
+        if (!skip_mma) {
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks)
+            if (ks < ksteps)
+            {
+              const uint32_t col = e_addr + tap * e_step + ks;   // even-aligned column address + 1-bit selector
+              umma_f16_sp_ss_lohi(d0, b_lo + 2 * ks, b_hi, a_tap + 4 * ks, a_hi, col & ~1u, idesc | (col & 1u), ks == 0 ? accum : 1u);
+            }
+        }
+        if (RING) commit_x<false>(bar_eb + 8 * sb);
+      }
+      accum = 1;
+      b_lo += b_step;
+      if (RING) {
+        if (++sb == b_slots) { sb = 0; phb ^= 1; b_lo = b_lo0; }
+      } else {
+        ++sb;
+      }
+    }
+    return;
+  }
   if (!RING && !wait_b) {
     // resident weights already in shared memory: nothing to wait for inside the chunk, so the whole 9-tap sequence
     // is ONE elected straight-line block (no per-tap elect / branch / reconvergence)
@@ -272,8 +345,11 @@ __device__ __forceinline__ void halo_chunk_mma(uint32_t d0, uint32_t d1, uint32_
 // RES:  0 = no residual; 1 = residual tile TMA-loaded into the staging buffer and added in registers;
 //       2 = the residual IS the destination (Bottleneck y = x + f(x) computed in place): the tile is stored with a TMA
 //           reduce-add, so the residual never passes through shared memory and the epilogue never waits for it
-template <int ACT, int RES, int MODE, bool PAIR>
+// SP:   2:4 sparse tensor-core variant (MODE 0 / 1, no pair): weights = sparse A operand of tcgen05.mma.sp (M = 128 output
+//       channels per MMA), pixels = B operand (N = 128), accumulator transposed (channels on lanes, pixels on columns)
+template <int ACT, int RES, int MODE, bool PAIR, bool SP = false>
 __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant__ ConvParams p) {
+  static_assert(!SP || (!PAIR && (MODE == 0 || MODE == 1)), "sparse variant: generic or single-half halo tiles, no CTA pair");
   constexpr bool HAS_RES = RES == 1;
   constexpr bool HALO = MODE == 1 || MODE == 2 || MODE == 4 || MODE == 5;
   constexpr bool RP = MODE >= 4;
@@ -327,6 +403,20 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  if (SP) {
+    // sparsity metadata of every output-channel tile -> tensor memory, once per CTA (weights are constants: this also
+    // overlaps the previous layer's tail).  Warp w of the first epilogue group owns TMEM lanes 32 * (w % 4) .. + 31.
+    if (warp >= 4 && warp < 8) {
+      const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + (uint32_t)p.sp_meta_col0;
+      const uint32_t* src = p.sp_meta + (warp & 3) * 32 + lane;
+      const int ncol = p.n_tiles_n * p.sp_cols_per_tile;
+      for (int c = 0; c < ncol; ++c) tmem_st_32x32b_x1(lane_addr + c, __ldg(src + c * 128));
+      tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
 
   // PAIR: the tile space is walked in units of CTA pairs; CTA `rank` owns the x-tile 2*tx + rank of every pair tile
   const int n_tiles = p.n_tiles_m * p.n_tiles_n;
@@ -460,7 +550,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
                 tma_load_3d_2sm(sB + s * b_stage_bytes, &p.tmW, bar_fb + 8 * s, kc * 64, tap, n0);
               } else {
                 mbar_expect_tx(bar_fb + 8 * s, b_stage_bytes);
-                tma_load_3d(sB + s * b_stage_bytes, &p.tmW, bar_fb + 8 * s, kc * 64, tap, n0);
+                tma_load_3d(sB + s * b_stage_bytes, &p.tmW, bar_fb + 8 * s, kc * (SP ? 32 : 64), tap, n0);  // SP: compressed rows
               }
             }
           }
@@ -473,11 +563,11 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
   } else if (warp == 1 && rank == 0) {
     // ================================ MMA issuer (leader CTA only in PAIR mode) ================================
     uint32_t t = 0, sa = 0, pha = 0, sb = 0, phb = 0;
-    const uint32_t a_hi = sdesc_hi(HALO && !RP ? kHaloW * 128 : 1024), b_hi = sdesc_hi(1024);
+    const uint32_t a_hi = sdesc_hi(HALO && !RP ? kHaloW * 128 : 1024), b_hi = SP ? sdesc_hi_sw64(512) : sdesc_hi(1024);
     const uint32_t a_lo0 = sdesc_lo(sA), a_step = p.a_stage_bytes >> 4;
     const uint32_t b_lo0 = sdesc_lo(sB), b_step = p.b_stage_bytes >> 4;
     uint32_t a_lo = a_lo0, b_lo = b_lo0;
-    const int ks_last = (p.cin - (k_chunks - 1) * 64) >> 4;
+    const int ks_last = SP ? (p.cin - (k_chunks - 1) * 64) >> 5 : (p.cin - (k_chunks - 1) * 64) >> 4;  // SP: K = 32 steps
     const int BN = p.BN, cout16 = p.cout16;
     const uint32_t acc_stride = p.acc_stride;
     const bool shared_ring = p.shared_ring != 0;
@@ -485,10 +575,12 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
     int nt = tile_first % n_tiles_n;
     for (int tile = tile_first; tile < n_tiles; tile += tile_step, ++t) {
       const int n0 = nt * BN;
+      // SP: first metadata column of this output-channel tile (one column per (tap, K = 32 step); tmem_base has column 0)
+      const uint32_t e_tile = SP ? tmem_base + (uint32_t)(p.sp_meta_col0 + nt * p.sp_cols_per_tile) : 0u;
       nt += p.step_nt;
       if (nt >= n_tiles_n) nt -= n_tiles_n;
       const int bn_cur = min(BN, cout16 - n0);
-      const uint32_t idesc = PAIR ? make_idesc_f16_m256(bn_cur) : make_idesc_f16(bn_cur);
+      const uint32_t idesc = SP ? make_idesc_f16_sp(128, 0) : (PAIR ? make_idesc_f16_m256(bn_cur) : make_idesc_f16(bn_cur));
       const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
       mbar_wait_acc(bar_tempty + 8 * acc, acc_ph ^ 1, tracing, w_acc2);
       tc_fence_after();
@@ -500,13 +592,14 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
         for (int kc = 0; kc < k_chunks; ++kc) {
           mbar_wait_acc(bar_fa + 8 * sa, pha, tracing, w_acc0);
           tc_fence_after();
-          const int ksteps = (kc == k_chunks - 1) ? ks_last : 4;
+          const int ksteps = (kc == k_chunks - 1) ? ks_last : (SP ? 2 : 4);
+          const uint32_t e_chunk = e_tile + 2u * (uint32_t)kc, e_step = (uint32_t)p.cin >> 5;
           if (resident)
-            halo_chunk_mma<MH, false, PAIR, RP>(d0, d1, a_lo, a_hi, b_lo, b_hi, idesc, accum, ksteps, bar_fb, bar_eb, sb, phb, b_slots, b_lo0,
-                                      b_step, !b_ready, tracing, w_acc1, (p.diag & 4) != 0);
+            halo_chunk_mma<MH, false, PAIR, RP, SP>(d0, d1, a_lo, a_hi, b_lo, b_hi, idesc, accum, ksteps, bar_fb, bar_eb, sb, phb, b_slots,
+                                                    b_lo0, b_step, !b_ready, tracing, w_acc1, (p.diag & 4) != 0, e_chunk, e_step);
           else
-            halo_chunk_mma<MH, true, PAIR, RP>(d0, d1, a_lo, a_hi, b_lo, b_hi, idesc, accum, ksteps, bar_fb, bar_eb, sb, phb, b_slots, b_lo0,
-                                     b_step, true, tracing, w_acc1, (p.diag & 4) != 0);
+            halo_chunk_mma<MH, true, PAIR, RP, SP>(d0, d1, a_lo, a_hi, b_lo, b_hi, idesc, accum, ksteps, bar_fb, bar_eb, sb, phb, b_slots,
+                                                   b_lo0, b_step, true, tracing, w_acc1, (p.diag & 4) != 0, e_chunk, e_step);
           if (elect_one()) commit_x<PAIR>(bar_ea + 8 * sa);
           a_lo += a_step;
           if (++sa == stages_a) { sa = 0; pha ^= 1; a_lo = a_lo0; }
@@ -515,6 +608,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
         const int k_iters = taps * k_chunks;
         const uint32_t half_units = (uint32_t)(p.TH / 2 * p.TW) * 8;  // MODE 3: second half starts (TH/2)*TW rows of 128 B later
         int kc = 0;
+        uint32_t sp_col = 0;   // SP: metadata column of the current (tap, chunk), relative to the tile's first column
         for (int i = 0; i < k_iters; ++i) {
           mbar_wait_acc(bar_fa + 8 * sa, pha, tracing, w_acc0);   // shared ring: covers the weights of this k-iteration too
           if (resident && !b_ready) mbar_wait_acc(bar_fb + 8 * sb, phb, tracing, w_acc1);
@@ -523,6 +617,13 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
           if (last) kc = 0;
           if (elect_one()) {
             if (p.diag & 4) {
+            } else if (SP) {  // metadata column of (tap, chunk, step) = tap * (cin / 32) + 2 * chunk + step
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks)
+                if (ks == 0 || !last || ks_last == 2) {
+                  const uint32_t col = e_tile + sp_col + ks;
+                  umma_f16_sp_ss_lohi(d0, b_lo + 2 * ks, b_hi, a_lo + 4 * ks, a_hi, col & ~1u, idesc | (col & 1u), ks == 0 ? accum : 1u);
+                }
             } else if (!last || ks_last == 4) {
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
@@ -540,6 +641,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
             commit_x<PAIR>(bar_ea + 8 * sa);  // frees the stage (A, and B when the ring is shared) when these MMAs retire
           }
           accum = 1;
+          if (SP) sp_col += last ? (uint32_t)ks_last : 2u;
           a_lo += a_step;
           b_lo += b_step;
           if (++sa == stages_a) { sa = 0; pha ^= 1; a_lo = a_lo0; if (shared_ring) b_lo = b_lo0; }
@@ -605,7 +707,15 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
         }
         if (HAS_RES) mbar_wait(bar_res + 8 * buf, (stage_bufs == 2 ? (u >> 1) : u) & 1);
         const uint32_t taddr = tmem_base + (acc * MH + h) * acc_stride + (static_cast<uint32_t>(q * 32) << 16);
-        if (!(p.diag & 1)) epilogue_convert<ACT, HAS_RES>(taddr, bn_cur, row, row_valid, sStage, sBias + tc.n0 * 4, group, epi_groups);
+        if (SP) {
+          if (!(p.diag & 1)) {
+            float bias = 0.0f;
+            if (row < bn_cur) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(bias) : "r"(sBias + (tc.n0 + row) * 4));
+            epilogue_convert_sp<ACT, HAS_RES>(taddr, HALO ? 128 : p.TH * p.TW, row, row < bn_cur, bias, sStage, group, epi_groups);
+          }
+        } else if (!(p.diag & 1)) {
+          epilogue_convert<ACT, HAS_RES>(taddr, bn_cur, row, row_valid, sStage, sBias + tc.n0 * 4, group, epi_groups);
+        }
         if (h == MH - 1) {  // accumulator drained -> MMA warp may overwrite it
           tc_fence_before();
           __syncwarp();
@@ -675,7 +785,7 @@ static EncodeTiledFn get_encode() {
 
 // rank-r fp16 tensor map; dims/strides innermost first; strides[0] implied (2 bytes)
 static int encode_map(CUtensorMap* m, void* addr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                      const uint32_t* box, bool swizzle128, const char* what) {
+                      const uint32_t* box, bool swizzle128, const char* what, bool swizzle64 = false) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
@@ -691,7 +801,7 @@ static int encode_map(CUtensorMap* m, void* addr, int rank, const uint64_t* dims
     if (i > 0) gs[i - 1] = strides_bytes[i];
   }
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, addr, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : (swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[512];
@@ -795,9 +905,30 @@ static bool halo_ok(const yx_op& op, const ConvGeom& g) {
   return eff16 <= 1.25;
 }
 
+constexpr int kSpMetaCol0 = 256, kSpMetaColsMax = 256;  // TMEM: two 128-column accumulators, then the metadata
+
+// Geometry the 2:4 sparse variant supports: a plain conv (no row-packed stem, no fused upsample) whose input channels are
+// whole K = 32 steps and whose metadata for all output-channel tiles fits the 256 TMEM columns behind the accumulators.
+bool sparse_shape_ok(const yx_op& op) {
+  if (op.kind != YX_OP_CONV || op.aux != 0 || op.up.c > 0) return false;
+  if (op.cin_pad % 32 != 0) return false;
+  const int taps = op.ksize * op.ksize, n_mt = ceil_div(op.cout_pad, 128);
+  return n_mt * taps * (op.cin_pad / 32) <= kSpMetaColsMax;
+}
+
+// YX_SPARSE: "0" never use the sparse variant, "force" use it wherever the weights allow (tests, experiments); otherwise
+// the tuner decides per layer by measurement
+static int sparse_env() {   // read on every call: tests switch it between engines
+  const char* e = getenv("YX_SPARSE");
+  return !e ? 1 : (strcmp(e, "0") == 0 ? 0 : (strcmp(e, "force") == 0 ? 2 : 1));
+}
+
+static ConvTune sparse_tune(const yx_op& op, const ConvGeom& g, int epi_groups, int stage_bufs);
+
 // The heuristic (untuned) launch shape.
-static ConvTune default_tune(const yx_op& op, const ConvGeom& g) {
+static ConvTune default_tune(const yx_op& op, const ConvGeom& g, bool sparse_ok = false) {
   static const int halo_env = getenv("YX_HALO") ? atoi(getenv("YX_HALO")) : 1;
+  if (sparse_ok && sparse_env() == 2) return sparse_tune(op, g, 1, 1);
   ConvTune t;
   memset(&t, 0, sizeof t);
   const int cout16 = op.cout_pad;
@@ -824,11 +955,31 @@ static ConvTune default_tune(const yx_op& op, const ConvGeom& g) {
   return t;
 }
 
-void conv_candidates(const yx_op& op, std::vector<ConvTune>* out) {
+static ConvTune sparse_tune(const yx_op& op, const ConvGeom& g, int epi_groups, int stage_bufs) {
+  ConvTune t;
+  memset(&t, 0, sizeof t);
+  t.variant = halo_ok(op, g) ? 2 : 1;
+  t.bn = 128; t.ctas = 1; t.mh = 1; t.epi_groups = epi_groups; t.stage_bufs = stage_bufs; t.w3 = t.variant == 2 ? 2 : 1;
+  t.sparse = 1;
+  return t;
+}
+
+void conv_candidates(const yx_op& op, std::vector<ConvTune>* out, bool sparse_ok) {
   out->clear();
   ConvGeom g;
   if (conv_geom(op, &g) != YX_OK) return;
-  out->push_back(default_tune(op, g));
+  out->push_back(default_tune(op, g, sparse_ok));
+  if (sparse_ok && sparse_env() == 2) return;   // forced: the sparse shape is the only candidate
+  if (sparse_ok && sparse_env() == 1)
+    for (int eg = 1; eg <= 2; ++eg)
+      for (int sb = 1; sb <= 2; ++sb) {
+        out->push_back(sparse_tune(op, g, eg, sb));
+        if (halo_ok(op, g)) {   // also the generic (one box per tap) sparse shape
+          ConvTune t = sparse_tune(op, g, eg, sb);
+          t.variant = 1; t.w3 = 1;
+          out->push_back(t);
+        }
+      }
   const int cout16 = op.cout_pad;
   std::vector<int> bns;
   auto add_bn = [&](int b) {
@@ -889,15 +1040,20 @@ void conv_candidates(const yx_op& op, std::vector<ConvTune>* out) {
 }
 
 int conv_plan(const yx_op& op, void* base, const void* weights, const void* biases, int num_sms, const ConvTune* tune,
-              ConvPlan* out) {
+              ConvPlan* out, const SparseWeights* spw) {
   const yx_view& s = op.src;
   const yx_view& d = op.dst;
   ConvGeom g;
   int rc = conv_geom(op, &g);
   if (rc != YX_OK) return rc;
-  const ConvTune t = tune ? *tune : default_tune(op, g);
+  const bool sparse_ok = spw != nullptr && spw->wc != nullptr && spw->meta != nullptr && sparse_shape_ok(op);
+  const ConvTune t = tune ? *tune : default_tune(op, g, sparse_ok);
   const bool halo = t.variant == 2;
   const bool pair = t.pair != 0;
+  const bool sp = t.sparse != 0;
+  YX_REQUIRE(!sp || sparse_ok, "conv tune: the sparse variant needs 2:4-compliant packed weights and a supported geometry");
+  YX_REQUIRE(!sp || (!pair && t.mh != 2 && t.ctas == 1 && t.bn == 128),
+             "conv tune: the sparse variant runs one CTA per SM with 128-channel M tiles and one 128-pixel tile");
   YX_REQUIRE(t.variant == 1 || t.variant == 2, "conv tune: variant must be 1 (generic) or 2 (halo)");
   YX_REQUIRE(!pair || (t.ctas == 1 && (!halo || t.mh != 2) && !g.rowpack),
              "conv tune: CTA-pair mode runs one CTA per SM and one 128-pixel half per CTA (not for the row-packed stem)");
@@ -924,21 +1080,26 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
   p.up_chunks = g.has_up ? op.up.c / 64 : 0;
   p.up_h = g.has_up ? op.up.h : 0;
   p.k_chunks = p.up_chunks + ceil_div(p.cin - p.up_chunks * 64, 64);
-  p.BN = std::min(t.bn, p.cout16);
+  p.BN = sp ? 128 : std::min(t.bn, p.cout16);   // sparse: the M = 128 rows of the sparse operand (a partial last tile is padded)
   p.n_tiles_n = ceil_div(p.cout16, p.BN);
   p.halo = halo ? 1 : 0;
   p.rowpack = g.rowpack ? 1 : 0;
   p.pair = pair ? 1 : 0;
+  p.sp = sp ? 1 : 0;
+  p.sp_meta = sp ? spw->meta : nullptr;
+  p.sp_cols_per_tile = g.taps * (op.cin_pad / 32);
+  p.sp_meta_col0 = kSpMetaCol0;
   p.epi_groups = t.epi_groups;
   p.bias_bytes = round_up(p.cout16 * 4, 128);
-  p.b_stage_bytes = (pair ? p.BN / 2 : p.BN) * 128;  // pair: each CTA holds half of the N tile's weight rows
+  p.b_stage_bytes = sp ? 128 * 64 : (pair ? p.BN / 2 : p.BN) * 128;  // pair: each CTA holds half of the N tile's weight rows;
+                                                                      // sparse: 128 rows of 32 stored fp16 (one 64-channel chunk)
   p.bias = reinterpret_cast<const float*>(static_cast<const uint8_t*>(biases) + op.b_offset);
   static const int diag_env = getenv("YX_CONV_DIAG") ? atoi(getenv("YX_CONV_DIAG")) : 0;  // experiments only (results are garbage)
   p.diag = diag_env;
   const int taps = g.taps;
   const int groups64 = ceil_div(p.BN, 64);
   int stride_cols = 32;
-  while (stride_cols < p.BN) stride_cols <<= 1;
+  while (stride_cols < p.BN) stride_cols <<= 1;   // (sparse: BN = 128 = the pixel columns of one transposed accumulator)
   int budget = t.ctas == 2 ? kSmemTwoCtas : kSmemLimit;
 
   if (halo) {
@@ -975,6 +1136,10 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
     p.tmem_cols = 32;
     while (p.tmem_cols < 2 * stride_cols) p.tmem_cols <<= 1;
     p.acc_stride = p.tmem_cols / 2;
+  }
+  if (sp) {   // two 128-column accumulators at columns 0 / 128, metadata from column 256 on
+    p.acc_stride = 128;
+    p.tmem_cols = 512;
   }
   YX_REQUIRE(t.ctas == 1 || p.tmem_cols <= 256, "conv tune: two CTAs per SM need <= 256 TMEM columns each");
   p.tiles_h = ceil_div(g.Hout, p.TH);
@@ -1084,7 +1249,13 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
         if ((rc = encode_map(&p.tmA[py * 2 + px], addr, 4, dims, st, box, true, "A-parity")) != YX_OK) return rc;
       }
   }
-  {
+  if (sp) {   // compressed weights [round_up(cout,128)][taps][cin/2]: rows of 32 stored fp16 per chunk, SWIZZLE_64B
+    const int half = op.cin_pad / 2;
+    uint64_t dims[3] = {(uint64_t)half, (uint64_t)taps, (uint64_t)round_up(op.cout_pad, 128)};
+    uint64_t st[3] = {2, (uint64_t)half * 2, (uint64_t)half * 2 * taps};
+    uint32_t box[3] = {32, 1, 128};
+    if ((rc = encode_map(&p.tmW, const_cast<void*>(spw->wc), 3, dims, st, box, false, "W-sparse", true)) != YX_OK) return rc;
+  } else {
     uint64_t dims[3] = {(uint64_t)op.cin_pad, (uint64_t)taps, (uint64_t)op.cout_pad};
     uint64_t st[3] = {2, (uint64_t)op.cin_pad * 2, (uint64_t)op.cin_pad * 2 * taps};
     uint32_t box[3] = {64, 1, (uint32_t)(pair ? p.BN / 2 : p.BN)};
@@ -1101,7 +1272,7 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
   }
   pl.flops = g.flops;
   pl.bytes = g.act_bytes + 2.0 * (double)d.c * g.cin_real * op.ksize * op.ksize;
-  snprintf(pl.desc, sizeof pl.desc, "%s%s%s BN%d%s mh%d ctas%d epi%d sbuf%d A%dx%dK B%d%s w3:%d grid%d smem%dK", p.has_res == 2 ? "inplace-" : "", pair ? "pair-" : "", halo ? "halo" : "generic",
+  snprintf(pl.desc, sizeof pl.desc, "%s%s%s%s BN%d%s mh%d ctas%d epi%d sbuf%d A%dx%dK B%d%s w3:%d grid%d smem%dK", sp ? "sparse24-" : "", p.has_res == 2 ? "inplace-" : "", pair ? "pair-" : "", halo ? "halo" : "generic",
            p.BN, p.n_tiles_n > 1 ? "*" : "", p.mh, t.ctas, p.epi_groups, p.stage_bufs, p.stages_a, p.a_stage_bytes >> 10, p.b_slots,
            p.b_resident ? "res" : "", p.w3_role, pl.grid, pl.smem_bytes >> 10);
   *out = pl;
@@ -1111,10 +1282,10 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
 #endif  // !YX_CONV_ACT_SLICE
 
 #ifdef YX_CONV_ACT_SLICE
-template <int ACT, int RES, int MODE, bool PAIR>
+template <int ACT, int RES, int MODE, bool PAIR, bool SP = false>
 static int launch_variant(const ConvPlan& plan, cudaStream_t stream) {
   static bool attr_set = false;
-  auto kernel = conv_gemm_kernel<ACT, RES, MODE, PAIR>;
+  auto kernel = conv_gemm_kernel<ACT, RES, MODE, PAIR, SP>;
   if (!attr_set) {
     YX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     attr_set = true;
@@ -1148,6 +1319,8 @@ static int launch_variant(const ConvPlan& plan, cudaStream_t stream) {
 
 template <int ACT, int RES>
 static int launch_mode(const ConvPlan& plan, cudaStream_t stream) {
+  if (plan.p.sp)
+    return plan.p.halo ? launch_variant<ACT, RES, 1, false, true>(plan, stream) : launch_variant<ACT, RES, 0, false, true>(plan, stream);
   if (plan.p.pair)
     return plan.p.halo ? launch_variant<ACT, RES, 1, true>(plan, stream) : launch_variant<ACT, RES, 0, true>(plan, stream);
   if (plan.p.halo && plan.p.rowpack)  // the stem has no residual: only RES = 0 is instantiated

@@ -27,6 +27,9 @@ struct Step {
   yx_op op;
   ConvPlan conv;  // valid when op.kind == YX_OP_CONV
   double flops = 0, bytes = 0;
+  SparseWeights sp;      // 2:4-packed weights when the layer's mask is compliant (sp_ok)
+  bool sp_ok = false;
+  const SparseWeights* spw() const { return sp_ok ? &sp : nullptr; }
 };
 
 }  // namespace yx
@@ -42,6 +45,7 @@ struct yx_engine {
   cudaGraphExec_t graph_exec = nullptr;
   cudaStream_t graph_stream = nullptr;  // private stream used only to capture the graph
   bool tuned = false;
+  std::vector<void*> owned;   // device memory the engine allocated itself (2:4-packed weights and metadata)
   std::vector<std::string> tune_mismatches;  // YX_TUNE_CHECK: candidates whose output differed from the default shape
 };
 
@@ -134,7 +138,36 @@ extern "C" int yx_engine_create(const yx_op* ops, int n_ops, void* arena, size_t
         set_error(std::string(where) + "weight/bias range outside the blobs");
         rc = YX_ERR_INVALID;
       } else {
-        rc = conv_plan(op, arena, weights, biases, sms, nullptr, &s.conv);
+        // 2:4-compliant masks (BASELINE config 3's second mask set; 01_mask_generator-style masks never are): pack the
+        // weights for the sparse tensor-core variant; whether a layer then RUNS sparse is the tuner's decision (YX_SPARSE)
+        const bool sparse_off = getenv("YX_SPARSE") && strcmp(getenv("YX_SPARSE"), "0") == 0;
+        if (!sparse_off && sparse_shape_ok(op)) {
+          const int taps = op.ksize * op.ksize, cout128 = round_up(op.cout_pad, 128);
+          const size_t wc_bytes = (size_t)cout128 * taps * (op.cin_pad / 2) * 2;
+          const size_t meta_bytes = (size_t)(cout128 / 128) * taps * (op.cin_pad / 32) * 128 * 4;
+          void *wc = nullptr, *meta = nullptr;
+          if (!e->owned.size()) {   // 4-byte counter shared by all packing launches
+            void* scratch = nullptr;
+            if (cudaMalloc(&scratch, 256) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "cudaMalloc", __FILE__, __LINE__);
+            else e->owned.push_back(scratch);
+          }
+          if (rc == YX_OK && (cudaMalloc(&wc, wc_bytes) != cudaSuccess || cudaMalloc(&meta, meta_bytes) != cudaSuccess)) {
+            rc = cuda_fail(cudaGetLastError(), "cudaMalloc (2:4-packed weights)", __FILE__, __LINE__);
+            if (wc) cudaFree(wc);
+          }
+          if (rc == YX_OK) {
+            int compliant = 0;
+            rc = sparse_pack(static_cast<const uint8_t*>(weights) + op.w_offset, op.cout_pad, taps, op.cin_pad, wc, meta,
+                             static_cast<int*>(e->owned[0]), &compliant, nullptr);
+            if (rc == YX_OK && compliant) {
+              s.sp.wc = wc; s.sp.meta = static_cast<const uint32_t*>(meta); s.sp_ok = true;
+              e->owned.push_back(wc); e->owned.push_back(meta);
+            } else {
+              cudaFree(wc); cudaFree(meta);
+            }
+          }
+        }
+        if (rc == YX_OK) rc = conv_plan(op, arena, weights, biases, sms, nullptr, &s.conv, s.spw());
         s.flops = s.conv.flops; s.bytes = s.conv.bytes;
         if (rc != YX_OK) set_error(std::string(where) + g_last_error);
       }
@@ -148,7 +181,7 @@ extern "C" int yx_engine_create(const yx_op* ops, int n_ops, void* arena, size_t
         s.flops = 2.0 * dpx * op.dst.c * op.ksize * op.ksize;
       }
     }
-    if (rc != YX_OK) { delete e; return rc; }
+    if (rc != YX_OK) { yx_engine_destroy(e); return rc; }
   }
   *out = e;
   return YX_OK;
@@ -158,6 +191,7 @@ extern "C" void yx_engine_destroy(yx_engine* e) {
   if (!e) return;
   if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
   if (e->graph_stream) cudaStreamDestroy(e->graph_stream);
+  for (void* ptr : e->owned) cudaFree(ptr);
   delete e;
 }
 
@@ -230,7 +264,7 @@ extern "C" int yx_engine_tune(yx_engine* e, const void* image, int image_dtype, 
       rc = run_step(e, s, image, image_dtype, in_scale, in_shift, st);
       continue;
     }
-    conv_candidates(s.op, &cands);
+    conv_candidates(s.op, &cands, s.sp_ok);
     float best_ms = 1e30f;
     ConvPlan best = s.conv;
     const bool inplace = s.conv.p.has_res == 2;
@@ -252,7 +286,7 @@ extern "C" int yx_engine_tune(yx_engine* e, const void* image, int image_dtype, 
     }
     for (const ConvTune& t : cands) {
       ConvPlan pl;
-      if (conv_plan(s.op, e->arena, e->weights, e->biases, e->num_sms, &t, &pl) != YX_OK) continue;  // shape does not fit
+      if (conv_plan(s.op, e->arena, e->weights, e->biases, e->num_sms, &t, &pl, s.spw()) != YX_OK) continue;  // shape does not fit
       pl.store_only = inplace ? 1 : 0;
       if ((rc = conv_launch(pl, st)) != YX_OK) break;  // warm-up (also sets the smem attribute)
       if (check) {
@@ -338,7 +372,7 @@ extern "C" int yx_engine_set_tune(yx_engine* e, int i, const yx_conv_tune* tune_
   YX_REQUIRE(s.op.kind == YX_OP_CONV, "not a conv op");
   const ConvTune t = tune_from_abi(*tune_host);
   ConvPlan pl;
-  int rc = conv_plan(s.op, e->arena, e->weights, e->biases, e->num_sms, &t, &pl);
+  int rc = conv_plan(s.op, e->arena, e->weights, e->biases, e->num_sms, &t, &pl, s.spw());
   if (rc != YX_OK) return rc;
   s.conv = pl;
   if (e->graph_exec) {  // a graph captured with the old shape is stale
@@ -417,6 +451,27 @@ extern "C" int yx_conv2d_ex(const yx_op* op, void* base, const void* weights, co
   ConvPlan plan;
   ConvTune t;
   if (tune) t = tune_from_abi(*tune);
+  if (tune && tune->sparse) {
+    // stand-alone sparse conv (parity tests): pack the 2:4 weights for this one call, run, wait, release
+    YX_REQUIRE(sparse_shape_ok(*op), "sparse conv: unsupported geometry (cin % 32, no fused upsample / row-packed stem, metadata <= 256 columns)");
+    const int taps = op->ksize * op->ksize, cout128 = round_up(op->cout_pad, 128);
+    void *wc = nullptr, *meta = nullptr, *scratch = nullptr;
+    YX_CUDA(cudaMalloc(&wc, (size_t)cout128 * taps * (op->cin_pad / 2) * 2));
+    YX_CUDA(cudaMalloc(&meta, (size_t)(cout128 / 128) * taps * (op->cin_pad / 32) * 128 * 4));
+    YX_CUDA(cudaMalloc(&scratch, 256));
+    int compliant = 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = sparse_pack(static_cast<const uint8_t*>(weights) + op->w_offset, op->cout_pad, taps, op->cin_pad, wc, meta,
+                         static_cast<int*>(scratch), &compliant, st);
+    if (rc == YX_OK && !compliant) { set_error("sparse conv: the weights are not 2:4-compliant along the input channels"); rc = YX_ERR_INVALID; }
+    SparseWeights spw;
+    spw.wc = wc; spw.meta = static_cast<const uint32_t*>(meta);
+    if (rc == YX_OK) rc = conv_plan(*op, base, weights, biases, sms, &t, &plan, &spw);
+    if (rc == YX_OK) rc = conv_launch(plan, st);
+    cudaStreamSynchronize(st);
+    cudaFree(wc); cudaFree(meta); cudaFree(scratch);
+    return rc;
+  }
   int rc = conv_plan(*op, base, weights, biases, sms, tune ? &t : nullptr, &plan);
   if (rc) return rc;
   if (getenv("YX_CONV_TRACE")) {  // diagnostics: print the per-tile timeline of CTA 0 (cycles)

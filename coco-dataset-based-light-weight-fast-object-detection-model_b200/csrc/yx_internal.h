@@ -57,6 +57,13 @@ struct ConvParams {
   int epi_groups;                // epilogue warpgroups (1 or 2)
   int w3_role;                   // warp 3: 0 idle, 1 second A producer, 2 second B producer
   int tmem_cols, acc_stride;     // TMEM columns allocated (power of two) and columns per accumulator
+  // 2:4 sparse tensor-core variant (SP): the weights are the sparse A operand (M = 128 couts per MMA, compressed rows of
+  // 64 bytes per 64-channel chunk, SWIZZLE_64B), the pixels the B operand (N = 128), the accumulator holds couts on the
+  // TMEM lanes and pixels on the columns; metadata columns sit behind the two accumulators
+  int sp;                        // 1: sparse variant
+  const uint32_t* sp_meta;       // [n_tiles_n][sp_cols_per_tile][128] metadata words (device)
+  int sp_cols_per_tile;          // taps * (cin / 32): one column per (tap, K = 32 step)
+  int sp_meta_col0;              // first TMEM column of the metadata
   int diag;                      // experiments (YX_CONV_DIAG): 1 no epilogue work, 2 no A loads, 4 no MMAs
   long long* trace;              // diagnostics: per-tile timeline of CTA 0 (nullptr = off)
 };
@@ -86,9 +93,18 @@ struct ConvPlan {
   char desc[160];
 };
 
+// A conv's 2:4-packed weights (yx_sparse.cu), when its mask is compliant: device pointers owned by the engine.
+struct SparseWeights {
+  const void* wc = nullptr;        // compressed [round_up(cout_pad,128)][taps][cin_pad/2] fp16
+  const uint32_t* meta = nullptr;  // [n_mt][taps * cin_pad / 32][128]
+};
+int sparse_pack(const void* weights_krsc, int cout_pad, int taps, int cin_pad, void* wc_out, void* meta_out, int* scratch_dev,
+                int* compliant, cudaStream_t stream);
+bool sparse_shape_ok(const yx_op& op);   // geometry the sparse variant supports (before looking at the weights)
+
 int conv_plan(const yx_op& op, void* base, const void* weights, const void* biases, int num_sms, const ConvTune* tune,
-              ConvPlan* out);
-void conv_candidates(const yx_op& op, std::vector<ConvTune>* out);
+              ConvPlan* out, const SparseWeights* sp = nullptr);
+void conv_candidates(const yx_op& op, std::vector<ConvTune>* out, bool sparse_ok = false);
 int conv_launch(const ConvPlan& plan, cudaStream_t stream);
 
 // ------------------------------------------------------------------ aux ops (yx_aux.cu)

@@ -188,6 +188,38 @@ __device__ __forceinline__ uint32_t make_idesc_f16(uint32_t n) {
   return (1u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
+// ---------------------------------------------------------------- 2:4 structured-sparse MMA (tcgen05.mma.sp)
+// D[tmem] (+)= A_sparse[smem, compressed 2:4 along K] * B[smem]^T.  One instruction covers K = 32 LOGICAL fp16 of A (16 stored)
+// and reads B over the same 32 K.  The sparsity metadata lives in tensor memory: ONE 32-bit column per instruction,
+//   lane L = (m & 7) + 8 * kh + 16 * (m >> 4)          m = row of A (0..127), kh = which 16-wide half of the K = 32 slice
+//   nibble j = g + 4 * ((m >> 3) & 1)                   g = group of four K positions inside that half (0..3)
+//   nibble value = idx0 | idx1 << 2                     positions (0..3, idx0 < idx1) of the two stored values of the group
+// and the instruction takes an EVEN column address plus a 1-bit selector (idesc bits [0,2)) choosing that column or the
+// next one (odd addresses fault, selector values 2 / 3 are illegal instructions).  All of this was established on a B200
+// with tools/sp_probe.cu (profiles/r02_sparse_mma_probe.txt); it agrees with cute::UMMA::tmem_e_frg of the vendored CUTLASS.
+__device__ __forceinline__ void umma_f16_sp_ss_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                    uint32_t e_tmem, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %7, 0;\n\t"
+      "tcgen05.mma.sp.cta_group::1.kind::f16 [%0], da, db, [%5], %6, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(e_tmem), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// instruction descriptor of the sparse MMA: M = 128 rows of A, N = n, selector = which column of the even-aligned pair
+__device__ __forceinline__ uint32_t make_idesc_f16_sp(uint32_t n, uint32_t selector) {
+  return (selector & 1u) | (1u << 2) | (1u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+// high word of a K-major SWIZZLE_64B descriptor: rows of 64 bytes (32 fp16), 8-row atoms SBO bytes apart
+__device__ __forceinline__ uint32_t sdesc_hi_sw64(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14) | (4u << 29); }
+// one 32-bit value per thread -> column `taddr` of the thread's TMEM lane (warp w may touch lanes 32*(w%4) .. +31)
+__device__ __forceinline__ void tmem_st_32x32b_x1(uint32_t taddr, uint32_t v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // ---------------------------------------------------------------- CTA pair (cta_group::2) variants
 // Two CTAs of a cluster (same TPC) execute ONE tcgen05.mma of M = 256: each CTA holds its own 128 rows of A and HALF of
 // the N rows of B in its shared memory (same offsets in both CTAs), and receives its 128 accumulator rows in its own

@@ -18,7 +18,7 @@ def _rup(a, b):
 
 
 def run_conv_case(cin, cout, k, stride, H, W, B=2, act="silu", res=False, src_pitch=None, src_off=0,
-                  dst_pitch=None, dst_off=0, seed=0, dst_c=None, device="cuda", tune=None, up_c=0):
+                  dst_pitch=None, dst_off=0, seed=0, dst_c=None, device="cuda", tune=None, up_c=0, mask24=False):
     """Returns dict(max_err, ref_scale, out, ref).  src/dst may be channel slices of wider buffers
     (pitch/off in channels).  dst_c: channels of the dst view (>= cout, e.g. 8 for the 5-channel reg+obj pred).
     tune: dict of yx_conv_tune fields forcing one launch shape (None = the library's heuristic).
@@ -33,6 +33,13 @@ def run_conv_case(cin, cout, k, stride, H, W, B=2, act="silu", res=False, src_pi
     dst_pitch = dst_pitch or dst_c
     x = (torch.randn(B, H, W, src_pitch, generator=g) * 1.0).half()
     w = (torch.randn(cout, cin + up_c, k, k, generator=g) * (1.0 / np.sqrt((cin + up_c) * k * k))).half()
+    if mask24:   # 2:4-compliant along the input channels: keep the two largest |w| of every four (some groups keep fewer)
+        a = w.float().abs().permute(0, 2, 3, 1).reshape(-1, 4)
+        m = torch.zeros_like(a, dtype=torch.bool)
+        m.scatter_(1, a.argsort(dim=1, descending=True, stable=True)[:, :2], True)
+        m[::7, :] &= torch.tensor([True, False, True, True])       # groups with one or zero survivors
+        m[::11, :] = False
+        w = w * m.reshape(cout, k, k, cin + up_c).permute(0, 3, 1, 2).to(w.dtype)
     xu = (torch.randn(B, H // 2, W // 2, max(up_c, 8), generator=g) * 1.0).half()
     b = torch.randn(cout, generator=g) * 0.5
     r = (torch.randn(B, Ho, Wo, dst_pitch, generator=g) * 1.0).half() if res else None
@@ -132,9 +139,33 @@ CASES = [
 ]
 
 
-def _t(variant, n_tile, ctas=1, halves=1, eg=1, sb=2, w3=1, nores=0, pair=0):
+def _t(variant, n_tile, ctas=1, halves=1, eg=1, sb=2, w3=1, nores=0, pair=0, sparse=0):
     return dict(variant=variant, n_tile=n_tile, ctas_per_sm=ctas, halves=halves, epilogue_groups=eg, staging_buffers=sb,
-                second_producer=w3, no_resident_weights=nores, cta_pair=pair)
+                second_producer=w3, no_resident_weights=nores, cta_pair=pair, sparse=sparse)
+
+
+def _sp(variant, eg=1, sb=1, nores=0):
+    return _t(variant, 128, eg=eg, sb=sb, w3=2 if variant == 2 else 1, nores=nores, sparse=1)
+
+
+# the 2:4 sparse tensor-core variant (tcgen05.mma.sp; weights masked 2:4 along Cin) on every geometry it supports
+SPARSE_CASES = [
+    dict(cin=64, cout=128, k=1, stride=1, H=16, W=16, act="none", tune=_sp(1)),                       # one M tile, one chunk
+    dict(cin=96, cout=96, k=1, stride=1, H=32, W=32, act="hard_swish", tune=_sp(1)),                   # K tail (32), partial M tile
+    dict(cin=192, cout=192, k=1, stride=1, H=40, W=40, act="silu", tune=_sp(1, eg=2, sb=2)),           # M tiles 128 + 64
+    dict(cin=96, cout=96, k=3, stride=1, H=48, W=40, act="hard_swish", tune=_sp(2)),                   # halo, resident compressed weights
+    dict(cin=96, cout=96, k=3, stride=1, H=48, W=40, act="hard_swish", res=True, tune=_sp(2, nores=1)),  # streamed, residual via staging
+    dict(cin=96, cout=96, k=3, stride=1, H=64, W=64, act="hard_swish", res="inplace", tune=_sp(2, eg=2)),  # TMA reduce-add store
+    dict(cin=192, cout=192, k=3, stride=1, H=80, W=80, act="hard_swish", tune=_sp(2)),                 # the 192-channel bottleneck conv
+    dict(cin=192, cout=192, k=3, stride=1, H=40, W=40, act="silu", tune=_sp(1, sb=2)),                 # generic 3x3 (one box per tap)
+    dict(cin=288, cout=288, k=3, stride=1, H=40, W=40, act="hard_swish", tune=_sp(2)),                 # 3 M tiles, K tail 32
+    dict(cin=384, cout=384, k=3, stride=1, H=20, W=20, act="hard_swish", tune=_sp(2)),                 # 3 x 108 metadata columns > 256: rejected (see the test)
+    dict(cin=192, cout=384, k=3, stride=2, H=80, W=80, act="hard_swish", tune=_sp(1)),                 # stride 2 (parity views)
+    dict(cin=96, cout=192, k=4, stride=2, H=64, W=48, act="silu", tune=_sp(1)),                        # 4x4 stride 2 (P6-v2)
+    dict(cin=768, cout=576, k=1, stride=1, H=20, W=20, act="hard_swish", tune=_sp(1)),                 # deep K 1x1, 5 M tiles (last 64)
+    dict(cin=384, cout=192, k=1, stride=1, H=44, W=36, act="silu", src_pitch=768, src_off=384, dst_pitch=384, dst_off=192,
+         tune=_sp(1)),                                                                                 # concat slices, ragged tiles
+]
 
 
 # every launch shape the tuner may pick, forced on layers it applies to

@@ -4,7 +4,7 @@ O(1..8) values) after fp32 accumulation in a different order => abs 1.5e-2."""
 import pytest
 import torch
 
-from tests.conv_util import CASES, TUNED_CASES, run_conv_case, tolerance
+from tests.conv_util import CASES, SPARSE_CASES, TUNED_CASES, run_conv_case, tolerance
 
 pytestmark = pytest.mark.gpu
 
@@ -35,6 +35,27 @@ def test_conv_forced_launch_shapes(case):
     r = run_conv_case(B=3, **case)
     assert r["max_err"] <= tolerance(case), r["max_err"]
     assert not r["clobbered"]
+
+
+@pytest.mark.parametrize("case", SPARSE_CASES, ids=[_id(c) + f"_sparse_v{c['tune']['variant']}" for c in SPARSE_CASES])
+def test_conv_sparse_24(case):
+    """The 2:4 sparse tensor-core variant (tcgen05.mma.sp: weights = sparse A operand, pixels = B, transposed accumulator)
+    against torch's dense fp32 conv on the same 2:4-masked weights (main.py:52-55 densifies them; 01_mask_generator.py)."""
+    if case["cin"] == 384 and case["k"] == 3:     # 3 M tiles x 9 taps x 12 steps = 324 metadata columns > the 256 behind the accumulators
+        with pytest.raises(RuntimeError, match="sparse"):
+            run_conv_case(B=2, mask24=True, **case)
+        return
+    r = run_conv_case(B=3, mask24=True, **case)
+    assert r["max_err"] <= tolerance(case), r["max_err"]
+    assert not r["clobbered"] and not r["pad_nonzero"]
+
+
+def test_conv_sparse_rejects_dense_weights():
+    from tests.conv_util import _sp
+    with pytest.raises(RuntimeError, match="2:4"):
+        run_conv_case(cin=64, cout=128, k=1, stride=1, H=16, W=16, tune=_sp(1))          # unmasked weights
+    with pytest.raises(RuntimeError, match="sparse"):
+        run_conv_case(cin=48, cout=96, k=1, stride=1, H=16, W=16, mask24=True, tune=_sp(1))   # cin not a multiple of 32
 
 
 def test_conv_rejects_unfit_shape():

@@ -354,3 +354,48 @@ def test_pruned_checkpoint_through_build_yolox(masks, tmp_path):
     reg, obj, cls = model(x.cuda().half())
     rr, ro, rc = mr.forward_raw(_q16(fused), cfg, x.half().float())
     _check(reg, rr, "reg"); _check(obj, ro, "obj"); _check(cls, rc, "cls")
+    eng = model.engine_for(x.cuda().half())
+    n_sparse = sum("sparse24" in eng.op_desc(i) for i in range(len(eng.graph.ops)))
+    if masks == "magnitude49":
+        assert n_sparse == 0, "unstructured 49 % masks are never 2:4-compliant: dense-with-zeros is the only path"
+
+
+@pytest.mark.parametrize("name,H,W,B", [("tiny_p6", 128, 192, 2), ("yolox_m_p6", 320, 320, 2), ("yolox_m_p6", 640, 640, 1)])
+def test_two_four_masks_run_on_sparse_tensor_cores(name, H, W, B, monkeypatch):
+    """north_star (1) / SURVEY 8d config 3: a 2:4-compliant mask set runs on the sparse tensor-core path.  With
+    YX_SPARSE=force every conv whose packed weights are compliant and whose geometry the variant supports launches the
+    tcgen05.mma.sp kernel (asserted from the engine's own launch-shape descriptions); logits vs the oracle on the same
+    masked weights, anchored on torch fp16 CUDA like every whole-network comparison; and the dense-with-zeros run of
+    the same weights (YX_SPARSE=0) must agree with the sparse run to within the same anchor."""
+    cfg = mr.CONFIGS[name]
+    train = mr.synth_train_state(cfg, 8, calib_hw=(H, W))
+    fused = mr.apply_masks(mr.fold_bn(train), mr.two_four_masks(train))
+    x = mr.synth_images(12, B, H, W)
+    rr, ro, rc = mr.forward_raw(_q16(fused), cfg, x.half().float())
+    tr, to, tc = _torch_fp16_cuda(fused, cfg, x)
+    outs = {}
+    for mode in ("force", "0"):
+        monkeypatch.setenv("YX_SPARSE", mode)
+        monkeypatch.setenv("YX_TUNE", "0")
+        model = yb.infer.YOLOXP6(cfg.depth, cfg.width, act=cfg.act, num_classes=cfg.num_classes)
+        model.load_state_dict(fused, strict=True)
+        model = model.cuda().half()
+        reg, obj, cls = model(x.cuda().half())
+        eng = model.engine_for(x.cuda().half())
+        descs = [eng.op_desc(i) for i in range(len(eng.graph.ops))]
+        n_sparse = sum("sparse24" in d for d in descs)
+        if mode == "force":
+            # every non-head conv with cin % 32 == 0 (and metadata that fits) is eligible; the head is dense (unmasked)
+            eligible = [op for op in eng.graph.ops if op.kind == 0 and not op.name.startswith("head") and op.cin_pad % 32 == 0
+                        and op.aux == 0 and op.up is None
+                        and -(-op.cout_pad // 128) * op.ksize * op.ksize * (op.cin_pad // 32) <= 256]
+            assert n_sparse == len(eligible) and n_sparse >= 10, (n_sparse, len(eligible))
+            assert not any("sparse24" in d for d, op in zip(descs, eng.graph.ops) if op.name.startswith("head"))
+        else:
+            assert n_sparse == 0
+        _check_anchored(reg, rr, tr, f"reg (YX_SPARSE={mode})")
+        _check_anchored(obj, ro, to, f"obj (YX_SPARSE={mode})")
+        _check_anchored(cls, rc, tc, f"cls (YX_SPARSE={mode})")
+        outs[mode] = (reg.float().cpu(), cls.float().cpu())
+    for a, b, t, want in zip(outs["force"], outs["0"], (tr, tc), (rr, rc)):
+        assert _rel_l2(a, b) <= ANCHOR_RATIO * _rel_l2(t, want) + ANCHOR_FLOOR
