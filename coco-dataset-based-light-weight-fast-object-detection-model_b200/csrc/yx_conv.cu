@@ -385,7 +385,8 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
       for (int s = 0; s < p.b_slots; ++s) { mbar_init(bar_fb + 8 * s, 1); mbar_init(bar_eb + 8 * s, 1); }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, (PAIR ? 8 : 4) * p.epi_groups);  // one arrive per epilogue warp (of both CTAs)
+      // one arrive per epilogue warp that drains this accumulator (of both CTAs); alternating groups: one group each
+      mbar_init(bar_tempty + 8 * a, (PAIR ? 8 : 4) * (p.epi_alt ? 1 : p.epi_groups));
       mbar_init(bar_res + 8 * a, 1);
     }
     fence_mbar_init();
@@ -433,6 +434,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
   const long long t_begin = tracing ? clock64() : 0;
   const bool is_a_prod = (warp == 0) || (warp == 3 && p.w3_role == 1);
   const bool is_b_prod = (warp == 2) || (warp == 3 && p.w3_role == 2);
+  const bool is_a_prod_late = warp == 2 && p.w2_role == 1;   // after its (resident) weight loads
 
   // Programmatic dependent launch: everything above (barrier init, TMEM allocation, bias copy: none of it touches an
   // activation) overlapped the previous layer's tail.  The weight producers go on without waiting -- weights are constants,
@@ -444,9 +446,51 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
   // Producer and MMA warps run their loops WARP-UNIFORMLY (all 32 lanes, uniform values) and elect one lane only
   // around the issue itself: under `if (lane == 0)` ptxas cannot prove uniformity and wraps every UTMALDG / UTCHMMA
   // in an ELECT + 8x R2UR.BROADCAST loop (~200 cycles per TMA instruction, profiles/r01_tma_issue_probe.txt).
-  if (is_a_prod) {
+  if (is_b_prod) {
+    // ================================ B (weight) producer(s) ================================
+    const uint32_t nprod = p.w3_role == 2 ? 2u : 1u, mine = warp == 2 ? 0u : 1u;
+    const uint32_t b_stage_bytes = p.b_stage_bytes;
+    const int BN = p.BN, cout16 = p.cout16;
+    uint32_t s = 0, ph = 0, turn = 0;
+    int nt = tile_first % n_tiles_n;
+    for (int tile = tile_first; tile < n_tiles; tile += tile_step) {
+      int n0 = nt * BN;
+      if (PAIR) n0 += (int)rank * (min(BN, cout16 - n0) >> 1);  // this CTA's half of the N tile
+      nt += p.step_nt;
+      if (nt >= n_tiles_n) nt -= n_tiles_n;
+      // ring order must match the MMA issuer: halo = (chunk, tap), generic = (tap, chunk)
+      const int outer = HALO ? k_chunks : taps, inner = HALO ? taps : k_chunks;
+      for (int o = 0; o < outer; ++o)
+        for (int i = 0; i < inner; ++i) {
+          const int kc = HALO ? o : i, tap = HALO ? i : o;
+          if (turn == mine) {
+            if (!resident) mbar_wait_acc(bar_eb + 8 * s, ph ^ 1, tracing, w_acc0);
+            if (elect_one()) {
+              if (PAIR) {
+                if (rank == 0) mbar_expect_tx(bar_fb + 8 * s, 2 * b_stage_bytes);
+                tma_load_3d_2sm(sB + s * b_stage_bytes, &p.tmW, bar_fb + 8 * s, kc * 64, tap, n0);
+              } else {
+                mbar_expect_tx(bar_fb + 8 * s, b_stage_bytes);
+                tma_load_3d(sB + s * b_stage_bytes, &p.tmW, bar_fb + 8 * s, kc * (SP ? 32 : 64), tap, n0);  // SP: compressed rows
+              }
+            }
+          }
+          if (++turn == nprod) turn = 0;
+          if (++s == b_slots) { s = 0; ph ^= 1; }
+        }
+      if (resident) break;  // one N tile per layer: the weights stay in smem for every later tile
+    }
+    if (warp == 2) YX_TRACE_SUM(TW_BPROD_EMPTY, w_acc0);
+    w_acc0 = 0;
+    // resident weights: this warp has nothing left to do for the rest of the kernel -> it becomes one more producer of
+    // the ACTIVATION operand (w2_role).  One issuing warp sustains roughly one TMA load per 400-1000 cycles (strided
+    // stride-2 boxes are the slow end), so the layers that load a box per filter tap are bound by how many warps issue.
+    if (is_a_prod_late) griddep_wait();
+  }
+  if (is_a_prod || is_a_prod_late) {
     // ================================ A producer(s) ================================
-    const uint32_t nprod = p.w3_role == 1 ? 2u : 1u, mine = warp == 0 ? 0u : 1u;
+    const uint32_t nprod = 1u + (p.w3_role == 1 ? 1u : 0u) + (p.w2_role == 1 ? 1u : 0u);
+    const uint32_t mine = warp == 0 ? 0u : (warp == 3 ? 1u : nprod - 1u);
     const uint32_t a_stage_bytes = p.a_stage_bytes, a_box_bytes = p.a_box_bytes;
     uint32_t s = 0, ph = 0, turn = 0;  // ring slot / phase / whose turn, all incremental
     const int TH = p.TH, TW = p.TW;
@@ -525,41 +569,6 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
       if (warp == 0 && lane == 0) YX_TRACE(0, (tile - tile_first) / tile_step);
     }
     if (warp == 0) YX_TRACE_SUM(TW_APROD_EMPTY, w_acc0);
-  } else if (is_b_prod) {
-    // ================================ B (weight) producer(s) ================================
-    const uint32_t nprod = p.w3_role == 2 ? 2u : 1u, mine = warp == 2 ? 0u : 1u;
-    const uint32_t b_stage_bytes = p.b_stage_bytes;
-    const int BN = p.BN, cout16 = p.cout16;
-    uint32_t s = 0, ph = 0, turn = 0;
-    int nt = tile_first % n_tiles_n;
-    for (int tile = tile_first; tile < n_tiles; tile += tile_step) {
-      int n0 = nt * BN;
-      if (PAIR) n0 += (int)rank * (min(BN, cout16 - n0) >> 1);  // this CTA's half of the N tile
-      nt += p.step_nt;
-      if (nt >= n_tiles_n) nt -= n_tiles_n;
-      // ring order must match the MMA issuer: halo = (chunk, tap), generic = (tap, chunk)
-      const int outer = HALO ? k_chunks : taps, inner = HALO ? taps : k_chunks;
-      for (int o = 0; o < outer; ++o)
-        for (int i = 0; i < inner; ++i) {
-          const int kc = HALO ? o : i, tap = HALO ? i : o;
-          if (turn == mine) {
-            if (!resident) mbar_wait_acc(bar_eb + 8 * s, ph ^ 1, tracing, w_acc0);
-            if (elect_one()) {
-              if (PAIR) {
-                if (rank == 0) mbar_expect_tx(bar_fb + 8 * s, 2 * b_stage_bytes);
-                tma_load_3d_2sm(sB + s * b_stage_bytes, &p.tmW, bar_fb + 8 * s, kc * 64, tap, n0);
-              } else {
-                mbar_expect_tx(bar_fb + 8 * s, b_stage_bytes);
-                tma_load_3d(sB + s * b_stage_bytes, &p.tmW, bar_fb + 8 * s, kc * (SP ? 32 : 64), tap, n0);  // SP: compressed rows
-              }
-            }
-          }
-          if (++turn == nprod) turn = 0;
-          if (++s == b_slots) { s = 0; ph ^= 1; }
-        }
-      if (resident) break;  // one N tile per layer: the weights stay in smem for every later tile
-    }
-    if (warp == 2) YX_TRACE_SUM(TW_BPROD_EMPTY, w_acc0);
   } else if (warp == 1 && rank == 0) {
     // ================================ MMA issuer (leader CTA only in PAIR mode) ================================
     uint32_t t = 0, sa = 0, pha = 0, sb = 0, phb = 0;
@@ -662,9 +671,17 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
     const int group = (warp - 4) >> 2;
     const int row = q * 32 + lane;
     const bool row_valid = HALO ? true : (row < p.TH / MH * p.TW);
-    const bool lead_warp = warp == 4;  // issues the residual loads and the stores (one elected lane)
+    // Two ways to use two epilogue warpgroups: split the COLUMNS of every tile between them (both walk every tile in
+    // lockstep), or ALTERNATE TILES (epi_alt): group g owns accumulator g, staging buffer g, its own named barriers and its
+    // own store-issuing warp, and drains tiles t = g (mod 2) on its own.  The per-tile chain (wait accumulator -> tcgen05.ld
+    // -> convert -> fence -> barrier -> TMA store) is latency-, not throughput-bound on the small-channel layers; with
+    // alternating groups two such chains overlap.
+    const bool alt = p.epi_alt != 0;
+    const bool lead_warp = alt ? (warp & 3) == 0 : warp == 4;  // issues the residual loads and the stores (one elected lane)
     const int epi_groups = p.epi_groups, stage_bufs = p.stage_bufs;
-    const uint32_t n_epi = 128u * epi_groups;
+    const uint32_t n_epi = alt ? 128u : 128u * epi_groups;
+    const uint32_t bar_id1 = alt ? 1u + 2u * group : 1u, bar_id2 = alt ? 2u + 2u * group : 2u;
+    const int cgroup = alt ? 0 : group, cgroups = alt ? 1 : epi_groups;   // column split inside a tile
     const int store_th = HALO ? 16 : p.TH / MH;
     const int BN = p.BN, cout16 = p.cout16;
     const uint32_t acc_stride = p.acc_stride;
@@ -678,20 +695,21 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
       const int bn_cur = min(BN, cout16 - tc.n0);
       const int groups_cur = (bn_cur + 63) >> 6;
       const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
+      if (alt && (int)acc != group) continue;   // the other group's tile
 #pragma unroll
       for (int h = 0; h < MH; ++h, ++u) {
         const int yh = tc.y0 + store_th * h;
-        const uint32_t buf = stage_bufs == 2 ? (u & 1) : 0;
+        const uint32_t buf = alt ? (uint32_t)group : (stage_bufs == 2 ? (u & 1) : 0);
         const uint32_t sStage = sStage0 + buf * stage_buf_bytes;
         // staging buffer `buf` is free once the store issued stage_bufs units ago has read it
         // (elect.sync picks the same lane for the same mask every time, so the bulk-group state stays with one thread)
         const long long ts0 = tracing ? clock64() : 0;
         if (lead_warp) {
           if (elect_one()) {
-            if (stage_bufs == 2) tma_store_wait_read1(); else tma_store_wait_read0();
+            if (stage_bufs == 2 && !alt) tma_store_wait_read1(); else tma_store_wait_read0();
           }
         }
-        named_bar_sync(1, n_epi);
+        named_bar_sync(bar_id1, n_epi);
         if (tracing) w_acc1 += clock64() - ts0;
         if (HAS_RES && lead_warp) {
           if (elect_one()) {
@@ -705,16 +723,16 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
           tc_fence_after();
           if (lead_warp && lane == 0) YX_TRACE(3, t);
         }
-        if (HAS_RES) mbar_wait(bar_res + 8 * buf, (stage_bufs == 2 ? (u >> 1) : u) & 1);
+        if (HAS_RES) mbar_wait(bar_res + 8 * buf, ((stage_bufs == 2 && !alt) ? (u >> 1) : u) & 1);
         const uint32_t taddr = tmem_base + (acc * MH + h) * acc_stride + (static_cast<uint32_t>(q * 32) << 16);
         if (SP) {
           if (!(p.diag & 1)) {
             float bias = 0.0f;
             if (row < bn_cur) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(bias) : "r"(sBias + (tc.n0 + row) * 4));
-            epilogue_convert_sp<ACT, HAS_RES>(taddr, HALO ? 128 : p.TH * p.TW, row, row < bn_cur, bias, sStage, group, epi_groups);
+            epilogue_convert_sp<ACT, HAS_RES>(taddr, HALO ? 128 : p.TH * p.TW, row, row < bn_cur, bias, sStage, cgroup, cgroups);
           }
         } else if (!(p.diag & 1)) {
-          epilogue_convert<ACT, HAS_RES>(taddr, bn_cur, row, row_valid, sStage, sBias + tc.n0 * 4, group, epi_groups);
+          epilogue_convert<ACT, HAS_RES>(taddr, bn_cur, row, row_valid, sStage, sBias + tc.n0 * 4, cgroup, cgroups);
         }
         if (h == MH - 1) {  // accumulator drained -> MMA warp may overwrite it
           tc_fence_before();
@@ -731,7 +749,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
         // publish the staged tile to the async proxy and store it
         fence_proxy_async_smem();
         if (lead_warp && lane == 0 && h == MH - 1) YX_TRACE(4, t);
-        named_bar_sync(2, n_epi);
+        named_bar_sync(bar_id2, n_epi);
         if (lead_warp && !(p.diag & 1)) {
           if (elect_one()) {
             for (int g = 0; g < groups_cur; ++g) {
@@ -996,10 +1014,17 @@ void conv_candidates(const yx_op& op, std::vector<ConvTune>* out, bool sparse_ok
     const int64_t m_tiles = (int64_t)op.dst.n * ceil_div(op.dst.h * op.dst.w, 128);
     if (cout16 > 64 && m_tiles * ceil_div(cout16, 128) < 148) add_bn(64);
   }
-  auto push = [&](ConvTune t) {
+  auto push1 = [&](const ConvTune& t) {
     for (const ConvTune& o : *out)
       if (memcmp(&o, &t, sizeof t) == 0) return;
     out->push_back(t);
+  };
+  auto push = [&](ConvTune t) {
+    push1(t);
+    if (t.epi_groups == 2 && t.stage_bufs == 2) {   // the same shape with the two groups alternating tiles
+      t.epi_alt = 1;
+      push1(t);
+    }
   };
   for (int bn : bns) {
     for (int ctas = 1; ctas <= 2; ++ctas)
@@ -1063,6 +1088,8 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
              "conv tune: N tile must be a multiple of 64 (or the whole padded Cout), at most 256");
   YX_REQUIRE(t.ctas == 1 || t.ctas == 2, "conv tune: ctas per SM must be 1 or 2");
   YX_REQUIRE(t.epi_groups == 1 || t.epi_groups == 2, "conv tune: epilogue groups must be 1 or 2");
+  YX_REQUIRE(!t.epi_alt || (t.epi_groups == 2 && t.stage_bufs != 1),
+             "conv tune: alternating epilogue groups need two groups and two staging buffers");
   YX_REQUIRE(op.cout_pad <= 4096, "cout too large");
 
   ConvPlan pl;
@@ -1090,6 +1117,7 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
   p.sp_cols_per_tile = g.taps * (op.cin_pad / 32);
   p.sp_meta_col0 = kSpMetaCol0;
   p.epi_groups = t.epi_groups;
+  p.epi_alt = t.epi_alt ? 1 : 0;
   p.bias_bytes = round_up(p.cout16 * 4, 128);
   p.b_stage_bytes = sp ? 128 * 64 : (pair ? p.BN / 2 : p.BN) * 128;  // pair: each CTA holds half of the N tile's weight rows;
                                                                       // sparse: 128 rows of 32 stored fp16 (one 64-channel chunk)
@@ -1178,7 +1206,7 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
       pl.smem_bytes = fixed + p.stages_a * p.a_stage_bytes + p.b_slots * p.b_stage_bytes;
       break;
     }
-    if (p.stage_bufs == 2) { p.stage_bufs = 1; continue; }
+    if (p.stage_bufs == 2 && !p.epi_alt) { p.stage_bufs = 1; continue; }
     set_error("conv plan: launch shape does not fit in shared memory");
     return YX_ERR_INVALID;
   }
@@ -1202,6 +1230,9 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
   p.w3_role = t.w3 == 0 ? 0 : (b_loads > a_loads ? 2 : 1);
   if (p.w3_role == 1 && p.stages_a < 2) p.w3_role = 0;
   if (p.w3_role == 2 && p.b_slots < 2) p.w3_role = 0;
+  // warp 2 (weight producer) joins the activation producers once its resident weights are in (YX_W2A=0: off, for A/B runs)
+  static const bool w2a_env = !(getenv("YX_W2A") && atoi(getenv("YX_W2A")) == 0);
+  p.w2_role = (w2a_env && p.b_resident && t.w3 != 0 && a_loads >= 3 && p.stages_a >= 3) ? 1 : 0;
 
   if (halo && g.rowpack) {
     uint64_t dims[4] = {64, (uint64_t)g.Wout, (uint64_t)s.h, (uint64_t)s.n};
@@ -1272,9 +1303,9 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
   }
   pl.flops = g.flops;
   pl.bytes = g.act_bytes + 2.0 * (double)d.c * g.cin_real * op.ksize * op.ksize;
-  snprintf(pl.desc, sizeof pl.desc, "%s%s%s%s BN%d%s mh%d ctas%d epi%d sbuf%d A%dx%dK B%d%s w3:%d grid%d smem%dK", sp ? "sparse24-" : "", p.has_res == 2 ? "inplace-" : "", pair ? "pair-" : "", halo ? "halo" : "generic",
-           p.BN, p.n_tiles_n > 1 ? "*" : "", p.mh, t.ctas, p.epi_groups, p.stage_bufs, p.stages_a, p.a_stage_bytes >> 10, p.b_slots,
-           p.b_resident ? "res" : "", p.w3_role, pl.grid, pl.smem_bytes >> 10);
+  snprintf(pl.desc, sizeof pl.desc, "%s%s%s%s BN%d%s mh%d ctas%d epi%d%s sbuf%d A%dx%dK B%d%s w3:%d%s grid%d smem%dK", sp ? "sparse24-" : "", p.has_res == 2 ? "inplace-" : "", pair ? "pair-" : "", halo ? "halo" : "generic",
+           p.BN, p.n_tiles_n > 1 ? "*" : "", p.mh, t.ctas, p.epi_groups, p.epi_alt ? "alt" : "", p.stage_bufs, p.stages_a, p.a_stage_bytes >> 10, p.b_slots,
+           p.b_resident ? "res" : "", p.w3_role, p.w2_role ? "+w2" : "", pl.grid, pl.smem_bytes >> 10);
   *out = pl;
   return YX_OK;
 }

@@ -55,7 +55,9 @@ struct ConvParams {
   int shared_ring;               // generic + streamed weights: A and B share one full/empty barrier pair per stage
   int stage_bufs, out_box_bytes, bias_bytes; // output staging buffers (1 or 2), bytes per 64-ch residual box
   int epi_groups;                // epilogue warpgroups (1 or 2)
+  int epi_alt;                   // two groups: 0 = split every tile's columns, 1 = alternate tiles (group g <-> accumulator g)
   int w3_role;                   // warp 3: 0 idle, 1 second A producer, 2 second B producer
+  int w2_role;                   // warp 2 (B producer): 1 = joins the A producers once its resident weights are loaded
   int tmem_cols, acc_stride;     // TMEM columns allocated (power of two) and columns per accumulator
   // 2:4 sparse tensor-core variant (SP): the weights are the sparse A operand (M = 128 couts per MMA, compressed rows of
   // 64 bytes per 64-channel chunk, SWIZZLE_64B), the pixels the B operand (N = 128), the accumulator holds couts on the
@@ -80,6 +82,7 @@ struct ConvTune {
   int no_resident;  // 1: never keep the weights resident (experiments)
   int pair;         // 1: CTA-pair mode (cta_group::2)
   int sparse;       // 1: 2:4 sparse tensor-core variant (weights = sparse A operand of tcgen05.mma.sp)
+  int epi_alt;      // 1: the two epilogue groups alternate tiles instead of splitting each tile's columns
 };
 
 struct ConvPlan {

@@ -140,7 +140,9 @@ typedef struct yx_conv_tune {
   int32_t cta_pair;            /* 1 = two-CTA clusters issuing cta_group::2 MMAs (M = 256), half of the weights per CTA */
   int32_t sparse;              /* 1 = the 2:4 sparse tensor-core variant (tcgen05.mma.sp, weights as the sparse A operand);
                                   only valid for a layer whose weights are 2:4-compliant along Cin */
-  int32_t reserved[2];         /* 0 */
+  int32_t epilogue_alternate;  /* with two epilogue groups: 0 = both convert half of every tile's columns, 1 = the groups
+                                  alternate tiles (each owns one accumulator and one staging buffer) */
+  int32_t reserved;            /* 0 */
 } yx_conv_tune;
 
 /* Per-layer launch-shape selection by measurement (the counterpart of torch.backends.cudnn.benchmark = True, which

@@ -139,9 +139,9 @@ CASES = [
 ]
 
 
-def _t(variant, n_tile, ctas=1, halves=1, eg=1, sb=2, w3=1, nores=0, pair=0, sparse=0):
+def _t(variant, n_tile, ctas=1, halves=1, eg=1, sb=2, w3=1, nores=0, pair=0, sparse=0, alt=0):
     return dict(variant=variant, n_tile=n_tile, ctas_per_sm=ctas, halves=halves, epilogue_groups=eg, staging_buffers=sb,
-                second_producer=w3, no_resident_weights=nores, cta_pair=pair, sparse=sparse)
+                second_producer=w3, no_resident_weights=nores, cta_pair=pair, sparse=sparse, epilogue_alternate=alt)
 
 
 def _sp(variant, eg=1, sb=1, nores=0):
@@ -203,6 +203,17 @@ TUNED_CASES = [
     dict(cin=768, cout=768, k=1, stride=1, H=40, W=40, act="hard_swish", tune=_t(1, 256, pair=1)),
     dict(cin=384, cout=384, k=1, stride=1, H=20, W=20, act="silu", tune=_t(1, 128, pair=1, sb=1)),
     dict(cin=192, cout=384, k=3, stride=2, H=80, W=80, act="hard_swish", tune=_t(1, 192, pair=1)),
+    # two epilogue groups alternating tiles (each owns one accumulator + one staging buffer)
+    dict(cin=48, cout=48, k=1, stride=1, H=64, W=64, act="hard_swish", tune=_t(1, 48, eg=2, alt=1)),
+    dict(cin=96, cout=96, k=1, stride=1, H=64, W=64, act="hard_swish", res=True, tune=_t(1, 96, eg=2, alt=1)),            # residual via staging
+    dict(cin=96, cout=96, k=1, stride=1, H=64, W=64, act="hard_swish", tune=_t(1, 64, eg=2, alt=1)),                      # 2 N tiles (64 + 32)
+    dict(cin=48, cout=48, k=3, stride=1, H=64, W=64, act="hard_swish", res="inplace", tune=_t(2, 48, halves=2, eg=2, alt=1)),   # halo, two halves
+    dict(cin=192, cout=192, k=3, stride=1, H=80, W=80, act="hard_swish", tune=_t(2, 192, eg=2, alt=1)),
+    dict(cin=96, cout=96, k=3, stride=1, H=48, W=40, act="hard_swish", res=True, tune=_t(2, 96, pair=1, eg=2, alt=1)),   # pair: both CTAs' group g drain accumulator g
+    dict(cin=192, cout=192, k=1, stride=1, H=40, W=40, act="hard_swish", tune=_t(1, 192, pair=1, eg=2, alt=1)),
+    dict(cin=96, cout=96, k=1, stride=1, H=64, W=64, act="hard_swish", tune=_t(1, 96, halves=2, eg=2, alt=1)),            # 256-pixel tiles
+    dict(cin=48, cout=96, k=3, stride=2, H=64, W=64, act="hard_swish", tune=_t(1, 96, eg=2, alt=1)),
+    dict(cin=16, cout=48, k=3, stride=1, H=64, W=64, act="silu", tune=_t(1, 48, halves=2, eg=2, alt=1)),
     # generic with 256-pixel tiles (two stacked halves per A box)
     dict(cin=96, cout=96, k=1, stride=1, H=64, W=64, act="hard_swish", tune=_t(1, 96, halves=2)),
     dict(cin=48, cout=96, k=3, stride=2, H=128, W=96, act="hard_swish", tune=_t(1, 96, halves=2, eg=2)),

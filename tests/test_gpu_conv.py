@@ -25,7 +25,8 @@ def test_conv_matches_torch(case):
 def _tid(c):
     t = c["tune"]
     return _id(c) + f"_v{t['variant']}bn{t['n_tile']}c{t['ctas_per_sm']}h{t['halves']}e{t['epilogue_groups']}s{t['staging_buffers']}" + \
-        ("_nores" if t["no_resident_weights"] else "") + ("_pair" if t["cta_pair"] else "") + (f"_up{c['up_c']}" if c.get("up_c") else "")
+        ("_nores" if t["no_resident_weights"] else "") + ("_pair" if t["cta_pair"] else "") + ("_alt" if t.get("epilogue_alternate") else "") + \
+        (f"_up{c['up_c']}" if c.get("up_c") else "")
 
 
 @pytest.mark.parametrize("case", TUNED_CASES, ids=[_tid(c) for c in TUNED_CASES])

@@ -142,17 +142,17 @@ def test_tune_cache_roundtrip(tmp_path, monkeypatch):
     assert any("inplace" in k for k in k1) and any("up" in k and "up-" not in k for k in k1)
     c = plan.TuneCache()
     assert c.load(None) == {}
-    c.store(None, {k1[0]: [1, 64, 1, 1, 1, 2, 1, 0, 0, 0]})
-    c.store(None, {k1[1]: [2, 96, 1, 2, 1, 2, 1, 0, 0, 0]})
+    c.store(None, {k1[0]: [1, 64, 1, 1, 1, 2, 1, 0, 0, 0, 0]})
+    c.store(None, {k1[1]: [2, 96, 1, 2, 1, 2, 1, 0, 0, 0, 1]})
     got = plan.TuneCache().load(None)
-    assert got == {k1[0]: [1, 64, 1, 1, 1, 2, 1, 0, 0, 0], k1[1]: [2, 96, 1, 2, 1, 2, 1, 0, 0, 0]}
+    assert got == {k1[0]: [1, 64, 1, 1, 1, 2, 1, 0, 0, 0, 0], k1[1]: [2, 96, 1, 2, 1, 2, 1, 0, 0, 0, 1]}
     monkeypatch.setattr(plan.TuneCache, "section", lambda self, device: "fake B200|rev2")
     assert plan.TuneCache().load(None) == {}
-    plan.TuneCache().store(None, {k1[0]: [1, 128, 1, 1, 1, 2, 1, 0, 0, 0]})
+    plan.TuneCache().store(None, {k1[0]: [1, 128, 1, 1, 1, 2, 1, 0, 0, 0, 0]})
     import json
     assert list(json.load(open(tmp_path / "tc.json"))) == ["fake B200|rev2"]
     monkeypatch.setenv("YX_TUNE_CACHE", "0")
     assert plan.TuneCache().load(None) == {}
     from yolox_b200 import _capi
-    t = _capi.ConvTune.from_list([2, 96, 1, 2, 1, 2, 1, 0, 1, 0])
-    assert t.as_list() == [2, 96, 1, 2, 1, 2, 1, 0, 1, 0] and t.cta_pair == 1
+    t = _capi.ConvTune.from_list([2, 96, 1, 2, 1, 2, 1, 0, 1, 0, 1])
+    assert t.as_list() == [2, 96, 1, 2, 1, 2, 1, 0, 1, 0, 1] and t.cta_pair == 1 and t.epilogue_alternate == 1
