@@ -235,6 +235,12 @@ def gpu_reference_run(model, size, batch, steps):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
+        e0.record()
+        for _ in range(steps):                                       # the network alone (no decode / NMS)
+            mr.forward_raw(sdi, cfg, xi)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_fwd = e0.elapsed_time(e1) / steps
         x1 = xi[:1].contiguous(memory_format=torch.channels_last) if cl else xi[:1].contiguous()
         for _ in range(8):
             one(x1, sdi)
@@ -246,7 +252,8 @@ def gpu_reference_run(model, size, batch, steps):
             b.record()
             torch.cuda.synchronize()
             lat.append(a.elapsed_time(b))
-        out[fmt] = dict(images_per_s=batch / ms * 1e3, ms_per_step=ms, latency_bs1_ms_p50=statistics.median(lat))
+        out[fmt] = dict(images_per_s=batch / ms * 1e3, ms_per_step=ms, forward_only_ms_per_step=ms_fwd,
+                        forward_only_images_per_s=batch / ms_fwd * 1e3, latency_bs1_ms_p50=statistics.median(lat))
         del sdi, xi
     torch.backends.cudnn.benchmark = prev
     torch.cuda.empty_cache()
@@ -255,6 +262,9 @@ def gpu_reference_run(model, size, batch, steps):
                      "decode + per-image torchvision.batched_nms, same masked weights, same box, same process",
                 batch=batch, size=size, steps=steps, nchw=out["nchw"], channels_last=out["channels_last"],
                 best_images_per_s=best["images_per_s"], best_latency_bs1_ms_p50=min(d["latency_bs1_ms_p50"] for d in out.values()),
+                best_forward_only_images_per_s=max(d["forward_only_images_per_s"] for d in out.values()),
+                note="the synthetic workload keeps ~all 34 000 anchors per image above conf 0.001, the worst case for the reference's "
+                     "per-image Python loop (argsort + batched_nms + host syncs); forward_only_* isolates the network",
                 torch=torch.__version__)
 
 
@@ -617,6 +627,7 @@ def run_ours(args, rank, world, local_rank):
             gpu_ref = gpu_reference_run(model, S, B, steps=5)
             ours_ips = B * world * args.steps / (ms_dev * 1e-3)
             gpu_ref["ours_over_best_reference_throughput"] = ours_ips / gpu_ref["best_images_per_s"]
+            gpu_ref["ours_network_over_best_reference_forward_only"] = (B / net_ms_step * 1e3) / gpu_ref["best_forward_only_images_per_s"]
             gpu_ref["ours_latency_bs1_ms_p50"] = lat_p50
         except Exception as e:  # noqa: BLE001  (the baseline must never cost the headline line)
             gpu_ref = dict(error=f"{type(e).__name__}: {e}")

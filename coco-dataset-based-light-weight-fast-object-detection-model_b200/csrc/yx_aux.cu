@@ -7,6 +7,8 @@
 
 #include <algorithm>
 
+#include <cstdlib>
+
 #include "yx_internal.h"
 
 namespace yx {
@@ -312,6 +314,84 @@ __global__ void dwconv_kernel(const __half* __restrict__ src, __half* __restrict
   }
 }
 
+// Register-blocked form for stride 1: one thread = 8 channels x a strip of TX consecutive output pixels.  Per filter row the
+// thread loads the TX + K - 1 input vectors of the strip ONCE (the k*k-loads-per-output form above re-reads every input
+// k*k times through L1) and the K weight vectors of that row; consecutive threads are consecutive channel vectors of the
+// same strip, so every load / store instruction of a warp is one contiguous run of up to 512 bytes.
+template <int K, int TX>
+__global__ void __launch_bounds__(256) dwconv_strip_kernel(const __half* __restrict__ src, __half* __restrict__ dst,
+                                                           const __half* __restrict__ wgt, const float* __restrict__ bias, int B,
+                                                           int H, int W, int C, int act, int spitch, int dpitch, int64_t sn,
+                                                           int64_t dn) {
+  constexpr int PAD = K / 2;
+  const int cv = C >> 3, strips = (W + TX - 1) / TX;
+  const int64_t total = (int64_t)B * H * strips * cv;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = i % cv;
+    const int64_t r = i / cv;
+    const int x0 = (int)(r % strips) * TX, y = (int)((r / strips) % H), b = (int)(r / ((int64_t)strips * H));
+    float acc[TX][8];
+#pragma unroll
+    for (int t = 0; t < TX; ++t)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < K; ++dy) {
+      const int yy = y + dy - PAD;
+      if (yy < 0 || yy >= H) continue;
+      float wf[K][8];   // this filter row's weights, converted ONCE (the kernel is fp32-FMA-issue bound, not HBM bound)
+#pragma unroll
+      for (int dx = 0; dx < K; ++dx) {
+        const uint4 wv = __ldg(reinterpret_cast<const uint4*>(wgt + (int64_t)(dy * K + dx) * C) + c8);
+        const __half2* wh = reinterpret_cast<const __half2*>(&wv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 ww = __half22float2(wh[j]);
+          wf[dx][2 * j] = ww.x; wf[dx][2 * j + 1] = ww.y;
+        }
+      }
+      const __half* row = src + b * sn + (int64_t)yy * W * spitch;
+#pragma unroll
+      for (int xi = 0; xi < TX + K - 1; ++xi) {
+        const int xx = x0 + xi - PAD;
+        if (xx < 0 || xx >= W) continue;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(row + (int64_t)xx * spitch) + c8);
+        const __half2* vh = reinterpret_cast<const __half2*>(&v);
+        float a[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(vh[j]);
+          a[2 * j] = f.x; a[2 * j + 1] = f.y;
+        }
+#pragma unroll
+        for (int dx = 0; dx < K; ++dx) {   // input column xi feeds output t = xi - dx through tap dx
+          const int t = xi - dx;
+          if (t < 0 || t >= TX) continue;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(a[j], wf[dx][j], acc[t][j]);
+        }
+      }
+    }
+    float bv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bv[j] = bias[c8 * 8 + j];
+#pragma unroll
+    for (int t = 0; t < TX; ++t) {
+      if (x0 + t >= W) break;
+      uint4 o;
+      __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float f0 = acc[t][2 * j] + bv[2 * j], f1 = acc[t][2 * j + 1] + bv[2 * j + 1];
+        f0 = act_f(__half2float(__float2half_rn(f0)), act);
+        f1 = act_f(__half2float(__float2half_rn(f1)), act);
+        oh[j] = __floats2half2_rn(f0, f1);
+      }
+      reinterpret_cast<uint4*>(dst + b * dn + ((int64_t)y * W + x0 + t) * dpitch)[c8] = o;
+    }
+  }
+}
+
 int dwconv_launch(void* base, const yx_op& op, const void* weights, const void* biases, cudaStream_t stream) {
   const yx_view& s = op.src;
   const yx_view& d = op.dst;
@@ -322,6 +402,22 @@ int dwconv_launch(void* base, const yx_op& op, const void* weights, const void* 
   YX_REQUIRE(d.h == Ho && d.w == Wo && d.c == s.c && d.n == s.n && s.c % 8 == 0, "depthwise dst geometry");
   YX_REQUIRE(s.offset % 16 == 0 && d.offset % 16 == 0 && s.pitch % 8 == 0 && d.pitch % 8 == 0 && op.w_offset % 16 == 0,
              "depthwise alignment");
+  static const bool strip_env = !(getenv("YX_DW_STRIP") && atoi(getenv("YX_DW_STRIP")) == 0);
+  if (op.stride == 1 && strip_env) {
+    constexpr int TX = 8;
+    const int64_t n_threads = (int64_t)d.n * Ho * ((Wo + TX - 1) / TX) * (d.c / 8);
+    const int nb = (int)std::min<int64_t>((n_threads + 255) / 256, 148 * 16);
+    const __half* sp = reinterpret_cast<const __half*>(static_cast<uint8_t*>(base) + s.offset);
+    __half* dp = reinterpret_cast<__half*>(static_cast<uint8_t*>(base) + d.offset);
+    const __half* wp = reinterpret_cast<const __half*>(static_cast<const uint8_t*>(weights) + op.w_offset);
+    const float* bp = reinterpret_cast<const float*>(static_cast<const uint8_t*>(biases) + op.b_offset);
+    if (op.ksize == 3)
+      dwconv_strip_kernel<3, TX><<<nb, 256, 0, stream>>>(sp, dp, wp, bp, s.n, s.h, s.w, s.c, op.act, s.pitch, d.pitch, s.nstride, d.nstride);
+    else
+      dwconv_strip_kernel<5, TX><<<nb, 256, 0, stream>>>(sp, dp, wp, bp, s.n, s.h, s.w, s.c, op.act, s.pitch, d.pitch, s.nstride, d.nstride);
+    YX_CUDA(cudaGetLastError());
+    return YX_OK;
+  }
   const int64_t total = (int64_t)d.n * Ho * Wo * (d.c / 8);
   const int threads = 256;
   const int blocks = (int)std::min<int64_t>((total + threads - 1) / threads, 148 * 16);
