@@ -214,6 +214,16 @@ class Focus(nn.Module):
 
     def emit(self, g, name, out=None):
         c = self.conv
+        if (c.ksize == 3 and c.stride == 1 and c.groups == 1 and os.environ.get("YX_FUSE_S2D", "1") != "0"
+                and c.conv.out_channels <= 96      # nine resident weight taps + halo stages + raw patches must fit in smem
+                and g.in_w % 16 == 0 and g.in_h // 2 >= 16 and g.in_w // 2 >= 8
+                and -(-(g.in_h // 2) // 16) * 16 * (-(-(g.in_w // 2) // 8) * 8) <= 1.25 * (g.in_h // 2) * (g.in_w // 2)):
+            # image-fed stem: the conv kernel's producer warps build the halo operand tiles straight from the NCHW image
+            # (space-to-depth + input affine fused into the stem's operand build): no s2d launch, no s2d tensor
+            w, b = c.folded()
+            if out is None:
+                out = g.new_buf(name + ".conv", g.in_h // 2, g.in_w // 2, w.shape[0]).view()
+            return g.conv_stem_image(name + ".conv", out, w, b, c.act_type, self.order)
         if c.ksize == 3 and c.stride == 1 and c.groups == 1:
             # row-packed stem: padded s2d rows + overlapping-view conv (3 taps of K=48 instead of 9 of K=16)
             s2d = g.new_buf(name + ".s2d", g.in_h // 2, g.in_w // 2 + 4, 16)

@@ -26,6 +26,7 @@
 // Warp roles: 0 = A producer, 1 = MMA issuer, 2 = B producer (+TMEM alloc), 3 = second producer,
 //             4..7 = epilogue group 0, 8..11 = epilogue group 1 (optional).
 #include <algorithm>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
@@ -216,6 +217,149 @@ struct TileIter {
 };
 #define YX_TILE_NEXT(it) (it).next(n_tiles_n, tiles_w, tiles_h, p.step_nt, p.step_x, p.step_y, p.step_img)
 
+// ---- image-fed stem (IMG): the space-to-depth of the NCHW input image (Focus / FocusCustom, network_blocks.py:330-361,
+// blocks.py:286-304) is done by the conv kernel's own producer warps, straight into the swizzled operand tile, so the
+// 16-channel s2d tensor (1.3 GB written and read back per bs64 step, a separate write-bound kernel) never exists.
+// Input affine exactly as the stand-alone s2d kernel applies it (yx_aux.cu affine_in: the predict loop's
+// img.mul_(s).add_(b) in the image dtype, main.py:164).
+template <typename T> __device__ __forceinline__ float img_affine(T v, float scale, float shift, bool on);
+template <> __device__ __forceinline__ float img_affine<__half>(__half v, float scale, float shift, bool on) {
+  float x = __half2float(v);
+  if (on) {
+    x = __half2float(__float2half_rn(x * scale));
+    x = __half2float(__float2half_rn(x + shift));
+  }
+  return x;
+}
+template <> __device__ __forceinline__ float img_affine<uint8_t>(uint8_t v, float scale, float shift, bool on) {
+  return img_affine<__half>(__ushort2half_rn(v), scale, shift, on);
+}
+template <> __device__ __forceinline__ float img_affine<float>(float v, float scale, float shift, bool on) {
+  return on ? (v * scale) + shift : v;
+}
+
+constexpr int kImgProdThreads = 224;  // warps 0, 2, 3 + one extra warpgroup behind the epilogue warps (the tile builder is
+                                      // latency-bound per task: more warps, not fewer instructions, is what speeds it up)
+
+// One tile of the stem's halo operand from the raw image.  Tile = TH x 8 s2d pixels at (y0, x0); the operand is the
+// (TH + 2) x 10 halo of s2d pixels, one 128-byte swizzled smem row each (16 channels = 32 bytes used: 12 real + 4 zero;
+// the nine filter taps are nine descriptors into it, K = 16 per tap), out-of-image pixels zero (the conv's padding acts on
+// the s2d tensor).  The raw patch (3 planes x 2(TH+2) rows x 32 pixels) arrives in a scratch buffer by ONE TMA load (issued
+// a tile ahead into the other scratch buffer); one task per s2d pixel then converts its 2x2x3 values and writes 32 bytes.
+// Plain C++ shared-memory accesses through generic pointers (not asm volatile): the compiler may overlap them.
+template <typename T>
+__device__ __forceinline__ void img_build_tile(const ConvParams& p, uint8_t* stageA, const uint8_t* scratch, uint32_t scratch_u32,
+                                               const unsigned short* lut, int tid, int x0, int y0, int TH) {
+  const int H2 = p.img_h >> 1, W2 = p.img_w >> 1;
+  const int prow = 2 * (TH + 2);
+  const bool affine = p.img_affine != 0;
+  const float scale = p.img_scale, shift = p.img_shift;
+  const int order = p.img_order;
+  const int tasks = (TH + 2) * kHaloW;
+#pragma unroll 2
+  for (int t = tid; t < tasks; t += kImgProdThreads) {
+    const int pp = t % kHaloW, yy = t / kHaloW;
+    const int sx = x0 - 1 + pp, sy = y0 - 1 + yy;
+    unsigned short v[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) v[k] = 0;
+    if (sx >= 0 && sx < W2 && sy >= 0 && sy < H2) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        unsigned short h[2][2];
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+          // the patch arrives as 128-byte rows in the TMA's 128-byte swizzle (16-byte chunk index ^ (row & 7)); the pixel
+          // pair of s2d column pp sits at byte 2 * pp * sizeof(T) of patch row R = plane * prow + image row
+          // (the row starts kImgLead<T> pixels left of the tile's first needed pixel 2*x0 - 2: see img_producer_loop)
+          const uint32_t R = (uint32_t)(c * prow + 2 * yy + dy), byte = (uint32_t)(16 / (int)sizeof(T) - 2 + 2 * pp) * (uint32_t)sizeof(T);
+          // (the swizzle XORs the chunk index with bits [7,10) of the shared-memory ADDRESS of the row: the patch buffers are
+          // 128- but not 1024-byte aligned, so the row's position inside its 1024-byte window comes from the address)
+          const uint8_t* src = scratch + R * 128u + ((((byte >> 4) ^ ((scratch_u32 >> 7) + R)) & 7u) << 4) + (byte & 15u);
+          if (sizeof(T) == 1) {
+            // uint8 pixels: the affine + fp16 roundings come from a 256-entry table built once per CTA (exactly the
+            // values img_affine<uint8_t> gives): two table reads instead of ~16 conversion instructions per pixel pair
+            const unsigned short w = *reinterpret_cast<const unsigned short*>(src);
+            h[dy][0] = lut[w & 0xffu];
+            h[dy][1] = lut[w >> 8];
+          } else if (sizeof(T) == 2) {
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(src);
+            h[dy][0] = __half_as_ushort(__float2half_rn(img_affine<__half>(__ushort_as_half((unsigned short)(w & 0xffff)), scale, shift, affine)));
+            h[dy][1] = __half_as_ushort(__float2half_rn(img_affine<__half>(__ushort_as_half((unsigned short)(w >> 16)), scale, shift, affine)));
+          } else {
+            const float2 w = *reinterpret_cast<const float2*>(src);
+            h[dy][0] = __half_as_ushort(__float2half_rn(img_affine<float>(w.x, scale, shift, affine)));
+            h[dy][1] = __half_as_ushort(__float2half_rn(img_affine<float>(w.y, scale, shift, affine)));
+          }
+        }
+        if (order == 1) {   // pixel_unshuffle: channel = c*4 + dy*2 + dx
+          v[c * 4 + 0] = h[0][0]; v[c * 4 + 1] = h[0][1]; v[c * 4 + 2] = h[1][0]; v[c * 4 + 3] = h[1][1];
+        } else {            // Focus: [TL, BL, TR, BR] patch-major
+          v[0 + c] = h[0][0]; v[3 + c] = h[1][0]; v[6 + c] = h[0][1]; v[9 + c] = h[1][1];
+        }
+      }
+    }
+    uint4 lo, hi;
+    lo.x = v[0] | ((uint32_t)v[1] << 16); lo.y = v[2] | ((uint32_t)v[3] << 16); lo.z = v[4] | ((uint32_t)v[5] << 16); lo.w = v[6] | ((uint32_t)v[7] << 16);
+    hi.x = v[8] | ((uint32_t)v[9] << 16); hi.y = v[10] | ((uint32_t)v[11] << 16); hi.z = 0u; hi.w = 0u;
+    const uint32_t r = (uint32_t)t;   // halo row = yy * 10 + pp
+    uint8_t* line = stageA + r * 128;
+    *reinterpret_cast<uint4*>(line + ((0u ^ (r & 7u)) << 4)) = lo;
+    *reinterpret_cast<uint4*>(line + ((1u ^ (r & 7u)) << 4)) = hi;
+  }
+  fence_proxy_async_smem();   // generic-proxy writes of this thread -> visible to the tensor core's async-proxy reads
+}
+
+// the producers' loop over this CTA's tiles for one image dtype (tm_img = &p.tmImg taken in the kernel body, so that it is
+// certainly a param-space address)
+template <typename T>
+__device__ __forceinline__ void img_producer_loop(const ConvParams& p, const CUtensorMap* tm_img, uint8_t* smem_gen, uint32_t smem_gen_u32, uint32_t sA,
+                                                  uint32_t sScratch, uint32_t bar_fa, uint32_t bar_ea, uint32_t bar_patch, int tid,
+                                                  int tile_first, int n_tiles, int tile_step, uint32_t stages_a) {
+  const int n_tiles_n = p.n_tiles_n, tiles_w = p.tiles_w, tiles_h = p.tiles_h, TH = p.TH;
+  // the image is described to the TMA as fp16 PAIRS OF BYTES (any pixel type): inner box = 64 such elements = 128 bytes
+  // per patch row, SWIZZLE_128B -- the one tensor-map shape class this kernel family is known to run (a plain unswizzled
+  // 4-D byte / fp16 map of the same tensor raised "illegal instruction" on this driver, whatever its parameters)
+  const uint32_t patch_bytes = (uint32_t)(3 * 2 * (TH + 2)) * 128u;
+  const uint32_t buf_bytes = patch_bytes;
+  // The innermost TMA coordinate must address a 16-BYTE ALIGNED element (a start 4 bytes left of an aligned pixel is an
+  // "illegal instruction"): rows start lead = 16 / sizeof(T) pixels (exactly 16 bytes) left of pixel 2*x0 = 16*tx, and the
+  // builder skips lead - 2 pixels.  x coordinate in fp16-sized elements: (16*tx - lead) * sizeof(T) / 2 = 8*tx*sizeof(T) - 8.
+  const int xs = (int)sizeof(T);
+  // uint8 images: value table behind the two patch buffers (the scratch region is sized for fp32 pixels)
+  const uint32_t sLut = sScratch + 2u * buf_bytes;
+  if (sizeof(T) == 1) {
+    for (int i = tid; i < 256; i += kImgProdThreads) {
+      const unsigned short h = __half_as_ushort(__float2half_rn(img_affine<uint8_t>((uint8_t)i, p.img_scale, p.img_shift, p.img_affine != 0)));
+      asm volatile("st.shared.u16 [%0], %1;" ::"r"(sLut + 2u * i), "h"(h) : "memory");
+    }
+  }
+  named_bar_sync(5, kImgProdThreads);
+  uint32_t s = 0, ph = 0, i = 0;
+  TileIter ti;
+  ti.init(p, tile_first);
+  if (tid == 0 && tile_first < n_tiles) {   // the first tile's patch
+    mbar_expect_tx(bar_patch, patch_bytes);
+    tma_load_4d(sScratch, tm_img, bar_patch, ti.tx * p.TW * xs - 8, 2 * (ti.ty * TH - 1), 0, ti.img);
+  }
+  for (int tile = tile_first; tile < n_tiles; tile += tile_step, ++i) {
+    const int x0 = ti.tx * p.TW, y0 = ti.ty * TH;
+    YX_TILE_NEXT(ti);
+    const uint32_t b = i & 1u;
+    if (tid == 0 && tile + tile_step < n_tiles) {   // next tile's patch into the other buffer: its last reader (tile i - 1) passed
+      mbar_expect_tx(bar_patch + 8 * (b ^ 1u), patch_bytes);                                  // barrier 6 before this point
+      tma_load_4d(sScratch + (b ^ 1u) * buf_bytes, tm_img, bar_patch + 8 * (b ^ 1u), ti.tx * p.TW * xs - 8, 2 * (ti.ty * TH - 1), 0, ti.img);
+    }
+    mbar_wait(bar_ea + 8 * s, ph ^ 1);
+    mbar_wait(bar_patch + 8 * b, (i >> 1) & 1u);
+    img_build_tile<T>(p, smem_gen + (sA + s * p.a_stage_bytes - smem_gen_u32), smem_gen + (sScratch + b * buf_bytes - smem_gen_u32),
+                      sScratch + b * buf_bytes, reinterpret_cast<const unsigned short*>(smem_gen + (sLut - smem_gen_u32)), tid, x0, y0, TH);
+    named_bar_sync(6, kImgProdThreads);
+    if (tid == 0) mbar_arrive(bar_fa + 8 * s);   // after the producers' barrier: every thread's fenced writes are in
+    if (++s == stages_a) { s = 0; ph ^= 1; }
+  }
+}
+
 // ---- MMA issue helpers.  Everything here runs in the single MMA warp, warp-uniformly; the tensor pipe can only be as
 // busy as this warp is fast (ncu: with ~85 SASS instructions per tap the warp, not the tensor core, was the limiter
 // of every layer with N <= 192), so the tap sequence is fully unrolled and all loop state lives in locals.
@@ -347,9 +491,11 @@ __device__ __forceinline__ void halo_chunk_mma(uint32_t d0, uint32_t d1, uint32_
 //           reduce-add, so the residual never passes through shared memory and the epilogue never waits for it
 // SP:   2:4 sparse tensor-core variant (MODE 0 / 1, no pair): weights = sparse A operand of tcgen05.mma.sp (M = 128 output
 //       channels per MMA), pixels = B operand (N = 128), accumulator transposed (channels on lanes, pixels on columns)
-template <int ACT, int RES, int MODE, bool PAIR, bool SP = false>
-__global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant__ ConvParams p) {
+// IMG:  image-fed stem (MODE 1 / 2): the halo operand tile is built from the raw NCHW image by warps 0, 2, 3
+template <int ACT, int RES, int MODE, bool PAIR, bool SP = false, bool IMG = false>
+__global__ void __launch_bounds__(IMG ? 512 : 384, 1) conv_gemm_kernel(const __grid_constant__ ConvParams p) {
   static_assert(!SP || (!PAIR && (MODE == 0 || MODE == 1)), "sparse variant: generic or single-half halo tiles, no CTA pair");
+  static_assert(!IMG || (!PAIR && !SP && RES == 0 && (MODE == 1 || MODE == 2)), "image-fed variant: single-CTA halo tiles, no residual");
   constexpr bool HAS_RES = RES == 1;
   constexpr bool HALO = MODE == 1 || MODE == 2 || MODE == 4 || MODE == 5;
   constexpr bool RP = MODE >= 4;
@@ -367,6 +513,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
   const uint32_t stage_buf_bytes = groups64 * kTileBytes;
   const uint32_t sBias = sStage0 + p.stage_bufs * stage_buf_bytes;
   const uint32_t sBar = sBias + p.bias_bytes;
+  const uint32_t sScratch = sBar + kBarBytes;   // IMG: raw image patch of the tile being built
   // barriers (8 bytes each): fullA[8] emptyA[8] fullB[32] emptyB[32] tfull[2] tempty[2] res[2], then the TMEM slot.
   // shared_ring (generic, streamed weights): A and B of a k-iteration share fullA/emptyA (two producer arrivals), so
   // the MMA warp waits and commits once per k-iteration.
@@ -375,6 +522,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
   const uint32_t bar_tfull = sBar + 640, bar_tempty = sBar + 656, bar_res = sBar + 672, tmem_slot = sBar + 688;
 
   if (warp == 0 && lane == 0) {
+    if (IMG) tma_prefetch_desc(&p.tmImg);
     tma_prefetch_desc(&p.tmA[0]);
     tma_prefetch_desc(&p.tmW);
     tma_prefetch_desc(&p.tmOut);
@@ -383,6 +531,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
     for (int s = 0; s < p.stages_a; ++s) { mbar_init(bar_fa + 8 * s, p.shared_ring ? 2 : 1); mbar_init(bar_ea + 8 * s, 1); }
     if (!p.shared_ring)
       for (int s = 0; s < p.b_slots; ++s) { mbar_init(bar_fb + 8 * s, 1); mbar_init(bar_eb + 8 * s, 1); }
+    if (IMG) { mbar_init(sBar + 768, 1); mbar_init(sBar + 776, 1); }   // raw-patch buffers (TMA completion)
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
       // one arrive per epilogue warp that drains this accumulator (of both CTAs); alternating groups: one group each
@@ -432,9 +581,11 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
   const bool tracing = p.trace != nullptr;
   long long w_acc0 = 0, w_acc1 = 0, w_acc2 = 0;
   const long long t_begin = tracing ? clock64() : 0;
-  const bool is_a_prod = (warp == 0) || (warp == 3 && p.w3_role == 1);
+  const bool is_a_prod = !IMG && ((warp == 0) || (warp == 3 && p.w3_role == 1));
   const bool is_b_prod = (warp == 2) || (warp == 3 && p.w3_role == 2);
-  const bool is_a_prod_late = warp == 2 && p.w2_role == 1;   // after its (resident) weight loads
+  const bool is_a_prod_late = !IMG && warp == 2 && p.w2_role == 1;   // after its (resident) weight loads
+  const int img_extra0 = 4 + 4 * p.epi_groups;   // IMG: first warp of the extra builder warpgroup
+  const bool is_img_prod = IMG && (warp == 0 || warp == 2 || warp == 3 || warp >= img_extra0);
 
   // Programmatic dependent launch: everything above (barrier init, TMEM allocation, bias copy: none of it touches an
   // activation) overlapped the previous layer's tail.  The weight producers go on without waiting -- weights are constants,
@@ -485,9 +636,15 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
     // resident weights: this warp has nothing left to do for the rest of the kernel -> it becomes one more producer of
     // the ACTIVATION operand (w2_role).  One issuing warp sustains roughly one TMA load per 400-1000 cycles (strided
     // stride-2 boxes are the slow end), so the layers that load a box per filter tap are bound by how many warps issue.
-    if (is_a_prod_late) griddep_wait();
+    if (is_a_prod_late || (IMG && warp == 2)) griddep_wait();
   }
-  if (is_a_prod || is_a_prod_late) {
+  if (is_img_prod) {
+    // ================================ image producers (IMG): warps 0, 2, 3 build every tile together ================
+    const int tid = (warp >= img_extra0 ? 3 + (warp - img_extra0) : (warp == 0 ? 0 : warp - 1)) * 32 + lane;
+    if (p.img_dtype == YX_U8) img_producer_loop<uint8_t>(p, &p.tmImg, smem_raw, smem_u32(smem_raw), sA, sScratch, bar_fa, bar_ea, sBar + 768, tid, tile_first, n_tiles, tile_step, stages_a);
+    else if (p.img_dtype == YX_F16) img_producer_loop<__half>(p, &p.tmImg, smem_raw, smem_u32(smem_raw), sA, sScratch, bar_fa, bar_ea, sBar + 768, tid, tile_first, n_tiles, tile_step, stages_a);
+    else img_producer_loop<float>(p, &p.tmImg, smem_raw, smem_u32(smem_raw), sA, sScratch, bar_fa, bar_ea, sBar + 768, tid, tile_first, n_tiles, tile_step, stages_a);
+  } else if (is_a_prod || is_a_prod_late) {
     // ================================ A producer(s) ================================
     const uint32_t nprod = 1u + (p.w3_role == 1 ? 1u : 0u) + (p.w2_role == 1 ? 1u : 0u);
     const uint32_t mine = warp == 0 ? 0u : (warp == 3 ? 1u : nprod - 1u);
@@ -665,7 +822,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
     YX_TRACE_SUM(TW_MMA_FULLB, w_acc1);
     YX_TRACE_SUM(TW_MMA_TEMPTY, w_acc2);
     YX_TRACE_SUM(TW_TOTAL, clock64() - t_begin);
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && (!IMG || warp < img_extra0)) {
     // ================================ epilogue (warps 4..7 [, 8..11]) ================================
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     const int group = (warp - 4) >> 2;
@@ -863,7 +1020,7 @@ static void choose_tile(int H, int W, int* th, int* tw, bool even = false, int p
 }
 
 struct ConvGeom {
-  bool rowpack, has_res, has_up;
+  bool rowpack, has_res, has_up, img;
   int Hout, Wout, taps, cin_real;
   double flops, act_bytes;
 };
@@ -875,7 +1032,8 @@ static int conv_geom(const yx_op& op, ConvGeom* g) {
   YX_REQUIRE(op.stride == 1 || op.stride == 2, "conv stride must be 1 or 2");
   YX_REQUIRE(op.cin_pad % 16 == 0 && op.cout_pad % 16 == 0, "cin_pad/cout_pad must be multiples of 16");
   YX_REQUIRE(s.c % 8 == 0, "src channels must be a multiple of 8");
-  YX_REQUIRE(op.aux == 0 || op.aux == 1, "conv aux must be 0 or 1 (row-packed)");
+  YX_REQUIRE(op.aux == 0 || op.aux == 1 || op.aux == 4 || op.aux == 12,
+             "conv aux must be 0, 1 (row-packed), or 4 / 12 (stem fed from the image: Focus / pixel_unshuffle order)");
   YX_REQUIRE(d.c % 8 == 0 && d.c <= op.cout_pad, "dst channels must be a multiple of 8 and <= cout_pad");
   YX_REQUIRE(s.pitch % 8 == 0 && d.pitch % 8 == 0 && s.offset % 16 == 0 && d.offset % 16 == 0 && s.nstride % 8 == 0 &&
                  d.nstride % 8 == 0,
@@ -884,13 +1042,19 @@ static int conv_geom(const yx_op& op, ConvGeom* g) {
   // the right (the s2d output).  TMA reads it through an OVERLAPPING view (64 channels per pixel, pixel pitch 16),
   // so the 128-byte smem row of pixel x holds pixels x-1..x+2 = the three horizontal taps (+1 ignored): the
   // conv becomes 3 vertical taps with K = 48 instead of 9 taps with K = 16, and every TMA row is a full line.
-  g->rowpack = op.aux == 1;
+  g->rowpack = (op.aux & 1) != 0;
+  // aux & 4: a 3x3 stem conv FED FROM THE IMAGE -- the kernel's producer warps do the space-to-depth themselves, there is
+  // no s2d tensor (op.src is not read; the image pointer arrives with every launch); aux & 8: pixel_unshuffle order
+  g->img = (op.aux & 4) != 0;
   if (g->rowpack)
     YX_REQUIRE(op.ksize == 3 && op.stride == 1 && s.c == 16 && s.pitch == 16 && op.cin_pad == 48 && s.w > 4 && op.res.c == 0,
                "row-packed conv needs k=3, s=1, a padded 16-channel source and cin_pad = 48");
+  if (g->img)
+    YX_REQUIRE(op.ksize == 3 && op.stride == 1 && op.cin_pad == 16 && op.res.c == 0 && op.up.c == 0 && d.w % 8 == 0 && d.h >= 16 && d.w >= 8,
+               "image-fed stem needs k=3, s=1, cin_pad = 16, no residual, an image width that is a multiple of 16 and a map of >= 16x8");
   const int pad = (op.ksize - 1) / 2;  // BaseConv: pad = (ksize - 1) // 2 (network_blocks.py:54); 4x4/s2 (P6-v2) pads 1
-  g->Hout = g->rowpack ? s.h : (s.h + 2 * pad - op.ksize) / op.stride + 1;
-  g->Wout = g->rowpack ? s.w - 4 : (s.w + 2 * pad - op.ksize) / op.stride + 1;
+  g->Hout = g->img ? d.h : (g->rowpack ? s.h : (s.h + 2 * pad - op.ksize) / op.stride + 1);
+  g->Wout = g->img ? d.w : (g->rowpack ? s.w - 4 : (s.w + 2 * pad - op.ksize) / op.stride + 1);
   YX_REQUIRE(d.h == g->Hout && d.w == g->Wout && d.n == s.n, "dst spatial dims do not match the conv geometry");
   g->has_res = op.res.c > 0;
   if (g->has_res)
@@ -909,10 +1073,11 @@ static int conv_geom(const yx_op& op, ConvGeom* g) {
     YX_REQUIRE(s.c <= op.cin_pad, "src channels must be <= cin_pad");
   }
   g->taps = g->rowpack ? 3 : op.ksize * op.ksize;
-  g->cin_real = g->rowpack ? 12 : s.c + (g->has_up ? op.up.c : 0);
+  g->cin_real = (g->rowpack || g->img) ? 12 : s.c + (g->has_up ? op.up.c : 0);
   const double px_out = (double)d.n * g->Hout * g->Wout;
   g->flops = 2.0 * px_out * d.c * g->cin_real * op.ksize * op.ksize;
   g->act_bytes = 2.0 * ((double)s.n * s.h * s.w * (g->rowpack ? 12 : s.c) + px_out * d.c * (g->has_res ? 2 : 1));
+  if (g->img) g->act_bytes = px_out * 12.0 * 2.0 + 2.0 * px_out * d.c;   // the image once (counted as fp16, like the s2d op) + the output
   if (g->has_up) g->act_bytes += 2.0 * (double)op.up.n * op.up.h * op.up.w * op.up.c;  // read once at LOW resolution
   return YX_OK;
 }
@@ -953,6 +1118,12 @@ static ConvTune default_tune(const yx_op& op, const ConvGeom& g, bool sparse_ok 
   const bool mem_bound = g.flops / g.act_bytes < mem_bound_ai();
   t.epi_groups = 1;
   t.stage_bufs = 2;
+  if (g.img) {   // the image-fed stem only exists as the vertical-halo shape
+    // two stacked halves while the nine resident weight taps, two 43 KB halo stages and the two raw patches fit (cout <= 48)
+    t.variant = 2; t.bn = cout16; t.mh = cout16 <= 48 ? 2 : 1; t.ctas = 1; t.w3 = 1; t.epi_groups = cout16 <= 48 ? 2 : 1;
+    t.stage_bufs = cout16 <= 64 ? 2 : 1;
+    return t;
+  }
   if (halo_env && halo_ok(op, g) && op.src.c <= 96) {
     t.variant = 2;
     t.bn = cout16 <= 256 ? cout16 : round_up(ceil_div(cout16, ceil_div(cout16, 256)), 64);
@@ -987,6 +1158,19 @@ void conv_candidates(const yx_op& op, std::vector<ConvTune>* out, bool sparse_ok
   ConvGeom g;
   if (conv_geom(op, &g) != YX_OK) return;
   out->push_back(default_tune(op, g, sparse_ok));
+  if (g.img) {
+    for (int mh = 1; mh <= 2; ++mh)
+      for (int eg = 1; eg <= 2; ++eg)
+        for (int sb = 2; sb >= 1; --sb)
+          for (int alt = 0; alt <= ((eg == 2 && sb == 2) ? 1 : 0); ++alt) {
+            ConvTune t = (*out)[0];
+            t.mh = mh; t.epi_groups = eg; t.stage_bufs = sb; t.epi_alt = alt;
+            bool dup = false;
+            for (const ConvTune& o : *out) dup = dup || memcmp(&o, &t, sizeof t) == 0;
+            if (!dup) out->push_back(t);
+          }
+    return;
+  }
   if (sparse_ok && sparse_env() == 2) return;   // forced: the sparse shape is the only candidate
   if (sparse_ok && sparse_env() == 1)
     for (int eg = 1; eg <= 2; ++eg)
@@ -1083,6 +1267,7 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
   YX_REQUIRE(!pair || (t.ctas == 1 && (!halo || t.mh != 2) && !g.rowpack),
              "conv tune: CTA-pair mode runs one CTA per SM and one 128-pixel half per CTA (not for the row-packed stem)");
   YX_REQUIRE(!halo || halo_ok(op, g), "conv tune: halo variant needs a 3x3 stride-1 conv on a map of at least 16x8");
+  YX_REQUIRE(!g.img || (halo && !pair && !sp && t.ctas == 1), "conv tune: the image-fed stem runs as the vertical-halo shape, one CTA per SM");
   YX_REQUIRE(!g.has_up || !halo, "fused upsample is a 1x1 conv: generic variant only");
   YX_REQUIRE(t.bn >= 16 && t.bn <= 256 && t.bn % 16 == 0 && (t.bn % 64 == 0 || t.bn >= op.cout_pad),
              "conv tune: N tile must be a multiple of 64 (or the whole padded Cout), at most 256");
@@ -1112,6 +1297,8 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
   p.halo = halo ? 1 : 0;
   p.rowpack = g.rowpack ? 1 : 0;
   p.pair = pair ? 1 : 0;
+  p.img_fused = g.img ? 1 : 0;
+  p.img_h = 2 * d.h; p.img_w = 2 * d.w; p.img_order = (op.aux & 8) ? 1 : 0;
   p.sp = sp ? 1 : 0;
   p.sp_meta = sp ? spw->meta : nullptr;
   p.sp_cols_per_tile = g.taps * (op.cin_pad / 32);
@@ -1179,7 +1366,10 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
   p.stage_bufs = t.stage_bufs == 1 ? 1 : 2;
   const int k_loads_b = taps * p.k_chunks;  // B tiles per output tile
   for (;;) {
-    const int fixed = 1024 + kBarBytes + p.bias_bytes + p.stage_bufs * groups64 * kTileBytes;
+    // (image-fed stem: + two raw image patches (this tile's and the next one's): 3 planes x 2(TH+2) rows x 128 bytes each,
+    // + the 512-byte uint8 value table)
+    const int fixed = 1024 + kBarBytes + p.bias_bytes + p.stage_bufs * groups64 * kTileBytes +
+                      (g.img ? 2 * (3 * 2 * (p.TH + 2) * 128) + 512 : 0);
     const int avail = budget - fixed;
     const int min_a = (halo ? 2 : 2) * p.a_stage_bytes;
     // (pair: each CTA keeps ITS half of the weight rows resident -> the 96-channel 3x3 layers, whose 166 KB of weights
@@ -1223,7 +1413,7 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
     p.step_y = st % p.tiles_h;
     p.step_img = st / p.tiles_h;
   }
-  pl.threads = 128 + 128 * p.epi_groups;
+  pl.threads = 128 + 128 * p.epi_groups + (g.img ? 128 : 0);   // image-fed stem: + one warpgroup of tile builders
   // warp 3: second producer for the operand with more loads per tile (none when B is resident and A is one load)
   const int a_loads = halo ? p.k_chunks : k_loads_b;
   const int b_loads = p.b_resident ? 0 : k_loads_b;
@@ -1231,10 +1421,14 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
   if (p.w3_role == 1 && p.stages_a < 2) p.w3_role = 0;
   if (p.w3_role == 2 && p.b_slots < 2) p.w3_role = 0;
   // warp 2 (weight producer) joins the activation producers once its resident weights are in (YX_W2A=0: off, for A/B runs)
+  if (g.img) p.w3_role = 1;   // warps 0, 2, 3 build the operand tiles together; warp 2 first issues the (resident) weight loads
   static const bool w2a_env = !(getenv("YX_W2A") && atoi(getenv("YX_W2A")) == 0);
-  p.w2_role = (w2a_env && p.b_resident && t.w3 != 0 && a_loads >= 3 && p.stages_a >= 3) ? 1 : 0;
+  p.w2_role = (w2a_env && p.b_resident && t.w3 != 0 && a_loads >= 3 && p.stages_a >= 3 && !g.img) ? 1 : 0;
+  YX_REQUIRE(!g.img || p.b_resident, "image-fed stem: the weights must stay resident");
 
-  if (halo && g.rowpack) {
+  if (g.img) {
+    p.tmA[0] = p.tmA[1] = p.tmA[2] = p.tmA[3] = CUtensorMap{};   // no tensor map: the producers read the image themselves
+  } else if (halo && g.rowpack) {
     uint64_t dims[4] = {64, (uint64_t)g.Wout, (uint64_t)s.h, (uint64_t)s.n};
     uint64_t st[4] = {2, 32, (uint64_t)s.w * 32, (uint64_t)s.nstride * 2};
     uint32_t box[4] = {64, 8, (uint32_t)(p.TH + 2), 1};
@@ -1303,20 +1497,47 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
   }
   pl.flops = g.flops;
   pl.bytes = g.act_bytes + 2.0 * (double)d.c * g.cin_real * op.ksize * op.ksize;
-  snprintf(pl.desc, sizeof pl.desc, "%s%s%s%s BN%d%s mh%d ctas%d epi%d%s sbuf%d A%dx%dK B%d%s w3:%d%s grid%d smem%dK", sp ? "sparse24-" : "", p.has_res == 2 ? "inplace-" : "", pair ? "pair-" : "", halo ? "halo" : "generic",
+  snprintf(pl.desc, sizeof pl.desc, "%s%s%s%s%s BN%d%s mh%d ctas%d epi%d%s sbuf%d A%dx%dK B%d%s w3:%d%s grid%d smem%dK", g.img ? "image-fed-" : "", sp ? "sparse24-" : "", p.has_res == 2 ? "inplace-" : "", pair ? "pair-" : "", halo ? "halo" : "generic",
            p.BN, p.n_tiles_n > 1 ? "*" : "", p.mh, t.ctas, p.epi_groups, p.epi_alt ? "alt" : "", p.stage_bufs, p.stages_a, p.a_stage_bytes >> 10, p.b_slots,
            p.b_resident ? "res" : "", p.w3_role, p.w2_role ? "+w2" : "", pl.grid, pl.smem_bytes >> 10);
   *out = pl;
   return YX_OK;
 }
 
+// Binds the caller's image to an image-fed stem plan: the raw-patch tensor map (W, H, 3, B) of the image dtype with box
+// (128 bytes, 2(TH+2) rows, 3 planes, 1), out-of-image elements zero-filled (the builder never uses them: it zeroes
+// out-of-image s2d pixels AFTER the input affine).  Called once per launch (the image pointer is the caller's).
+int conv_bind_image(ConvPlan* plan, const void* image, int image_dtype, float scale, float shift) {
+  ConvParams& p = plan->p;
+  YX_REQUIRE(p.img_fused, "not an image-fed plan");
+  YX_REQUIRE(image != nullptr && (reinterpret_cast<uintptr_t>(image) & 15) == 0, "image pointer must be 16-byte aligned");
+  uint64_t es;
+  switch (image_dtype) {
+    case YX_U8: es = 1; break;
+    case YX_F16: es = 2; break;
+    case YX_F32: es = 4; break;
+    default: set_error("image dtype must be YX_F16, YX_F32 or YX_U8"); return YX_ERR_INVALID;
+  }
+  YX_REQUIRE(((uint64_t)p.img_w * es) % 16 == 0, "image-fed stem: image rows must be a multiple of 16 bytes");
+  const int B = p.n_tiles_m / (p.tiles_h * p.tiles_w);
+  // (W * es / 2 fp16-sized elements, H, 3, B); box (64 elements = 128 bytes, 2(TH+2) rows, 3 planes, 1), SWIZZLE_128B
+  uint64_t dims[4] = {(uint64_t)p.img_w * es / 2, (uint64_t)p.img_h, 3, (uint64_t)B};
+  uint64_t st[4] = {2, (uint64_t)p.img_w * es, (uint64_t)p.img_w * p.img_h * es, (uint64_t)p.img_w * p.img_h * 3 * es};
+  uint32_t box[4] = {64, (uint32_t)(2 * (p.TH + 2)), 3, 1};
+  int rc = encode_map(&p.tmImg, const_cast<void*>(image), 4, dims, st, box, true, "image");
+  if (rc != YX_OK) return rc;
+  p.img = image; p.img_dtype = image_dtype; p.img_scale = scale; p.img_shift = shift;
+  p.img_affine = (scale != 1.0f || shift != 0.0f) ? 1 : 0;
+  return YX_OK;
+}
+
 #endif  // !YX_CONV_ACT_SLICE
 
 #ifdef YX_CONV_ACT_SLICE
-template <int ACT, int RES, int MODE, bool PAIR, bool SP = false>
+template <int ACT, int RES, int MODE, bool PAIR, bool SP = false, bool IMG = false>
 static int launch_variant(const ConvPlan& plan, cudaStream_t stream) {
   static bool attr_set = false;
-  auto kernel = conv_gemm_kernel<ACT, RES, MODE, PAIR, SP>;
+  auto kernel = conv_gemm_kernel<ACT, RES, MODE, PAIR, SP, IMG>;
   if (!attr_set) {
     YX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     attr_set = true;
@@ -1354,6 +1575,14 @@ static int launch_mode(const ConvPlan& plan, cudaStream_t stream) {
     return plan.p.halo ? launch_variant<ACT, RES, 1, false, true>(plan, stream) : launch_variant<ACT, RES, 0, false, true>(plan, stream);
   if (plan.p.pair)
     return plan.p.halo ? launch_variant<ACT, RES, 1, true>(plan, stream) : launch_variant<ACT, RES, 0, true>(plan, stream);
+  if (plan.p.img_fused) {
+    if (plan.p.img == nullptr || (reinterpret_cast<uintptr_t>(plan.p.img) & 15) != 0) {
+      set_error("image-fed stem: the image pointer must be set and 16-byte aligned");
+      return YX_ERR_INVALID;
+    }
+    return plan.p.mh == 2 ? launch_variant<ACT, 0, 2, false, false, true>(plan, stream)
+                          : launch_variant<ACT, 0, 1, false, false, true>(plan, stream);
+  }
   if (plan.p.halo && plan.p.rowpack)  // the stem has no residual: only RES = 0 is instantiated
     return plan.p.mh == 2 ? launch_variant<ACT, 0, 5, false>(plan, stream) : launch_variant<ACT, 0, 4, false>(plan, stream);
   if (plan.p.halo && plan.p.mh == 2) return launch_variant<ACT, RES, 2, false>(plan, stream);

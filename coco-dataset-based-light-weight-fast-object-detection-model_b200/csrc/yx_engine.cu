@@ -58,10 +58,18 @@ static bool view_ok(const yx_view& v, size_t arena_bytes) {
   return end <= arena_bytes;
 }
 
+// launches a conv plan; the image-fed stem gets the caller's image bound at launch time
+static int launch_conv(const ConvPlan& plan, const void* image, int image_dtype, float in_scale, float in_shift, cudaStream_t st) {
+  if (!plan.p.img_fused) return conv_launch(plan, st);
+  ConvPlan pl = plan;
+  int rc = conv_bind_image(&pl, image, image_dtype, in_scale, in_shift);
+  return rc != YX_OK ? rc : conv_launch(pl, st);
+}
+
 static int run_step(yx_engine* e, const Step& s, const void* image, int image_dtype, float in_scale, float in_shift,
                     cudaStream_t st) {
   switch (s.op.kind) {
-    case YX_OP_CONV: return conv_launch(s.conv, st);
+    case YX_OP_CONV: return launch_conv(s.conv, image, image_dtype, in_scale, in_shift, st);
     case YX_OP_S2D:
       return s2d_launch(image, image_dtype, s.op.aux, e->batch, e->in_h, e->in_w, in_scale, in_shift, e->arena, s.op.dst, st);
     case YX_OP_SPP: return spp_launch(e->arena, s.op.src, s.op.dst, st);
@@ -103,7 +111,10 @@ extern "C" int yx_engine_create(const yx_op* ops, int n_ops, void* arena, size_t
   YX_REQUIRE(ops && n_ops > 0 && arena && weights && biases && out, "null argument");
   YX_REQUIRE(((uintptr_t)arena % 1024) == 0 && ((uintptr_t)weights % 256) == 0 && ((uintptr_t)biases % 256) == 0,
              "arena must be 1024-byte aligned, weights/biases 256-byte aligned");
-  YX_REQUIRE(ops[0].kind == YX_OP_S2D, "the first op must be the image space-to-depth");
+  YX_REQUIRE(ops[0].kind == YX_OP_S2D || (ops[0].kind == YX_OP_CONV && (ops[0].aux & 4)),
+             "the first op must read the image: the space-to-depth op or the image-fed stem conv");
+  for (int i = 1; i < n_ops; ++i)
+    YX_REQUIRE(!(ops[i].kind == YX_OP_CONV && (ops[i].aux & 4)), "only the first op may be fed from the image");
   int dev = 0, sms = 148;
   YX_CUDA(cudaGetDevice(&dev));
   YX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -124,7 +135,7 @@ extern "C" int yx_engine_create(const yx_op* ops, int n_ops, void* arena, size_t
     char where[64];
     snprintf(where, sizeof where, "op %d: ", i);
     bool ok = view_ok(op.dst, arena_bytes);
-    if (op.kind != YX_OP_S2D) ok = ok && view_ok(op.src, arena_bytes);
+    if (op.kind != YX_OP_S2D && !(op.kind == YX_OP_CONV && (op.aux & 4))) ok = ok && view_ok(op.src, arena_bytes);
     if (op.kind == YX_OP_CONV && op.res.c > 0) ok = ok && view_ok(op.res, arena_bytes);
     if (op.kind == YX_OP_CONV && op.up.c > 0) ok = ok && view_ok(op.up, arena_bytes);
     int rc = YX_OK;
@@ -132,7 +143,7 @@ extern "C" int yx_engine_create(const yx_op* ops, int n_ops, void* arena, size_t
       set_error(std::string(where) + "view outside the arena");
       rc = YX_ERR_INVALID;
     } else if (op.kind == YX_OP_CONV) {
-      const size_t wend = (size_t)op.w_offset + (size_t)op.cout_pad * op.ksize * (op.aux == 1 ? 1 : op.ksize) * op.cin_pad * 2;
+      const size_t wend = (size_t)op.w_offset + (size_t)op.cout_pad * op.ksize * ((op.aux & 1) ? 1 : op.ksize) * op.cin_pad * 2;
       const size_t bend = (size_t)op.b_offset + (size_t)op.cout_pad * 4;
       if (wend > weights_bytes || bend > bias_bytes || op.b_offset % 16 != 0) {
         set_error(std::string(where) + "weight/bias range outside the blobs");
@@ -282,13 +293,14 @@ extern "C" int yx_engine_tune(yx_engine* e, const void* image, int image_dtype, 
         rc = cuda_fail(cudaGetLastError(), "tune check alloc", __FILE__, __LINE__);
         break;
       }
-      if ((rc = conv_launch(ref_plan, st)) != YX_OK || (rc = view_gather(e->arena, s.op.dst, check_ref, st)) != YX_OK) break;
+      if ((rc = launch_conv(ref_plan, image, image_dtype, in_scale, in_shift, st)) != YX_OK ||
+          (rc = view_gather(e->arena, s.op.dst, check_ref, st)) != YX_OK) break;
     }
     for (const ConvTune& t : cands) {
       ConvPlan pl;
       if (conv_plan(s.op, e->arena, e->weights, e->biases, e->num_sms, &t, &pl, s.spw()) != YX_OK) continue;  // shape does not fit
       pl.store_only = inplace ? 1 : 0;
-      if ((rc = conv_launch(pl, st)) != YX_OK) break;  // warm-up (also sets the smem attribute)
+      if ((rc = launch_conv(pl, image, image_dtype, in_scale, in_shift, st)) != YX_OK) break;  // warm-up (also sets the smem attribute)
       if (check) {
         unsigned int bits = 0;
         // a conv that adds a separately loaded residual rounds f(x) to fp16 before the add: a one-step difference of f(x)
@@ -310,7 +322,7 @@ extern "C" int yx_engine_tune(yx_engine* e, const void* image, int image_dtype, 
       float ms_min = 1e30f;
       for (int k = 0; k < iters && rc == YX_OK; ++k) {
         cudaEventRecord(ev0, st);
-        rc = conv_launch(pl, st);
+        rc = launch_conv(pl, image, image_dtype, in_scale, in_shift, st);
         cudaEventRecord(ev1, st);
         if (cudaEventSynchronize(ev1) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "tune sync", __FILE__, __LINE__); break; }
         float ms = 0;
@@ -328,7 +340,7 @@ extern "C" int yx_engine_tune(yx_engine* e, const void* image, int image_dtype, 
     s.conv = best;
     if (verbose) fprintf(stderr, "tune op %zu -> %s  %.4f ms\n", i, best.desc, best_ms);
     if (inplace) rc = snap.restore(st);
-    if (rc == YX_OK) rc = conv_launch(s.conv, st);  // leave the chosen variant's output in the arena
+    if (rc == YX_OK) rc = launch_conv(s.conv, image, image_dtype, in_scale, in_shift, st);  // leave the chosen variant's output in the arena
     snap.release(st);
   }
   cudaEventDestroy(ev0);

@@ -66,6 +66,12 @@ struct ConvParams {
   const uint32_t* sp_meta;       // [n_tiles_n][sp_cols_per_tile][128] metadata words (device)
   int sp_cols_per_tile;          // taps * (cin / 32): one column per (tap, K = 32 step)
   int sp_meta_col0;              // first TMEM column of the metadata
+  // image-fed row-packed stem (IMG): the A operand is built by the kernel from the caller's NCHW image (set per launch)
+  CUtensorMap tmImg;             // raw image (W, H, 3, B), box (32 px, 2(TH+2) rows, 3, 1): encoded per launch
+  int img_fused;                 // 1: IMG variant
+  const void* img;               // [B,3,img_h,img_w] of img_dtype
+  int img_dtype, img_h, img_w, img_order, img_affine;   // order 1 = pixel_unshuffle, 0 = Focus; affine: x*scale+shift on
+  float img_scale, img_shift;
   int diag;                      // experiments (YX_CONV_DIAG): 1 no epilogue work, 2 no A loads, 4 no MMAs
   long long* trace;              // diagnostics: per-tile timeline of CTA 0 (nullptr = off)
 };
@@ -109,6 +115,7 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
               ConvPlan* out, const SparseWeights* sp = nullptr);
 void conv_candidates(const yx_op& op, std::vector<ConvTune>* out, bool sparse_ok = false);
 int conv_launch(const ConvPlan& plan, cudaStream_t stream);
+int conv_bind_image(ConvPlan* plan, const void* image, int image_dtype, float scale, float shift);   // image-fed stem: per launch
 
 // ------------------------------------------------------------------ aux ops (yx_aux.cu)
 int s2d_launch(const void* image, int image_dtype, int aux, int B, int H, int W, float scale, float shift,

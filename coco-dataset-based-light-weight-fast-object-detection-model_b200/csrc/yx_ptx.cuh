@@ -7,6 +7,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace yx {
 
@@ -52,7 +53,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+#ifdef YX_DEBUG_TRAP
+    if (++spins > (1u << 22)) {
+      if ((threadIdx.x & 31) == 0) printf("mbar_wait stuck: block %d warp %d bar_off %u parity %u\n", blockIdx.x, threadIdx.x >> 5, bar & 1023u, parity);
+      __trap();
+    }
+#else
     if (++spins > (1u << 26)) { __trap(); }
+#endif
   }
 }
 

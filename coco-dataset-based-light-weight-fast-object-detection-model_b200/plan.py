@@ -146,6 +146,18 @@ class Graph:
         return self._add(PlannedOp(_capi.OP_CONV, name, src, dst, None, 3, 1, _capi.act_code(act), w48,
                                    bias.detach().float().cpu(), aux=1, cin_pad=48, cout_pad=_rup(cout, 16)))
 
+    def conv_stem_image(self, name: str, dst: V, weight: torch.Tensor, bias: torch.Tensor, act: str, order: str) -> V:
+        """The 3x3 stem conv FED FROM THE IMAGE: the kernel's producer warps do the space-to-depth (and the input affine)
+        themselves while building the halo operand tiles, so neither the s2d op nor its 16-channel tensor exists.
+        Must be the graph's first op.  aux = 4 (image-fed) | 8 (pixel_unshuffle order); ordinary KRSC weights, K = 16."""
+        cout, cin, k, k2 = weight.shape
+        assert (cin, k, k2) == (12, 3, 3) and dst.c == cout and not self.ops, "the image-fed stem is the first op of a graph"
+        assert (dst.H, dst.W) == (self.in_h // 2, self.in_w // 2)
+        src = V(dst.buf, dst.c_off, 16)                                  # placeholder: the op reads the image, not the arena
+        return self._add(PlannedOp(_capi.OP_CONV, name, src, dst, None, 3, 1, _capi.act_code(act), weight.detach().float().cpu(),
+                                   bias.detach().float().cpu(), aux=4 | (8 if order == "unshuffle" else 0), cin_pad=16,
+                                   cout_pad=_rup(cout, 16)))
+
     @staticmethod
     def can_fuse_upsample(up: V) -> bool:
         """The engine folds nearest x2 upsample + concat into a 1x1 conv's loads when the upsampled part is whole
@@ -263,7 +275,7 @@ class Graph:
     def conv_flops(self) -> float:
         t = 0.0
         for op in self.ops:
-            if op.kind == _capi.OP_CONV and op.aux == 1:
+            if op.kind == _capi.OP_CONV and (op.aux & 1):
                 t += 2.0 * self.batch * op.dst.H * op.dst.W * op.weight.shape[0] * 12 * 9
             elif op.kind == _capi.OP_CONV:
                 cout, cin, k, _ = op.weight.shape

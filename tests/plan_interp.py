@@ -32,18 +32,21 @@ def eval_op(o, image, src, res, wblob, bblob, q, want_band=False, up=None):
     """Evaluate one planned op in fp32.  o: _capi.Op; image NCHW fp32 (S2D only); src/res NHWC fp32;
     wblob fp32 view of the fp16 weight blob, bblob fp32.  q: rounding applied where the engine rounds to
     fp16 (identity for an exact evaluation).  Returns NHWC [n,h,w,dst.c]."""
-    if o.kind == _capi.OP_S2D:
-        x = image
+    def s2d(x, unshuffle, padded):
         tl, tr, bl, br = x[..., ::2, ::2], x[..., ::2, 1::2], x[..., 1::2, ::2], x[..., 1::2, 1::2]
-        if o.aux & 1:
+        if unshuffle:
             y = torch.stack((tl, tr, bl, br), dim=2).reshape(x.shape[0], 12, x.shape[2] // 2, x.shape[3] // 2)
         else:
             y = torch.cat((tl, bl, tr, br), dim=1)
         y = F.pad(y, (0, 0, 0, 0, 0, 4))
-        if o.aux & 2:                      # padded rows: [0 | pixels | 0 0 0]
+        if padded:                         # padded rows: [0 | pixels | 0 0 0]
             y = F.pad(y, (1, 3))
         return q(y.permute(0, 2, 3, 1))
-    if o.kind == _capi.OP_CONV and o.aux == 1:
+    if o.kind == _capi.OP_S2D:
+        return s2d(image, o.aux & 1, o.aux & 2)
+    if o.kind == _capi.OP_CONV and (o.aux & 4):      # image-fed stem: the kernel does the (fp16-rounded) s2d itself
+        src = s2d(image, o.aux & 8, False)
+    if o.kind == _capi.OP_CONV and (o.aux & 1):
         # row-packed stem conv: pixel x of the GEMM sees buffer columns x, x+1, x+2 (= image pixels x-1, x, x+1)
         W = src.shape[2] - 4
         x48 = torch.cat([src[:, :, 0:W], src[:, :, 1:W + 1], src[:, :, 2:W + 2]], dim=3).permute(0, 3, 1, 2)
@@ -125,7 +128,7 @@ def run_graph_cpu(g, image, quantize=False):
     ops = g.c_ops()
     for i, pop in enumerate(g.ops):
         o = ops[i]
-        src = arena.read(o.src) if o.kind != _capi.OP_S2D else None
+        src = arena.read(o.src) if (o.kind != _capi.OP_S2D and not (o.kind == _capi.OP_CONV and (o.aux & 4))) else None
         res = arena.read(o.res) if (o.kind == _capi.OP_CONV and o.res.c > 0) else None
         up = arena.read(o.up) if (o.kind == _capi.OP_CONV and o.up.c > 0) else None
         for t, what in ((src, "src"), (res, "residual"), (up, "upsample source")):
@@ -155,7 +158,7 @@ def teacher_forced_errors(model, x):
         out = []
         for i, pop in enumerate(g.ops):
             o = ops[i]
-            src = eng.view_tensor(o.src).float() if o.kind != _capi.OP_S2D else None
+            src = eng.view_tensor(o.src).float() if (o.kind != _capi.OP_S2D and not (o.kind == _capi.OP_CONV and (o.aux & 4))) else None
             res = eng.view_tensor(o.res).float().clone() if (o.kind == _capi.OP_CONV and o.res.c > 0) else None
             band = None
             up = eng.view_tensor(o.up).float() if (o.kind == _capi.OP_CONV and o.up.c > 0) else None

@@ -82,6 +82,34 @@ def test_infer_logits_match_oracle(name, H, W, B):
     assert torch.equal(reg8[..., :4], reg) and torch.equal(cls2[..., :cfg.num_classes], cls)
 
 
+@pytest.mark.parametrize("name,H,W,B", [("tiny_p6", 128, 192, 2), ("tiny", 96, 160, 3), ("yolox_m_p6", 320, 320, 1)])
+def test_stand_alone_s2d_path(name, H, W, B, monkeypatch):
+    """YX_FUSE_S2D=0: the stand-alone space-to-depth kernel + the row-packed stem conv (what runs when the image-fed stem does
+    not apply, e.g. an image width that is not a multiple of 16) -- logits vs the oracle with the usual anchor, every op
+    teacher-forced, and bit-identity of the network's FIRST activation with the image-fed stem for fp16 and uint8 input
+    (both build the same fp16 s2d values and sum the same products; the launch shapes differ, so only the op-level bound
+    applies further down)."""
+    from tests.plan_interp import teacher_forced_errors
+    cfg, fused, model = _build(name, H, W, 3)
+    x = mr.synth_images(11, B, H, W)
+    rr, ro, rc = mr.forward_raw(_q16(fused), cfg, x.half().float())
+    tr, to, tc = _torch_fp16_cuda(fused, cfg, x)
+    for fuse in ("0", "1"):
+        monkeypatch.setenv("YX_FUSE_S2D", fuse)
+        monkeypatch.setenv("YX_TUNE", "0")
+        model.invalidate_engines()
+        reg, obj, cls = model(x.cuda().half())
+        kinds = [op.kind for op in model.engine_for(x.cuda().half()).graph.ops]
+        assert (kinds[0] == 1) == (fuse == "0"), "op 0 must be the s2d kernel exactly when the fusion is off"
+        _check_anchored(reg, rr, tr, f"reg fuse={fuse}"); _check_anchored(cls, rc, tc, f"cls fuse={fuse}")
+        bad = [e for e in teacher_forced_errors(model, x.cuda().half()) if e[2] > 2.0]
+        assert not bad, (fuse, bad[:5])
+        u8 = torch.randint(0, 256, (B, 3, H, W), dtype=torch.uint8, device="cuda")          # uint8 batches: same values as fp16
+        a = model(u8)
+        b = model(u8.half())
+        assert all(torch.equal(p, q) for p, q in zip(a, b)), f"uint8 and fp16 input disagree (fuse={fuse})"
+
+
 @pytest.mark.parametrize("name,H,W,seed", [("tiny_p6_v2", 128, 128, 4), ("tiny_dw", 96, 128, 5)])
 def test_variant_reference_golden(name, H, W, seed):
     """P6-v2 / depthwise inference twins: the engine vs the reference's raw logits (tests/golden/infer_*.npz)."""

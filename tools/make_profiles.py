@@ -11,6 +11,7 @@ OUT = os.path.join(ROOT, "profiles")
 GO = os.path.join(ROOT, "gpurun_out")
 os.makedirs(OUT, exist_ok=True)
 TAG = sys.argv[1] if len(sys.argv) > 1 else "r01"
+ONLY = sys.argv[2] if len(sys.argv) > 2 else ""      # only the gpurun_out files whose name contains this (e.g. "r02")
 peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) \
     else dict(hbm_gbs=6650.0, bf16_tflops_sustained=1400.0)
 HBM, TF = peaks["hbm_gbs"], peaks["bf16_tflops_sustained"]
@@ -131,11 +132,13 @@ def ncu(rep, dst, note):
 if __name__ == "__main__":
     for name in sorted(os.listdir(GO)):
         p = os.path.join(GO, name)
+        if ONLY and ONLY not in name:
+            continue
         if name.startswith("profile_") and name.endswith(".json"):
-            per_op(p, os.path.join(OUT, f"{TAG}_per_op_{name[8:-5]}.md"), f"Per-op profile ({name})")
+            per_op(p, os.path.join(OUT, f"{TAG}_per_op_{name[8:-5].replace('_' + ONLY, '') if ONLY else name[8:-5]}.md"), f"Per-op profile ({name})")
         elif name.startswith("launches") and name.endswith(".csv"):
-            launches(p, os.path.join(OUT, f"{TAG}_ncu_{name[:-4]}.md"))
+            launches(p, os.path.join(OUT, f"{TAG}_ncu_{name[:-4].replace('_' + ONLY, '') if ONLY else name[:-4]}.md"))
         elif name.endswith(".ncu-rep"):
             ncu(p, os.path.join(OUT, f"{TAG}_ncu_{name[:-8]}.txt"), name)
         elif name.endswith("_raw.csv"):
-            ncu(p, os.path.join(OUT, f"{TAG}_ncu_{name[:-8]}.txt"), name)
+            ncu(p, os.path.join(OUT, f"{TAG}_ncu_{name[:-8].replace(ONLY + '_', '') if ONLY else name[:-8]}.txt"), name)
