@@ -193,6 +193,11 @@ __global__ void select_infer_kernel(const T* __restrict__ reg, int64_t reg_sb, i
       // logit of the running best cannot have a strictly greater score: the exact first-max of the 80 products
       // needs a sigmoid only when a new running-max logit appears (~5 of 80 on average).
       const uint4* cv = reinterpret_cast<const uint4*>(c);
+      // (Tried in round 2 and measured slower than this loop's 0.21 ms at B = 64, A = 34 000, C = 80 -- kept out: requesting all
+      // ten 16-byte chunks of the row before the scan, 0.29 ms (64 more registers); a warp-cooperative version streaming 32
+      // rows as one contiguous run with the per-chunk results combined through shared memory, 0.28 ms, and its refinement
+      // with prefix maxima that needs only ~8 sigmoids per row, 0.51 ms.  The kernel is bound by the scan's dependent
+      // compare / branch chain per thread, not by HBM: DRAM traffic is the algorithmic 383 MB either way.)
       float best_logit = -INFINITY;
       {  // class 0 is always evaluated (also covers a -inf logit, whose score 0 still beats the -1 sentinel)
         const float x0 = ldf(c);
@@ -230,83 +235,6 @@ __global__ void select_infer_kernel(const T* __restrict__ reg, int64_t reg_sb, i
       const int pos = warp_agg_inc(ws.count + b);
       ws.keys[(int64_t)b * ws.Apad + pos] = make_key(best, a);
     }
-  }
-}
-
-// Warp-cooperative form of the same selection for the engine's own layout (fp16 class logits in contiguous rows of C = 8k
-// values, 16-byte aligned): a warp takes 32 consecutive anchors of one image and streams their rows as ONE contiguous run of
-// 16-byte chunks (lane l loads chunks l, l + 32, ...: fully coalesced 512-byte requests) instead of every thread walking its
-// own 160-byte row (32 rows per request: 0.33 of HBM peak, profiles/r01).  Each chunk is scanned in class order with the
-// running-maximum rule of select_infer_kernel (a sigmoid only when the logit exceeds the running best of the chunk), the
-// per-chunk (score, class) pairs meet in shared memory, and lane r reduces the chunks of row r in class order keeping the
-// FIRST maximum: the result is the exact first-max of the C products, bit-identical to the scalar kernel.
-constexpr int kSelWarps = 8;
-__global__ void __launch_bounds__(kSelWarps * 32) select_infer_rows_kernel(
-    const __half* __restrict__ reg, int64_t reg_sb, int64_t reg_sa, const __half* __restrict__ obj, int64_t obj_sb, int64_t obj_sa,
-    const __half* __restrict__ cls, int64_t cls_sb, int B, int A, int C, LevelsDev lv, float thr, Workspace ws) {
-  extern __shared__ float2 s_chunk[];   // [warp][32 * cpr] (score, class)
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int cpr = C >> 3;               // 16-byte chunks per row
-  float2* mine = s_chunk + (size_t)wib * 32 * cpr;
-  const int groups_per_img = (A + 31) >> 5;
-  const int64_t n_groups = (int64_t)B * groups_per_img;
-  for (int64_t g = (int64_t)blockIdx.x * kSelWarps + wib; g < n_groups; g += (int64_t)gridDim.x * kSelWarps) {
-    const int b = (int)(g / groups_per_img), a0 = (int)(g % groups_per_img) << 5;
-    const int nrows = min(32, A - a0), a = a0 + lane;
-    const bool row_ok = lane < nrows;
-    float oc = 0.0f;
-    if (row_ok) oc = sigmoid_f(__half2float(obj[b * obj_sb + a * obj_sa]));
-    const uint4* src = reinterpret_cast<const uint4*>(cls + b * cls_sb + (int64_t)a0 * C);
-    const int n_chunks = nrows * cpr;
-    for (int c = lane; c < 32 * cpr; c += 32) {          // warp-uniform trip count (cpr iterations)
-      const int r = c / cpr;
-      const float ocr = __shfl_sync(0xffffffffu, oc, r & 31);
-      if (c < n_chunks) {
-        const uint4 v = __ldg(src + c);
-        const __half2* h = reinterpret_cast<const __half2*>(&v);
-        const int k0 = (c - r * cpr) << 3;
-        float best = -1.0f, best_logit = -INFINITY;
-        int bi = k0;
-        {  // the chunk's first class is always evaluated (see select_infer_kernel)
-          const float x0 = __half2float(__low2half(h[0]));
-          best = __fmul_rn(sigmoid_f(x0), ocr); best_logit = x0;
-          if (!(best > -1.0f)) { best = -1.0f; best_logit = -INFINITY; }   // NaN score: never selected, like s > best
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = __half22float2(h[j]);
-          if (j > 0 && (f.x > best_logit || f.x != f.x)) {
-            const float s0 = __fmul_rn(sigmoid_f(f.x), ocr);
-            if (s0 > best) { best = s0; bi = k0 + 2 * j; best_logit = f.x; }
-          }
-          if (f.y > best_logit || f.y != f.y) {
-            const float s1 = __fmul_rn(sigmoid_f(f.y), ocr);
-            if (s1 > best) { best = s1; bi = k0 + 2 * j + 1; best_logit = f.y; }
-          }
-        }
-        mine[c] = make_float2(best, __int_as_float(bi));
-      }
-    }
-    __syncwarp();
-    if (row_ok) {
-      float best = -1.0f;
-      int bi = 0;
-      for (int k = 0; k < cpr; ++k) {                     // class order: strict '>' keeps the first maximum
-        const float2 e = mine[lane * cpr + k];
-        if (e.x > best) { best = e.x; bi = __float_as_int(e.y); }
-      }
-      if (best >= thr) {
-        const int64_t i = (int64_t)b * A + a;
-        float gx, gy, s;
-        anchor_geom(lv, a, &gx, &gy, &s);
-        const __half* r = reg + b * reg_sb + a * reg_sa;
-        ws.box[i] = decode_box_xyxy(ldf(r), ldf(r + 1), ldf(r + 2), ldf(r + 3), gx, gy, s);
-        ws.objc[i] = oc; ws.col5[i] = best; ws.score[i] = best; ws.label[i] = bi;
-        const int pos = warp_agg_inc(ws.count + b);
-        ws.keys[(int64_t)b * ws.Apad + pos] = make_key(best, a);
-      }
-    }
-    __syncwarp();
   }
 }
 
@@ -925,15 +853,7 @@ static int detect_main_impl(const void* reg, int64_t reg_sb, int64_t reg_sa, con
   const int g = grid_for((int64_t)B * A, 128);
   if (logits_dtype == YX_F16) {
     const bool vec = (C % 8 == 0) && (cls_sa % 8 == 0) && (cls_sb % 8 == 0) && (((uintptr_t)cls) % 16 == 0);
-    static const bool rows_env = !(getenv("YX_SELECT_ROWS") && atoi(getenv("YX_SELECT_ROWS")) == 0);
-    if (vec && cls_sa == C && C <= 512 && rows_env) {   // contiguous rows: the warp-cooperative streaming kernel
-      const int cpr = C >> 3;
-      const size_t smem = (size_t)kSelWarps * 32 * cpr * sizeof(float2);
-      const int64_t n_groups = (int64_t)B * ((A + 31) / 32);
-      const int grid = (int)std::min<int64_t>((n_groups + kSelWarps - 1) / kSelWarps, 148 * 8);
-      select_infer_rows_kernel<<<grid, kSelWarps * 32, smem, st>>>((const __half*)reg, reg_sb, reg_sa, (const __half*)obj, obj_sb,
-                                                                   obj_sa, (const __half*)cls, cls_sb, B, A, C, lv, conf_thr, ws);
-    } else if (vec)
+    if (vec)
       select_infer_kernel<__half, true><<<g, 128, 0, st>>>((const __half*)reg, reg_sb, reg_sa, (const __half*)obj, obj_sb,
                                                            obj_sa, (const __half*)cls, cls_sb, cls_sa, B, A, C, lv, conf_thr, ws);
     else

@@ -276,22 +276,24 @@ def test_decode_alternating_grid_shapes():
         yb.postprocess.yolox_postprocess_output_torch_batch(r, o, c, grids[:, :-1], scales)
 
 
-@pytest.mark.parametrize("A,C", [(34000, 80), (8400, 80), (1000, 8), (37, 24)])
-def test_select_rows_kernel_equals_scalar_kernel(A, C):
-    """The warp-cooperative selection kernel (contiguous class rows) against the thread-per-anchor one (forced by handing the
-    same logits over as a strided slice of a wider tensor): identical detections bit for bit, on logits that include
-    saturated values (ties between DIFFERENT logits: sigmoid rounds to 1 / underflows to 0), exact duplicates, +-inf and NaN."""
+@pytest.mark.parametrize("A,C", [(34000, 80), (8400, 80), (1000, 8), (37, 24), (500, 128), (300, 136)])
+def test_select_vector_kernel_equals_scalar_kernel(A, C):
+    """The vectorised selection kernel (16-byte chunks of the class row, a sigmoid only for a new running-maximum logit)
+    against the plain one-class-at-a-time kernel (forced by handing the same logits over as a slice of a tensor whose row
+    pitch is not a multiple of 8): identical detections bit for bit, on logits that include saturated values (ties between
+    DIFFERENT logits: sigmoid rounds to 1 / underflows to 0), exact duplicates, +-inf and NaN."""
     B = 3
     g = torch.Generator().manual_seed(A + C)
     cls = (torch.randn(B, A, C, generator=g) * 6).half()
     cls[:, ::5, :] = (torch.randn(B, (A + 4) // 5, C, generator=g) * 2 + 18).half()     # saturated rows: many score ties
     cls[:, 1::7, : C // 2] = cls[:, 1::7, C // 2: 2 * (C // 2)]                        # duplicated logits
     cls[:, 3::11, 0] = float("inf"); cls[:, 4::13, C - 1] = float("-inf"); cls[:, 5::17, C // 3] = float("nan")
+    cls[:, 8::23, 0] = float("nan"); cls[:, 9::29, :] = float("-inf")
     obj = (torch.randn(B, A, 1, generator=g) * 3).half()
     obj[:, 6::19] = float("nan")
     reg = torch.randn(B, A, 4, generator=g).half()
     hw, strides = [(A, 1)], [8]
-    wide = torch.zeros(B, A, C + 8, dtype=torch.float16)
+    wide = torch.zeros(B, A, C + 4, dtype=torch.float16)
     wide[..., :C] = cls
     a = yb.postprocess.detect_main(reg.to(DEV), obj.to(DEV), cls.to(DEV), hw, strides, 0.001, 0.65, 5000, 300)
     b = yb.postprocess.detect_main(reg.to(DEV), obj.to(DEV), wide.to(DEV)[..., :C], hw, strides, 0.001, 0.65, 5000, 300)
