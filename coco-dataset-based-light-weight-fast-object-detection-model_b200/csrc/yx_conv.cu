@@ -480,6 +480,52 @@ __device__ __forceinline__ void halo_chunk_mma(uint32_t d0, uint32_t d1, uint32_
   }
 }
 
+// Streamed weights with ONE RING STAGE PER FILTER ROW (p.b_taps == 3): per stage one wait, one elected straight-line block of
+// 3 taps x ksteps MMAs, one commit.  b_tap = descriptor units between the taps of a stage.  DIAG: tracing / role-ablation
+// build of the same loop (blocked-cycle accounting, MMAs optionally skipped); the product path is DIAG = false.
+template <int MH, bool PAIR, bool DIAG>
+__device__ __forceinline__ void halo_chunk_mma_rows(uint32_t d0, uint32_t d1, uint32_t a0, uint32_t a_hi, uint32_t& b_lo, uint32_t b_hi,
+                                                    uint32_t idesc, uint32_t& accum, int ksteps, uint32_t bar_fb, uint32_t bar_eb,
+                                                    uint32_t& sb, uint32_t& phb, uint32_t b_slots, uint32_t b_lo0, uint32_t b_step,
+                                                    uint32_t b_tap, bool tracing, long long& w_acc, bool skip_mma) {
+#pragma unroll
+  for (int row = 0; row < 3; ++row) {
+    if (DIAG) mbar_wait_acc(bar_fb + 8 * sb, phb, tracing, w_acc);
+    else mbar_wait(bar_fb + 8 * sb, phb);
+    tc_fence_after();
+    if (elect_one()) {
+      if (!DIAG || !skip_mma) {
+        if (ksteps == 4) {
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            const uint32_t a_tap = a0 + (row * kHaloW + dx) * 8, b_t = b_lo + dx * b_tap;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              umma_x<PAIR>(d0, a_tap + 2 * ks, a_hi, b_t + 2 * ks, b_hi, idesc, (dx | ks) == 0 ? accum : 1u);
+              if (MH == 2) umma_x<PAIR>(d1, a_tap + 16 * kHaloW * 8 + 2 * ks, a_hi, b_t + 2 * ks, b_hi, idesc, (dx | ks) == 0 ? accum : 1u);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            const uint32_t a_tap = a0 + (row * kHaloW + dx) * 8, b_t = b_lo + dx * b_tap;
+#pragma unroll
+            for (int ks = 0; ks < 3; ++ks)
+              if (ks < ksteps) {
+                umma_x<PAIR>(d0, a_tap + 2 * ks, a_hi, b_t + 2 * ks, b_hi, idesc, (dx | ks) == 0 ? accum : 1u);
+                if (MH == 2) umma_x<PAIR>(d1, a_tap + 16 * kHaloW * 8 + 2 * ks, a_hi, b_t + 2 * ks, b_hi, idesc, (dx | ks) == 0 ? accum : 1u);
+              }
+          }
+        }
+      }
+      commit_x<PAIR>(bar_eb + 8 * sb);
+    }
+    accum = 1;
+    b_lo += b_step;
+    if (++sb == b_slots) { sb = 0; phb ^= 1; b_lo = b_lo0; }
+  }
+}
+
 // MODE: 0 = generic (one A box per tap), 1 = halo with one 128-pixel half per CTA, 2 = halo with two stacked halves,
 //       3 = generic with a 256-pixel tile (two 128-row halves per A box): halves every per-tile fixed cost of the
 //           HBM-bound small-channel layers (N <= 128)
@@ -610,19 +656,21 @@ __global__ void __launch_bounds__(IMG ? 512 : 384, 1) conv_gemm_kernel(const __g
       nt += p.step_nt;
       if (nt >= n_tiles_n) nt -= n_tiles_n;
       // ring order must match the MMA issuer: halo = (chunk, tap), generic = (tap, chunk)
-      const int outer = HALO ? k_chunks : taps, inner = HALO ? taps : k_chunks;
+      const int b_taps = p.b_taps;   // halo ring: taps per stage (3 = one filter row per load)
+      const int outer = HALO ? k_chunks : taps, inner = HALO ? taps / b_taps : k_chunks;
       for (int o = 0; o < outer; ++o)
         for (int i = 0; i < inner; ++i) {
-          const int kc = HALO ? o : i, tap = HALO ? i : o;
+          const int kc = HALO ? o : i, tap = HALO ? i * b_taps : o;
           if (turn == mine) {
             if (!resident) mbar_wait_acc(bar_eb + 8 * s, ph ^ 1, tracing, w_acc0);
             if (elect_one()) {
               if (PAIR) {
                 if (rank == 0) mbar_expect_tx(bar_fb + 8 * s, 2 * b_stage_bytes);
-                tma_load_3d_2sm(sB + s * b_stage_bytes, &p.tmW, bar_fb + 8 * s, kc * 64, tap, n0);
+                tma_load_3d_2sm(sB + s * b_stage_bytes, &p.tmW, bar_fb + 8 * s, kc * 64, n0, tap);
               } else {
                 mbar_expect_tx(bar_fb + 8 * s, b_stage_bytes);
-                tma_load_3d(sB + s * b_stage_bytes, &p.tmW, bar_fb + 8 * s, kc * (SP ? 32 : 64), tap, n0);  // SP: compressed rows
+                if (SP) tma_load_3d(sB + s * b_stage_bytes, &p.tmW, bar_fb + 8 * s, kc * 32, tap, n0);  // SP: compressed rows, (cin/2, tap, cout)
+                else tma_load_3d(sB + s * b_stage_bytes, &p.tmW, bar_fb + 8 * s, kc * 64, n0, tap);
               }
             }
           }
@@ -737,6 +785,10 @@ __global__ void __launch_bounds__(IMG ? 512 : 384, 1) conv_gemm_kernel(const __g
     const int BN = p.BN, cout16 = p.cout16;
     const uint32_t acc_stride = p.acc_stride;
     const bool shared_ring = p.shared_ring != 0;
+    const bool diag_path = tracing || p.diag != 0;
+    const bool b_rows = p.b_taps == 3;                       // halo ring: one stage per filter row
+    const uint32_t b_tap_units = (p.b_stage_bytes / 3) >> 4;   // descriptor units between the taps of such a stage
+    const bool fast_ok = !tracing && p.diag == 0 && ks_last == 4;   // (YX_CONV_DIAG=16: the general loop, results unchanged)
     bool b_ready = false;  // resident weights: wait for them during the first tile only
     int nt = tile_first % n_tiles_n;
     for (int tile = tile_first; tile < n_tiles; tile += tile_step, ++t) {
@@ -760,7 +812,14 @@ __global__ void __launch_bounds__(IMG ? 512 : 384, 1) conv_gemm_kernel(const __g
           tc_fence_after();
           const int ksteps = (kc == k_chunks - 1) ? ks_last : (SP ? 2 : 4);
           const uint32_t e_chunk = e_tile + 2u * (uint32_t)kc, e_step = (uint32_t)p.cin >> 5;
-          if (resident)
+          if (!SP && !RP && b_rows) {
+            if (diag_path)
+              halo_chunk_mma_rows<MH, PAIR, true>(d0, d1, a_lo, a_hi, b_lo, b_hi, idesc, accum, ksteps, bar_fb, bar_eb, sb, phb, b_slots,
+                                                  b_lo0, b_step, b_tap_units, tracing, w_acc1, (p.diag & 4) != 0);
+            else
+              halo_chunk_mma_rows<MH, PAIR, false>(d0, d1, a_lo, a_hi, b_lo, b_hi, idesc, accum, ksteps, bar_fb, bar_eb, sb, phb, b_slots,
+                                                   b_lo0, b_step, b_tap_units, false, w_acc1, false);
+          } else if (resident)
             halo_chunk_mma<MH, false, PAIR, RP, SP>(d0, d1, a_lo, a_hi, b_lo, b_hi, idesc, accum, ksteps, bar_fb, bar_eb, sb, phb, b_slots,
                                                     b_lo0, b_step, !b_ready, tracing, w_acc1, (p.diag & 4) != 0, e_chunk, e_step);
           else
@@ -775,6 +834,28 @@ __global__ void __launch_bounds__(IMG ? 512 : 384, 1) conv_gemm_kernel(const __g
         const uint32_t half_units = (uint32_t)(p.TH / 2 * p.TW) * 8;  // MODE 3: second half starts (TH/2)*TW rows of 128 B later
         int kc = 0;
         uint32_t sp_col = 0;   // SP: metadata column of the current (tap, chunk), relative to the tile's first column
+        // The common case (whole 64-channel chunks, weights streamed or already resident, no diagnostics) gets a loop with
+        // nothing in it but wait -> 4 MMAs -> commit: every instruction here is serial latency of the tensor pipe's only
+        // feeder (conv_trace: a k-iteration of the general loop below costs ~420 cycles of issue, more than the 384 cycles
+        // its four N = 192 MMAs take, so every streamed layer with N <= 192 ran at the issue rate, not the MMA rate).
+        if (!SP && fast_ok && (!resident || b_ready)) {
+          for (int i = 0; i < k_iters; ++i) {
+            mbar_wait(bar_fa + 8 * sa, pha);
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                umma_x<PAIR>(d0, a_lo + 2 * ks, a_hi, b_lo + 2 * ks, b_hi, idesc, ks == 0 ? accum : 1u);
+                if (MH == 2) umma_x<PAIR>(d1, a_lo + half_units + 2 * ks, a_hi, b_lo + 2 * ks, b_hi, idesc, ks == 0 ? accum : 1u);
+              }
+              commit_x<PAIR>(bar_ea + 8 * sa);
+            }
+            accum = 1;
+            a_lo += a_step;
+            b_lo += b_step;
+            if (++sa == stages_a) { sa = 0; pha ^= 1; a_lo = a_lo0; if (shared_ring) b_lo = b_lo0; }
+          }
+        } else
         for (int i = 0; i < k_iters; ++i) {
           mbar_wait_acc(bar_fa + 8 * sa, pha, tracing, w_acc0);   // shared ring: covers the weights of this k-iteration too
           if (resident && !b_ready) mbar_wait_acc(bar_fb + 8 * sb, phb, tracing, w_acc1);
@@ -1365,7 +1446,11 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
   // ---- shared-memory budget: [A ring][B ring or resident B][staging x stage_bufs][bias][barriers] ----
   p.stage_bufs = t.stage_bufs == 1 ? 1 : 2;
   const int k_loads_b = taps * p.k_chunks;  // B tiles per output tile
+  const int tap_stage_bytes = p.b_stage_bytes;   // one tap's weight tile (of this CTA)
+  p.b_taps = 1;
   for (;;) {
+    p.b_stage_bytes = tap_stage_bytes;
+    p.b_taps = 1;
     // (image-fed stem: + two raw image patches (this tile's and the next one's): 3 planes x 2(TH+2) rows x 128 bytes each,
     // + the 512-byte uint8 value table)
     const int fixed = 1024 + kBarBytes + p.bias_bytes + p.stage_bufs * groups64 * kTileBytes +
@@ -1382,8 +1467,29 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
       p.stages_a = std::min(halo ? 3 : kMaxARing, (avail - k_loads_b * p.b_stage_bytes) / p.a_stage_bytes);
     } else if (halo) {
       p.b_resident = 0;
-      p.stages_a = (avail - 3 * p.a_stage_bytes >= 4 * p.b_stage_bytes) ? 3 : 2;
-      p.b_slots = std::min(12, (avail - p.stages_a * p.a_stage_bytes) / p.b_stage_bytes);
+      // Streamed weights of a 3x3 halo conv: ONE ring stage per filter ROW (three taps, one TMA load, one wait and one
+      // commit in the MMA warp) whenever two such stages fit beside two halo stages: the MMA warp's per-stage bookkeeping
+      // (~420 cycles: wait, fence, elect, commit, ring advance) exceeded the 384 cycles four N = 192 MMAs take, so with
+      // one tap per stage every streamed halo layer ran at the issue rate of that warp (tools/conv_trace.py).
+      static const bool btaps_env = !(getenv("YX_BTAPS") && atoi(getenv("YX_BTAPS")) == 1);
+      p.b_taps = 1;
+      if (btaps_env && !sp && !g.rowpack && taps == 9) {
+        const int b3 = 3 * tap_stage_bytes;
+        const int try_ab[4][2] = {{3, 3}, {2, 3}, {3, 2}, {2, 2}};
+        for (int i = 0; i < 4 && p.b_taps == 1; ++i)
+          if (try_ab[i][0] * p.a_stage_bytes + try_ab[i][1] * b3 <= avail) {
+            p.b_taps = 3;
+            p.stages_a = try_ab[i][0];
+            p.b_slots = try_ab[i][1];
+          }
+      }
+      if (p.b_taps == 3) {
+        p.b_stage_bytes = 3 * tap_stage_bytes;
+      } else {
+        p.b_stage_bytes = tap_stage_bytes;
+        p.stages_a = (avail - 3 * p.a_stage_bytes >= 4 * p.b_stage_bytes) ? 3 : 2;
+        p.b_slots = std::min(12, (avail - p.stages_a * p.a_stage_bytes) / p.b_stage_bytes);
+      }
     } else {
       p.b_resident = 0;
       const int st = std::min(kMaxARing, avail / (p.a_stage_bytes + p.b_stage_bytes));
@@ -1391,7 +1497,7 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
       p.b_slots = st;
     }
     p.shared_ring = (!halo && !p.b_resident) ? 1 : 0;
-    const bool fits = p.stages_a >= 2 && p.b_slots >= (p.b_resident ? 1 : (halo ? 3 : 2));
+    const bool fits = p.stages_a >= 2 && p.b_slots >= (p.b_resident ? 1 : ((halo && p.b_taps == 1) ? 3 : 2));
     if (fits) {
       pl.smem_bytes = fixed + p.stages_a * p.a_stage_bytes + p.b_slots * p.b_stage_bytes;
       break;
@@ -1406,6 +1512,19 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
   else pl.smem_bytes = std::max(pl.smem_bytes, 80 * 1024);
   pl.grid = std::min(p.n_tiles_m * p.n_tiles_n, t.ctas * num_sms);
   if (pair) pl.grid = 2 * std::min(p.n_tiles_m * p.n_tiles_n, num_sms / 2);
+  {
+    // Unequal N tiles (Cout = 288 as 192 + 96): with the N tile fastest and a static stride of `units` tiles, a stride that
+    // shares a factor with n_tiles_n pins every CTA to the SAME N tile for the whole launch -- half of the SMs would only
+    // ever see the 192-wide tiles and the other half finish in half the time (the 288-channel 3x3 layers ran at 0.66 of the
+    // tensor peak for exactly this reason).  A stride coprime to n_tiles_n rotates every CTA through all N tiles.
+    static const bool rot_env = !(getenv("YX_NROT") && atoi(getenv("YX_NROT")) == 0);
+    int units = pair ? pl.grid / 2 : pl.grid;
+    auto gcd = [](int a, int b) { while (b) { const int r = a % b; a = b; b = r; } return a; };
+    if (rot_env && p.n_tiles_n > 1 && p.cout16 % p.BN != 0 && p.n_tiles_m * p.n_tiles_n > units) {
+      while (units > 1 && gcd(units, p.n_tiles_n) != 1) --units;
+      pl.grid = pair ? 2 * units : units;
+    }
+  }
   {  // mixed-radix digits of the persistent-tile step (see TileIter)
     int st = pair ? pl.grid / 2 : pl.grid;
     p.step_nt = st % p.n_tiles_n; st /= p.n_tiles_n;
@@ -1416,7 +1535,7 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
   pl.threads = 128 + 128 * p.epi_groups + (g.img ? 128 : 0);   // image-fed stem: + one warpgroup of tile builders
   // warp 3: second producer for the operand with more loads per tile (none when B is resident and A is one load)
   const int a_loads = halo ? p.k_chunks : k_loads_b;
-  const int b_loads = p.b_resident ? 0 : k_loads_b;
+  const int b_loads = p.b_resident ? 0 : k_loads_b / p.b_taps;
   p.w3_role = t.w3 == 0 ? 0 : (b_loads > a_loads ? 2 : 1);
   if (p.w3_role == 1 && p.stages_a < 2) p.w3_role = 0;
   if (p.w3_role == 2 && p.b_slots < 2) p.w3_role = 0;
@@ -1481,9 +1600,11 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
     uint32_t box[3] = {32, 1, 128};
     if ((rc = encode_map(&p.tmW, const_cast<void*>(spw->wc), 3, dims, st, box, false, "W-sparse", true)) != YX_OK) return rc;
   } else {
-    uint64_t dims[3] = {(uint64_t)op.cin_pad, (uint64_t)taps, (uint64_t)op.cout_pad};
-    uint64_t st[3] = {2, (uint64_t)op.cin_pad * 2, (uint64_t)op.cin_pad * 2 * taps};
-    uint32_t box[3] = {64, 1, (uint32_t)(pair ? p.BN / 2 : p.BN)};
+    // memory order [cout][tap][cin]; the map puts the taps OUTERMOST so that one box can cover several taps of the same
+    // rows and lands in shared memory tap by tap, each tap a complete K-major weight tile
+    uint64_t dims[3] = {(uint64_t)op.cin_pad, (uint64_t)op.cout_pad, (uint64_t)taps};
+    uint64_t st[3] = {2, (uint64_t)op.cin_pad * 2 * taps, (uint64_t)op.cin_pad * 2};
+    uint32_t box[3] = {64, (uint32_t)(pair ? p.BN / 2 : p.BN), (uint32_t)p.b_taps};
     uint8_t* addr = const_cast<uint8_t*>(static_cast<const uint8_t*>(weights)) + op.w_offset;
     YX_REQUIRE(op.w_offset % 16 == 0, "weight offset must be 16-byte aligned");
     if ((rc = encode_map(&p.tmW, addr, 3, dims, st, box, true, "W")) != YX_OK) return rc;
@@ -1497,9 +1618,9 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
   }
   pl.flops = g.flops;
   pl.bytes = g.act_bytes + 2.0 * (double)d.c * g.cin_real * op.ksize * op.ksize;
-  snprintf(pl.desc, sizeof pl.desc, "%s%s%s%s%s BN%d%s mh%d ctas%d epi%d%s sbuf%d A%dx%dK B%d%s w3:%d%s grid%d smem%dK", g.img ? "image-fed-" : "", sp ? "sparse24-" : "", p.has_res == 2 ? "inplace-" : "", pair ? "pair-" : "", halo ? "halo" : "generic",
+  snprintf(pl.desc, sizeof pl.desc, "%s%s%s%s%s BN%d%s mh%d ctas%d epi%d%s sbuf%d A%dx%dK B%d%s%s w3:%d%s grid%d smem%dK", g.img ? "image-fed-" : "", sp ? "sparse24-" : "", p.has_res == 2 ? "inplace-" : "", pair ? "pair-" : "", halo ? "halo" : "generic",
            p.BN, p.n_tiles_n > 1 ? "*" : "", p.mh, t.ctas, p.epi_groups, p.epi_alt ? "alt" : "", p.stage_bufs, p.stages_a, p.a_stage_bytes >> 10, p.b_slots,
-           p.b_resident ? "res" : "", p.w3_role, p.w2_role ? "+w2" : "", pl.grid, pl.smem_bytes >> 10);
+           p.b_resident ? "res" : "", p.b_taps == 3 ? "x3" : "", p.w3_role, p.w2_role ? "+w2" : "", pl.grid, pl.smem_bytes >> 10);
   *out = pl;
   return YX_OK;
 }

@@ -34,7 +34,7 @@ inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
 // ------------------------------------------------------------------ conv (yx_conv.cu)
 struct ConvParams {
   CUtensorMap tmA[4];  // activation source(s): [0] for stride 1 / halo, [py*2+px] parity views for stride 2
-  CUtensorMap tmW;     // weights  (cin_pad, taps, cout_pad), box (64, 1, BN)
+  CUtensorMap tmW;     // weights  (cin_pad, cout_pad, taps) [memory order is cout, tap, cin], box (64, BN, b_taps)
   CUtensorMap tmOut;   // output   (c, W, H, N),             box (64, TW, TH or 16, 1)
   CUtensorMap tmRes;   // residual, same geometry as tmOut
   CUtensorMap tmUp;    // fused upsample source: (c, dup_x, w/2, dup_y, n*h/2) with stride-0 dup dims, box (64, 2, TW/2, 2, TH/2)
@@ -52,6 +52,8 @@ struct ConvParams {
   int rowpack;                   // row-packed stem (aux == 1); with halo: vertical halo of 8-pixel rows, 3 taps
   int stages_a, a_stage_bytes, a_box_bytes;  // A ring
   int b_slots, b_stage_bytes, b_resident;    // B ring (or the whole weight tile, loaded once)
+  int b_taps;                    // filter taps per B ring stage (halo + streamed weights: 3 = one filter row per stage, one TMA
+                                 // load, one wait and one commit per three taps; otherwise 1)
   int shared_ring;               // generic + streamed weights: A and B share one full/empty barrier pair per stage
   int stage_bufs, out_box_bytes, bias_bytes; // output staging buffers (1 or 2), bytes per 64-ch residual box
   int epi_groups;                // epilogue warpgroups (1 or 2)
@@ -72,7 +74,7 @@ struct ConvParams {
   const void* img;               // [B,3,img_h,img_w] of img_dtype
   int img_dtype, img_h, img_w, img_order, img_affine;   // order 1 = pixel_unshuffle, 0 = Focus; affine: x*scale+shift on
   float img_scale, img_shift;
-  int diag;                      // experiments (YX_CONV_DIAG): 1 no epilogue work, 2 no A loads, 4 no MMAs
+  int diag;                      // experiments (YX_CONV_DIAG): 1 no epilogue work, 2 no A loads, 4 no MMAs, 16 general MMA-issue loops only (valid results)
   long long* trace;              // diagnostics: per-tile timeline of CTA 0 (nullptr = off)
 };
 

@@ -18,7 +18,7 @@ def _rup(a, b):
 
 
 def run_conv_case(cin, cout, k, stride, H, W, B=2, act="silu", res=False, src_pitch=None, src_off=0,
-                  dst_pitch=None, dst_off=0, seed=0, dst_c=None, device="cuda", tune=None, up_c=0, mask24=False):
+                  dst_pitch=None, dst_off=0, seed=0, dst_c=None, device="cuda", tune=None, up_c=0, mask24=False, time_iters=0):
     """Returns dict(max_err, ref_scale, out, ref).  src/dst may be channel slices of wider buffers
     (pitch/off in channels).  dst_c: channels of the dst view (>= cout, e.g. 8 for the 5-channel reg+obj pred).
     tune: dict of yx_conv_tune fields forcing one launch shape (None = the library's heuristic).
@@ -90,6 +90,22 @@ def run_conv_case(cin, cout, k, stride, H, W, B=2, act="silu", res=False, src_pi
         _capi.check(lib.yx_conv2d_ex(ctypes.byref(op), base, wd.data_ptr(), bd.data_ptr(), ctypes.byref(ct),
                                      torch.cuda.current_stream().cuda_stream), "yx_conv2d_ex")
     torch.cuda.synchronize()
+    ms = None
+    if time_iters:   # CUDA-event time of the same launch repeated back to back (tools/conv_time.py; not for in-place residuals)
+        def launch():
+            if tune is None:
+                lib.yx_conv2d(ctypes.byref(op), base, wd.data_ptr(), bd.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            else:
+                lib.yx_conv2d_ex(ctypes.byref(op), base, wd.data_ptr(), bd.data_ptr(), ctypes.byref(ct), torch.cuda.current_stream().cuda_stream)
+        for _ in range(3):
+            launch()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(time_iters):
+            launch()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / time_iters
     out_full = region(sb, B * Ho * Wo * dst_pitch).view(B, Ho, Wo, dst_pitch).float().cpu()
     out = out_full[..., dst_off:dst_off + cout]
 
@@ -109,7 +125,7 @@ def run_conv_case(cin, cout, k, stride, H, W, B=2, act="silu", res=False, src_pi
     clobbered = bool((out_full[..., mask] != untouched).any()) if mask.any() else False
     pad_bad = bool((out_full[..., dst_off + cout:dst_off + dst_c] != 0).any()) if dst_c > cout else False
     return dict(max_err=float(err.max()), mean_err=float(err.mean()), ref_scale=float(ref.abs().mean()),
-                clobbered=clobbered, pad_nonzero=pad_bad, out=out, ref=ref)
+                clobbered=clobbered, pad_nonzero=pad_bad, out=out, ref=ref, ms=ms)
 
 
 CASES = [
