@@ -788,7 +788,7 @@ __global__ void __launch_bounds__(IMG ? 512 : 384, 1) conv_gemm_kernel(const __g
     const bool diag_path = tracing || p.diag != 0;
     const bool b_rows = p.b_taps == 3;                       // halo ring: one stage per filter row
     const uint32_t b_tap_units = (p.b_stage_bytes / 3) >> 4;   // descriptor units between the taps of such a stage
-    const bool fast_ok = !tracing && p.diag == 0 && ks_last == 4;   // (YX_CONV_DIAG=16: the general loop, results unchanged)
+    const bool fast_ok = !tracing && p.diag == 0;   // (YX_CONV_DIAG=16: the general loop, results unchanged)
     bool b_ready = false;  // resident weights: wait for them during the first tile only
     int nt = tile_first % n_tiles_n;
     for (int tile = tile_first; tile < n_tiles; tile += tile_step, ++t) {
@@ -839,22 +839,33 @@ __global__ void __launch_bounds__(IMG ? 512 : 384, 1) conv_gemm_kernel(const __g
         // feeder (conv_trace: a k-iteration of the general loop below costs ~420 cycles of issue, more than the 384 cycles
         // its four N = 192 MMAs take, so every streamed layer with N <= 192 ran at the issue rate, not the MMA rate).
         if (!SP && fast_ok && (!resident || b_ready)) {
-          for (int i = 0; i < k_iters; ++i) {
-            mbar_wait(bar_fa + 8 * sa, pha);
-            tc_fence_after();
-            if (elect_one()) {
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                umma_x<PAIR>(d0, a_lo + 2 * ks, a_hi, b_lo + 2 * ks, b_hi, idesc, ks == 0 ? accum : 1u);
-                if (MH == 2) umma_x<PAIR>(d1, a_lo + half_units + 2 * ks, a_hi, b_lo + 2 * ks, b_hi, idesc, ks == 0 ? accum : 1u);
-              }
-              commit_x<PAIR>(bar_ea + 8 * sa);
-            }
-            accum = 1;
-            a_lo += a_step;
-            b_lo += b_step;
-            if (++sa == stages_a) { sa = 0; pha ^= 1; a_lo = a_lo0; if (shared_ring) b_lo = b_lo0; }
+          // one k-iteration: FULL = four K = 16 steps, otherwise the ks_last (1..3) steps of a partial last chunk
+#define YX_FAST_ITER(FULL)                                                                                              \
+          {                                                                                                             \
+            mbar_wait(bar_fa + 8 * sa, pha);                                                                            \
+            tc_fence_after();                                                                                           \
+            if (elect_one()) {                                                                                          \
+              _Pragma("unroll") for (int ks = 0; ks < (FULL ? 4 : 3); ++ks)                                             \
+                if (FULL || ks < ks_last) {                                                                             \
+                  umma_x<PAIR>(d0, a_lo + 2 * ks, a_hi, b_lo + 2 * ks, b_hi, idesc, ks == 0 ? accum : 1u);              \
+                  if (MH == 2) umma_x<PAIR>(d1, a_lo + half_units + 2 * ks, a_hi, b_lo + 2 * ks, b_hi, idesc, ks == 0 ? accum : 1u); \
+                }                                                                                                       \
+              commit_x<PAIR>(bar_ea + 8 * sa);                                                                          \
+            }                                                                                                           \
+            accum = 1;                                                                                                  \
+            a_lo += a_step;                                                                                             \
+            b_lo += b_step;                                                                                             \
+            if (++sa == stages_a) { sa = 0; pha ^= 1; a_lo = a_lo0; if (shared_ring) b_lo = b_lo0; }                    \
           }
+          if (ks_last == 4) {
+            for (int i = 0; i < k_iters; ++i) YX_FAST_ITER(true)
+          } else {
+            for (int tap = 0; tap < taps; ++tap) {
+              for (int c = 1; c < k_chunks; ++c) YX_FAST_ITER(true)
+              YX_FAST_ITER(false)
+            }
+          }
+#undef YX_FAST_ITER
         } else
         for (int i = 0; i < k_iters; ++i) {
           mbar_wait_acc(bar_fa + 8 * sa, pha, tracing, w_acc0);   // shared ring: covers the weights of this k-iteration too

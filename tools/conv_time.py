@@ -15,6 +15,24 @@ CASES = {
         ("pair-halo BN256 sb1", _t(2, 256, sb=1, w3=2, pair=1)), ("pair-halo BN128 sb1", _t(2, 128, sb=1, w3=2, pair=1)),
         ("halo BN128 sb1", _t(2, 128, sb=1, w3=2)), ("halo BN256 sb1", _t(2, 256, sb=1, w3=2)),
     ]),
+    # the stem's MMA + epilogue structure without the image builder (A = a 16-channel NHWC tensor through TMA halo loads)
+    "stem16": (dict(cin=16, cout=48, k=3, stride=1, H=640, W=640, B=16, act="hard_swish"), [
+        ("halo BN48 mh2 eg2 alt", _t(2, 48, halves=2, eg=2, alt=1)), ("halo BN48 mh2 eg2", _t(2, 48, halves=2, eg=2)),
+        ("halo BN48 mh2 eg1", _t(2, 48, halves=2, eg=1)), ("halo BN48 mh1 eg2 alt", _t(2, 48, halves=1, eg=2, alt=1)),
+        ("halo BN48 mh1 eg1", _t(2, 48, halves=1, eg=1)),
+    ]),
+    "d20": (dict(cin=48, cout=96, k=3, stride=2, H=640, W=640, B=16, act="hard_swish"), [
+        ("generic BN96 eg2 sb2", _t(1, 96, eg=2, sb=2)), ("generic BN96 eg1 sb1", _t(1, 96, eg=1, sb=1)),
+        ("generic BN96 mh2 eg2", _t(1, 96, halves=2, eg=2)), ("pair-generic BN96 sb2", _t(1, 96, pair=1)),
+    ]),
+    "d30": (dict(cin=96, cout=192, k=3, stride=2, H=320, W=320, B=16, act="hard_swish"), [
+        ("pair-generic BN192 sb1", _t(1, 192, sb=1, pair=1)), ("generic BN192 sb1", _t(1, 192, sb=1)),
+        ("generic BN128 mh2 eg2", _t(1, 128, halves=2, eg=2)),
+    ]),
+    "c96x1": (dict(cin=96, cout=96, k=1, stride=1, H=160, W=160, B=64, act="hard_swish", src_pitch=192), [
+        ("generic BN96 eg2 sb1", _t(1, 96, eg=2, sb=1)), ("pair-generic BN96 sb2", _t(1, 96, pair=1)),
+        ("generic BN96 mh2 eg2", _t(1, 96, halves=2, eg=2)), ("generic BN96 ctas2", _t(1, 96, ctas=2)),
+    ]),
     "h192": (dict(cin=192, cout=192, k=3, stride=1, H=160, W=160, B=16, act="hard_swish"), [
         ("pair-halo BN192 sb1", _t(2, 192, sb=1, w3=2, pair=1)), ("halo BN192 sb1", _t(2, 192, sb=1, w3=2)),
         ("halo BN192 eg2 sb2 alt", _t(2, 192, eg=2, sb=2, w3=2, alt=1)),
