@@ -73,7 +73,8 @@ def _build_locked(verbose: bool, build_dir: str) -> str:
         src, defs, name = unit
         obj = os.path.join(build_dir, name + ".o")
         cmd = [nvcc] + NVCC_FLAGS + defs + (["-Xptxas", "-v"] if verbose else []) + \
-            (["-DYX_DEBUG_TRAP"] if os.environ.get("YX_DEBUG_TRAP") else []) + ["-c", src, "-o", obj]
+            (["-DYX_DEBUG_TRAP"] if os.environ.get("YX_DEBUG_TRAP") else []) + os.environ.get("YX_NVCC_DEFS", "").split() + \
+            ["-c", src, "-o", obj]
         subprocess.check_call(cmd)
         return obj
 

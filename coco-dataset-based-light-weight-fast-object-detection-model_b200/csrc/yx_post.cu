@@ -391,11 +391,77 @@ __global__ void decode_outputs_kernel(T* __restrict__ out, int B, int A, int D, 
 // ------------------------------------------------------------------------------------------------
 // per-image bitonic sort of the candidate keys, descending (one CTA per image)
 // ------------------------------------------------------------------------------------------------
+#ifdef YX_POST_DBG   // experiments: phase timeline of image 0 (thread 0), read back with yx_post_dbg_read
+__device__ long long g_post_dbg[64];
+#define YX_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_post_dbg[i] = clock64(); } while (0)
+#else
+#define YX_STAMP(i) do { } while (0)
+#endif
 constexpr int kSortThreads = 1024;
 constexpr int kSortChunk = 8192;  // keys resident in shared memory (64 KB)
 
 __device__ __forceinline__ void cmpx(uint64_t& a, uint64_t& b, bool desc) {
   if ((a < b) == desc) { const uint64_t t = a; a = b; b = t; }
+}
+
+// Descending bitonic sort of the 8192 keys in sk[] by 1024 threads.  Warp w owns the 256 keys sk[256 w ...], thread (w, lane)
+// holds the eight keys 256 w + 32 r + lane in registers: exchange distances 1..16 are warp shuffles, 32..128 are register
+// swaps, only distances >= 256 go through shared memory and a block barrier (15 of the 91 phases; the all-shared-memory
+// form spent 72 us per image on 91 barriers and 64-bit bank conflicts).
+__device__ __forceinline__ void bitonic_inwarp(uint64_t (&v)[8], int k, int i0 /* index of v[0] */, int lane) {
+  // desc(i): the pair whose lower index is i sorts descending iff (i & k) == 0; the bit k of i is the same for both
+  // elements of a pair (k > distance)
+  if (k > 128) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) cmpx(v[r], v[r + 4], ((i0 + 32 * r) & k) == 0);
+  }
+  if (k > 64) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) if ((r & 2) == 0) cmpx(v[r], v[r + 2], ((i0 + 32 * r) & k) == 0);
+  }
+  if (k > 32) {
+#pragma unroll
+    for (int r = 0; r < 8; r += 2) cmpx(v[r], v[r + 1], ((i0 + 32 * r) & k) == 0);
+  }
+#pragma unroll
+  for (int j = 16; j >= 1; j >>= 1) {
+    if (k > j) {
+      const bool lower = (lane & j) == 0;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const uint64_t o = __shfl_xor_sync(0xffffffffu, v[r], j);
+        const bool desc = ((i0 + 32 * r) & k) == 0;
+        const bool keep_max = desc == lower;
+        v[r] = ((v[r] > o) == keep_max) ? v[r] : o;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void bitonic_sort_8192_desc(uint64_t* sk) {
+  const int lane = threadIdx.x & 31, wbase = (threadIdx.x >> 5) * 256, i0 = wbase + lane;
+  uint64_t v[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) v[r] = sk[i0 + 32 * r];
+  for (int k = 2; k <= 256; k <<= 1) bitonic_inwarp(v, k, i0, lane);
+  for (int k = 512; k <= kSortChunk; k <<= 1) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) sk[i0 + 32 * r] = v[r];
+    __syncthreads();
+    for (int j = k >> 1; j >= 256; j >>= 1) {
+      for (int t = threadIdx.x; t < (kSortChunk >> 1); t += kSortThreads) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        cmpx(sk[i], sk[i | j], ((i & k) == 0));
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) v[r] = sk[i0 + 32 * r];
+    bitonic_inwarp(v, k, i0, lane);
+  }
+#pragma unroll
+  for (int r = 0; r < 8; ++r) sk[i0 + 32 * r] = v[r];
+  __syncthreads();
 }
 
 __global__ void __launch_bounds__(kSortThreads, 1) sort_keys_kernel(Workspace ws, int max_nms) {
@@ -404,15 +470,21 @@ __global__ void __launch_bounds__(kSortThreads, 1) sort_keys_kernel(Workspace ws
   __shared__ unsigned long long s_prefix;
   __shared__ int s_need, s_cnt;
   const int b = blockIdx.x;
+  YX_STAMP(0);
   const int n = ws.count[b];
   if (n <= 1) return;
   uint64_t* keys = ws.keys + (int64_t)b * ws.Apad;
 
   if (max_nms > 0 && n > max_nms && max_nms <= kSortChunk) {
     // ---- top-k first (postprocess_utils.py:100-103 keeps the max_nms best): MSB-first radix SELECT of the
-    // k-th largest 64-bit key (8 passes of 8 bits over L2-resident keys), then only those k keys are sorted,
-    // entirely in shared memory.  Keys are unique (anchor index in the low word), so ">= pivot" is exactly k.
-    if (threadIdx.x == 0) { s_prefix = 0ull; s_need = max_nms; }
+    // k-th largest 64-bit key (up to 8 passes of 8 bits over L2-resident keys), then only those k keys are sorted,
+    // entirely in shared memory / registers.  Keys are unique (anchor index in the low word), so ">= pivot" is exactly k.
+    // The select stops at the first pass whose boundary bin is needed WHOLE (pivot = that prefix with the remaining bits
+    // zero): three passes instead of eight on tie-free scores.
+    const int lane = threadIdx.x & 31;
+    __shared__ int s_done;
+    if (threadIdx.x == 0) { s_prefix = 0ull; s_need = max_nms; s_done = 0; }
+    int shift_done = 0;
     for (int pass = 0; pass < 8; ++pass) {
       const int shift = 56 - 8 * pass;
       for (int i = threadIdx.x; i < 256; i += kSortThreads) s_hist[i] = 0;
@@ -420,6 +492,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) sort_keys_kernel(Workspace ws
       const unsigned long long prefix = s_prefix;
       for (int i = threadIdx.x; i < n; i += kSortThreads) {
         const unsigned long long key = keys[i];
+        // (plain shared-memory atomics: a __match_any_sync aggregation of same-bin adds measured 3x SLOWER per pass)
         if (pass == 0 || (key >> (shift + 8)) == prefix) atomicAdd(&s_hist[(key >> shift) & 255ull], 1);
       }
       __syncthreads();
@@ -431,27 +504,42 @@ __global__ void __launch_bounds__(kSortThreads, 1) sort_keys_kernel(Workspace ws
         }
         s_need = need;
         s_prefix = (prefix << 8) | (unsigned long long)bin;
+        if (s_hist[bin] == need) s_done = 1;   // every key of this bin is selected: no need to look at lower bits
       }
       __syncthreads();
+      YX_STAMP(1 + pass);
+      shift_done = shift;
+      if (s_done) break;
     }
-    const unsigned long long pivot = s_prefix;
+    const unsigned long long pivot = s_prefix << shift_done;
     if (threadIdx.x == 0) s_cnt = 0;
     for (int i = threadIdx.x; i < kSortChunk; i += kSortThreads) sk[i] = 0ull;
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += kSortThreads) {
-      const unsigned long long key = keys[i];
-      if (key >= pivot) sk[atomicAdd(&s_cnt, 1)] = key;
+    for (int i0 = 0; i0 < n; i0 += 4 * kSortThreads) {   // compaction: four loads in flight, one shared-memory atomic per warp and key slot
+      unsigned long long key[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * kSortThreads + threadIdx.x;
+        key[u] = i < n ? keys[i] : 0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool sel = i0 + u * kSortThreads + (int)threadIdx.x < n && key[u] >= pivot;
+        const unsigned bal = __ballot_sync(0xffffffffu, sel);
+        if (bal) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(&s_cnt, __popc(bal));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (sel) sk[base + __popc(bal & ((1u << lane) - 1u))] = key[u];
+        }
+      }
     }
     __syncthreads();
-    for (int k = 2; k <= kSortChunk; k <<= 1)
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int t = threadIdx.x; t < (kSortChunk >> 1); t += kSortThreads) {
-          const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-          cmpx(sk[i], sk[i | j], ((i & k) == 0));
-        }
-        __syncthreads();
-      }
+    YX_STAMP(9);
+    bitonic_sort_8192_desc(sk);
+    YX_STAMP(10);
     for (int i = threadIdx.x; i < max_nms; i += kSortThreads) keys[i] = sk[i];
+    YX_STAMP(11);
     return;
   }
 
@@ -544,6 +632,7 @@ nms_kernel(Workspace ws, int A, float nms_thr, int max_nms, int max_det, int mod
   __shared__ int s_kept;
 
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  YX_STAMP(16);
   int n = ws.count[b];
   if (max_nms > 0 && n > max_nms) n = max_nms;
   if (mode == YX_NMS_AUTO) mode = (4 * (int64_t)n > 100000) ? YX_NMS_VANILLA : YX_NMS_TRICK;
@@ -568,6 +657,7 @@ nms_kernel(Workspace ws, int A, float nms_thr, int max_nms, int max_det, int mod
     slab[i] = K > 1 ? id % K : ws.label[ib + a];
     mx = fmaxf(fmaxf(mx, fmaxf(bx.x, bx.y)), fmaxf(bx.z, bx.w));
   }
+  YX_STAMP(17);
   if (mode == YX_NMS_TRICK) {
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if (lane == 0) s_red[wid] = mx;
@@ -584,6 +674,7 @@ nms_kernel(Workspace ws, int A, float nms_thr, int max_nms, int max_det, int mod
   }
   if (tid == 0) s_kept = 0;
   __syncthreads();
+  YX_STAMP(18);
 
   // ---- greedy pass -------------------------------------------------------------------------------
   const bool same_class_only = (mode == YX_NMS_VANILLA);
@@ -596,6 +687,7 @@ nms_kernel(Workspace ws, int A, float nms_thr, int max_nms, int max_det, int mod
       if (tid < m) { s_cbox[tid] = sbox[base + tid]; s_clab[tid] = slab[base + tid]; }
     }
     __syncthreads();
+    if (base == 64) YX_STAMP(24);
     bool sup = false;
     unsigned long long bits = 0ull;
     if (ci < m) {
@@ -615,24 +707,52 @@ nms_kernel(Workspace ws, int A, float nms_thr, int max_nms, int max_det, int mod
     const bool any_sup = ((bal >> (lane & 16)) & 0xFFFFu) != 0;
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) bits |= __shfl_xor_sync(0xffffffffu, bits, o);
+    if (base == 64) YX_STAMP(25);
     if (sub == 0 && ci < m) { s_pre[ci] = any_sup ? 1 : 0; s_mask[ci] = bits; }
     __syncthreads();
-    if (tid == 0) {
-      unsigned long long keptmask = 0ull;
-      int kn = kept;
-      for (int i = 0; i < m && kn < cap; ++i) {
-        if (!s_pre[i] && !(s_mask[i] & keptmask)) {
-          keptmask |= (1ull << i);
-          kbox[kn] = s_cbox[i]; klab[kn] = s_clab[i]; kidx[kn] = base + i;
-          ++kn;
+    if (base == 64) YX_STAMP(26);
+    // Resolve the block in score order.  The chain (candidate i survives iff no EARLIER SURVIVOR of the block suppresses
+    // it) is inherently serial; every lane of warp 0 runs it redundantly on the 64 masks read straight from shared memory
+    // (broadcast loads, independent of the chain, so the unrolled loop issues them ahead) with a branch-free update: one
+    // AND / test / OR per candidate.  (A thread-0 loop that also appended to the kept list took ~300 cycles per candidate,
+    // a shuffle-fed loop ~85; this one ~20.)  The survivors are then appended to the kept list by all lanes at once
+    // (position = popcount of the lower survivor bits).
+    if (wid == 0) {
+      const unsigned dead_lo = __ballot_sync(0xffffffffu, lane >= m || s_pre[lane] != 0);
+      const unsigned dead_hi = __ballot_sync(0xffffffffu, lane + 32 >= m || s_pre[lane + 32] != 0);
+      const unsigned long long dead = ((unsigned long long)dead_hi << 32) | dead_lo;
+      unsigned klo = 0u, khi = 0u;   // survivors of the block (a row's mask only holds EARLIER candidates: rows < 32 have no high half)
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        const uint2 mi = *reinterpret_cast<const uint2*>(&s_mask[i]);   // (rows >= m are stale: their dead bit is set)
+        const unsigned hit = i < 32 ? (mi.x & klo) : ((mi.x & klo) | (mi.y & khi));
+        const bool take = !((dead >> i) & 1ull) && hit == 0u;
+        if (i < 32) klo |= take ? (1u << i) : 0u;
+        else khi |= take ? (1u << (i - 32)) : 0u;
+      }
+      unsigned long long keptmask = ((unsigned long long)khi << 32) | klo;
+      // the cap (max_det) is applied afterwards: survivors do not depend on later candidates, so keeping the FIRST
+      // `cap - kept` of them equals stopping the scan there
+      while (__popcll(keptmask) > cap - kept) keptmask &= ~(1ull << (63 - __clzll(keptmask)));
+      const int kn = kept + __popcll(keptmask);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = lane + 32 * h;
+        if ((keptmask >> c) & 1ull) {
+          const int pos = kept + __popcll(keptmask & ((1ull << c) - 1ull));
+          kbox[pos] = s_cbox[c]; klab[pos] = s_clab[c]; kidx[pos] = base + c;
         }
       }
-      s_kept = kn;
+      if (lane == 0) s_kept = kn;
     }
+    if (base == 64) YX_STAMP(27);
     __syncthreads();
+    if (base == 64) YX_STAMP(28);
+    if (base == 0) YX_STAMP(23);
   }
 
   // ---- write detections (score order) -----------------------------------------------------------
+  YX_STAMP(19);
   const int kept = s_kept;
   if (tid == 0) det_count[b] = kept;
   float* drow = det + (int64_t)b * det_rows * 7;
@@ -661,6 +781,7 @@ nms_kernel(Workspace ws, int A, float nms_thr, int max_nms, int max_det, int mod
       for (int j = 0; j < 7; ++j) r[j] = d[j];
     }
   }
+  YX_STAMP(20);
   if (po.world > 0) {
     if (tid < po.world) po.cnt[tid][b] = kept;
     __threadfence_system();  // every thread: its own rows / count are ordered before what follows, system-wide
@@ -744,6 +865,13 @@ static int check_ws(int B, int A, void* workspace, size_t bytes, Workspace* ws, 
 }  // namespace yx
 
 using namespace yx;
+
+#ifdef YX_POST_DBG
+extern "C" int yx_post_dbg_read(long long* out64) {
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(out64, g_post_dbg, sizeof(long long) * 64) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 extern "C" size_t yx_detect_workspace_bytes(int B, int A) {
   if (B < 1 || A < 1) return 0;
