@@ -600,12 +600,13 @@ def run_ours(args, rank, world, local_rank):
     hbm_bound = [p for p in conv if p["flops"] / max(p["bytes"], 1) < peaks["tflops"] * 1e12 / (peaks["hbm_gbs"] * 1e9)]
     hbm_ms, hbm_bytes = sum(p["ms"] for p in hbm_bound), sum(p["bytes"] for p in hbm_bound)
     traffic, traffic_src = None, None   # measured DRAM bytes per conv launch, from the committed ncu launch list
-    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tp):
-        tj = json.load(open(tp))
+    import glob
+    tps = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))   # newest round's ncu launch list
+    if tps:
+        tj = json.load(open(tps[-1]))
         fam = tj["families"].get("conv_gemm_kernel")
         if fam:
-            traffic, traffic_src = fam["dram_bytes_per_launch"], f"profiles/r01_traffic.json ({tj['source']})"
+            traffic, traffic_src = fam["dram_bytes_per_launch"], f"profiles/{os.path.basename(tps[-1])} ({tj['source']})"
     roof = dict(bound="tensor", kernel="conv_gemm_kernel (all instantiations)", achieved=achieved_tf, peak=peaks["tflops"],
                 unit="TFLOP/s", frac=achieved_tf / peaks["tflops"], traffic=traffic, traffic_source=traffic_src,
                 algorithmic_bytes_per_launch=sum(p["bytes"] for p in conv) / max(len(conv), 1),

@@ -306,8 +306,8 @@ __global__ void dwconv_kernel(const __half* __restrict__ src, __half* __restrict
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float f0 = acc[2 * j] + bias[c8 * 8 + 2 * j], f1 = acc[2 * j + 1] + bias[c8 * 8 + 2 * j + 1];
-      f0 = act_f(__half2float(__float2half_rn(f0)), act);
-      f1 = act_f(__half2float(__float2half_rn(f1)), act);
+      f0 = act_f(f0, act);   // activation on the fp32 sum, ONE rounding to fp16: the conv kernel's rule
+      f1 = act_f(f1, act);
       oh[j] = __floats2half2_rn(f0, f1);
     }
     reinterpret_cast<uint4*>(dst + b * dn + ((int64_t)y * Wo + x) * dpitch)[c8] = o;
@@ -383,12 +383,111 @@ __global__ void __launch_bounds__(256) dwconv_strip_kernel(const __half* __restr
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         float f0 = acc[t][2 * j] + bv[2 * j], f1 = acc[t][2 * j + 1] + bv[2 * j + 1];
-        f0 = act_f(__half2float(__float2half_rn(f0)), act);
-        f1 = act_f(__half2float(__float2half_rn(f1)), act);
+        f0 = act_f(f0, act);   // activation on the fp32 sum, ONE rounding to fp16: the conv kernel's rule
+        f1 = act_f(f1, act);
         oh[j] = __floats2half2_rn(f0, f1);
       }
       reinterpret_cast<uint4*>(dst + b * dn + ((int64_t)y * W + x0 + t) * dpitch)[c8] = o;
     }
+  }
+}
+
+// Shared-memory tiled form for stride 1 (round 2): a CTA owns an 8 x 16 pixel tile of 64 channels.  The (8+K-1) x (16+K-1)
+// halo tile is loaded ONCE, cooperatively and coalesced (eight 16-byte channel vectors = 128 contiguous bytes per pixel), so
+// every input byte leaves L2 once per tile instead of up to K times per output row, and the K x (4+K-1) vector reads of a thread's
+// 4-pixel strip come from shared memory: the compute phase has no global-memory latency in it, and with three resident CTAs
+// per SM one CTA's loads overlap the others' FMAs (the register-blocked strip kernel above ran at 0.4 IPC, 0.11 of HBM: every
+// one of its five row passes waited for its own L2 loads).  Accumulation order per output = the strip kernel's (dy, then dx).
+template <int K>
+__global__ void __launch_bounds__(256, 3) dwconv_tile_kernel(const __half* __restrict__ src, __half* __restrict__ dst,
+                                                          const __half* __restrict__ wgt, const float* __restrict__ bias, int B,
+                                                          int H, int W, int C, int act, int spitch, int dpitch, int64_t sn,
+                                                          int64_t dn, int tiles_x, int tiles_y, int cgroups) {
+  constexpr int PAD = K / 2, TH = 8, TW = 16, TX = 4, HH = TH + K - 1, HW = TW + K - 1;
+  __shared__ uint4 s_in[HH * HW * 8];
+  const int tid = threadIdx.x;
+  const int c8 = tid & 7, strip = (tid >> 3) & 3, row = tid >> 5;
+  const int64_t n_tiles = (int64_t)B * tiles_y * tiles_x * cgroups;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int cg = (int)(tile % cgroups);
+    int64_t r = tile / cgroups;
+    const int tx = (int)(r % tiles_x); r /= tiles_x;
+    const int ty = (int)(r % tiles_y);
+    const int b = (int)(r / tiles_y);
+    const int x0 = tx * TW, y0 = ty * TH, c0 = cg * 64;
+    const __half* img = src + b * sn;
+    for (int i = tid; i < HH * HW * 8; i += 256) {
+      const int v = i & 7, p = i >> 3, hx = p % HW, hy = p / HW;
+      const int gy = y0 - PAD + hy, gx = x0 - PAD + hx, c = c0 + v * 8;
+      uint4 val = make_uint4(0u, 0u, 0u, 0u);
+      if (gy >= 0 && gy < H && gx >= 0 && gx < W && c < C)
+        val = __ldg(reinterpret_cast<const uint4*>(img + ((int64_t)gy * W + gx) * spitch + c));
+      s_in[i] = val;
+    }
+    __syncthreads();
+    const int c = c0 + c8 * 8;
+    if (c < C) {
+      float acc[TX][8];
+#pragma unroll
+      for (int t = 0; t < TX; ++t)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+#pragma unroll
+      for (int dy = 0; dy < K; ++dy) {
+        float wf[K][8];
+#pragma unroll
+        for (int dx = 0; dx < K; ++dx) {
+          const uint4 wv = __ldg(reinterpret_cast<const uint4*>(wgt + (int64_t)(dy * K + dx) * C + c));
+          const __half2* wh = reinterpret_cast<const __half2*>(&wv);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 ww = __half22float2(wh[j]);
+            wf[dx][2 * j] = ww.x; wf[dx][2 * j + 1] = ww.y;
+          }
+        }
+        const uint4* line = s_in + ((row + dy) * HW + strip * TX) * 8 + c8;
+#pragma unroll
+        for (int xi = 0; xi < TX + K - 1; ++xi) {
+          const uint4 v = line[xi * 8];
+          const __half2* vh = reinterpret_cast<const __half2*>(&v);
+          float a[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = __half22float2(vh[j]);
+            a[2 * j] = f.x; a[2 * j + 1] = f.y;
+          }
+#pragma unroll
+          for (int dx = 0; dx < K; ++dx) {
+            const int t = xi - dx;
+            if (t < 0 || t >= TX) continue;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(a[j], wf[dx][j], acc[t][j]);
+          }
+        }
+      }
+      const int y = y0 + row;
+      if (y < H) {
+        float bv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bv[j] = bias[c + j];
+#pragma unroll
+        for (int t = 0; t < TX; ++t) {
+          const int x = x0 + strip * TX + t;
+          if (x >= W) break;
+          uint4 o;
+          __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float f0 = acc[t][2 * j] + bv[2 * j], f1 = acc[t][2 * j + 1] + bv[2 * j + 1];
+            f0 = act_f(f0, act);   // activation on the fp32 sum, ONE rounding to fp16: the conv kernel's rule
+            f1 = act_f(f1, act);
+            oh[j] = __floats2half2_rn(f0, f1);
+          }
+          *reinterpret_cast<uint4*>(dst + b * dn + ((int64_t)y * W + x) * dpitch + c) = o;
+        }
+      }
+    }
+    __syncthreads();   // the next tile's loads overwrite s_in
   }
 }
 
@@ -403,6 +502,22 @@ int dwconv_launch(void* base, const yx_op& op, const void* weights, const void* 
   YX_REQUIRE(s.offset % 16 == 0 && d.offset % 16 == 0 && s.pitch % 8 == 0 && d.pitch % 8 == 0 && op.w_offset % 16 == 0,
              "depthwise alignment");
   static const bool strip_env = !(getenv("YX_DW_STRIP") && atoi(getenv("YX_DW_STRIP")) == 0);
+  static const bool tile_env = !(getenv("YX_DW_TILE") && atoi(getenv("YX_DW_TILE")) == 0);
+  if (op.stride == 1 && tile_env) {
+    const int tiles_x = (Wo + 15) / 16, tiles_y = (Ho + 7) / 8, cgroups = (d.c + 63) / 64;
+    const int64_t n_tiles = (int64_t)d.n * tiles_x * tiles_y * cgroups;
+    const int nb = (int)std::min<int64_t>(n_tiles, 148 * 6);
+    const __half* sp = reinterpret_cast<const __half*>(static_cast<uint8_t*>(base) + s.offset);
+    __half* dp = reinterpret_cast<__half*>(static_cast<uint8_t*>(base) + d.offset);
+    const __half* wp = reinterpret_cast<const __half*>(static_cast<const uint8_t*>(weights) + op.w_offset);
+    const float* bp = reinterpret_cast<const float*>(static_cast<const uint8_t*>(biases) + op.b_offset);
+    if (op.ksize == 3)
+      dwconv_tile_kernel<3><<<nb, 256, 0, stream>>>(sp, dp, wp, bp, s.n, s.h, s.w, s.c, op.act, s.pitch, d.pitch, s.nstride, d.nstride, tiles_x, tiles_y, cgroups);
+    else
+      dwconv_tile_kernel<5><<<nb, 256, 0, stream>>>(sp, dp, wp, bp, s.n, s.h, s.w, s.c, op.act, s.pitch, d.pitch, s.nstride, d.nstride, tiles_x, tiles_y, cgroups);
+    YX_CUDA(cudaGetLastError());
+    return YX_OK;
+  }
   if (op.stride == 1 && strip_env) {
     constexpr int TX = 8;
     const int64_t n_threads = (int64_t)d.n * Ho * ((Wo + TX - 1) / TX) * (d.c / 8);

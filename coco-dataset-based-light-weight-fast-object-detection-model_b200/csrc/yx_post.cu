@@ -94,7 +94,7 @@ struct Workspace {
   float* score;    // [B][A]  NMS score
   int* label;      // [B][A]
   uint64_t* keys;  // [B][Apad]
-  float4* sbox;    // [B][A]  sorted (and offset) boxes
+  float4* sbox;    // [B][A]  boxes in score order (the coordinate-trick offset is added when a block is loaded)
   int* slabel;     // [B][A]
   float4* kbox;    // [B][A]  kept boxes (uncapped mode)
   int* klabel;     // [B][A]
@@ -647,30 +647,46 @@ nms_kernel(Workspace ws, int A, float nms_thr, int max_nms, int max_det, int mod
   int* klab = kept_in_smem ? s_klab : (ws.klabel + ic);
   const int cap = max_det > 0 ? max_det : 0x7fffffff;
 
-  // ---- gather the selected candidates in score order; coordinate-trick offsets -----------------
+  // ---- gather the selected candidates in score order (four independent key -> box chains in flight per thread) ------
   float mx = -INFINITY;
-  for (int i = tid; i < n; i += kNmsThreads) {
-    const int id = key_id(keys[i]);
-    const int a = K > 1 ? id / K : id;
-    const float4 bx = ws.box[ib + a];
-    sbox[i] = bx;
-    slab[i] = K > 1 ? id % K : ws.label[ib + a];
-    mx = fmaxf(fmaxf(mx, fmaxf(bx.x, bx.y)), fmaxf(bx.z, bx.w));
+  for (int i0 = 0; i0 < n; i0 += 4 * kNmsThreads) {
+    int id[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * kNmsThreads + tid;
+      id[u] = i < n ? key_id(keys[i]) : -1;
+    }
+    float4 bx[4];
+    int lb[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int a = K > 1 ? id[u] / K : id[u];
+      if (id[u] >= 0) {
+        bx[u] = ws.box[ib + a];
+        lb[u] = K > 1 ? id[u] % K : ws.label[ib + a];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * kNmsThreads + tid;
+      if (id[u] >= 0) {
+        sbox[i] = bx[u];
+        slab[i] = lb[u];
+        mx = fmaxf(fmaxf(mx, fmaxf(bx[u].x, bx[u].y)), fmaxf(bx[u].z, bx[u].w));
+      }
+    }
   }
   YX_STAMP(17);
+  // coordinate trick (torchvision batched_nms): boxes + label * (boxes.max() + 1).  The offset is added when a block of
+  // candidates is loaded below (same two roundings as adding it here), which saves a second pass over the sorted boxes.
+  float m1 = 0.0f;
   if (mode == YX_NMS_TRICK) {
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if (lane == 0) s_red[wid] = mx;
     __syncthreads();
     mx = s_red[0];
     for (int i = 1; i < kNmsThreads / 32; ++i) mx = fmaxf(mx, s_red[i]);
-    const float m1 = __fadd_rn(mx, 1.0f);  // boxes.max() + 1
-    for (int i = tid; i < n; i += kNmsThreads) {  // each thread re-reads only what it wrote
-      const float off = __fmul_rn((float)slab[i], m1);
-      float4 bx = sbox[i];
-      bx.x = __fadd_rn(bx.x, off); bx.y = __fadd_rn(bx.y, off); bx.z = __fadd_rn(bx.z, off); bx.w = __fadd_rn(bx.w, off);
-      sbox[i] = bx;
-    }
+    m1 = __fadd_rn(mx, 1.0f);  // boxes.max() + 1
   }
   if (tid == 0) s_kept = 0;
   __syncthreads();
@@ -684,7 +700,15 @@ nms_kernel(Workspace ws, int A, float nms_thr, int max_nms, int max_det, int mod
     if (kept >= cap) break;
     const int m = min(64, n - base);
     if (tid < 64) {
-      if (tid < m) { s_cbox[tid] = sbox[base + tid]; s_clab[tid] = slab[base + tid]; }
+      if (tid < m) {
+        float4 bx = sbox[base + tid];
+        const int lb = slab[base + tid];
+        if (mode == YX_NMS_TRICK) {
+          const float off = __fmul_rn((float)lb, m1);
+          bx.x = __fadd_rn(bx.x, off); bx.y = __fadd_rn(bx.y, off); bx.z = __fadd_rn(bx.z, off); bx.w = __fadd_rn(bx.w, off);
+        }
+        s_cbox[tid] = bx; s_clab[tid] = lb;
+      }
     }
     __syncthreads();
     if (base == 64) YX_STAMP(24);

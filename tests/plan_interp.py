@@ -89,7 +89,12 @@ def eval_op(o, image, src, res, wblob, bblob, q, want_band=False, up=None):
         c = x.shape[1]
         w = wblob[o.w_offset // 2: o.w_offset // 2 + k * k * c].view(k, k, c).permute(2, 0, 1).unsqueeze(1)
         b = bblob[o.b_offset // 4: o.b_offset // 4 + c]
-        y = _act(q(F.conv2d(x, w, b, stride=o.stride, padding=k // 2, groups=c)), o.act)
+        y0 = q(F.conv2d(x, w, b, stride=o.stride, padding=k // 2, groups=c))
+        y = _act(y0, o.act)
+        if want_band:  # as for the dense conv: the kernel applies the activation to the fp32 sum and rounds once
+            u = ulp16(y0)
+            band = torch.maximum((_act(y0 + u, o.act) - y).abs(), (_act(y0 - u, o.act) - y).abs()).permute(0, 2, 3, 1)
+            return q(y.permute(0, 2, 3, 1)), band
         return q(y.permute(0, 2, 3, 1))
     if o.kind == _capi.OP_SPP:
         x = src.permute(0, 3, 1, 2)
@@ -162,7 +167,7 @@ def teacher_forced_errors(model, x):
             res = eng.view_tensor(o.res).float().clone() if (o.kind == _capi.OP_CONV and o.res.c > 0) else None
             band = None
             up = eng.view_tensor(o.up).float() if (o.kind == _capi.OP_CONV and o.up.c > 0) else None
-            if o.kind == _capi.OP_CONV:                            # before the op runs (dst may alias res)
+            if o.kind in (_capi.OP_CONV, _capi.OP_DWCONV):         # before the op runs (dst may alias res)
                 ref, band = eval_op(o, xf, src, res, wblob, bblob, q, want_band=True, up=up)
             else:
                 ref = eval_op(o, xf, src, res, wblob, bblob, q)

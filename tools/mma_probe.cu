@@ -55,12 +55,24 @@ __global__ void __launch_bounds__(512, 1) probe(P p) {
     const long long t0 = clock64();
     uint32_t st = 0, acc = 0;
     for (int it = 0; it < p.iters; ++it) {
-      const uint32_t a_lo = sdesc_lo(sA + st * 24 * 1024 + p.a_off), b_lo = sdesc_lo(sB + st * 24 * 1024);
-      const uint32_t d = tmem + acc * 256;
+      const uint32_t stg = p.ksteps >= 9 ? 0u : st;   // (the tap patterns span more than one 24 KB stage)
+      const uint32_t a_lo = sdesc_lo(sA + stg * 24 * 1024 + p.a_off), b_lo = sdesc_lo(sB + stg * 24 * 1024);
+      const uint32_t d = tmem + acc * (p.n_acc > 2 ? 128 : 256);
       if (p.fence) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (elect_one()) {
+        if (p.ksteps == 9) {   // "taps" pattern of the stem: nine K = 16 MMAs with nine different A / B tile bases, straight-line
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) if (ks < p.ksteps) umma(d, a_lo + 2 * ks, a_hi, b_lo + 2 * ks, b_hi, idesc, 1u);
+          for (int t = 0; t < 9; ++t) umma(d, a_lo + ((t / 3) * 10 + (t % 3)) * 8, a_hi, b_lo + t * 384, b_hi, idesc, 1u);
+        } else if (p.ksteps == 18) {   // the same with two accumulators per tap (two stacked halves)
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            umma(d, a_lo + ((t / 3) * 10 + (t % 3)) * 8, a_hi, b_lo + t * 384, b_hi, idesc, 1u);
+            umma(d + 64, a_lo + 1280 + ((t / 3) * 10 + (t % 3)) * 8, a_hi, b_lo + t * 384, b_hi, idesc, 1u);
+          }
+        } else {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) if (ks < p.ksteps) umma(d, a_lo + 2 * ks, a_hi, b_lo + 2 * ks, b_hi, idesc, 1u);
+        }
       }
       if (++st == (uint32_t)p.stages) st = 0;
       if (++acc == (uint32_t)p.n_acc) acc = 0;
@@ -101,11 +113,28 @@ __global__ void __launch_bounds__(512, 1) probe(P p) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
 
-int main() {
+int main(int argc, char** argv) {
   int sms = 0; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
   long long* d; CK(cudaMalloc(&d, 8192 * 8));
   CK(cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   printf("%5s %6s %6s %5s %5s %5s %5s | %12s %12s %10s\n", "N", "ksteps", "fence", "spin", "ld", "st", "geom", "cyc/MMA", "issue/MMA", "ideal N/2");
+  if (argc > 1) {   // dependent-chain sweep: small N, 1 or 4 K steps per accumulator visit, 1 / 2 / 4 accumulators alternated
+    for (int n : {48, 96, 192})
+      for (int ksteps : {1, 4, 9, 18})
+        for (int n_acc : {1, 2, 4}) {
+          if (n_acc * 256 > 512 && n > 64) continue;
+          P p; p.n = n; p.iters = 4000; p.n_acc = n_acc; p.stages = 4; p.cyc = d;
+          p.ksteps = ksteps; p.fence = 0; p.spin_warps = 0; p.ld_warps = 0; p.st_warps = 0; p.a_sbo = 1280; p.a_off = 11 * 128;
+          probe<<<sms, 512, 2048 + 8 * 24 * 1024 + 8 * 1024>>>(p);
+          CK(cudaDeviceSynchronize());
+          std::vector<long long> c(sms * 2);
+          CK(cudaMemcpy(c.data(), d, sms * 16, cudaMemcpyDeviceToHost));
+          double tot = 0, iss = 0; for (int i = 0; i < sms; ++i) { tot += c[2 * i]; iss += c[2 * i + 1]; }
+          printf("N %3d  ksteps/visit %d  accumulators %d : %7.1f cycles per MMA (issue %6.1f)\n", n, ksteps, n_acc,
+                 tot / sms / (p.iters * (double)ksteps), iss / sms / (p.iters * (double)ksteps));
+        }
+    return 0;
+  }
   struct M { int ksteps, fence, spin, ld, st; };
   const M modes[] = {{4, 0, 0, 0, 0}, {3, 1, 0, 0, 0}, {4, 1, 4, 0, 0}, {4, 1, 8, 0, 0}, {4, 1, 0, 4, 0}, {4, 1, 0, 4, 1}, {4, 1, 4, 4, 1}, {3, 1, 8, 4, 1}};
   for (int n : {48, 96, 192})
