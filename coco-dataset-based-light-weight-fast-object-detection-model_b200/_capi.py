@@ -92,7 +92,7 @@ class PeerOut(ctypes.Structure):
 
 
 SYMBOLS = ["yx_last_error", "yx_abi_version", "yx_engine_create", "yx_engine_destroy", "yx_engine_run",
-           "yx_engine_profile", "yx_engine_run_ops", "yx_engine_num_launches", "yx_engine_tune", "yx_engine_get_tune", "yx_engine_set_tune", "yx_engine_op_desc", "yx_engine_tune_mismatches",
+           "yx_engine_profile", "yx_engine_run_ops", "yx_engine_num_launches", "yx_engine_tune", "yx_engine_get_tune", "yx_engine_set_tune", "yx_engine_op_desc", "yx_engine_op_sparse_ok", "yx_engine_tune_mismatches",
            "yx_conv2d", "yx_conv2d_ex", "yx_decode_infer", "yx_decode_infer_grids", "yx_detect_workspace_bytes",
            "yx_nms_main", "yx_nms_main_ex", "yx_nms_workspace_bytes", "yx_detect_main",
            "yx_detect_main_gather", "yx_peer_wait", "yx_ipc_export", "yx_ipc_open", "yx_ipc_close", "yx_head_assemble", "yx_decode_outputs", "yx_postprocess_yolox",
@@ -136,6 +136,7 @@ def load():
     lib.yx_engine_get_tune.argtypes = [c_vp, c_i32, ctypes.POINTER(ConvTune)]
     lib.yx_engine_set_tune.argtypes = [c_vp, c_i32, ctypes.POINTER(ConvTune)]
     lib.yx_engine_op_desc.argtypes = [c_vp, c_i32, ctypes.c_char_p, c_i32]
+    lib.yx_engine_op_sparse_ok.argtypes = [c_vp, c_i32]
     lib.yx_engine_tune_mismatches.argtypes = [c_vp, ctypes.c_char_p, c_i32]
     logits = [c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64]
     lib.yx_decode_infer.argtypes = logits + [c_i32, c_i32, c_i32, c_i32, ctypes.POINTER(Levels), c_vp, c_vp, c_vp, c_vp]

@@ -501,8 +501,9 @@ int dwconv_launch(void* base, const yx_op& op, const void* weights, const void* 
   YX_REQUIRE(d.h == Ho && d.w == Wo && d.c == s.c && d.n == s.n && s.c % 8 == 0, "depthwise dst geometry");
   YX_REQUIRE(s.offset % 16 == 0 && d.offset % 16 == 0 && s.pitch % 8 == 0 && d.pitch % 8 == 0 && op.w_offset % 16 == 0,
              "depthwise alignment");
-  static const bool strip_env = !(getenv("YX_DW_STRIP") && atoi(getenv("YX_DW_STRIP")) == 0);
-  static const bool tile_env = !(getenv("YX_DW_TILE") && atoi(getenv("YX_DW_TILE")) == 0);
+  // (read on every call: the tests switch kernels between engines of one process)
+  const bool strip_env = !(getenv("YX_DW_STRIP") && atoi(getenv("YX_DW_STRIP")) == 0);
+  const bool tile_env = !(getenv("YX_DW_TILE") && atoi(getenv("YX_DW_TILE")) == 0);
   if (op.stride == 1 && tile_env) {
     const int tiles_x = (Wo + 15) / 16, tiles_y = (Ho + 7) / 8, cgroups = (d.c + 63) / 64;
     const int64_t n_tiles = (int64_t)d.n * tiles_x * tiles_y * cgroups;

@@ -812,7 +812,7 @@ __global__ void __launch_bounds__(IMG ? 512 : 384, 1) conv_gemm_kernel(const __g
           tc_fence_after();
           const int ksteps = (kc == k_chunks - 1) ? ks_last : (SP ? 2 : 4);
           const uint32_t e_chunk = e_tile + 2u * (uint32_t)kc, e_step = (uint32_t)p.cin >> 5;
-          if (!SP && !RP && b_rows) {
+          if (!SP && !RP && !IMG && b_rows) {   // (the image-fed stem always keeps its weights resident)
             if (diag_path)
               halo_chunk_mma_rows<MH, PAIR, true>(d0, d1, a_lo, a_hi, b_lo, b_hi, idesc, accum, ksteps, bar_fb, bar_eb, sb, phb, b_slots,
                                                   b_lo0, b_step, b_tap_units, tracing, w_acc1, (p.diag & 4) != 0);

@@ -412,6 +412,11 @@ extern "C" int yx_engine_op_desc(const yx_engine* e, int i, char* buf_host, int 
   return YX_OK;
 }
 
+extern "C" int yx_engine_op_sparse_ok(const yx_engine* e, int i) {
+  if (!e || i < 0 || i >= (int)e->steps.size()) return 0;
+  return (e->steps[i].op.kind == YX_OP_CONV && e->steps[i].sp_ok) ? 1 : 0;
+}
+
 extern "C" int yx_engine_profile(yx_engine* e, const void* image, int image_dtype, int iters, void* stream,
                                  float* ms_host, double* flops_host, double* bytes_host, int n_ops) {
   YX_REQUIRE(e && image && ms_host && n_ops == (int)e->steps.size() && iters >= 1, "bad profile arguments");

@@ -303,12 +303,14 @@ class TuneCache:
         self.path = env if env not in ("", "0", "1") else os.path.join(os.path.dirname(os.path.abspath(__file__)), "tune_cache.json")
 
     @staticmethod
-    def op_key(op: "PlannedOp", batch: int) -> str:
+    def op_key(op: "PlannedOp", batch: int, sparse_ok: bool = False) -> str:
         def v(x):
             return "-" if x is None else f"{x.H}x{x.W}x{x.c}p{x.buf.c}" + (f"@{x.lvl_off}" if x.lvl_off or x.nstride else "")
         inplace = op.res is not None and op.res.buf is op.dst.buf and op.res.c_off == op.dst.c_off
+        # a layer with 2:4-compliant weights has the sparse tensor-core shapes among its candidates (and YX_SPARSE changes which)
+        sp = f" sp24:{os.environ.get('YX_SPARSE', 'auto')}" if sparse_ok else ""
         return (f"b{batch} k{op.ksize} s{op.stride} act{op.act} aux{op.aux} cin{op.cin_pad} cout{op.cout_pad} "
-                f"src{v(op.src)} dst{v(op.dst)} res{'inplace' if inplace else v(op.res)} up{v(op.up)}")
+                f"src{v(op.src)} dst{v(op.dst)} res{'inplace' if inplace else v(op.res)} up{v(op.up)}{sp}")
 
     def section(self, device) -> str:
         import torch
@@ -411,6 +413,9 @@ class Engine:
     def _conv_ops(self):
         return [(i, op) for i, op in enumerate(self.graph.ops) if op.kind == _capi.OP_CONV]
 
+    def _op_key(self, i, op) -> str:
+        return TuneCache.op_key(op, self.graph.batch, bool(self.lib.yx_engine_op_sparse_ok(self.handle, i)))
+
     def _shapes_from_cache(self) -> bool:
         import ctypes
         if os.environ.get("YX_TUNE", "1") == "force" or os.environ.get("YX_TUNE_CHECK"):
@@ -418,7 +423,7 @@ class Engine:
         cache = TuneCache()
         entries = cache.load(self.device)
         convs = self._conv_ops()
-        keys = [TuneCache.op_key(op, self.graph.batch) for _, op in convs]
+        keys = [self._op_key(i, op) for i, op in convs]
         if not entries or any(k not in entries for k in keys):
             return False
         previous = []
@@ -440,7 +445,7 @@ class Engine:
         for i, op in self._conv_ops():
             t = _capi.ConvTune()
             _capi.check(self.lib.yx_engine_get_tune(self.handle, i, ctypes.byref(t)), "yx_engine_get_tune")
-            entries[TuneCache.op_key(op, self.graph.batch)] = t.as_list()
+            entries[self._op_key(i, op)] = t.as_list()
         TuneCache().store(self.device, entries)
 
     def run_ops(self, image, first: int, count: int, in_scale: float = 1.0, in_shift: float = 0.0):

@@ -163,6 +163,10 @@ int yx_engine_get_tune(const yx_engine* e, int i, yx_conv_tune* out_host);
 int yx_engine_set_tune(yx_engine* e, int i, const yx_conv_tune* tune_host);
 /* Human-readable description of op i and of the launch shape chosen for it (diagnostics / profiles). */
 int yx_engine_op_desc(const yx_engine* e, int i, char* buf_host, int buf_len);
+/* 1 when op i is a conv whose weights are 2:4-compliant and were packed for the sparse tensor-core variant at creation (the
+ * ingest contract of choijhanyangackr/main.py:52-55: masks arrive as zeros in the dense weights); the tuner then has more
+ * candidates for this layer, so a persisted launch-shape choice must be keyed on it. */
+int yx_engine_op_sparse_ok(const yx_engine* e, int i);
 
 /* ---- stand-alone operators (used by tests and by the reference-style Python functions) ---------- */
 

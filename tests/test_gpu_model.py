@@ -110,6 +110,24 @@ def test_stand_alone_s2d_path(name, H, W, B, monkeypatch):
         assert all(torch.equal(p, q) for p, q in zip(a, b)), f"uint8 and fp16 input disagree (fuse={fuse})"
 
 
+def test_depthwise_kernels_agree(monkeypatch):
+    """The three stride-1 depthwise kernels (shared-memory tile, register-blocked strip, one thread per output) sum the
+    same products in the same order: the whole depthwise model's logits must be bit-identical whichever runs."""
+    cfg, fused, model = _build("tiny_dw", 128, 96, 5)
+    x = mr.synth_images(12, 2, 128, 96).cuda().half()
+    monkeypatch.setenv("YX_TUNE", "0")
+    outs = []
+    for tile, strip in (("1", "1"), ("0", "1"), ("0", "0")):
+        monkeypatch.setenv("YX_DW_TILE", tile)
+        monkeypatch.setenv("YX_DW_STRIP", strip)
+        model.invalidate_engines()
+        outs.append([t.clone() for t in model(x)])
+    kinds = [op.kind for op in model.engine_for(x).graph.ops]
+    assert 4 in kinds, "the depthwise model must contain depthwise ops"
+    for other in outs[1:]:
+        assert all(torch.equal(a, b) for a, b in zip(outs[0], other))
+
+
 @pytest.mark.parametrize("name,H,W,seed", [("tiny_p6_v2", 128, 128, 4), ("tiny_dw", 96, 128, 5)])
 def test_variant_reference_golden(name, H, W, seed):
     """P6-v2 / depthwise inference twins: the engine vs the reference's raw logits (tests/golden/infer_*.npz)."""

@@ -136,6 +136,8 @@ def test_tune_cache_roundtrip(tmp_path, monkeypatch):
     cfg, model = _infer_model("tiny_p6")
     g1, g2 = model.build_graph(1, 64, 64), model.build_graph(2, 64, 64)
     convs = [op for op in g1.ops if op.kind == 0]
+    # a layer with 2:4-compliant weights is tuned over more candidates: its persisted choice has its own key
+    assert plan.TuneCache.op_key(convs[3], 1, sparse_ok=True) != plan.TuneCache.op_key(convs[3], 1)
     k1 = [plan.TuneCache.op_key(op, 1) for op in convs]
     k2 = [plan.TuneCache.op_key(op, 2) for op in g2.ops if op.kind == 0]
     assert len(set(k1)) <= len(k1) and not set(k1) & set(k2)          # batch is part of the key

@@ -29,7 +29,7 @@ cap post "select_infer|sort_keys|nms_kernel|spp_" 0 4 YX_B=64
 YX_MASKS=two_four YX_SPARSE=force YX_STEPS=2 timeout 600 python tools/ncu_target.py > gpurun_out/ncu_plain_sparse_r02.log 2>&1 &&
 cap sparse "conv_gemm_kernel<.int.2, .int.[02], .int.1, .bool.0, .bool.1, .bool.0>" 8 1 "YX_B=64 YX_MASKS=two_four YX_SPARSE=force"
 YX_MODEL=dw YX_B=32 YX_S=640 YX_STEPS=2 timeout 600 python tools/ncu_target.py > gpurun_out/ncu_plain_dw_r02.log 2>&1 &&
-cap dwconv "dwconv_strip_kernel" 3 2 "YX_B=32 YX_S=640 YX_MODEL=dw"
+cap dwconv "dwconv_tile_kernel" 3 2 "YX_B=32 YX_S=640 YX_MODEL=dw"
 fi
 grep -E "exit=|sum ops" $LOG
 cut -c1-300 gpurun_out/bench_r02_n1.json
