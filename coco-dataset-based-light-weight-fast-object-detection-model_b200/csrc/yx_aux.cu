@@ -216,6 +216,9 @@ int spp_launch(void* base, const yx_view& src, const yx_view& dst, cudaStream_t 
   const int64_t pix_bytes = (int64_t)src.h * src.w * 16 * 2;  // two buffers, per 8-channel vector
   int CV = (int)std::min<int64_t>(4, (96 * 1024) / std::max<int64_t>(pix_bytes, 1));
   CV = std::min(CV, cv);
+  // small batches (bs1 latency, 8 images per GPU): fewer vectors per CTA until the grid covers the SMs -- a CTA's time is
+  // seven block barriers and 6 x ceil(H*W*CV/256) passes, so at bs1 twelve CTAs of CV = 4 took 19 us for 0.6 MB
+  while (CV > 1 && (int64_t)src.n * ((cv + CV - 1) / CV) < 148) --CV;
   if (CV >= 1 && !direct_only) {
     static bool attr = false;
     if (!attr) {
