@@ -49,10 +49,10 @@ class ConvTune(ctypes.Structure):
     """Mirror of yx_conv_tune (include/yolox_b200.h)."""
     _fields_ = [("variant", c_i32), ("n_tile", c_i32), ("ctas_per_sm", c_i32), ("halves", c_i32),
                 ("epilogue_groups", c_i32), ("staging_buffers", c_i32), ("second_producer", c_i32),
-                ("no_resident_weights", c_i32), ("cta_pair", c_i32), ("sparse", c_i32), ("epilogue_alternate", c_i32), ("a_stationary", c_i32)]
+                ("no_resident_weights", c_i32), ("cta_pair", c_i32), ("sparse", c_i32), ("epilogue_alternate", c_i32), ("reserved", c_i32)]
 
     FIELDS = ("variant", "n_tile", "ctas_per_sm", "halves", "epilogue_groups", "staging_buffers", "second_producer",
-              "no_resident_weights", "cta_pair", "sparse", "epilogue_alternate", "a_stationary")
+              "no_resident_weights", "cta_pair", "sparse", "epilogue_alternate")
 
     def as_list(self):
         return [int(getattr(self, f)) for f in self.FIELDS]

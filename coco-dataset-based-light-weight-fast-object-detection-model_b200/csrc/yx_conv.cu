@@ -195,9 +195,9 @@ enum { TW_APROD_EMPTY = 0, TW_BPROD_EMPTY = 1, TW_MMA_FULLA = 2, TW_MMA_FULLB = 
 // three runtime integer divisions of a plain decode cost ~450 cycles of dependent latency per tile in EVERY role.
 struct TileIter {
   int nt, tx, ty, img;
-  __device__ __forceinline__ void init(const ConvParams& p, int tile, int n_tiles_n) {
-    nt = tile % n_tiles_n;
-    int r = tile / n_tiles_n;
+  __device__ __forceinline__ void init(const ConvParams& p, int tile) {
+    nt = tile % p.n_tiles_n;
+    int r = tile / p.n_tiles_n;
     tx = r % p.tiles_w; r /= p.tiles_w;
     ty = r % p.tiles_h;
     img = r / p.tiles_h;
@@ -337,7 +337,7 @@ __device__ __forceinline__ void img_producer_loop(const ConvParams& p, const CUt
   named_bar_sync(5, kImgProdThreads);
   uint32_t s = 0, ph = 0, i = 0;
   TileIter ti;
-  ti.init(p, tile_first, n_tiles_n);
+  ti.init(p, tile_first);
   if (tid == 0 && tile_first < n_tiles) {   // the first tile's patch
     mbar_expect_tx(bar_patch, patch_bytes);
     tma_load_4d(sScratch, tm_img, bar_patch, ti.tx * p.TW * xs - 8, 2 * (ti.ty * TH - 1), 0, ti.img);
@@ -615,17 +615,10 @@ __global__ void __launch_bounds__(IMG ? 512 : 384, 1) conv_gemm_kernel(const __g
   }
 
   // PAIR: the tile space is walked in units of CTA pairs; CTA `rank` owns the x-tile 2*tx + rank of every pair tile
-  // A-stationary (generic, streamed weights, several N tiles): the SCHEDULE walks pixel tiles only (n_tiles_n = 1 below, the
-  // host computed the step digits the same way) and every role loops over the layer's n_nt N tiles itself; the activation
-  // tile of a pixel tile is loaded once (ring stage i = k-iteration i) and released during the last N tile.
-  constexpr bool AK = MODE == 0 && !SP && !IMG;
-  const bool akeep = AK && p.a_keep != 0;
-  const int n_nt = p.n_tiles_n;
-  const int n_tiles_n = akeep ? 1 : n_nt, nt_inner = akeep ? n_nt : 1;
-  const int n_tiles = p.n_tiles_m * n_tiles_n;
+  const int n_tiles = p.n_tiles_m * p.n_tiles_n;
   const int tile_step = PAIR ? (gridDim.x >> 1) : gridDim.x;
   const int tile_first = PAIR ? (blockIdx.x >> 1) : blockIdx.x;
-  const int tiles_w = p.tiles_w, tiles_h = p.tiles_h;
+  const int n_tiles_n = p.n_tiles_n, tiles_w = p.tiles_w, tiles_h = p.tiles_h;
   const int taps = p.ky * p.kx;
   const int k_chunks = p.k_chunks;
   const uint32_t stages_a = p.stages_a, b_slots = p.b_slots;
@@ -658,12 +651,10 @@ __global__ void __launch_bounds__(IMG ? 512 : 384, 1) conv_gemm_kernel(const __g
     uint32_t s = 0, ph = 0, turn = 0;
     int nt = tile_first % n_tiles_n;
     for (int tile = tile_first; tile < n_tiles; tile += tile_step) {
-     const int nt_sched = nt;
-     nt += p.step_nt;
-     if (nt >= n_tiles_n) nt -= n_tiles_n;
-     for (int nti = 0; nti < nt_inner; ++nti) {
-      int n0 = (akeep ? nti : nt_sched) * BN;
+      int n0 = nt * BN;
       if (PAIR) n0 += (int)rank * (min(BN, cout16 - n0) >> 1);  // this CTA's half of the N tile
+      nt += p.step_nt;
+      if (nt >= n_tiles_n) nt -= n_tiles_n;
       // ring order must match the MMA issuer: halo = (chunk, tap), generic = (tap, chunk)
       const int b_taps = p.b_taps;   // halo ring: taps per stage (3 = one filter row per load)
       const int outer = HALO ? k_chunks : taps, inner = HALO ? taps / b_taps : k_chunks;
@@ -686,7 +677,6 @@ __global__ void __launch_bounds__(IMG ? 512 : 384, 1) conv_gemm_kernel(const __g
           if (++turn == nprod) turn = 0;
           if (++s == b_slots) { s = 0; ph ^= 1; }
         }
-     }
       if (resident) break;  // one N tile per layer: the weights stay in smem for every later tile
     }
     if (warp == 2) YX_TRACE_SUM(TW_BPROD_EMPTY, w_acc0);
@@ -710,7 +700,7 @@ __global__ void __launch_bounds__(IMG ? 512 : 384, 1) conv_gemm_kernel(const __g
     uint32_t s = 0, ph = 0, turn = 0;  // ring slot / phase / whose turn, all incremental
     const int TH = p.TH, TW = p.TW;
     TileIter ti;
-    ti.init(p, tile_first, n_tiles_n);
+    ti.init(p, tile_first);
     for (int tile = tile_first; tile < n_tiles; tile += tile_step) {
       const int x0 = (PAIR ? 2 * ti.tx + (int)rank : ti.tx) * TW, y0 = ti.ty * TH, img = ti.img;
       YX_TILE_NEXT(ti);
@@ -801,16 +791,12 @@ __global__ void __launch_bounds__(IMG ? 512 : 384, 1) conv_gemm_kernel(const __g
     const bool fast_ok = !tracing && p.diag == 0;   // (YX_CONV_DIAG=16: the general loop, results unchanged)
     bool b_ready = false;  // resident weights: wait for them during the first tile only
     int nt = tile_first % n_tiles_n;
-    uint32_t pha_tile = 0;   // A-stationary: phase of the pixel tile's "full" barriers (every stage is filled once per pixel tile)
-    for (int tile = tile_first; tile < n_tiles; tile += tile_step) {
-     const int nt_sched = nt;
-     nt += p.step_nt;
-     if (nt >= n_tiles_n) nt -= n_tiles_n;
-     for (int nti = 0; nti < nt_inner; ++nti, ++t) {
-      const int nt_cur = akeep ? nti : nt_sched;
-      const int n0 = nt_cur * BN;
+    for (int tile = tile_first; tile < n_tiles; tile += tile_step, ++t) {
+      const int n0 = nt * BN;
       // SP: first metadata column of this output-channel tile (one column per (tap, K = 32 step); tmem_base has column 0)
-      const uint32_t e_tile = SP ? tmem_base + (uint32_t)(p.sp_meta_col0 + nt_cur * p.sp_cols_per_tile) : 0u;
+      const uint32_t e_tile = SP ? tmem_base + (uint32_t)(p.sp_meta_col0 + nt * p.sp_cols_per_tile) : 0u;
+      nt += p.step_nt;
+      if (nt >= n_tiles_n) nt -= n_tiles_n;
       const int bn_cur = min(BN, cout16 - n0);
       const uint32_t idesc = SP ? make_idesc_f16_sp(128, 0) : (PAIR ? make_idesc_f16_m256(bn_cur) : make_idesc_f16(bn_cur));
       const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
@@ -852,35 +838,7 @@ __global__ void __launch_bounds__(IMG ? 512 : 384, 1) conv_gemm_kernel(const __g
         // nothing in it but wait -> 4 MMAs -> commit: every instruction here is serial latency of the tensor pipe's only
         // feeder (conv_trace: a k-iteration of the general loop below costs ~420 cycles of issue, more than the 384 cycles
         // its four N = 192 MMAs take, so every streamed layer with N <= 192 ran at the issue rate, not the MMA rate).
-        if (AK && akeep) {
-          // A-stationary: stage i of the A ring IS k-iteration i of this pixel tile; it is waited for during the first N tile
-          // only and released (commit -> its "empty" barrier) during the last one, so the next pixel tile's loads overlap the
-          // last N tile's MMAs.  The weights stream through their own ring.
-          const bool first_n = nti == 0, last_n = nti == nt_inner - 1;
-          uint32_t a_cur = a_lo0;
-          int kcc = 0;
-          for (int i = 0; i < k_iters; ++i) {
-            if (first_n) mbar_wait_acc(bar_fa + 8 * i, pha_tile, tracing, w_acc0);
-            mbar_wait_acc(bar_fb + 8 * sb, phb, tracing, w_acc1);
-            tc_fence_after();
-            const bool lastc = ++kcc == k_chunks;
-            if (lastc) kcc = 0;
-            if (elect_one()) {
-              if (!(p.diag & 4)) {
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                  if (!lastc || ks < ks_last) umma_x<PAIR>(d0, a_cur + 2 * ks, a_hi, b_lo + 2 * ks, b_hi, idesc, ks == 0 ? accum : 1u);
-              }
-              commit_x<PAIR>(bar_eb + 8 * sb);
-              if (last_n) commit_x<PAIR>(bar_ea + 8 * i);
-            }
-            accum = 1;
-            a_cur += a_step;
-            b_lo += b_step;
-            if (++sb == b_slots) { sb = 0; phb ^= 1; b_lo = b_lo0; }
-          }
-          if (last_n) pha_tile ^= 1;
-        } else if (!SP && fast_ok && (!resident || b_ready)) {
+        if (!SP && fast_ok && (!resident || b_ready)) {
           // one k-iteration: FULL = four K = 16 steps, otherwise the ks_last (1..3) steps of a partial last chunk
 #define YX_FAST_ITER(FULL)                                                                                              \
           {                                                                                                             \
@@ -951,7 +909,6 @@ __global__ void __launch_bounds__(IMG ? 512 : 384, 1) conv_gemm_kernel(const __g
       if (resident) b_ready = true;
       if (elect_one()) commit_x<PAIR>(bar_tfull + 8 * acc);  // accumulator complete -> epilogue (of both CTAs)
       if (lane == 0) YX_TRACE(2, t);
-     }
     }
     YX_TRACE_SUM(TW_MMA_FULLA, w_acc0);
     YX_TRACE_SUM(TW_MMA_FULLB, w_acc1);
@@ -980,12 +937,10 @@ __global__ void __launch_bounds__(IMG ? 512 : 384, 1) conv_gemm_kernel(const __g
     uint32_t t = 0, u = 0;  // tile counter, staging-unit counter (MH units per tile)
     const int TH = p.TH, TW = p.TW;
     TileIter ti;
-    ti.init(p, tile_first, n_tiles_n);
-    for (int tile = tile_first; tile < n_tiles; tile += tile_step) {
-     struct { int x0, y0, img, n0; } tc = {(PAIR ? 2 * ti.tx + (int)rank : ti.tx) * TW, ti.ty * TH, ti.img, ti.nt * BN};
-     YX_TILE_NEXT(ti);
-     for (int nti = 0; nti < nt_inner; ++nti, ++t) {
-      if (akeep) tc.n0 = nti * BN;
+    ti.init(p, tile_first);
+    for (int tile = tile_first; tile < n_tiles; tile += tile_step, ++t) {
+      struct { int x0, y0, img, n0; } tc = {(PAIR ? 2 * ti.tx + (int)rank : ti.tx) * TW, ti.ty * TH, ti.img, ti.nt * BN};
+      YX_TILE_NEXT(ti);
       const int bn_cur = min(BN, cout16 - tc.n0);
       const int groups_cur = (bn_cur + 63) >> 6;
       const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
@@ -1055,7 +1010,6 @@ __global__ void __launch_bounds__(IMG ? 512 : 384, 1) conv_gemm_kernel(const __g
           }
         }
       }
-     }
     }
     if (lead_warp) {
       if (elect_one()) tma_store_wait_all0();
@@ -1341,18 +1295,10 @@ void conv_candidates(const yx_op& op, std::vector<ConvTune>* out, bool sparse_ok
       if (memcmp(&o, &t, sizeof t) == 0) return;
     out->push_back(t);
   };
-  static const bool akeep_env = !(getenv("YX_AKEEP") && atoi(getenv("YX_AKEEP")) == 0);
-  const int k_iters_all = g.taps * ((op.up.c > 0 ? op.up.c / 64 : 0) + ceil_div(op.cin_pad - (op.up.c > 0 ? op.up.c : 0), 64));
   auto push = [&](ConvTune t) {
     push1(t);
     if (t.epi_groups == 2 && t.stage_bufs == 2) {   // the same shape with the two groups alternating tiles
-      ConvTune a = t;
-      a.epi_alt = 1;
-      push1(a);
-    }
-    // the A-stationary twin of a generic shape with several N tiles (a plan that does not fit is skipped by the tuner)
-    if (akeep_env && t.variant == 1 && t.mh != 2 && t.ctas == 1 && !g.rowpack && t.bn < cout16 && k_iters_all <= kMaxARing) {
-      t.a_keep = 1;
+      t.epi_alt = 1;
       push1(t);
     }
   };
@@ -1422,9 +1368,6 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
   YX_REQUIRE(!t.epi_alt || (t.epi_groups == 2 && t.stage_bufs != 1),
              "conv tune: alternating epilogue groups need two groups and two staging buffers");
   YX_REQUIRE(op.cout_pad <= 4096, "cout too large");
-  const bool akeep = t.a_keep != 0;
-  YX_REQUIRE(!akeep || (!halo && !sp && !g.rowpack && !g.img && t.mh != 2 && t.ctas == 1),
-             "conv tune: the A-stationary N loop is a generic-variant shape with one 128-pixel tile and one CTA per SM");
 
   ConvPlan pl;
   memset(&pl, 0, sizeof pl);
@@ -1558,23 +1501,13 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
         p.stages_a = (avail - 3 * p.a_stage_bytes >= 4 * p.b_stage_bytes) ? 3 : 2;
         p.b_slots = std::min(12, (avail - p.stages_a * p.a_stage_bytes) / p.b_stage_bytes);
       }
-    } else if (akeep) {
-      // A-stationary: one A stage per k-iteration of the pixel tile (all of them live at once), weights through their own ring
-      p.b_resident = 0;
-      p.stages_a = k_loads_b;
-      p.b_slots = std::min(8, (avail - k_loads_b * p.a_stage_bytes) / p.b_stage_bytes);
-      if (k_loads_b > kMaxARing || p.n_tiles_n < 2 || avail < k_loads_b * p.a_stage_bytes || p.b_slots < 3) {
-        set_error("conv plan: the A-stationary N loop needs several N tiles, at most 8 k-iterations per tile and room for them plus 3 weight stages");
-        return YX_ERR_INVALID;
-      }
     } else {
       p.b_resident = 0;
       const int st = std::min(kMaxARing, avail / (p.a_stage_bytes + p.b_stage_bytes));
       p.stages_a = st;
       p.b_slots = st;
     }
-    p.a_keep = (akeep && !p.b_resident) ? 1 : 0;
-    p.shared_ring = (!halo && !p.b_resident && !p.a_keep) ? 1 : 0;
+    p.shared_ring = (!halo && !p.b_resident) ? 1 : 0;
     const bool fits = p.stages_a >= 2 && p.b_slots >= (p.b_resident ? 1 : ((halo && p.b_taps == 1) ? 3 : 2));
     if (fits) {
       pl.smem_bytes = fixed + p.stages_a * p.a_stage_bytes + p.b_slots * p.b_stage_bytes;
@@ -1584,14 +1517,12 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
     set_error("conv plan: launch shape does not fit in shared memory");
     return YX_ERR_INVALID;
   }
-  YX_REQUIRE(!akeep || p.a_keep, "conv tune: the A-stationary N loop is for streamed weights (this layer keeps them resident)");
   // never let an extra CTA (which would stall in tcgen05.alloc) fit on an SM
   if (t.ctas == 2) pl.smem_bytes = std::max(pl.smem_bytes, 80 * 1024);
   else if (p.tmem_cols > 256) pl.smem_bytes = std::max(pl.smem_bytes, 120 * 1024);
   else pl.smem_bytes = std::max(pl.smem_bytes, 80 * 1024);
-  const int sched_ntn = p.a_keep ? 1 : p.n_tiles_n;   // A-stationary: the schedule walks pixel tiles, the kernel loops over N
-  pl.grid = std::min(p.n_tiles_m * sched_ntn, t.ctas * num_sms);
-  if (pair) pl.grid = 2 * std::min(p.n_tiles_m * sched_ntn, num_sms / 2);
+  pl.grid = std::min(p.n_tiles_m * p.n_tiles_n, t.ctas * num_sms);
+  if (pair) pl.grid = 2 * std::min(p.n_tiles_m * p.n_tiles_n, num_sms / 2);
   {
     // Unequal N tiles (Cout = 288 as 192 + 96): with the N tile fastest and a static stride of `units` tiles, a stride that
     // shares a factor with n_tiles_n pins every CTA to the SAME N tile for the whole launch -- half of the SMs would only
@@ -1600,14 +1531,14 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
     static const bool rot_env = !(getenv("YX_NROT") && atoi(getenv("YX_NROT")) == 0);
     int units = pair ? pl.grid / 2 : pl.grid;
     auto gcd = [](int a, int b) { while (b) { const int r = a % b; a = b; b = r; } return a; };
-    if (rot_env && !p.a_keep && p.n_tiles_n > 1 && p.cout16 % p.BN != 0 && p.n_tiles_m * p.n_tiles_n > units) {
+    if (rot_env && p.n_tiles_n > 1 && p.cout16 % p.BN != 0 && p.n_tiles_m * p.n_tiles_n > units) {
       while (units > 1 && gcd(units, p.n_tiles_n) != 1) --units;
       pl.grid = pair ? 2 * units : units;
     }
   }
   {  // mixed-radix digits of the persistent-tile step (see TileIter)
     int st = pair ? pl.grid / 2 : pl.grid;
-    p.step_nt = st % sched_ntn; st /= sched_ntn;
+    p.step_nt = st % p.n_tiles_n; st /= p.n_tiles_n;
     p.step_x = st % p.tiles_w; st /= p.tiles_w;
     p.step_y = st % p.tiles_h;
     p.step_img = st / p.tiles_h;
@@ -1621,7 +1552,6 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
   if (p.w3_role == 2 && p.b_slots < 2) p.w3_role = 0;
   // warp 2 (weight producer) joins the activation producers once its resident weights are in (YX_W2A=0: off, for A/B runs)
   if (g.img) p.w3_role = 1;   // warps 0, 2, 3 build the operand tiles together; warp 2 first issues the (resident) weight loads
-  if (p.a_keep && t.w3 != 0) p.w3_role = 2;   // the weights are re-streamed per N tile, the activations loaded once: help the weights
   static const bool w2a_env = !(getenv("YX_W2A") && atoi(getenv("YX_W2A")) == 0);
   p.w2_role = (w2a_env && p.b_resident && t.w3 != 0 && a_loads >= 3 && p.stages_a >= 3 && !g.img) ? 1 : 0;
   YX_REQUIRE(!g.img || p.b_resident, "image-fed stem: the weights must stay resident");
@@ -1701,7 +1631,7 @@ int conv_plan(const yx_op& op, void* base, const void* weights, const void* bias
   pl.bytes = g.act_bytes + 2.0 * (double)d.c * g.cin_real * op.ksize * op.ksize;
   snprintf(pl.desc, sizeof pl.desc, "%s%s%s%s%s BN%d%s mh%d ctas%d epi%d%s sbuf%d A%dx%dK B%d%s%s w3:%d%s grid%d smem%dK", g.img ? "image-fed-" : "", sp ? "sparse24-" : "", p.has_res == 2 ? "inplace-" : "", pair ? "pair-" : "", halo ? "halo" : "generic",
            p.BN, p.n_tiles_n > 1 ? "*" : "", p.mh, t.ctas, p.epi_groups, p.epi_alt ? "alt" : "", p.stage_bufs, p.stages_a, p.a_stage_bytes >> 10, p.b_slots,
-           p.b_resident ? "res" : (p.a_keep ? " Akeep" : ""), p.b_taps == 3 ? "x3" : "", p.w3_role, p.w2_role ? "+w2" : "", pl.grid, pl.smem_bytes >> 10);
+           p.b_resident ? "res" : "", p.b_taps == 3 ? "x3" : "", p.w3_role, p.w2_role ? "+w2" : "", pl.grid, pl.smem_bytes >> 10);
   *out = pl;
   return YX_OK;
 }

@@ -359,7 +359,7 @@ static ConvTune tune_from_abi(const yx_conv_tune& a) {
   memset(&t, 0, sizeof t);
   t.variant = a.variant; t.bn = a.n_tile; t.ctas = a.ctas_per_sm; t.mh = a.halves;
   t.epi_groups = a.epilogue_groups; t.stage_bufs = a.staging_buffers; t.w3 = a.second_producer;
-  t.no_resident = a.no_resident_weights; t.pair = a.cta_pair; t.sparse = a.sparse; t.epi_alt = a.epilogue_alternate; t.a_keep = a.a_stationary;
+  t.no_resident = a.no_resident_weights; t.pair = a.cta_pair; t.sparse = a.sparse; t.epi_alt = a.epilogue_alternate;
   return t;
 }
 static yx_conv_tune tune_to_abi(const ConvTune& t) {
@@ -367,7 +367,7 @@ static yx_conv_tune tune_to_abi(const ConvTune& t) {
   memset(&a, 0, sizeof a);
   a.variant = t.variant; a.n_tile = t.bn; a.ctas_per_sm = t.ctas; a.halves = t.mh;
   a.epilogue_groups = t.epi_groups; a.staging_buffers = t.stage_bufs; a.second_producer = t.w3;
-  a.no_resident_weights = t.no_resident; a.cta_pair = t.pair; a.sparse = t.sparse; a.epilogue_alternate = t.epi_alt; a.a_stationary = t.a_keep;
+  a.no_resident_weights = t.no_resident; a.cta_pair = t.pair; a.sparse = t.sparse; a.epilogue_alternate = t.epi_alt;
   return a;
 }
 

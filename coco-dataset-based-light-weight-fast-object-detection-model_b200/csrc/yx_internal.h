@@ -55,8 +55,6 @@ struct ConvParams {
   int b_taps;                    // filter taps per B ring stage (halo + streamed weights: 3 = one filter row per stage, one TMA
                                  // load, one wait and one commit per three taps; otherwise 1)
   int shared_ring;               // generic + streamed weights: A and B share one full/empty barrier pair per stage
-  int a_keep;                    // A-stationary: the schedule walks PIXEL tiles (step digits computed with one N tile) and every
-                                 // role loops over the n_tiles_n N tiles itself; A ring stage i = k-iteration i, loaded once per pixel tile
   int stage_bufs, out_box_bytes, bias_bytes; // output staging buffers (1 or 2), bytes per 64-ch residual box
   int epi_groups;                // epilogue warpgroups (1 or 2)
   int epi_alt;                   // two groups: 0 = split every tile's columns, 1 = alternate tiles (group g <-> accumulator g)
@@ -93,7 +91,6 @@ struct ConvTune {
   int pair;         // 1: CTA-pair mode (cta_group::2)
   int sparse;       // 1: 2:4 sparse tensor-core variant (weights = sparse A operand of tcgen05.mma.sp)
   int epi_alt;      // 1: the two epilogue groups alternate tiles instead of splitting each tile's columns
-  int a_keep;       // 1: A-stationary N loop (generic, streamed weights): the activation tile stays in smem for all N tiles
 };
 
 struct ConvPlan {

@@ -142,9 +142,7 @@ typedef struct yx_conv_tune {
                                   only valid for a layer whose weights are 2:4-compliant along Cin */
   int32_t epilogue_alternate;  /* with two epilogue groups: 0 = both convert half of every tile's columns, 1 = the groups
                                   alternate tiles (each owns one accumulator and one staging buffer) */
-  int32_t a_stationary;        /* variant 1, streamed weights, several N tiles, K <= 8 chunk-taps: 1 = a CTA walks PIXEL tiles and
-                                  loops over the N tiles itself, keeping the activation tile in shared memory for all of them
-                                  (the activation bytes cross L2 -> shared memory once instead of once per N tile) */
+  int32_t reserved;            /* 0 */
 } yx_conv_tune;
 
 /* Per-layer launch-shape selection by measurement (the counterpart of torch.backends.cudnn.benchmark = True, which

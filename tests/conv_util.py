@@ -155,10 +155,9 @@ CASES = [
 ]
 
 
-def _t(variant, n_tile, ctas=1, halves=1, eg=1, sb=2, w3=1, nores=0, pair=0, sparse=0, alt=0, akeep=0):
+def _t(variant, n_tile, ctas=1, halves=1, eg=1, sb=2, w3=1, nores=0, pair=0, sparse=0, alt=0):
     return dict(variant=variant, n_tile=n_tile, ctas_per_sm=ctas, halves=halves, epilogue_groups=eg, staging_buffers=sb,
-                second_producer=w3, no_resident_weights=nores, cta_pair=pair, sparse=sparse, epilogue_alternate=alt,
-                a_stationary=akeep)
+                second_producer=w3, no_resident_weights=nores, cta_pair=pair, sparse=sparse, epilogue_alternate=alt)
 
 
 def _sp(variant, eg=1, sb=1, nores=0):
@@ -205,14 +204,6 @@ TUNED_CASES = [
     dict(cin=48, cout=96, k=3, stride=2, H=64, W=64, act="hard_swish", tune=_t(1, 96, ctas=2)),
     dict(cin=48, cout=96, k=3, stride=2, H=64, W=64, act="hard_swish", tune=_t(1, 96, eg=2)),
     dict(cin=96, cout=192, k=3, stride=2, H=64, W=64, act="hard_swish", tune=_t(1, 192, w3=0)),
-    # A-stationary N loop (the activation tile stays in smem for all N tiles; weights through their own ring)
-    dict(cin=384, cout=384, k=1, stride=1, H=32, W=32, act="silu", tune=_t(1, 128, akeep=1)),                   # 3 N tiles, 6 k-iterations
-    dict(cin=384, cout=384, k=1, stride=1, H=40, W=40, act="hard_swish", tune=_t(1, 192, pair=1, sb=1, akeep=1)),  # pair, odd x tiles
-    dict(cin=384, cout=384, k=1, stride=1, H=80, W=80, act="hard_swish", tune=_t(1, 128, pair=1, eg=2, akeep=1)),   # many tiles per CTA, 2 epilogue groups
-    dict(cin=288, cout=288, k=1, stride=1, H=40, W=40, act="hard_swish", tune=_t(1, 128, akeep=1)),                # K tail (32), N tiles 128+128+32
-    dict(cin=192, cout=384, k=1, stride=1, H=64, W=64, act="hard_swish", up_c=192, tune=_t(1, 128, pair=1, sb=1, akeep=1)),  # fused upsample + concat
-    dict(cin=48, cout=96, k=3, stride=2, H=64, W=64, act="hard_swish", tune=_t(1, 64, nores=1, akeep=1)),           # 9 taps > 8 stages: rejected (see the test)
-    dict(cin=96, cout=288, k=1, stride=1, H=32, W=32, act="silu", res=True, tune=_t(1, 128, nores=1, akeep=1)),     # residual via staging
     # CTA-pair (cta_group::2) shapes
     dict(cin=192, cout=192, k=3, stride=1, H=80, W=80, act="hard_swish", tune=_t(2, 192, pair=1)),
     dict(cin=192, cout=192, k=3, stride=1, H=40, W=40, act="hard_swish", tune=_t(2, 192, pair=1, sb=1)),            # odd number of x tiles

@@ -157,6 +157,4 @@ def test_tune_cache_roundtrip(tmp_path, monkeypatch):
     assert plan.TuneCache().load(None) == {}
     from yolox_b200 import _capi
     t = _capi.ConvTune.from_list([2, 96, 1, 2, 1, 2, 1, 0, 1, 0, 1])
-    # (an 11-entry list written before the a_stationary field existed still loads: the new field defaults to 0)
-    assert t.as_list() == [2, 96, 1, 2, 1, 2, 1, 0, 1, 0, 1, 0] and t.cta_pair == 1 and t.epilogue_alternate == 1
-    assert _capi.ConvTune.from_list([1, 128, 1, 1, 1, 2, 1, 0, 1, 0, 0, 1]).a_stationary == 1
+    assert t.as_list() == [2, 96, 1, 2, 1, 2, 1, 0, 1, 0, 1] and t.cta_pair == 1 and t.epilogue_alternate == 1

@@ -53,16 +53,7 @@ CASES = {
         ("pair-generic BN192 sb1", _t(1, 192, sb=1, pair=1)), ("generic BN192 sb1", _t(1, 192, sb=1)),
         ("pair-generic BN128 sb1", _t(1, 128, sb=1, pair=1)),
     ]),
-    "p3c12": (dict(cin=192, cout=384, k=1, stride=1, H=160, W=160, B=16, act="hard_swish", up_c=192), [
-        ("pair-generic BN128 sb2", _t(1, 128, pair=1)), ("pair-generic BN128 sb2 akeep", _t(1, 128, pair=1, akeep=1)),
-        ("pair-generic BN192 sb1", _t(1, 192, pair=1, sb=1)), ("pair-generic BN192 sb1 akeep", _t(1, 192, pair=1, sb=1, akeep=1)),
-        ("generic BN128 mh2 sb1", _t(1, 128, halves=2, sb=1)), ("generic BN128 akeep", _t(1, 128, akeep=1)),
-        ("generic BN192 sb1 akeep", _t(1, 192, sb=1, akeep=1)),
-    ]),
     "c384x1": (dict(cin=384, cout=384, k=1, stride=1, H=80, W=80, B=64, act="hard_swish"), [
-        ("pair-generic BN128 akeep", _t(1, 128, pair=1, akeep=1)), ("pair-generic BN192 sb1 akeep", _t(1, 192, pair=1, sb=1, akeep=1)),
-        ("pair-generic BN128 eg2 akeep", _t(1, 128, pair=1, eg=2, akeep=1)), ("generic BN128 akeep", _t(1, 128, akeep=1)),
-        ("generic BN192 sb1 akeep", _t(1, 192, sb=1, akeep=1)), ("pair-generic BN128 sb2", _t(1, 128, pair=1)),
         ("generic BN128 mh2", _t(1, 128, halves=2, eg=2)), ("pair-generic BN192 sb1", _t(1, 192, sb=1, pair=1)),
         ("pair-generic BN256 sb1", _t(1, 256, sb=1, pair=1)), ("generic BN192 sb1", _t(1, 192, sb=1)),
     ]),
