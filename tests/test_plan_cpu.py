@@ -158,3 +158,21 @@ def test_tune_cache_roundtrip(tmp_path, monkeypatch):
     from yolox_b200 import _capi
     t = _capi.ConvTune.from_list([2, 96, 1, 2, 1, 2, 1, 0, 1, 0, 1])
     assert t.as_list() == [2, 96, 1, 2, 1, 2, 1, 0, 1, 0, 1] and t.cta_pair == 1 and t.epilogue_alternate == 1
+
+
+def test_shipped_tune_cache_matches_kernel_revision():
+    """The launch-shape cache shipped next to the package is only ever USED for the kernel revision it was measured on
+    (plan.TuneCache keys it by device name and a hash of the conv kernel sources); a stale file is dead weight that makes
+    every first run tune and rewrite it, so shipping one is a mistake this test catches."""
+    import importlib
+    import json
+    import os
+    from yolox_b200 import plan
+    b = importlib.import_module(plan.__package__ + "._build")
+    path = os.path.join(os.path.dirname(plan.__file__), "tune_cache.json")
+    if not os.path.exists(path):
+        pytest.skip("no launch-shape cache shipped")
+    sections = list(json.load(open(path)))
+    assert sections and all(s.endswith("|" + b.kernel_rev()) for s in sections), (sections, b.kernel_rev())
+    entries = json.load(open(path))[sections[0]]
+    assert all(len(v) in (11, 12) for v in entries.values())
