@@ -1690,7 +1690,7 @@ static int launch_variant(const ConvPlan& plan, cudaStream_t stream) {
     attr[na].val.clusterDim.z = 1;
     ++na;
   }
-  if (pdl) {  // may start while the previous kernel of the stream drains; the kernel orders itself with griddepcontrol.wait
+  if (pdl && !plan.no_pdl) {  // may start while the previous kernel of the stream drains; the kernel orders itself with griddepcontrol.wait
     attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;

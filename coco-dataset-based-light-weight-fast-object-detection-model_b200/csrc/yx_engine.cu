@@ -47,6 +47,19 @@ struct yx_engine {
   bool tuned = false;
   std::vector<void*> owned;   // device memory the engine allocated itself (2:4-packed weights and metadata)
   std::vector<std::string> tune_mismatches;  // YX_TUNE_CHECK: candidates whose output differed from the default shape
+  // ---- lanes: small batches (bs1 latency, 8 images per GPU) leave most SMs idle in the deep layers, and the head's four
+  // pyramid levels (and its cls / reg branches) do not depend on each other: ops are spread over a few streams, ordered by
+  // events derived from the arena byte ranges every op reads and writes (RAW, WAR and WAW, so the arena's live-range reuse
+  // stays safe).  Lane 0 is the caller's stream.
+  static constexpr int kLanes = 4;
+  bool lanes_on = false;
+  std::vector<int> lane;                    // per step
+  std::vector<std::vector<int>> waits;      // per step: steps on OTHER lanes whose completion events it waits for
+  std::vector<char> needs_event;            // per step: another lane waits for it
+  std::vector<cudaEvent_t> events;          // per step (created when needs_event), + fork + one join event per side lane
+  cudaStream_t lane_streams[kLanes] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t fork_event = nullptr, join_events[kLanes] = {nullptr, nullptr, nullptr, nullptr};
+  int lanes_used = 1;
 };
 
 using namespace yx;
@@ -59,7 +72,13 @@ static bool view_ok(const yx_view& v, size_t arena_bytes) {
 }
 
 // launches a conv plan; the image-fed stem gets the caller's image bound at launch time
-static int launch_conv(const ConvPlan& plan, const void* image, int image_dtype, float in_scale, float in_shift, cudaStream_t st) {
+static int launch_conv(const ConvPlan& plan, const void* image, int image_dtype, float in_scale, float in_shift, cudaStream_t st,
+                       bool no_pdl = false) {
+  if (no_pdl && !plan.p.img_fused) {
+    ConvPlan pl = plan;
+    pl.no_pdl = 1;
+    return conv_launch(pl, st);
+  }
   if (!plan.p.img_fused) return conv_launch(plan, st);
   ConvPlan pl = plan;
   int rc = conv_bind_image(&pl, image, image_dtype, in_scale, in_shift);
@@ -67,9 +86,9 @@ static int launch_conv(const ConvPlan& plan, const void* image, int image_dtype,
 }
 
 static int run_step(yx_engine* e, const Step& s, const void* image, int image_dtype, float in_scale, float in_shift,
-                    cudaStream_t st) {
+                    cudaStream_t st, bool no_pdl = false) {
   switch (s.op.kind) {
-    case YX_OP_CONV: return launch_conv(s.conv, image, image_dtype, in_scale, in_shift, st);
+    case YX_OP_CONV: return launch_conv(s.conv, image, image_dtype, in_scale, in_shift, st, no_pdl);
     case YX_OP_S2D:
       return s2d_launch(image, image_dtype, s.op.aux, e->batch, e->in_h, e->in_w, in_scale, in_shift, e->arena, s.op.dst, st);
     case YX_OP_SPP: return spp_launch(e->arena, s.op.src, s.op.dst, st);
@@ -101,6 +120,135 @@ struct DstSnapshot {
     if (copy) { cudaStreamSynchronize(st); cudaFree(copy); copy = nullptr; }
   }
 };
+
+// ---- lanes -------------------------------------------------------------------------------------------------------
+namespace {
+struct ByteView { int64_t off, nstride, len; int n; };   // n intervals [off + i*nstride, + len), bytes
+ByteView bytes_of(const yx_view& v) {
+  return {v.offset, v.nstride * 2, (((int64_t)v.h * v.w - 1) * v.pitch + v.c) * 2, v.n};
+}
+bool overlap(const ByteView& a, const ByteView& b) {
+  const int64_t a_end = a.off + (a.n - 1) * a.nstride + a.len, b_end = b.off + (b.n - 1) * b.nstride + b.len;
+  if (a_end <= b.off || b_end <= a.off) return false;                      // bounding ranges
+  for (int i = 0; i < a.n; ++i) {                                          // per-image intervals (level windows of [B,A,C])
+    const int64_t a0 = a.off + i * a.nstride, a1 = a0 + a.len;
+    for (int j = 0; j < b.n; ++j) {
+      const int64_t b0 = b.off + j * b.nstride, b1 = b0 + b.len;
+      if (a0 < b1 && b0 < a1) return true;
+    }
+  }
+  return false;
+}
+struct Access { std::vector<ByteView> r, w; };
+Access access_of(const yx_op& op) {
+  Access a;
+  a.w.push_back(bytes_of(op.dst));
+  const bool reads_src = op.kind != YX_OP_S2D && !(op.kind == YX_OP_CONV && (op.aux & 4));
+  if (reads_src) a.r.push_back(bytes_of(op.src));
+  if (op.kind == YX_OP_CONV && op.res.c > 0) a.r.push_back(bytes_of(op.res));
+  if (op.kind == YX_OP_CONV && op.up.c > 0) a.r.push_back(bytes_of(op.up));
+  return a;
+}
+bool any_overlap(const std::vector<ByteView>& x, const std::vector<ByteView>& y) {
+  for (const ByteView& a : x)
+    for (const ByteView& b : y)
+      if (overlap(a, b)) return true;
+  return false;
+}
+}  // namespace
+
+// Assigns every step a lane and the cross-lane events it has to wait for.  Greedy list scheduling in program order: a step
+// continues the lane whose LAST step it depends on (the latest such dependency), otherwise it takes a lane nothing has used
+// yet, otherwise the least recently used one; dependencies already ordered before it (same lane, or implied by an earlier
+// wait: `seen`) need no event.
+static void plan_lanes(yx_engine* e) {
+  const int n = (int)e->steps.size(), K = yx_engine::kLanes;
+  e->lane.assign(n, 0);
+  e->waits.assign(n, {});
+  e->needs_event.assign(n, 0);
+  std::vector<Access> acc(n);
+  for (int i = 0; i < n; ++i) acc[i] = access_of(e->steps[i].op);
+  std::vector<int> last(K, -1);                        // last step on each lane
+  std::vector<std::vector<int>> seen(K, std::vector<int>(K, -1));   // seen[L][M]: latest step of lane M ordered before lane L's next step
+  std::vector<std::vector<int>> snap(n);               // seen[] of a step's lane right after the step (for transitive ordering)
+  last[0] = 0;                                         // step 0 (reads the caller's image) runs on the caller's stream, before the fork
+  for (int k = 0; k < K; ++k) seen[k][0] = 0;          // ... so every lane is ordered after it
+  snap[0] = seen[0];
+  for (int i = 1; i < n; ++i) {
+    std::vector<int> deps;
+    for (int j = i - 1; j >= 0; --j)
+      if (any_overlap(acc[j].w, acc[i].r) || any_overlap(acc[j].r, acc[i].w) || any_overlap(acc[j].w, acc[i].w)) deps.push_back(j);
+    int L = -1;
+    for (int d : deps) {                               // deps are in decreasing order: the latest dependency first
+      const int ld = e->lane[d];
+      if (last[ld] == d) { L = ld; break; }
+    }
+    if (L < 0)
+      for (int k = 0; k < K && L < 0; ++k)
+        if (last[k] < 0) L = k;
+    if (L < 0) {
+      L = 0;
+      for (int k = 1; k < K; ++k)
+        if (last[k] < last[L]) L = k;
+    }
+    e->lane[i] = L;
+    for (int d : deps) {
+      const int ld = e->lane[d];
+      if (ld == L || seen[L][ld] >= d) continue;       // same lane, or already ordered by an earlier wait
+      e->waits[i].push_back(d);
+      e->needs_event[d] = 1;
+      seen[L][ld] = d;
+      for (int k = 0; k < K; ++k) seen[L][k] = std::max(seen[L][k], snap[d][k]);
+    }
+    last[L] = i;
+    seen[L][L] = i;
+    snap[i] = seen[L];
+  }
+  e->lanes_used = 1;
+  for (int i = 0; i < n; ++i) e->lanes_used = std::max(e->lanes_used, e->lane[i] + 1);
+  if (getenv("YX_LANES_VERBOSE"))
+    for (int i = 0; i < n; ++i) {
+      fprintf(stderr, "lanes: step %3d lane %d%s waits", i, e->lane[i], e->needs_event[i] ? " (event)" : "");
+      for (int d : e->waits[i]) fprintf(stderr, " %d", d);
+      fprintf(stderr, "\n");
+    }
+}
+
+static int lanes_init(yx_engine* e) {
+  plan_lanes(e);
+  e->events.assign(e->steps.size(), nullptr);
+  for (size_t i = 0; i < e->steps.size(); ++i)
+    if (e->needs_event[i]) YX_CUDA(cudaEventCreateWithFlags(&e->events[i], cudaEventDisableTiming));
+  YX_CUDA(cudaEventCreateWithFlags(&e->fork_event, cudaEventDisableTiming));
+  for (int k = 1; k < e->lanes_used; ++k) {
+    YX_CUDA(cudaStreamCreateWithFlags(&e->lane_streams[k], cudaStreamNonBlocking));
+    YX_CUDA(cudaEventCreateWithFlags(&e->join_events[k], cudaEventDisableTiming));
+  }
+  return YX_OK;
+}
+
+// Steps [first, n) over the lanes; `st` is lane 0.  Works under stream capture too (the side streams join the capture through
+// the fork event and rejoin `st` before it returns).
+static int run_lanes(yx_engine* e, size_t first, const void* image, int image_dtype, float in_scale, float in_shift, cudaStream_t st) {
+  YX_CUDA(cudaEventRecord(e->fork_event, st));
+  for (int k = 1; k < e->lanes_used; ++k) YX_CUDA(cudaStreamWaitEvent(e->lane_streams[k], e->fork_event, 0));
+  int rc = YX_OK;
+  bool started[yx_engine::kLanes] = {true, false, false, false};
+  for (size_t i = first; i < e->steps.size() && rc == YX_OK; ++i) {
+    cudaStream_t s = e->lane[i] == 0 ? st : e->lane_streams[e->lane[i]];
+    bool waited = !started[e->lane[i]];   // (first kernel of a side lane: it follows the fork's event wait, not a kernel)
+    started[e->lane[i]] = true;
+    for (int d : e->waits[i])
+      if ((size_t)d >= first) { YX_CUDA(cudaStreamWaitEvent(s, e->events[d], 0)); waited = true; }
+    rc = run_step(e, e->steps[i], image, image_dtype, in_scale, in_shift, s, waited);
+    if (rc == YX_OK && e->needs_event[i]) YX_CUDA(cudaEventRecord(e->events[i], s));
+  }
+  for (int k = 1; k < e->lanes_used; ++k) {   // always rejoin (also after an error: a capture must not be left forked)
+    cudaEventRecord(e->join_events[k], e->lane_streams[k]);
+    cudaStreamWaitEvent(st, e->join_events[k], 0);
+  }
+  return rc;
+}
 
 extern "C" const char* yx_last_error(void) { return g_last_error.c_str(); }
 extern "C" int yx_abi_version(void) { return YX_ABI_VERSION; }
@@ -194,12 +342,27 @@ extern "C" int yx_engine_create(const yx_op* ops, int n_ops, void* arena, size_t
     }
     if (rc != YX_OK) { yx_engine_destroy(e); return rc; }
   }
+  {  // lanes: on for small batches (YX_LANES=1 forces them on for any batch, 0 turns them off)
+    const char* le = getenv("YX_LANES");
+    e->lanes_on = le ? atoi(le) != 0 : batch <= 8;
+    if (e->lanes_on) {
+      int rc = lanes_init(e);
+      if (rc != YX_OK) { yx_engine_destroy(e); return rc; }
+      if (e->lanes_used < 2) e->lanes_on = false;
+    }
+  }
   *out = e;
   return YX_OK;
 }
 
 extern "C" void yx_engine_destroy(yx_engine* e) {
   if (!e) return;
+  for (cudaEvent_t ev : e->events) if (ev) cudaEventDestroy(ev);
+  if (e->fork_event) cudaEventDestroy(e->fork_event);
+  for (int k = 1; k < yx_engine::kLanes; ++k) {
+    if (e->join_events[k]) cudaEventDestroy(e->join_events[k]);
+    if (e->lane_streams[k]) cudaStreamDestroy(e->lane_streams[k]);
+  }
   if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
   if (e->graph_stream) cudaStreamDestroy(e->graph_stream);
   for (void* ptr : e->owned) cudaFree(ptr);
@@ -215,6 +378,7 @@ extern "C" int yx_engine_run(yx_engine* e, const void* image, int image_dtype, f
   int rc = run_step(e, e->steps[0], image, image_dtype, in_scale, in_shift, st);
   if (rc) return rc;
   if (!use_graph) {
+    if (e->lanes_on) return run_lanes(e, 1, image, image_dtype, in_scale, in_shift, st);
     for (size_t i = 1; i < e->steps.size(); ++i)
       if ((rc = run_step(e, e->steps[i], image, image_dtype, in_scale, in_shift, st)) != YX_OK) return rc;
     return YX_OK;
@@ -227,8 +391,10 @@ extern "C" int yx_engine_run(yx_engine* e, const void* image, int image_dtype, f
     if (!e->graph_stream) YX_CUDA(cudaStreamCreateWithFlags(&e->graph_stream, cudaStreamNonBlocking));
     cudaStream_t cs = e->graph_stream;
     YX_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-    for (size_t i = 1; i < e->steps.size() && rc == YX_OK; ++i)
-      rc = run_step(e, e->steps[i], image, image_dtype, in_scale, in_shift, cs);
+    if (e->lanes_on) rc = run_lanes(e, 1, image, image_dtype, in_scale, in_shift, cs);
+    else
+      for (size_t i = 1; i < e->steps.size() && rc == YX_OK; ++i)
+        rc = run_step(e, e->steps[i], image, image_dtype, in_scale, in_shift, cs);
     cudaError_t ce = cudaStreamEndCapture(cs, &graph);
     if (rc != YX_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
     YX_CUDA(ce);

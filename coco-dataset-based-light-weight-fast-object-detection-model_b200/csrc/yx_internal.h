@@ -98,6 +98,7 @@ struct ConvPlan {
   ConvTune tune;
   int grid, threads;
   int store_only;  // launch an in-place residual conv (p.has_res == 2) with plain stores (tuning / profiling only)
+  int no_pdl;      // launch without the programmatic-dependent-launch attribute (an op that waits on another stream's event)
   int smem_bytes;
   double flops;  // algorithmic: 2*N*Hout*Wout*Cout*Cin*k*k (real channel counts)
   double bytes;  // algorithmic: fp16 in + out (+ residual) + weights

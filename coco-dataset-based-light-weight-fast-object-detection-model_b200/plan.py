@@ -205,10 +205,18 @@ class Graph:
     def place_buffers(self):
         """Greedy-by-size first-fit over [first,last] live ranges."""
         n_ops = len(self.ops)
+        # Small batches run the op list over several streams (csrc/yx_engine.cu "lanes": the head's pyramid levels, its cls /
+        # reg branches and the bottom-up path side by side), ordered by the arena ranges every op reads and writes.  Reusing a
+        # dead buffer's memory would add write-after-read / write-after-write edges between otherwise independent ops, so every
+        # buffer keeps its own range there (all of YOLOX-M-P6 1280x1280 is 0.55 GB per image).
+        lanes = os.environ.get("YX_LANES")
+        no_reuse = self.batch <= 8 and (lanes is None or lanes != "0")
         for b in self.bufs:
             assert b.last >= 0, f"buffer {b.name} is never used"
             if b.pinned:
                 b.last = n_ops
+            if no_reuse:
+                b.first, b.last = 0, n_ops
         placed: List[Buf] = []
         for b in sorted(self.bufs, key=lambda x: -x.nbytes):
             busy = sorted((p.offset, p.offset + p.nbytes) for p in placed

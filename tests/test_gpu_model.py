@@ -110,6 +110,28 @@ def test_stand_alone_s2d_path(name, H, W, B, monkeypatch):
         assert all(torch.equal(p, q) for p, q in zip(a, b)), f"uint8 and fp16 input disagree (fuse={fuse})"
 
 
+@pytest.mark.parametrize("name,H,W,B", [("yolox_m_p6", 320, 320, 1), ("tiny_p6", 128, 192, 2), ("tiny", 96, 160, 3), ("tiny_dw", 128, 96, 1)])
+def test_lanes_equal_single_stream(name, H, W, B, monkeypatch):
+    """Small batches run the op list over several streams (the head's pyramid levels and cls / reg branches side by side),
+    ordered by events derived from the arena ranges each op reads and writes.  The same kernels run either way, so the
+    logits must be bit-identical to the single-stream run -- eagerly, from the engine's CUDA graph, and over repeated runs
+    (a missing dependency would show as an intermittent difference)."""
+    cfg, fused, model = _build(name, H, W, 7)
+    x = mr.synth_images(13, B, H, W).cuda().half()
+    monkeypatch.setenv("YX_TUNE", "0")
+    monkeypatch.setenv("YX_LANES", "0")
+    model.invalidate_engines()
+    _, reg8, cls = model.run_engine(x)
+    ref = (reg8.clone(), cls.clone())
+    monkeypatch.setenv("YX_LANES", "1")
+    model.invalidate_engines()
+    for use_graph in (False, True):                                # eagerly, then from the engine's own CUDA graph
+        for it in range(6):
+            _, reg8, cls = model.run_engine(x, 1.0, 0.0, use_graph)
+            torch.cuda.synchronize()
+            assert torch.equal(reg8, ref[0]) and torch.equal(cls, ref[1]), f"run {it} (graph={use_graph}) differs from the single-stream result"
+
+
 def test_depthwise_kernels_agree(monkeypatch):
     """The three stride-1 depthwise kernels (shared-memory tile, register-blocked strip, one thread per output) sum the
     same products in the same order: the whole depthwise model's logits must be bit-identical whichever runs."""
