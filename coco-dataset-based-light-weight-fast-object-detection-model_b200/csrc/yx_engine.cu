@@ -344,7 +344,8 @@ extern "C" int yx_engine_create(const yx_op* ops, int n_ops, void* arena, size_t
   }
   {  // lanes: on for small batches (YX_LANES=1 forces them on for any batch, 0 turns them off)
     const char* le = getenv("YX_LANES");
-    e->lanes_on = le ? atoi(le) != 0 : batch <= 8;
+    const char* mb = getenv("YX_LANES_MAX_BATCH");   // (experiments; the arena planner reads the same variable)
+    e->lanes_on = le ? atoi(le) != 0 : batch <= (mb ? atoi(mb) : 8);
     if (e->lanes_on) {
       int rc = lanes_init(e);
       if (rc != YX_OK) { yx_engine_destroy(e); return rc; }

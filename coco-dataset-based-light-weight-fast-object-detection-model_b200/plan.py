@@ -210,7 +210,7 @@ class Graph:
         # dead buffer's memory would add write-after-read / write-after-write edges between otherwise independent ops, so every
         # buffer keeps its own range there (all of YOLOX-M-P6 1280x1280 is 0.55 GB per image).
         lanes = os.environ.get("YX_LANES")
-        no_reuse = self.batch <= 8 and (lanes is None or lanes != "0")
+        no_reuse = self.batch <= int(os.environ.get("YX_LANES_MAX_BATCH", "8")) and (lanes is None or lanes != "0")
         for b in self.bufs:
             assert b.last >= 0, f"buffer {b.name} is never used"
             if b.pinned:
